@@ -1,0 +1,201 @@
+/* pp_b200.h -- C ABI of the B200-native local-planner hot path (libpp_b200.so).
+ *
+ * This is the drop-in boundary below the reference's C++ class API.  The reference has no FFI: its
+ * callers (src/local_planner.cpp:158-166, :204-205, :241, :287-288, :316 and utils/\*\/test_*.cpp)
+ * use the C++ classes of include/path_planning_pkg/ directly.  The replacement keeps those classes
+ * (include/path_planning_pkg/\*.h in this repo, implemented in path_planning_pkg_b200/csrc/host/)
+ * as thin host-side handles and routes every per-cell / per-state / per-query computation through
+ * the entry points below into hand-written sm_100a kernels.  Plain pointers and sizes only; every
+ * function returns 0 on success or a negative pp_status, pp_last_error() gives the text.
+ * There is NO CPU implementation behind this ABI: without a CUDA device pp_create() fails.
+ *
+ * Each entry point cites the reference interface it replaces (paths relative to the reference repo).
+ */
+#ifndef PP_B200_H
+#define PP_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PP_API_MAX_STEER 16
+
+enum pp_status_code
+{
+    PP_SUCCESS = 0,
+    PP_ERR_INVALID = -1,      /* bad argument */
+    PP_ERR_CUDA = -2,         /* CUDA runtime error, see pp_last_error() */
+    PP_ERR_NO_DEVICE = -3,    /* no CUDA device: the library has no CPU path */
+    PP_ERR_CAPACITY = -4      /* a per-query capacity was exceeded (reported per query in pp_result.status) */
+};
+
+/* The 20 constructor arguments of HybridAStar<T> (include/path_planning_pkg/HybridAStar.h:33-38). */
+typedef struct pp_params
+{
+    int   shot_interval;            /* dubins_shot_interval */
+    int   shot_decay;               /* dubins_shot_interval_decay */
+    float resolution;               /* grid_resolution */
+    float obstacle_threshold;
+    float prob_min;
+    float prob_max;
+    float prob_free;
+    int   grid_size;
+    int   allow_diag;               /* grid_2d_allow_diag_moves */
+    float step_size;
+    float max_lat_acc;
+    float max_long_dec;
+    float wheelbase;
+    float rear_to_cg;
+    float apf_rep_constant;
+    float apf_active_angle;
+    int   num_angle_bins;
+    int   num_actions;
+    int   num_steering;
+    float steering[PP_API_MAX_STEER];
+    float curvature_weights[PP_API_MAX_STEER];
+} pp_params;
+
+/* Derived constants (what the reference constructors compute), for inspection and tests. */
+typedef struct pp_consts_info
+{
+    float log_threshold, log_min, log_max, log_free;
+    float precision, r_min, ang_step;
+    int   n2, n45;
+} pp_consts_info;
+
+/* Frame of one (map, goal) group after pp_update_goal. */
+typedef struct pp_frame_info
+{
+    float grid_heading;
+    float goal_world[3];
+    float goal_grid[3];
+    int   goal_bin, goal_ci, goal_cj;
+    int   num_apf;
+} pp_frame_info;
+
+/* Node3D (include/path_planning_pkg/Node3D.h:17-25) without the raw pointers. */
+typedef struct pp_state
+{
+    float x, y, heading;
+    float g, f;
+    float vmin_sqr;
+    int   curvature_index;
+    int   angle_bin;
+    int   ci, cj;
+} pp_state;
+
+typedef struct pp_pop
+{
+    int   ci, cj, bin;
+    float x, y, heading;
+    float g, f;
+} pp_pop;
+
+/* One query of a batch: HybridAStar::find_path(vel_init, start, ...) on planner `group`. */
+typedef struct pp_query
+{
+    float x, y, heading;   /* start pose, world frame */
+    float vel;             /* vel_init */
+    int   group;
+} pp_query;
+
+typedef struct pp_result
+{
+    int   success;
+    int   status;            /* 0 or PP_STATUS_* capacity bits (pp_defs.h) */
+    float cost;
+    int   n_pops;            /* node expansions */
+    int   n_pops_bin_oob;    /* expansions in heading bin == num_angle_bins (undefined in the reference) */
+    int   n_chain;
+    int   n_dubins;
+    int   n_lazy_searches;
+    int   n_lazy_pops;
+    int   max_open;
+    int   n_closed;
+    int   n_path;            /* points written to the path output (= n_dubins + n_chain) */
+} pp_result;
+
+typedef struct pp_search_opts
+{
+    int max_expansions;      /* closed-log capacity per query (reference: unbounded) */
+    int max_open;            /* 3D open-list pool per query */
+    int max_open2d;          /* 2D open-list pool per query */
+    int path_cap;            /* path points per query in the output arrays */
+    int trace_cap;           /* pops recorded per query (0 = no trace) */
+    int max_slots;           /* resident query slots (0 = auto from free memory) */
+} pp_search_opts;
+
+typedef struct pp_context pp_context;
+
+const char* pp_last_error(void);
+int  pp_device_count(void);
+
+/* HybridAStar<T>::HybridAStar(...) (lib/HybridAStar.cpp:7-24): one context = shared parameters and
+ * `num_groups` independent planner instances (map + goal frame + APF list each). */
+int  pp_create(const pp_params* params, int device, int num_groups, pp_context** out);
+void pp_destroy(pp_context* ctx);
+int  pp_get_consts(pp_context* ctx, pp_consts_info* out);
+int  pp_get_frame(pp_context* ctx, int group, pp_frame_info* out);
+/* VehicleModel tables (lib/VehicleModel.cpp:31-40): offset_xy[S][bins][2], heading offsets, costs, |curvature| */
+int  pp_get_tables(pp_context* ctx, float* offset_xy, float* offset_heading, float* actions_cost, float* abs_curv);
+
+/* HybridAStar::update_goal (lib/HybridAStar.cpp:55-59 -> Grid3D::update_goal_heading, Grid3D.cpp:102-124,
+ * including relocate_obstacles, Grid3D.cpp:169-203). */
+int  pp_update_goal(pp_context* ctx, int group, const float* goal3, const float* start3);
+/* HybridAStar::reset (lib/HybridAStar.cpp:49-52).  The lazy A* cache is per query here, so this is a no-op kept for API parity. */
+int  pp_reset(pp_context* ctx, int group);
+/* HybridAStar::update_obstacles(boxes, confidence, apf_added_radius) (lib/HybridAStar.cpp:29-33 ->
+ * Grid3D.cpp:22-44 -> Grid2D.cpp:99-139).  boxes = n x (x, y, dx, dy), world frame. */
+int  pp_update_obstacles_boxes(pp_context* ctx, int group, const float* boxes_xydxdy, const float* confidence,
+                               int n, float apf_added_radius);
+/* Grid2D::update_obstacles(boxes, confidence) only (no APF list rebuild), lib/Grid2D.cpp:99-139 */
+int  pp_update_obstacles_boxes_2d(pp_context* ctx, int group, const float* boxes_xydxdy, const float* confidence, int n);
+/* HybridAStar::update_obstacles(lines, confidence, line_width) (lib/HybridAStar.cpp:36-40 -> Grid2D.cpp:142-194) */
+int  pp_update_obstacles_lines(pp_context* ctx, int group, const float* lines_x1y1x2y2, const float* confidence,
+                               int n, float line_width);
+/* HybridAStar::update_obstacles() (lib/HybridAStar.cpp:43-46 -> Grid2D.cpp:197-208) */
+int  pp_update_obstacles_decay(pp_context* ctx, int group);
+/* HybridAStar::get_obstacles() (lib/HybridAStar.cpp:62-65): N*N floats, row = i (grid x) */
+int  pp_map_download(pp_context* ctx, int group, float* out_nn);
+int  pp_map_upload(pp_context* ctx, int group, const float* in_nn);
+/* device pointer of a group's map (for NCCL broadcast by the caller) */
+void* pp_map_device_ptr(pp_context* ctx, int group);
+int  pp_sync(pp_context* ctx);
+
+/* Grid3D::set_start_node (lib/Grid3D.cpp:127-160) + HybridAStar.cpp:73-74 for n queries (host side) */
+int  pp_set_start_batch(pp_context* ctx, const pp_query* queries, int n, pp_state* out);
+
+/* ---- stateless batched kernels (each directly comparable with one reference function) ---- */
+/* VehicleModel::get_neighbors (lib/VehicleModel.cpp:63-105): out[n][2A+1], count per state, neglect flag */
+int  pp_rollout_batch(pp_context* ctx, const pp_state* in, int n, pp_state* out, int* n_out, int* flags);
+/* Grid3D::get_neighbors (lib/Grid3D.cpp:47-74): roll-out + bounds/collision lookup + APF cost */
+int  pp_expand_batch(pp_context* ctx, int group, const pp_state* in, int n, pp_state* out, int* n_out, int* flags);
+/* successor collision lookup alone (lib/Grid3D.cpp:56-59): free[k] = 1 when in bounds and below threshold; cells out */
+int  pp_collision_batch(pp_context* ctx, int group, const float* xy, int n, int* free_out, int* cells_ij);
+/* Grid3D::get_field_intensity (lib/Grid3D.cpp:206-227) for n poses (x, y, heading) */
+int  pp_apf_batch(pp_context* ctx, int group, const float* xyh, int n, float* out);
+/* Grid3D::check_path (lib/Grid3D.cpp:78-93): blocked[k] per point, returns collision-free flag in *free_out */
+int  pp_check_path(pp_context* ctx, int group, const float* xyh, int n, int* free_out);
+/* Dubins::get_shortest_path_length (lib/Dubins.cpp:19-69) for n starts and one goal */
+int  pp_dubins_length_batch(pp_context* ctx, const float* starts_xyh, int n, const float* goal3, float* length,
+                            int* type, float* params4);
+/* Dubins::get_shortest_path (lib/Dubins.cpp:125-153): returns sample count in *n_out */
+int  pp_dubins_path(pp_context* ctx, const float* start3, const float* goal3, float* xyh, float* curvature, int cap,
+                    int* n_out, float* length, int* long_turn_flag);
+/* AStar::find_path(i, j) (lib/AStar.cpp:100-113) called in sequence on a fresh cache for n cells */
+int  pp_astar_lazy_batch(pp_context* ctx, int group, const int* ij, int n, float* out);
+
+/* ---- the search: HybridAStar::find_path (lib/HybridAStar.cpp:68-88) for a batch of queries ---- */
+/* paths: n x path_cap x (x, y, heading) world frame in the reference's order (goal -> start);
+ * curvature: n x path_cap; trace: n x trace_cap pops (may be NULL). */
+int  pp_find_path_batch(pp_context* ctx, const pp_query* queries, int n, const pp_search_opts* opts,
+                        pp_result* results, float* paths_xyh, float* curvature, pp_pop* trace);
+/* Split form used by bench.py: upload once, run (timed on the device), fetch. */
+int  pp_batch_upload(pp_context* ctx, const pp_query* queries, int n, const pp_search_opts* opts);
+int  pp_batch_run(pp_context* ctx, float* kernel_ms);
+int  pp_batch_fetch(pp_context* ctx, pp_result* results, float* paths_xyh, float* curvature, pp_pop* trace);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

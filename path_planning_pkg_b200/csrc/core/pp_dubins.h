@@ -1,0 +1,207 @@
+// Dubins CSC paths (RSR, RSL, LSR, LSL): shortest length = non-holonomic heuristic, and the sampled
+// path of the analytic "Dubins shot".  Behaviour follows lib/Dubins.cpp of the reference:
+//   length  : Dubins.cpp:19-69 (candidate order RSR,RSL,LSR,LSL, strict '<', NaN never wins)
+//   params  : Dubins.cpp:180-323 (one +-2*pi correction only; M_PI_2 sums in double, stored as float)
+//   sampling: Dubins.cpp:326-563 (theta accumulated in float; headings through wrap_pi<double>)
+// The four candidates are independent, so a warp evaluates (successor, candidate) pairs on separate
+// lanes and folds them in candidate order; this header provides the per-candidate pieces.
+#ifndef PP_DUBINS_H
+#define PP_DUBINS_H
+
+#include "pp_math.h"
+
+enum { PP_RSR = 0, PP_RSL = 1, PP_LSR = 2, PP_LSL = 3 };
+
+struct PPDubinsCenters
+{
+    float srx, sry, slx, sly;   // start right / left circle centres
+    float grx, gry, glx, gly;   // goal right / left circle centres
+};
+
+// Dubins.cpp:23-34
+PP_HD void pp_dubins_centers(float r, float sx, float sy, float sh, float gx, float gy, float gh,
+                             PPDubinsCenters& c)
+{
+    float ss = pp_sinf(sh), cs = pp_cosf(sh);
+    float sg = pp_sinf(gh), cg = pp_cosf(gh);
+    c.srx = sx + r * ss; c.sry = sy - r * cs;
+    c.slx = sx - r * ss; c.sly = sy + r * cs;
+    c.grx = gx + r * sg; c.gry = gy - r * cg;
+    c.glx = gx - r * sg; c.gly = gy + r * cg;
+}
+
+// centre pair used by candidate `type` (Dubins.cpp:37, :42, :51, :60)
+PP_HD void pp_dubins_pick(const PPDubinsCenters& c, int type, float& csx, float& csy, float& cgx, float& cgy)
+{
+    bool s_right = (type == PP_RSR) || (type == PP_RSL);
+    bool g_right = (type == PP_RSR) || (type == PP_LSR);
+    csx = s_right ? c.srx : c.slx; csy = s_right ? c.sry : c.sly;
+    cgx = g_right ? c.grx : c.glx; cgy = g_right ? c.gry : c.gly;
+}
+
+// One candidate: get_params_{rsr,rsl,lsr,lsl} (Dubins.cpp:180-323).  p[4] = {start angle, delta on the
+// start circle, start angle on the goal circle, delta on the goal circle}.  Returns the path length
+// (NaN for RSL/LSR when the centres are closer than 2r).
+PP_HD float pp_dubins_candidate(int type, float r, float sh, float gh,
+                                float csx, float csy, float cgx, float cgy, float p[4])
+{
+    float dcx = cgx - csx, dcy = cgy - csy;
+    float theta = pp_atan2f(dcy, dcx);
+    if (type == PP_RSR)
+    {
+        p[0] = (float)(PP_PI_2 + (double)sh);
+        float theta_t1 = (float)(PP_PI_2 + (double)theta);
+        p[2] = theta_t1;
+        float theta_g = (float)(PP_PI_2 + (double)gh);
+        p[1] = theta_t1 - p[0];
+        if (p[1] > 0) p[1] = (float)((double)p[1] - 2 * PP_PI);
+        p[3] = theta_g - p[2];
+        if (p[3] > 0) p[3] = (float)((double)p[3] - 2 * PP_PI);
+        float dist_st = sqrtf(dcx * dcx + dcy * dcy);
+        return dist_st + r * -(p[1] + p[3]);
+    }
+    if (type == PP_LSL)
+    {
+        p[0] = (float)(-PP_PI_2 + (double)sh);
+        float theta_t1 = (float)(-PP_PI_2 + (double)theta);
+        p[2] = theta_t1;
+        float theta_g = (float)(-PP_PI_2 + (double)gh);
+        p[1] = theta_t1 - p[0];
+        if (p[1] < 0) p[1] = (float)((double)p[1] + 2 * PP_PI);
+        p[3] = theta_g - p[2];
+        if (p[3] < 0) p[3] = (float)((double)p[3] + 2 * PP_PI);
+        float dist_st = sqrtf(dcx * dcx + dcy * dcy);
+        return dist_st + r * (p[1] + p[3]);
+    }
+    float dist = sqrtf(dcx * dcx + dcy * dcy);
+    float ac = pp_acosf(2 * r / dist);
+    float theta_t1;
+    if (type == PP_RSL)
+    {
+        p[0] = (float)(PP_PI_2 + (double)sh);
+        theta_t1 = ac + theta;
+        p[2] = (float)((double)theta_t1 - PP_PI);
+        float theta_g = (float)(-PP_PI_2 + (double)gh);
+        p[1] = theta_t1 - p[0];
+        if (p[1] > 0) p[1] = (float)((double)p[1] - 2 * PP_PI);
+        p[3] = theta_g - p[2];
+        if (p[3] < 0) p[3] = (float)((double)p[3] + 2 * PP_PI);
+    }
+    else // PP_LSR
+    {
+        p[0] = (float)(-PP_PI_2 + (double)sh);
+        theta_t1 = -ac + theta;
+        p[2] = (float)((double)theta_t1 + PP_PI);
+        float theta_g = (float)(PP_PI_2 + (double)gh);
+        p[1] = theta_t1 - p[0];
+        if (p[1] < 0) p[1] = (float)((double)p[1] + 2 * PP_PI);
+        p[3] = theta_g - p[2];
+        if (p[3] > 0) p[3] = (float)((double)p[3] - 2 * PP_PI);
+    }
+    float ssx = csx + r * pp_cosf(theta_t1);
+    float ssy = csy + r * pp_sinf(theta_t1);
+    float esx = cgx + r * pp_cosf(p[2]);
+    float esy = cgy + r * pp_sinf(p[2]);
+    float dx = esx - ssx, dy = esy - ssy;
+    float dist_st = sqrtf(dx * dx + dy * dy);
+    if (type == PP_RSL) return dist_st + r * (-p[1] + p[3]);
+    return dist_st + r * (p[1] - p[3]);
+}
+
+// Sequential fold of the four candidates, Dubins.cpp:36-68.
+PP_HD float pp_dubins_shortest(float r, float sx, float sy, float sh, float gx, float gy, float gh,
+                               int& best_type, float best_p[4], PPDubinsCenters& c)
+{
+    pp_dubins_centers(r, sx, sy, sh, gx, gy, gh, c);
+    float best = 0.0f;
+    best_type = PP_RSR;
+    for (int type = 0; type < 4; type++)
+    {
+        float csx, csy, cgx, cgy, p[4];
+        pp_dubins_pick(c, type, csx, csy, cgx, cgy);
+        float len = pp_dubins_candidate(type, r, sh, gh, csx, csy, cgx, cgy, p);
+        if (type == 0 || len < best)
+        {
+            best = len; best_type = type;
+            best_p[0] = p[0]; best_p[1] = p[1]; best_p[2] = p[2]; best_p[3] = p[3];
+        }
+    }
+    return best;
+}
+
+// Geometry of the sampled path, shared by all samples (sample_path_*, Dubins.cpp:326-563).
+struct PPDubinsPlan
+{
+    int   type;
+    float p[4];
+    float csx, csy, cgx, cgy;   // centres of the chosen start / goal circles
+    float ssx, ssy;             // start of the straight segment
+    float st_theta, st_cos, st_sin;
+    int   size_1, size_2, size_3;   // cumulative sample counts; total samples = size_3 + 1
+    float s1, s2;               // +1 for a left arc, -1 for a right arc
+    float curvature;            // 1 / r_min
+};
+
+PP_HD void pp_dubins_plan(float r, float step, float ang_step, int type, const float p[4],
+                          const PPDubinsCenters& c, PPDubinsPlan& pl)
+{
+    pl.type = type;
+    pl.p[0] = p[0]; pl.p[1] = p[1]; pl.p[2] = p[2]; pl.p[3] = p[3];
+    pp_dubins_pick(c, type, pl.csx, pl.csy, pl.cgx, pl.cgy);
+    pl.s1 = ((type == PP_RSR) || (type == PP_RSL)) ? -1.0f : 1.0f;
+    pl.s2 = ((type == PP_RSR) || (type == PP_LSR)) ? -1.0f : 1.0f;
+    pl.ssx = pl.csx + r * pp_cosf(p[0] + p[1]);
+    pl.ssy = pl.csy + r * pp_sinf(p[0] + p[1]);
+    float esx = pl.cgx + r * pp_cosf(p[2]);
+    float esy = pl.cgy + r * pp_sinf(p[2]);
+    float dx = esx - pl.ssx, dy = esy - pl.ssy;
+    float length_st = sqrtf(dx * dx + dy * dy);
+    // floor(-p1/as) for a right first arc, floor(p1/as) for a left one (Dubins.cpp:342, :407, :467, :527)
+    float a1 = (pl.s1 < 0) ? -p[1] : p[1];
+    float a3 = (pl.s2 < 0) ? -p[3] : p[3];
+    pl.size_1 = (int)floorf(a1 / ang_step);
+    pl.size_2 = pl.size_1 + (int)floorf(length_st / step);
+    pl.size_3 = pl.size_2 + (int)floorf(a3 / ang_step);
+    pl.st_theta = pp_atan2f(dy, dx);
+    pl.st_cos = pp_cosf(pl.st_theta);
+    pl.st_sin = pp_sinf(pl.st_theta);
+    pl.curvature = 1 / r;
+}
+
+// Sample k of the plan.  `acc` is the float accumulator of the segment the sample lies on:
+// theta (arcs; p0 -/+ k*ang_step accumulated one step at a time) or dist (straight; k*step likewise).
+PP_HD void pp_dubins_sample(const PPDubinsPlan& pl, float r, int k, float acc,
+                            float& x, float& y, float& heading, float& curvature)
+{
+    if (k < pl.size_1)
+    {
+        x = pl.csx + r * pp_cosf(acc);
+        y = pl.csy + r * pp_sinf(acc);
+        heading = (float)pp_wrap_pi_d((double)acc + (double)pl.s1 * PP_PI_2);
+        curvature = pl.curvature;
+    }
+    else if (k < pl.size_2)
+    {
+        x = pl.ssx + acc * pl.st_cos;
+        y = pl.ssy + acc * pl.st_sin;
+        heading = pl.st_theta;
+        curvature = 0.0f;
+    }
+    else if (k < pl.size_3)
+    {
+        x = pl.cgx + r * pp_cosf(acc);
+        y = pl.cgy + r * pp_sinf(acc);
+        heading = (float)pp_wrap_pi_d((double)acc + (double)pl.s2 * PP_PI_2);
+        curvature = pl.curvature;
+    }
+    else
+    {
+        float a = pl.p[2] + pl.p[3];
+        x = pl.cgx + r * pp_cosf(a);
+        y = pl.cgy + r * pp_sinf(a);
+        heading = (float)pp_wrap_pi_d((double)a + (double)pl.s2 * PP_PI_2);
+        curvature = 0.0f;
+    }
+}
+
+#endif

@@ -1,0 +1,58 @@
+// Scalar arithmetic of the hot path with the reference's float<->double promotions reproduced
+// operation by operation.  Compile WITHOUT fused multiply-add contraction
+// (nvcc -fmad=false, g++ -ffp-contract=off): the reference is built for baseline x86-64, which has
+// no FMA, so every a*b+c below must round twice.
+//
+// Float transcendentals: the reference calls glibc's sinf/cosf/atan2f/acosf, which are not
+// correctly rounded and are libm-version dependent.  The device evaluates them in double and rounds
+// once to float ("pinned libm"); oracle/_ref/libref_oracle_crm.so is the reference
+// built against the same definition.
+#ifndef PP_MATH_H
+#define PP_MATH_H
+
+#include "pp_defs.h"
+
+#define PP_PI    3.14159265358979323846   /* M_PI   */
+#define PP_PI_2  1.57079632679489661923   /* M_PI_2 */
+
+PP_HD float pp_sinf(float x) { return (float)sin((double)x); }
+PP_HD float pp_cosf(float x) { return (float)cos((double)x); }
+PP_HD float pp_atan2f(float y, float x) { return (float)atan2((double)y, (double)x); }
+PP_HD float pp_acosf(float x) { return (float)acos((double)x); }
+
+// glibc hypotf == (float)sqrt((double)x*x + (double)y*y) (checked on 2e8 random pairs)
+PP_HD float pp_hypotf(float x, float y)
+{
+    double dx = (double)x, dy = (double)y;
+    return (float)sqrt(dx * dx + dy * dy);
+}
+
+// wrap_pi<float> (common.h:15-29): fmod in double rounded to float, comparisons against M_PI in
+// double, correction in double rounded to float.
+PP_HD float pp_wrap_pi(float angle)
+{
+    float w = (float)fmod((double)angle, 2 * PP_PI);
+    if ((double)w > PP_PI) return (float)((double)w - 2 * PP_PI);
+    if ((double)w < -PP_PI) return (float)((double)w + 2 * PP_PI);
+    return w;
+}
+
+// wrap_pi<double> (common.h:15-29): what `wrap_pi(theta - M_PI_2)` instantiates when theta is
+// float (Dubins.cpp:354, :376, :385 ...), result then rounded to float by the assignment.
+PP_HD double pp_wrap_pi_d(double angle)
+{
+    double w = fmod(angle, 2 * PP_PI);
+    if (w > PP_PI) return w - 2 * PP_PI;
+    if (w < -PP_PI) return w + 2 * PP_PI;
+    return w;
+}
+
+// get_heading_index<float> (common.h:9-12, :32-36): roundf(h/p)*p in float, (+M_PI)/p in double,
+// truncation.  Returns `bins` (one past the end) for headings >= pi - p/2.
+PP_HD int pp_heading_index(float heading, float precision)
+{
+    float rounded = roundf(heading / precision) * precision;
+    return (int)(((double)rounded + PP_PI) / (double)precision);
+}
+
+#endif

@@ -1,0 +1,711 @@
+// EXACT (single-pop) Hybrid A* search of one query, executed by one warp.
+//
+// Parity target: the expanded-node sequence, cost and path of the unmodified reference
+// (lib/HybridAStar.cpp:93-199) on a freshly constructed planner.  To get there the
+// two history-dependent containers of the reference are emulated, not "cleaned up":
+//   * 3D open list  : std::set<Node3D>   -> PPRbTree<PPNode3> under `(a != b) && a.f < b.f` (F5)
+//   * 3D closed set : unordered_set      -> exact (cell, bin) hash set + append-only log (F6)
+//   * holonomic h1  : AStar::find_path(i,j), the lazily evaluated, cached, early-terminating 2D A*
+//                     with its own std::set / unordered_set (F4) -> pp_lazy_astar() below.
+// Work split inside the warp (template parameter W = lane policy):
+//   control lane 0 : container walks (sequential by nature: every comparison depends on the last)
+//   all lanes      : successor roll-out (one lane per steering primitive), collision lookup,
+//                    APF (lanes over obstacles, order-preserving sum), Dubins candidates (lanes over
+//                    (successor, CSC type) pairs), Dubins-shot sampling + collision check, scratch init.
+// With W::LANES == 1 the same source runs on one host thread inside tests/cpp/host_emul.cpp.
+#ifndef PP_SEARCH_H
+#define PP_SEARCH_H
+
+#include "pp_defs.h"
+#include "pp_math.h"
+#include "pp_dubins.h"
+#include "pp_rbtree.h"
+
+#define PP_MAX_SUCC 16
+#define PP_NEAR_CAP 64
+
+// cell_state word of the lazy 2D A*: bit31 = _visted, bit30 = node_map entry touched this query,
+// bits 0..29 = id of the lazy search that closed the cell.
+#define PP_CS_VISITED 0x80000000u
+#define PP_CS_TOUCHED 0x40000000u
+#define PP_CS_STAMP   0x3fffffffu
+
+struct PPNode3   // 3D open-list entry: links + key in the first 32 B sector (all a tree walk reads)
+{
+    int      parent, left, right, color;
+    float    f;
+    unsigned key;        // (ci*N + cj)*(bins+1) + bin
+    float    g, x;
+    float    y, heading, vmin_sqr;
+    int      curv, prev, bin;
+    int      pad0, pad1;
+};
+
+struct PPNode2   // 2D open-list entry (copy of a Node2D at insertion time), 32 B
+{
+    int   parent, left, right, color;
+    float f;
+    int   cell;
+    float g;
+    int   prev;          // cell of the closed parent, -1 = none
+};
+
+struct PPClosed3
+{
+    float    x, y, heading, g, f, vmin_sqr;
+    int      curv, bin;
+    unsigned key;
+    int      prev;       // index of the parent in the closed log, -1 = none
+};
+
+struct PPPathPt { float x, y, heading, curvature; };
+
+struct PPSucc
+{
+    float x, y, heading, g, vmin_sqr;
+    int   curv, bin, ci, cj, ok;
+};
+
+// per (map, goal) group
+struct PPGroup
+{
+    const float* map;    // N*N log-odds, map[i*N + j]  (i along grid x)
+    const float* apf;    // K x (x, y, radius) in grid-frame metres (Grid3D.cpp:22-44)
+    int          K;
+    int          pad;
+    PPFrame      frame;
+};
+
+// per-query scratch (one slot per resident warp)
+struct PPWork
+{
+    PPNode3*   open3;      int open3_cap;
+    PPClosed3* closed;     int closed_cap;
+    int*       chash;      int chash_cap;     // power of two
+    unsigned*  cell_state;                    // N*N
+    float*     nm_g;                          // N*N  node_map[i][j]._cost_g
+    float*     nm_f;                          // N*N  node_map[i][j]._cost_f
+    float*     cl_g;                          // N*N  g of the closed copy (valid iff stamp == search id)
+    int*       cl_prev;                       // N*N  parent cell of the closed copy
+    PPNode2*   open2;      int open2_cap;
+    PPPathPt*  path;       int path_cap;      // [dubins samples (forward) | parent chain (terminal -> start)]
+    PPPop*     trace;      int trace_cap;     // optional
+};
+
+struct PPSmem   // per-warp staging area (shared memory on the device)
+{
+    PPSucc succ[PP_MAX_SUCC];
+    float  cand[PP_MAX_SUCC * 4];
+    int    near_idx[PP_NEAR_CAP];
+};
+
+// ---- lane policy for a single host thread (tests only); the device policy lives in pp_kernels.cu ----
+struct PPWarpSerial
+{
+    enum { LANES = 1 };
+    PP_HD int lane() const { return 0; }
+    PP_HD void sync() const {}
+    PP_HD unsigned ballot(bool p) const { return p ? 1u : 0u; }
+    PP_HD unsigned lanemask_lt() const { return 0u; }
+    template <class T> PP_HD T shfl(T v, int) const { return v; }
+};
+
+// ---------------------------------------------------------------------------------------------------
+// comparators of the reference (Node3D.h:39-54, Node2D.h:27-41)
+struct PPKey3 { unsigned key; float f; };
+struct PPLt3NK { PP_HD bool operator()(const PPNode3& a, const PPKey3& b) const { return (a.key != b.key) && (a.f < b.f); } };
+struct PPLt3KN { PP_HD bool operator()(const PPKey3& a, const PPNode3& b) const { return (a.key != b.key) && (a.f < b.f); } };
+struct PPKey2 { int cell; float f; };
+struct PPLt2NK { PP_HD bool operator()(const PPNode2& a, const PPKey2& b) const { return (a.cell != b.cell) && (a.f < b.f); } };
+struct PPLt2KN { PP_HD bool operator()(const PPKey2& a, const PPNode2& b) const { return (a.cell != b.cell) && (a.f < b.f); } };
+
+// Euclidean 2D heuristic, Grid2D.cpp:303-316 (recomputed instead of stored: 2 muls, 1 add, 1 sqrt)
+PP_HD float pp_h2d(const PPConsts& C, int i, int j)
+{
+    float dx = (C.n45 - i) * C.res;
+    float dy = (C.n2 - j) * C.res;
+    return sqrtf(dx * dx + dy * dy);
+}
+
+struct PPLazy
+{
+    PPRbTree<PPNode2> open;
+    unsigned search_id;
+    int status;
+    int n_searches, n_pops;
+};
+
+PP_HD void pp_lazy_touch(const PPConsts& C, PPWork& wk, int cell)
+{
+    unsigned st = wk.cell_state[cell];
+    if (!(st & PP_CS_TOUCHED))
+    {
+        wk.nm_g[cell] = 0.0f;
+        wk.nm_f[cell] = pp_h2d(C, cell / C.N, cell % C.N);
+        wk.cell_state[cell] = st | PP_CS_TOUCHED;
+    }
+}
+
+// AStar::update_visted + Grid2D::update_costs (AStar.cpp:209-218, Grid2D.cpp:219-227)
+PP_HD void pp_lazy_update_visited(const PPConsts& C, PPWork& wk, float total, int last_cell)
+{
+    int c = last_cell;
+    while (c >= 0)
+    {
+        pp_lazy_touch(C, wk, c);
+        wk.cell_state[c] |= PP_CS_VISITED;
+        wk.nm_f[c] = total - wk.cl_g[c];
+        c = wk.cl_prev[c];
+    }
+}
+
+PP_HD bool pp_lazy_insert(PPLazy& L, int cell, float g, float f, int prev)
+{
+    PPKey2 k; k.cell = cell; k.f = f;
+    int p; bool left;
+    if (!L.open.insert_pos(k, PPLt2NK(), PPLt2KN(), p, left)) return true;   // silently dropped (F5)
+    int s = L.open.alloc();
+    if (s == PP_RB_NIL) { L.status |= PP_STATUS_OPEN2D_OVERFLOW; return false; }
+    PPNode2& n = L.open.n[s];
+    n.f = f; n.cell = cell; n.g = g; n.prev = prev;
+    L.open.insert_and_rebalance(left, s, p);
+    return true;
+}
+
+// AStar::find_path(i, j) + a_star_search (AStar.cpp:100-113, :118-186) on per-query scratch that
+// starts in the freshly-constructed state (g = 0, f = Euclidean h, nothing visited).
+PP_HD_NOINLINE float pp_lazy_astar(const PPConsts& C, const float* map, const PPFrame& F, PPWork& wk,
+                                   PPLazy& L, int ci, int cj)
+{
+    const int N = C.N;
+    int cell = ci * N + cj;
+    unsigned st = wk.cell_state[cell];
+    if (st & PP_CS_VISITED) return wk.nm_f[cell];
+
+    // Grid2D::set_start_node_grid -> soft_reset (Node2D.cpp:34-39)
+    float h0 = pp_h2d(C, ci, cj);
+    wk.nm_g[cell] = 0.0f;
+    wk.nm_f[cell] = h0;
+    wk.cell_state[cell] = st | PP_CS_TOUCHED;
+
+    unsigned sid = ++L.search_id;
+    L.n_searches++;
+    L.open.clear();
+    if (!pp_lazy_insert(L, cell, 0.0f, h0, -1)) return FLT_MAX;
+    const int goal_cell = F.goal_ci * N + F.goal_cj;
+
+    while (!L.open.empty())
+    {
+        int it = L.open.begin();
+        int c = L.open.n[it].cell;
+        float cg;
+        unsigned cs = wk.cell_state[c];
+        if ((cs & PP_CS_STAMP) == sid) cg = wk.cl_g[c];   // re-pop: unordered_set::insert returns the old copy
+        else
+        {
+            cg = L.open.n[it].g;
+            wk.cl_g[c] = cg;
+            wk.cl_prev[c] = L.open.n[it].prev;
+            wk.cell_state[c] = (cs & ~PP_CS_STAMP) | sid;
+        }
+        L.open.erase(it);
+        L.n_pops++;
+
+        int pi = c / N, pj = c - pi * N;
+        if (c == goal_cell)
+        {
+            float total = cg + pp_h2d(C, pi, pj);   // copy's _cost_f = g + h
+            pp_lazy_update_visited(C, wk, total, c);
+            return total;
+        }
+
+        // Grid2D::get_neighbors (Grid2D.cpp:72-96): all valid neighbours first, in action order
+        int   nb_cell[8];
+        float nb_cost[8];
+        int   nn = 0;
+        for (int k = 0; k < C.n_act2d; k++)
+        {
+            int i = pi + C.act_di[k], j = pj + C.act_dj[k];
+            if (i > -1 && i < N && j > -1 && j < N && map[i * N + j] < C.log_thr)
+            {
+                nb_cell[nn] = i * N + j; nb_cost[nn] = C.act_cost[k]; nn++;
+            }
+        }
+        for (int q = 0; q < nn; q++)
+        {
+            int nb = nb_cell[q];
+            float w = nb_cost[q];
+            unsigned ns = wk.cell_state[nb];
+            if (ns & PP_CS_VISITED)
+            {
+                float total = wk.nm_f[nb] + cg + w;
+                pp_lazy_update_visited(C, wk, total, c);
+                return total;
+            }
+            if ((ns & PP_CS_STAMP) == sid) continue;    // in the closed set of this search
+            pp_lazy_touch(C, wk, nb);
+            PPKey2 k; k.cell = nb; k.f = wk.nm_f[nb];    // node_map's current (possibly stale) f
+            int it_node = L.open.find(k, PPLt2NK(), PPLt2KN());
+            float newg = cg + w;
+            if (it_node == PP_RB_NIL)
+            {
+                float nf = newg + pp_h2d(C, nb / N, nb % N);
+                wk.nm_g[nb] = newg; wk.nm_f[nb] = nf;
+                if (!pp_lazy_insert(L, nb, newg, nf, c)) return FLT_MAX;
+            }
+            else if (newg < L.open.n[it_node].g)
+            {
+                L.open.erase(it_node);
+                float nf = newg + pp_h2d(C, nb / N, nb % N);
+                wk.nm_g[nb] = newg; wk.nm_f[nb] = nf;
+                if (!pp_lazy_insert(L, nb, newg, nf, c)) return FLT_MAX;
+            }
+        }
+    }
+    return FLT_MAX;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// stateless pieces (also exported one by one through the C ABI for parity tests)
+
+// One successor of VehicleModel::get_neighbors (VehicleModel.cpp:63-105) for steering index i.
+// off_xy is [S][bins+1][2]; column `bins` duplicates column 0.  Returns false when the
+// primitive is pruned by the lateral-acceleration limit.
+PP_HD bool pp_rollout_one(const PPConsts& C, const float* off_xy, float x, float y, float heading, float g,
+                          float vmin_sqr, int bin, int i, PPSucc& o)
+{
+    float v2 = 0.0f;
+    if (!(vmin_sqr < 1.0f))
+    {
+        float lat = vmin_sqr * C.abs_curv[i];
+        if (lat > C.max_lat_acc) return false;
+        float acc_long = (float)sqrt(1.0 - (double)((lat * lat) / C.max_lat_acc_sqr));
+        v2 = vmin_sqr - 2 * acc_long * C.ts;
+    }
+    const float* off = off_xy + ((size_t)i * (C.bins + 1) + bin) * 2;
+    o.x = x + off[0];
+    o.y = y + off[1];
+    o.heading = pp_wrap_pi(heading + C.off_heading[i]);
+    o.g = g + C.act_cost3d[i];
+    o.vmin_sqr = v2;
+    o.curv = i;
+    o.bin = pp_heading_index(o.heading, C.precision);
+    return true;
+}
+
+// bounds + collision lookup of Grid3D::get_neighbors (Grid3D.cpp:56-59)
+PP_HD bool pp_collision_free(const PPConsts& C, const float* map, float x, float y, int& ci, int& cj)
+{
+    ci = (int)(x / C.res);
+    cj = (int)(y / C.res);
+    return (ci > -1) && (ci < C.N) && (cj > -1) && (cj < C.N) && (map[ci * C.N + cj] < C.log_thr);
+}
+
+// rounded-index lookup of Grid3D::check_path (Grid3D.cpp:83-90); true = blocked
+PP_HD bool pp_path_point_blocked(const PPConsts& C, const float* map, float x, float y)
+{
+    int i1 = (int)roundf(x / C.res);
+    int j1 = (int)roundf(y / C.res);
+    return (i1 < 0) || (i1 >= C.N) || (j1 < 0) || (j1 >= C.N) || (map[i1 * C.N + j1] >= C.log_thr);
+}
+
+// one obstacle's term of Grid3D::get_field_intensity (Grid3D.cpp:209-223)
+PP_HD float pp_apf_term(const PPConsts& C, float ox, float oy, float radius, float x, float y, float heading)
+{
+    float dx = ox - x, dy = oy - y;
+    float distance = pp_hypotf(dx, dy);
+    if (!(distance < radius)) return 0.0f;
+    float angle = fabsf(pp_wrap_pi(heading - pp_atan2f(dy, dx)));
+    float a = C.apf_alpha - angle;
+    angle = (a < 0.0f) ? 0.0f : a;
+    double d = 1.0 / (double)distance - 1.0 / (double)radius;
+    float fp = (float)((double)C.apf_k * (d * d));
+    fp = fp * angle / C.apf_alpha;
+    return fp;
+}
+
+// Order-preserving warp sum of the APF terms over the obstacle index list idx[0..n) (or 0..n-1 when
+// idx == nullptr): std::accumulate from T(0) in obstacle order (Grid3D.cpp:226).  Zero terms are skipped
+// (x + 0 == x), non-zero terms are added one by one in index order.
+template <class W>
+PP_HD float pp_apf_sum(const W& w, const PPConsts& C, const float* apf, const int* idx, int n,
+                       float x, float y, float heading)
+{
+    float acc = 0.0f;
+    for (int base = 0; base < n; base += W::LANES)
+    {
+        int q = base + w.lane();
+        float term = 0.0f;
+        if (q < n)
+        {
+            int k = idx ? idx[q] : q;
+            float ox = apf[3 * k], oy = apf[3 * k + 1], r = apf[3 * k + 2];
+            // cheap conservative reject before the double-precision path
+            float dx = ox - x, dy = oy - y, lim = r * 1.001f + 1e-3f;
+            if (dx * dx + dy * dy <= lim * lim) term = pp_apf_term(C, ox, oy, r, x, y, heading);
+        }
+        unsigned m = w.ballot(term != 0.0f);
+        while (m)
+        {
+            int src = 0;
+            unsigned t = m;
+            while (!(t & 1u)) { t >>= 1; src++; }
+            acc = acc + w.shfl(term, src);
+            m &= m - 1;
+        }
+    }
+    return acc;
+}
+
+// Successors of one popped state, Grid3D::get_neighbors (Grid3D.cpp:47-74) = VehicleModel roll-out
+// (one lane per steering primitive) + bounds/collision lookup + APF cost (lanes over obstacles).
+// Results in sm.succ[0 .. 2A] (ok = 0 for pruned / colliding primitives); g includes the field cost.
+template <class W>
+PP_HD void pp_expand_warp(const W& w, const PPConsts& C, const float* off_xy, const PPGroup& G,
+                          float px, float py, float ph, float pg, float pv2, int pcurv, int pbin, PPSmem& sm)
+{
+    const int lane = w.lane();
+    const int n_succ_max = 2 * C.A + 1;
+    int start_index = pcurv - C.A;
+    if (start_index < 0) start_index = 0;
+    for (int s = lane; s < n_succ_max; s += W::LANES)
+    {
+        PPSucc o; o.ok = 0;
+        int i = start_index + s;
+        int bin = (pbin > C.bins) ? C.bins : pbin;
+        if (i < C.S && pp_rollout_one(C, off_xy, px, py, ph, pg, pv2, bin, i, o))
+            o.ok = pp_collision_free(C, G.map, o.x, o.y, o.ci, o.cj) ? 1 : 0;
+        sm.succ[s] = o;
+    }
+    // obstacles that can reach any successor (successors lie within ts of the parent), order kept
+    int n_near = 0;
+    for (int base = 0; base < G.K; base += W::LANES)
+    {
+        int k = base + lane;
+        bool nearp = false;
+        if (k < G.K)
+        {
+            float dx = G.apf[3 * k] - px, dy = G.apf[3 * k + 1] - py;
+            float lim = G.apf[3 * k + 2] + C.ts * 1.5f + 0.05f;
+            nearp = (dx * dx + dy * dy) <= lim * lim * 1.001f;
+        }
+        unsigned m = w.ballot(nearp);
+        if (nearp)
+        {
+            int pos = n_near;
+            unsigned below = m & w.lanemask_lt();
+            while (below) { pos++; below &= below - 1; }
+            if (pos < PP_NEAR_CAP) sm.near_idx[pos] = k;
+        }
+        while (m) { n_near++; m &= m - 1; }
+    }
+    const bool near_overflow = (n_near > PP_NEAR_CAP);
+    w.sync();
+    // APF per surviving successor, added to g (and f), Grid3D.cpp:61-63
+    for (int s = 0; s < n_succ_max; s++)
+    {
+        if (!sm.succ[s].ok) continue;
+        float sx = sm.succ[s].x, sy = sm.succ[s].y, sh = sm.succ[s].heading;
+        float field = near_overflow ? pp_apf_sum(w, C, G.apf, (const int*)0, G.K, sx, sy, sh)
+                                    : pp_apf_sum(w, C, G.apf, sm.near_idx, n_near, sx, sy, sh);
+        w.sync();
+        if (lane == 0) sm.succ[s].g = sm.succ[s].g + field;
+    }
+    w.sync();
+}
+
+// ---------------------------------------------------------------------------------------------------
+struct PPSearchState
+{
+    PPRbTree<PPNode3> open;
+    PPLazy lazy;
+    int n_closed;
+    int status;
+    int max_open;
+};
+
+PP_HD unsigned pp_hash_key(unsigned key) { key *= 2654435761u; return key ^ (key >> 15); }
+
+// closed-set lookup: index into the closed log or -1
+PP_HD int pp_closed_find(const PPWork& wk, unsigned key)
+{
+    unsigned mask = (unsigned)wk.chash_cap - 1u;
+    unsigned h = pp_hash_key(key) & mask;
+    for (;;)
+    {
+        int s = wk.chash[h];
+        if (s < 0) return -1;
+        if (wk.closed[s].key == key) return s;
+        h = (h + 1) & mask;
+    }
+}
+
+PP_HD void pp_closed_link(PPWork& wk, unsigned key, int idx)
+{
+    unsigned mask = (unsigned)wk.chash_cap - 1u;
+    unsigned h = pp_hash_key(key) & mask;
+    while (wk.chash[h] >= 0) h = (h + 1) & mask;
+    wk.chash[h] = idx;
+}
+
+// returns false when the pool is exhausted
+PP_HD bool pp_open3_insert(PPSearchState& S, const PPSucc& s, unsigned key, float f, int prev)
+{
+    PPKey3 k; k.key = key; k.f = f;
+    int p; bool left;
+    if (!S.open.insert_pos(k, PPLt3NK(), PPLt3KN(), p, left)) return true;   // equal-f drop (F5)
+    int slot = S.open.alloc();
+    if (slot == PP_RB_NIL) { S.status |= PP_STATUS_OPEN_OVERFLOW; return false; }
+    PPNode3& n = S.open.n[slot];
+    n.f = f; n.key = key; n.g = s.g; n.x = s.x; n.y = s.y; n.heading = s.heading;
+    n.vmin_sqr = s.vmin_sqr; n.curv = s.curv; n.prev = prev; n.bin = s.bin;
+    S.open.insert_and_rebalance(left, slot, p);
+    if (S.open.count > S.max_open) S.max_open = S.open.count;
+    return true;
+}
+
+// The search.  All lanes of the warp call it with identical arguments.
+template <class W>
+PP_HD_NOINLINE void pp_search_exact(const W& w, const PPConsts& C, const float* off_xy, const PPGroup& G,
+                                    const PPState& start, PPWork& wk, PPSmem& sm, PPResult& res)
+{
+    const int lane = w.lane();
+    const int N = C.N;
+    const PPFrame& F = G.frame;
+    const unsigned kb = (unsigned)(C.bins + 1);
+
+    // ---- scratch init (all lanes) ----
+    for (int c = lane; c < N * N; c += W::LANES) wk.cell_state[c] = 0u;
+    for (int c = lane; c < wk.chash_cap; c += W::LANES) wk.chash[c] = -1;
+    w.sync();
+
+    PPSearchState S;
+    int shot_counter = 0, shot_interval = C.shot_interval;
+    bool shot_allowed = false;
+    int n_pops = 0, n_oob = 0;
+    int n_chain = 0, n_dubins = 0, success = 0;
+    float cost = FLT_MAX;
+
+    if (lane == 0)
+    {
+        S.open.init(wk.open3, wk.open3_cap);
+        S.lazy.open.init(wk.open2, wk.open2_cap);
+        S.lazy.search_id = 0; S.lazy.status = 0; S.lazy.n_searches = 0; S.lazy.n_pops = 0;
+        S.n_closed = 0; S.status = 0; S.max_open = 0;
+        // _open_set.insert(start_node), HybridAStar.cpp:103
+        PPSucc s0;
+        s0.x = start.x; s0.y = start.y; s0.heading = start.heading; s0.g = start.g;
+        s0.vmin_sqr = start.vmin_sqr; s0.curv = start.curv; s0.bin = start.bin; s0.ci = start.ci; s0.cj = start.cj; s0.ok = 1;
+        unsigned key0 = (unsigned)(start.ci * N + start.cj) * kb + (unsigned)start.bin;
+        pp_open3_insert(S, s0, key0, start.f, -1);
+    }
+
+    const int n_succ_max = 2 * C.A + 1;
+    enum { ACT_EXPAND = 0, ACT_FAIL = 1, ACT_GOAL = 2, ACT_SHOT = 3, ACT_ABORT = 4 };
+
+    for (;;)
+    {
+        // ---------------- phase 1: pop (control lane) ----------------
+        int action = ACT_EXPAND, cur = -1;
+        if (lane == 0)
+        {
+            if (S.open.empty()) action = ACT_FAIL;
+            else
+            {
+                int it = S.open.begin();
+                const PPNode3& n = S.open.n[it];
+                cur = pp_closed_find(wk, n.key);       // _closed_set.insert(*it).first
+                if (cur < 0)
+                {
+                    if (S.n_closed >= wk.closed_cap) { S.status |= PP_STATUS_CLOSED_OVERFLOW; action = ACT_ABORT; }
+                    else
+                    {
+                        cur = S.n_closed++;
+                        PPClosed3& c = wk.closed[cur];
+                        c.x = n.x; c.y = n.y; c.heading = n.heading; c.g = n.g; c.f = n.f; c.vmin_sqr = n.vmin_sqr;
+                        c.curv = n.curv; c.bin = n.bin; c.key = n.key; c.prev = n.prev;
+                        pp_closed_link(wk, n.key, cur);
+                    }
+                }
+                if (action != ACT_ABORT)
+                {
+                    S.open.erase(it);
+                    unsigned cell = wk.closed[cur].key / kb;
+                    if (cell == (unsigned)(F.goal_ci * N + F.goal_cj)) action = ACT_GOAL;   // cell equality only (F6)
+                    else if (shot_allowed)
+                    {
+                        shot_counter++;
+                        if (shot_counter == shot_interval) action = ACT_SHOT;
+                    }
+                }
+            }
+        }
+        action = w.shfl(action, 0);
+        cur = w.shfl(cur, 0);
+        w.sync();
+        if (action == ACT_FAIL || action == ACT_ABORT) break;
+
+        // popped node, read by every lane
+        const PPClosed3 cn = wk.closed[cur];
+
+        if (action == ACT_GOAL)
+        {
+            success = 1; cost = cn.g;
+            if (lane == 0)
+            {
+                // reconstruct_path from _terminal_node = *it_first (HybridAStar.cpp:118, :238-256)
+                int c = cur;
+                while (c >= 0)
+                {
+                    if (n_chain < wk.path_cap)
+                    {
+                        PPPathPt& p = wk.path[n_chain];
+                        p.x = wk.closed[c].x; p.y = wk.closed[c].y; p.heading = wk.closed[c].heading;
+                        p.curvature = C.abs_curv[wk.closed[c].curv];
+                    }
+                    else S.status |= PP_STATUS_PATH_OVERFLOW;
+                    n_chain++;
+                    c = wk.closed[c].prev;
+                }
+            }
+            break;
+        }
+
+        if (action == ACT_SHOT)
+        {
+            // ---------------- Dubins shot (all lanes), HybridAStar.cpp:129-149 ----------------
+            int type; float p[4]; PPDubinsCenters cen; PPDubinsPlan pl;
+            float len = pp_dubins_shortest(C.r_min, cn.x, cn.y, cn.heading, F.goal_x, F.goal_y, F.goal_h, type, p, cen);
+            bool long_turn = fabsf(p[1]) > (float)PP_PI_2;     // Dubins.cpp:152
+            bool ok = !long_turn;
+            int total = 0;
+            if (ok)
+            {
+                pp_dubins_plan(C.r_min, C.step, C.ang_step, type, p, cen, pl);
+                total = pl.size_3 + 1;
+                bool blocked = false, overflow = false;
+                float acc = p[0];
+                for (int k = 0; k < total; k++)
+                {
+                    if (k == pl.size_1) acc = 0.0f;       // straight segment: dist accumulator
+                    if (k == pl.size_2) acc = p[2];       // goal arc: theta accumulator
+                    if ((k % W::LANES) == lane)
+                    {
+                        float x, y, h, kappa;
+                        pp_dubins_sample(pl, C.r_min, k, acc, x, y, h, kappa);
+                        if (pp_path_point_blocked(C, G.map, x, y)) blocked = true;
+                        if (k < wk.path_cap) { PPPathPt& q = wk.path[k]; q.x = x; q.y = y; q.heading = h; q.curvature = kappa; }
+                        else overflow = true;
+                    }
+                    if (k < pl.size_1) acc = (pl.s1 < 0) ? acc - C.ang_step : acc + C.ang_step;
+                    else if (k < pl.size_2) acc = acc + C.step;
+                    else if (k < pl.size_3) acc = (pl.s2 < 0) ? acc - C.ang_step : acc + C.ang_step;
+                }
+                ok = (w.ballot(blocked) == 0u);
+                if (ok && w.ballot(overflow) != 0u && lane == 0) S.status |= PP_STATUS_PATH_OVERFLOW;
+            }
+            if (ok)
+            {
+                success = 1; cost = cn.g + len; n_dubins = total;
+                if (lane == 0)
+                {
+                    // _terminal_node = *(it_first->_prev), HybridAStar.cpp:137
+                    int c = cn.prev;
+                    if (c < 0) S.status |= PP_STATUS_NULL_TERMINAL;
+                    while (c >= 0)
+                    {
+                        int at = n_dubins + n_chain;
+                        if (at < wk.path_cap)
+                        {
+                            PPPathPt& q = wk.path[at];
+                            q.x = wk.closed[c].x; q.y = wk.closed[c].y; q.heading = wk.closed[c].heading;
+                            q.curvature = C.abs_curv[wk.closed[c].curv];
+                        }
+                        else S.status |= PP_STATUS_PATH_OVERFLOW;
+                        n_chain++;
+                        c = wk.closed[c].prev;
+                    }
+                }
+                break;
+            }
+            shot_counter = 0;
+            int ni = shot_interval - C.shot_decay;
+            shot_interval = (ni < 50) ? 50 : ni;
+        }
+
+        // ---------------- phase 3: expansion (all lanes), Grid3D.cpp:47-74 ----------------
+        n_pops++;
+        if (cn.bin >= C.bins) n_oob++;
+        if (lane == 0 && wk.trace && (n_pops - 1) < wk.trace_cap)
+        {
+            PPPop& t = wk.trace[n_pops - 1];
+            unsigned cell = cn.key / kb;
+            t.ci = (int)(cell / (unsigned)N); t.cj = (int)(cell % (unsigned)N); t.bin = cn.bin;
+            t.x = cn.x; t.y = cn.y; t.heading = cn.heading; t.g = cn.g; t.f = cn.f;
+        }
+        shot_allowed = (cn.vmin_sqr < 1.0f);     // neglect_acceleration, VehicleModel.cpp:76
+        pp_expand_warp(w, C, off_xy, G, cn.x, cn.y, cn.heading, cn.g, cn.vmin_sqr, cn.curv, cn.bin, sm);
+        // Dubins candidates: one lane per (successor, CSC type)
+        for (int q = lane; q < n_succ_max * 4; q += W::LANES)
+        {
+            int s = q >> 2, type = q & 3;
+            if (sm.succ[s].ok)
+            {
+                PPDubinsCenters cen;
+                pp_dubins_centers(C.r_min, sm.succ[s].x, sm.succ[s].y, sm.succ[s].heading, F.goal_x, F.goal_y, F.goal_h, cen);
+                float csx, csy, cgx, cgy, pp[4];
+                pp_dubins_pick(cen, type, csx, csy, cgx, cgy);
+                sm.cand[q] = pp_dubins_candidate(type, C.r_min, sm.succ[s].heading, F.goal_h, csx, csy, cgx, cgy, pp);
+            }
+        }
+        w.sync();
+
+        // ---------------- phase 4: successors into the containers (control lane) ----------------
+        int abort = 0;
+        if (lane == 0)
+        {
+            for (int s = 0; s < n_succ_max && !abort; s++)
+            {
+                const PPSucc& sc = sm.succ[s];
+                if (!sc.ok) continue;
+                unsigned key = (unsigned)(sc.ci * N + sc.cj) * kb + (unsigned)sc.bin;
+                if (pp_closed_find(wk, key) >= 0) continue;                 // HybridAStar.cpp:162
+                PPKey3 k; k.key = key; k.f = sc.g;                          // f == g + field at find time
+                int it_node = S.open.find(k, PPLt3NK(), PPLt3KN());
+                bool do_insert = false;
+                if (it_node == PP_RB_NIL) do_insert = true;
+                else if (sc.g < S.open.n[it_node].g) { S.open.erase(it_node); do_insert = true; }
+                if (do_insert)
+                {
+                    float h1 = pp_lazy_astar(C, G.map, F, wk, S.lazy, sc.ci, sc.cj);
+                    float h2 = sm.cand[4 * s];
+                    for (int t = 1; t < 4; t++) if (sm.cand[4 * s + t] < h2) h2 = sm.cand[4 * s + t];
+                    float f = sc.g + ((h1 < h2) ? h2 : h1);
+                    if (!pp_open3_insert(S, sc, key, f, cur)) abort = 1;
+                    if (S.lazy.status) { S.status |= S.lazy.status; abort = 1; }
+                }
+            }
+        }
+        abort = w.shfl(abort, 0);
+        w.sync();
+        if (abort) break;
+    }
+
+    if (lane == 0)
+    {
+        res.success = success;
+        res.status = S.status;
+        res.cost = cost;
+        res.n_pops = n_pops;
+        res.n_pops_bin_oob = n_oob;
+        res.n_chain = n_chain;
+        res.n_dubins = n_dubins;
+        res.n_lazy_searches = S.lazy.n_searches;
+        res.n_lazy_pops = S.lazy.n_pops;
+        res.max_open = S.max_open;
+        res.n_closed = S.n_closed;
+        res.pad = 0;
+    }
+}
+
+#endif

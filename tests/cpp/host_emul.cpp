@@ -1,0 +1,367 @@
+// TEST INFRASTRUCTURE ONLY -- not part of the product, never loaded by path_planning_pkg_b200.
+//
+// Compiles the PRODUCT's PP_HD core (csrc/core/*.h: the code the CUDA kernels execute) with g++ for a
+// single "lane" (PPWarpSerial) and exports it behind the oracle ABI with the prefix `emu_`, so the
+// control logic of the kernels (libstdc++-exact red-black tree, lazy 2D A*, search loop, Dubins,
+// APF, rasteriser arithmetic) can be checked against the unmodified reference on a machine without a
+// GPU (`pytest -m "not gpu"`).  The GPU tests check the real kernels through libpp_b200.so.
+#include <vector>
+#include <cstring>
+#include <cstdio>
+#include <memory>
+
+#include "../../path_planning_pkg_b200/csrc/core/pp_search.h"
+#include "../../path_planning_pkg_b200/csrc/core/pp_map.h"
+#include "../../path_planning_pkg_b200/csrc/host/pp_host.h"
+#include "../../oracle/oracle_api.h"
+
+namespace
+{
+    struct Emu
+    {
+        pp_params p;
+        PPHostModel m;
+        PPHostFrame fr;
+        std::vector<float> map;     // N*N
+        std::vector<float> apf;     // K*3
+        // search scratch
+        std::vector<PPNode3> open3;
+        std::vector<PPClosed3> closed;
+        std::vector<int> chash;
+        std::vector<unsigned> cell_state;
+        std::vector<float> nm_g, nm_f, cl_g;
+        std::vector<int> cl_prev;
+        std::vector<PPNode2> open2;
+        std::vector<PPPathPt> path;
+        PPLazy lazy;               // persistent lazy-A* state for emu_astar_lazy_batch
+        bool lazy_init = false;
+    };
+
+    PPGroup group_of(Emu* e)
+    {
+        PPGroup g;
+        g.map = e->map.data();
+        g.apf = e->apf.empty() ? nullptr : e->apf.data();
+        g.K = (int)(e->apf.size() / 3);
+        g.pad = 0;
+        g.frame = e->fr.F;
+        return g;
+    }
+
+    void setup_work(Emu* e, PPWork& wk, int closed_cap, int open_cap, int open2_cap, int path_cap)
+    {
+        int N = e->m.C.N;
+        e->open3.resize(open_cap); e->closed.resize(closed_cap);
+        int hc = 1; while (hc < 2 * closed_cap) hc <<= 1;
+        e->chash.resize(hc);
+        e->cell_state.resize((size_t)N * N); e->nm_g.resize((size_t)N * N); e->nm_f.resize((size_t)N * N);
+        e->cl_g.resize((size_t)N * N); e->cl_prev.resize((size_t)N * N);
+        e->open2.resize(open2_cap); e->path.resize(path_cap);
+        wk.open3 = e->open3.data(); wk.open3_cap = open_cap;
+        wk.closed = e->closed.data(); wk.closed_cap = closed_cap;
+        wk.chash = e->chash.data(); wk.chash_cap = hc;
+        wk.cell_state = e->cell_state.data(); wk.nm_g = e->nm_g.data(); wk.nm_f = e->nm_f.data();
+        wk.cl_g = e->cl_g.data(); wk.cl_prev = e->cl_prev.data();
+        wk.open2 = e->open2.data(); wk.open2_cap = open2_cap;
+        wk.path = e->path.data(); wk.path_cap = path_cap;
+        wk.trace = nullptr; wk.trace_cap = 0;
+    }
+
+    PPState to_pp(const orc_state& s)
+    {
+        PPState o; o.x = s.x; o.y = s.y; o.heading = s.heading; o.g = s.g; o.f = s.f; o.vmin_sqr = s.vmin_sqr;
+        o.curv = s.curvature_index; o.bin = s.angle_bin; o.ci = s.ci; o.cj = s.cj; return o;
+    }
+}
+
+extern "C"
+{
+
+void* emu_create(const orc_params* p)
+{
+    static_assert(sizeof(orc_params) == sizeof(pp_params), "param structs must match");
+    Emu* e = new Emu();
+    std::memcpy(&e->p, p, sizeof(pp_params));
+    std::string err;
+    if (!pp_host_build_model(e->p, e->m, err)) { std::fprintf(stderr, "emu_create: %s\n", err.c_str()); delete e; return nullptr; }
+    e->map.assign((size_t)e->m.C.N * e->m.C.N, 0.0f);
+    float z[3] = {0, 0, 0};
+    pp_host_update_goal(e->m.C, z, z, e->fr);
+    e->fr.grid_heading = 0.0f;   // Grid2D ctor: atan2(0, 0) = 0
+    return e;
+}
+
+void emu_destroy(void* h) { delete static_cast<Emu*>(h); }
+
+void emu_update_goal(void* h, const float* goal3, const float* start3)
+{
+    Emu* e = static_cast<Emu*>(h);
+    // relocation of a non-zero map is exercised on the GPU path (pp_update_goal); the emulation only
+    // supports goal changes on an empty map
+    pp_host_update_goal(e->m.C, goal3, start3, e->fr);
+}
+
+void emu_reset(void*) {}
+void emu_scrub(void* h) { static_cast<Emu*>(h)->lazy_init = false; }
+
+void emu_update_boxes_2d(void* h, const float* boxes, const float* conf, int n)
+{
+    Emu* e = static_cast<Emu*>(h);
+    const PPConsts& C = e->m.C;
+    float ch, sh;
+    std::vector<PPBoxDesc> d;
+    pp_host_box_descs(C, e->fr, boxes, conf, n, ch, sh, d);
+    // gather form, one "thread" per cell of each box's bounding rectangle, boxes in order
+    for (int k = 0; k < n; k++)
+        for (int i = d[k].lo_i; i <= d[k].hi_i; i++)
+            for (int j = d[k].lo_j; j <= d[k].hi_j; j++)
+            {
+                int cnt = pp_box_count(d[k].ni, d[k].nj, ch, sh, i - d[k].start_i, j - d[k].start_j);
+                if (cnt) e->map[(size_t)i * C.N + j] = pp_box_apply(e->map[(size_t)i * C.N + j], cnt, d[k].delta, C.log_min, C.log_max);
+            }
+}
+
+void emu_update_boxes(void* h, const float* boxes, const float* conf, int n, float apf_added_radius)
+{
+    Emu* e = static_cast<Emu*>(h);
+    pp_host_apf_list(e->m.C, e->fr, boxes, n, apf_added_radius, e->apf);
+    emu_update_boxes_2d(h, boxes, conf, n);
+}
+
+void emu_update_lines(void* h, const float* l, const float* conf, int n, float width)
+{
+    Emu* e = static_cast<Emu*>(h);
+    const PPConsts& C = e->m.C;
+    std::vector<PPLineDesc> d;
+    pp_host_line_descs(C, e->fr, l, conf, n, d);
+    for (int k = 0; k < n; k++)
+    {
+        float pl = 0.0f;
+        for (int t = 0; t < 100 && pl <= d[k].length; t++)
+        {
+            for (float pw = 0.0f; pw <= width; pw += C.res)
+            {
+                int i1, j1, i2, j2;
+                pp_line_cells(d[k], C.res, C.n45, C.n2, pl, pw, i1, j1, i2, j2);
+                if (i1 > -1 && i1 < C.N && j1 > -1 && j1 < C.N)
+                    e->map[(size_t)i1 * C.N + j1] = pp_box_apply(e->map[(size_t)i1 * C.N + j1], 1, d[k].delta, C.log_min, C.log_max);
+                if (i2 > -1 && i2 < C.N && j2 > -1 && j2 < C.N)
+                    e->map[(size_t)i2 * C.N + j2] = pp_box_apply(e->map[(size_t)i2 * C.N + j2], 1, d[k].delta, C.log_min, C.log_max);
+            }
+            pl += C.res;
+        }
+    }
+}
+
+void emu_decay(void* h)
+{
+    Emu* e = static_cast<Emu*>(h);
+    const PPConsts& C = e->m.C;
+    for (auto& v : e->map) v = pp_map_decay_cell(v, C.log_free, C.log_min, C.log_max);
+}
+
+void emu_get_map(void* h, float* out) { Emu* e = static_cast<Emu*>(h); std::memcpy(out, e->map.data(), e->map.size() * 4); }
+void emu_set_map(void* h, const float* in) { Emu* e = static_cast<Emu*>(h); std::memcpy(e->map.data(), in, e->map.size() * 4); }
+
+void emu_get_consts(void* h, orc_consts* c)
+{
+    Emu* e = static_cast<Emu*>(h);
+    const PPConsts& C = e->m.C;
+    c->log_threshold = C.log_thr; c->log_min = C.log_min; c->log_max = C.log_max; c->log_free = C.log_free;
+    c->grid_heading = e->fr.grid_heading;
+    for (int q = 0; q < 3; q++) c->goal_world[q] = e->fr.goal_world[q];
+    c->goal_grid[0] = e->fr.F.goal_x; c->goal_grid[1] = e->fr.F.goal_y; c->goal_grid[2] = e->fr.F.goal_h;
+    c->goal_bin = e->fr.F.goal_bin; c->goal_ci = e->fr.F.goal_ci; c->goal_cj = e->fr.F.goal_cj;
+    c->precision = C.precision; c->r_min = C.r_min; c->ang_step = C.ang_step;
+    c->num_apf = (int)(e->apf.size() / 3);
+}
+
+void emu_get_apf(void* h, float* out) { Emu* e = static_cast<Emu*>(h); std::memcpy(out, e->apf.data(), e->apf.size() * 4); }
+
+void emu_get_tables(void* h, float* offset_xy, float* offset_heading, float* actions_cost, float* abs_curv)
+{
+    Emu* e = static_cast<Emu*>(h);
+    const PPConsts& C = e->m.C;
+    for (int i = 0; i < C.S; i++)
+    {
+        offset_heading[i] = C.off_heading[i]; actions_cost[i] = C.act_cost3d[i]; abs_curv[i] = C.abs_curv[i];
+        for (int j = 0; j < C.bins; j++)
+        {
+            offset_xy[((size_t)i * C.bins + j) * 2] = e->m.off_xy[((size_t)i * (C.bins + 1) + j) * 2];
+            offset_xy[((size_t)i * C.bins + j) * 2 + 1] = e->m.off_xy[((size_t)i * (C.bins + 1) + j) * 2 + 1];
+        }
+    }
+}
+
+void emu_set_start(void* h, const float* s, orc_state* out)
+{
+    Emu* e = static_cast<Emu*>(h);
+    PPState st = pp_host_set_start(e->m.C, e->fr, s[0], s[1], s[2], 0.0f);
+    out->x = st.x; out->y = st.y; out->heading = st.heading; out->g = 0.0f; out->f = 0.0f; out->vmin_sqr = 0.0f;
+    out->curvature_index = st.curv; out->angle_bin = st.bin; out->ci = st.ci; out->cj = st.cj;
+}
+
+static void emu_succ(Emu* e, const orc_state* in, int n, orc_state* out, int* n_out, int* flags, bool expand)
+{
+    const PPConsts& C = e->m.C;
+    PPWarpSerial w;
+    int stride = 2 * C.A + 1;
+    PPGroup G = group_of(e);
+    for (int k = 0; k < n; k++)
+    {
+        PPState s = to_pp(in[k]);
+        flags[k] = (s.vmin_sqr < 1.0f) ? 1 : 0;
+        int start_index = s.curv - C.A; if (start_index < 0) start_index = 0;
+        int cnt = 0;
+        for (int q = 0; q < stride; q++)
+        {
+            int i = start_index + q;
+            if (i >= C.S) break;
+            PPSucc o;
+            int bin = s.bin > C.bins ? C.bins : s.bin;
+            if (!pp_rollout_one(C, e->m.off_xy.data(), s.x, s.y, s.heading, s.g, s.vmin_sqr, bin, i, o)) continue;
+            o.ci = -1; o.cj = -1;
+            float f = o.g;
+            if (expand)
+            {
+                if (!pp_collision_free(C, G.map, o.x, o.y, o.ci, o.cj)) continue;
+                float field = pp_apf_sum(w, C, G.apf, (const int*)0, G.K, o.x, o.y, o.heading);
+                o.g = o.g + field; f = f + field;
+            }
+            orc_state& r = out[(size_t)k * stride + cnt];
+            r.x = o.x; r.y = o.y; r.heading = o.heading; r.g = o.g; r.f = f; r.vmin_sqr = o.vmin_sqr;
+            r.curvature_index = o.curv; r.angle_bin = o.bin; r.ci = o.ci; r.cj = o.cj;
+            cnt++;
+        }
+        n_out[k] = cnt;
+    }
+}
+
+void emu_rollout_batch(void* h, const orc_state* in, int n, orc_state* out, int* n_out, int* flags)
+{ emu_succ(static_cast<Emu*>(h), in, n, out, n_out, flags, false); }
+
+void emu_expand_batch(void* h, const orc_state* in, int n, orc_state* out, int* n_out, int* flags)
+{ emu_succ(static_cast<Emu*>(h), in, n, out, n_out, flags, true); }
+
+void emu_apf_batch(void* h, const float* xyh, int n, float* out)
+{
+    Emu* e = static_cast<Emu*>(h);
+    PPWarpSerial w;
+    PPGroup G = group_of(e);
+    for (int k = 0; k < n; k++)
+        out[k] = pp_apf_sum(w, e->m.C, G.apf, (const int*)0, G.K, xyh[3 * k], xyh[3 * k + 1], xyh[3 * k + 2]);
+}
+
+int emu_check_path(void* h, const float* xyh, int n)
+{
+    Emu* e = static_cast<Emu*>(h);
+    for (int k = 0; k < n; k++)
+        if (pp_path_point_blocked(e->m.C, e->map.data(), xyh[3 * k], xyh[3 * k + 1])) return 0;
+    return 1;
+}
+
+void emu_dubins_length_batch(void* h, const float* starts, int n, const float* goal3, float* len, int* type, float* params4)
+{
+    Emu* e = static_cast<Emu*>(h);
+    for (int k = 0; k < n; k++)
+    {
+        int t; float p[4]; PPDubinsCenters c;
+        len[k] = pp_dubins_shortest(e->m.C.r_min, starts[3 * k], starts[3 * k + 1], starts[3 * k + 2], goal3[0], goal3[1], goal3[2], t, p, c);
+        if (type) type[k] = t;
+        if (params4) for (int q = 0; q < 4; q++) params4[4 * k + q] = p[q];
+    }
+}
+
+int emu_dubins_path(void* h, const float* s, const float* g, float* xyh, float* curv, int cap, float* length, int* flag)
+{
+    Emu* e = static_cast<Emu*>(h);
+    const PPConsts& C = e->m.C;
+    int t; float p[4]; PPDubinsCenters c; PPDubinsPlan pl;
+    *length = pp_dubins_shortest(C.r_min, s[0], s[1], s[2], g[0], g[1], g[2], t, p, c);
+    *flag = (fabsf(p[1]) > (float)PP_PI_2) ? 1 : 0;
+    pp_dubins_plan(C.r_min, C.step, C.ang_step, t, p, c, pl);
+    int total = pl.size_3 + 1;
+    float acc = p[0];
+    for (int k = 0; k < total; k++)
+    {
+        if (k == pl.size_1) acc = 0.0f;
+        if (k == pl.size_2) acc = p[2];
+        float x, y, hh, kappa;
+        pp_dubins_sample(pl, C.r_min, k, acc, x, y, hh, kappa);
+        if (k < cap) { xyh[3 * k] = x; xyh[3 * k + 1] = y; xyh[3 * k + 2] = hh; curv[k] = kappa; }
+        if (k < pl.size_1) acc = (pl.s1 < 0) ? acc - C.ang_step : acc + C.ang_step;
+        else if (k < pl.size_2) acc = acc + C.step;
+        else if (k < pl.size_3) acc = (pl.s2 < 0) ? acc - C.ang_step : acc + C.ang_step;
+    }
+    return total;
+}
+
+void emu_astar_lazy_batch(void* h, const int* ij, int n, float* out)
+{
+    Emu* e = static_cast<Emu*>(h);
+    const PPConsts& C = e->m.C;
+    PPWork wk;
+    if (!e->lazy_init)
+    {
+        setup_work(e, wk, 16, 16, 1 << 16, 16);
+        std::fill(e->cell_state.begin(), e->cell_state.end(), 0u);
+        e->lazy.open.init(wk.open2, wk.open2_cap);
+        e->lazy.search_id = 0; e->lazy.status = 0; e->lazy.n_searches = 0; e->lazy.n_pops = 0;
+        e->lazy_init = true;
+    }
+    else setup_work(e, wk, 16, 16, 1 << 16, 16);
+    for (int k = 0; k < n; k++) out[k] = pp_lazy_astar(C, e->map.data(), e->fr.F, wk, e->lazy, ij[2 * k], ij[2 * k + 1]);
+}
+
+void emu_astar_dump(void* h, unsigned char* visited, float* g, float* f)
+{
+    Emu* e = static_cast<Emu*>(h);
+    const PPConsts& C = e->m.C;
+    for (int c = 0; c < C.N * C.N; c++)
+    {
+        unsigned st = e->cell_state.empty() ? 0u : e->cell_state[c];
+        if (visited) visited[c] = (st & PP_CS_VISITED) ? 1 : 0;
+        bool touched = (st & PP_CS_TOUCHED) != 0;
+        if (g) g[c] = touched ? e->nm_g[c] : 0.0f;
+        if (f) f[c] = touched ? e->nm_f[c] : pp_h2d(C, c / C.N, c % C.N);
+    }
+}
+
+void emu_find_path(void* h, float vel, const float* s, orc_result* res, float* path_xyh, float* curv,
+                   int path_cap, orc_pop* pops, int pop_cap)
+{
+    Emu* e = static_cast<Emu*>(h);
+    const PPConsts& C = e->m.C;
+    PPWork wk;
+    setup_work(e, wk, 1 << 20, 1 << 19, 1 << 16, 4096);
+    static_assert(sizeof(PPPop) == sizeof(orc_pop), "pop structs must match");
+    wk.trace = reinterpret_cast<PPPop*>(pops); wk.trace_cap = pops ? pop_cap : 0;
+    PPState st = pp_host_set_start(C, e->fr, s[0], s[1], s[2], vel);
+    PPGroup G = group_of(e);
+    PPSmem sm;
+    PPResult r;
+    PPWarpSerial w;
+    pp_search_exact(w, C, e->m.off_xy.data(), G, st, wk, sm, r);
+    e->lazy_init = false;
+    res->success = r.success; res->cost = r.cost; res->n_pops = r.n_pops; res->n_pops_bin_oob = r.n_pops_bin_oob;
+    if (r.status) std::fprintf(stderr, "emu_find_path: status %d\n", r.status);
+    // assemble in the reference's order (HybridAStar.cpp:208-262): reversed Dubins samples, then the chain
+    int n = 0;
+    if (r.success)
+    {
+        std::vector<PPPathPt> seq;
+        for (int k = r.n_dubins - 1; k >= 0; k--) seq.push_back(wk.path[k]);
+        for (int k = 0; k < r.n_chain; k++) seq.push_back(wk.path[r.n_dubins + k]);
+        n = (int)seq.size();
+        for (int k = 0; k < n && k < path_cap; k++)
+        {
+            float wx, wy, wh;
+            pp_host_to_world(e->fr, seq[k].x, seq[k].y, seq[k].heading, wx, wy, wh);
+            path_xyh[3 * k] = wx; path_xyh[3 * k + 1] = wy; path_xyh[3 * k + 2] = wh;
+            curv[k] = (k == 0) ? 0.0f : seq[k - 1].curvature;   // curvature shifted by one (HybridAStar.cpp:212, :261)
+        }
+    }
+    res->n_path = n;
+}
+
+} // extern "C"
