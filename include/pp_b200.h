@@ -194,6 +194,8 @@ int  pp_find_path_batch(pp_context* ctx, const pp_query* queries, int n, const p
 int  pp_batch_upload(pp_context* ctx, const pp_query* queries, int n, const pp_search_opts* opts);
 int  pp_batch_run(pp_context* ctx, float* kernel_ms);
 int  pp_batch_fetch(pp_context* ctx, pp_result* results, float* paths_xyh, float* curvature, pp_pop* trace);
+/* number of CUDA kernels this context has launched so far (bench.py's gpu_launches) */
+unsigned long long pp_kernel_launches(pp_context* ctx);
 
 #ifdef __cplusplus
 }

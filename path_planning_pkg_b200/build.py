@@ -1,0 +1,114 @@
+"""In-tree build of the native libraries (explicit nvcc / g++ command lines, no JIT cache).
+
+  lib/libpp_b200.so            CUDA kernels + C ABI (include/pp_b200.h), sm_100a
+  lib/libpath_planning_b200.so host C++ classes with the reference's API (include/path_planning_pkg/*.h)
+
+Flags that matter for parity: no FMA contraction anywhere (-fmad=false on the
+device, -ffp-contract=off on the host), IEEE division and square root, no flush-to-zero.
+"""
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+LIB = os.path.join(HERE, "lib")
+CSRC = os.path.join(HERE, "csrc")
+
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "-fmad=false", "-prec-div=true", "-prec-sqrt=true", "-ftz=false",
+              "-Xcompiler", "-fPIC,-ffp-contract=off,-O2", "-cudart", "static"]
+CXX_FLAGS = ["-std=c++14", "-O2", "-Wall", "-fPIC", "-ffp-contract=off"]
+
+
+def _newer(target, sources):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(s) > t for s in sources)
+
+
+def _sources(*dirs):
+    out = []
+    for d in dirs:
+        for r, _, fs in os.walk(d):
+            out += [os.path.join(r, f) for f in fs if f.endswith((".h", ".cuh", ".cu", ".cpp", ".c"))]
+    return out
+
+
+def _run(cmd, verbose):
+    if verbose:
+        print(" ".join(cmd), flush=True)
+    subprocess.check_call(cmd)
+
+
+def build_cuda(force=False, verbose=True, extra=()):
+    """nvcc -> lib/libpp_b200.so"""
+    os.makedirs(LIB, exist_ok=True)
+    target = os.path.join(LIB, "libpp_b200.so")
+    srcs = _sources(CSRC, os.path.join(ROOT, "include"))
+    if force or _newer(target, srcs):
+        nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+        _run([nvcc] + NVCC_FLAGS + list(extra) + ["-shared", "-o", target, os.path.join(CSRC, "cabi", "pp_cabi.cu")], verbose)
+    return target
+
+
+def build_cuda_profile(force=False, verbose=True):
+    """Development variant with per-phase cycle counters: lib/libpp_b200_prof.so (never loaded by the package)."""
+    os.makedirs(LIB, exist_ok=True)
+    target = os.path.join(LIB, "libpp_b200_prof.so")
+    srcs = _sources(CSRC, os.path.join(ROOT, "include"))
+    if force or _newer(target, srcs):
+        nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+        _run([nvcc] + NVCC_FLAGS + ["-DPP_PROFILE", "-shared", "-o", target, os.path.join(CSRC, "cabi", "pp_cabi.cu")], verbose)
+    return target
+
+
+def build_host(force=False, verbose=True):
+    """g++ -> lib/libpath_planning_b200.so (reference-compatible C++ classes over the C ABI)"""
+    os.makedirs(LIB, exist_ok=True)
+    target = os.path.join(LIB, "libpath_planning_b200.so")
+    hdir = os.path.join(CSRC, "host")
+    cpps = sorted(os.path.join(hdir, f) for f in os.listdir(hdir) if f.endswith(".cpp"))
+    if not cpps:
+        return None
+    srcs = _sources(CSRC, os.path.join(ROOT, "include"))
+    if force or _newer(target, srcs):
+        cxx = os.environ.get("CXX", "g++")
+        _run([cxx] + CXX_FLAGS + ["-I", os.path.join(ROOT, "include"), "-I", os.path.join(ROOT, "include", "path_planning_pkg"),
+                                  "-shared", "-o", target] + cpps +
+             ["-L", LIB, "-lpp_b200", "-Wl,-rpath,$ORIGIN"], verbose)
+    return target
+
+
+def build_host_emul(force=False, verbose=True):
+    """g++ -> tests/cpp/bin/libpp_host_emul.so (TEST ONLY: the PP_HD core on one host lane)"""
+    out_dir = os.path.join(ROOT, "tests", "cpp", "bin")
+    os.makedirs(out_dir, exist_ok=True)
+    target = os.path.join(out_dir, "libpp_host_emul.so")
+    src = os.path.join(ROOT, "tests", "cpp", "host_emul.cpp")
+    srcs = _sources(CSRC, os.path.join(ROOT, "include")) + [src, os.path.join(ROOT, "oracle", "oracle_api.h")]
+    if force or _newer(target, srcs):
+        cxx = os.environ.get("CXX", "g++")
+        _run([cxx] + CXX_FLAGS + ["-shared", "-o", target, src], verbose)
+    return target
+
+
+def build_oracle(verbose=True):
+    """make -C oracle: CPU restatement + (when /root/reference is present) the compiled reference"""
+    cmd = ["make", "-C", os.path.join(ROOT, "oracle"), "all"]
+    if verbose:
+        print(" ".join(cmd), flush=True)
+    subprocess.check_call(cmd, stdout=None if verbose else subprocess.DEVNULL)
+
+
+def build_all(force=False, verbose=True):
+    build_cuda(force, verbose)
+    build_host(force, verbose)
+    build_host_emul(force, verbose)
+    build_oracle(verbose)
+
+
+if __name__ == "__main__":
+    build_all(force="--force" in sys.argv)

@@ -1,0 +1,796 @@
+// C ABI of libpp_b200.so (declared in include/pp_b200.h): context management, host prologues
+// (csrc/host/pp_host.h) and kernel launches (csrc/kernels/pp_kernels.cuh).  No CPU compute path:
+// every entry point that computes launches a kernel on the context's stream.
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <algorithm>
+
+#include "../kernels/pp_kernels.cuh"
+#include "../host/pp_host.h"
+#include "../../../include/pp_b200.h"
+
+static thread_local std::string g_last_error;
+
+static int pp_fail(int code, const std::string& msg)
+{
+    g_last_error = msg;
+    return code;
+}
+
+#define PP_CUDA(call)                                                                                   \
+    do {                                                                                                \
+        cudaError_t e__ = (call);                                                                       \
+        if (e__ != cudaSuccess)                                                                         \
+            return pp_fail(PP_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__));           \
+    } while (0)
+
+template <class T>
+struct DevBuf
+{
+    T* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t n)
+    {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        cudaError_t e = cudaMalloc(&p, n * sizeof(T));
+        if (e == cudaSuccess) cap = n;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+// per-slot scratch pools of the search kernel
+struct WorkPools
+{
+    int alloc_slots = 0, chash_cap = 0, open3_cap = 0, closed_cap = 0, open2_cap = 0;
+    DevBuf<PPNode3> open3; DevBuf<PPClosed3> closed; DevBuf<int> chash;
+    DevBuf<unsigned> cell_state; DevBuf<float> nm_g, nm_f, cl_g; DevBuf<int> cl_prev; DevBuf<PPNode2> open2;
+    void release()
+    {
+        open3.release(); closed.release(); chash.release(); cell_state.release();
+        nm_g.release(); nm_f.release(); cl_g.release(); cl_prev.release(); open2.release();
+        alloc_slots = 0;
+    }
+};
+
+struct pp_context
+{
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    pp_params params;
+    PPHostModel model;
+    int num_groups = 0;
+    int sm_count = 0;
+    std::vector<PPHostFrame> frames;
+    std::vector<PPGroup> groups;          // host mirror of d_groups
+    std::vector<int> apf_cap;             // allocated obstacles per group
+    std::vector<float*> d_apf;            // per group
+    float* d_maps = nullptr;              // num_groups x N*N
+    float* d_map_tmp = nullptr;           // N*N (relocation double buffer)
+    int*   d_cell_scratch = nullptr;      // N*N ints (relocation indices / line sample counts), kept zeroed
+    float* d_off_xy = nullptr;
+    PPGroup* d_groups = nullptr;
+    bool groups_dirty = true;
+    // generic scratch for stateless calls and map descriptors
+    DevBuf<unsigned char> s0, s1, s2, s3, s4;
+    // batch state
+    int n_queries = 0;
+    pp_search_opts opts;
+    std::vector<PPQuery> h_queries;
+    DevBuf<PPQuery> d_queries;
+    DevBuf<PPResult> d_results;
+    DevBuf<PPPathPt> d_paths;
+    DevBuf<PPPop> d_trace;
+    int* d_counter = nullptr;
+    // per-slot scratch pools
+    int n_slots = 0;
+    WorkPools wp;          // first pass: every query, moderate capacities
+    WorkPools wp_retry;    // queries that hit a capacity are re-run here with 8x larger pools (the reference is unbounded)
+    DevBuf<int> d_qmap;
+    int retried = 0;       // queries re-run in the last pp_batch_run
+    unsigned long long launches = 0;      // kernels launched by this context
+};
+
+static size_t nn_of(const pp_context* c) { return (size_t)c->model.C.N * c->model.C.N; }
+
+static int sync_groups(pp_context* c)
+{
+    if (!c->groups_dirty) return PP_SUCCESS;
+    PP_CUDA(cudaMemcpyAsync(c->d_groups, c->groups.data(), sizeof(PPGroup) * c->num_groups, cudaMemcpyHostToDevice, c->stream));
+    c->groups_dirty = false;
+    return PP_SUCCESS;
+}
+
+static int check_group(pp_context* c, int g)
+{
+    if (!c) return pp_fail(PP_ERR_INVALID, "null context");
+    if (g < 0 || g >= c->num_groups) return pp_fail(PP_ERR_INVALID, "group index out of range");
+    return PP_SUCCESS;
+}
+
+extern "C"
+{
+
+const char* pp_last_error(void) { return g_last_error.c_str(); }
+
+int pp_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+int pp_create(const pp_params* params, int device, int num_groups, pp_context** out)
+{
+    if (!params || !out || num_groups < 1) return pp_fail(PP_ERR_INVALID, "pp_create: bad arguments");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return pp_fail(PP_ERR_NO_DEVICE, "pp_create: no CUDA device (this library has no CPU path)");
+    if (device < 0 || device >= ndev) return pp_fail(PP_ERR_INVALID, "pp_create: bad device index");
+    pp_context* c = new pp_context();
+    c->device = device;
+    c->params = *params;
+    std::string err;
+    if (!pp_host_build_model(*params, c->model, err)) { delete c; return pp_fail(PP_ERR_INVALID, "pp_create: " + err); }
+    PP_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    PP_CUDA(cudaGetDeviceProperties(&prop, device));
+    c->sm_count = prop.multiProcessorCount;
+    PP_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    PP_CUDA(cudaEventCreate(&c->ev0));
+    PP_CUDA(cudaEventCreate(&c->ev1));
+    c->num_groups = num_groups;
+    size_t nn = nn_of(c);
+    PP_CUDA(cudaMalloc(&c->d_maps, sizeof(float) * nn * num_groups));
+    PP_CUDA(cudaMemsetAsync(c->d_maps, 0, sizeof(float) * nn * num_groups, c->stream));
+    PP_CUDA(cudaMalloc(&c->d_map_tmp, sizeof(float) * nn));
+    PP_CUDA(cudaMalloc(&c->d_cell_scratch, sizeof(int) * nn));
+    PP_CUDA(cudaMemsetAsync(c->d_cell_scratch, 0, sizeof(int) * nn, c->stream));
+    PP_CUDA(cudaMalloc(&c->d_off_xy, sizeof(float) * c->model.off_xy.size()));
+    PP_CUDA(cudaMemcpyAsync(c->d_off_xy, c->model.off_xy.data(), sizeof(float) * c->model.off_xy.size(), cudaMemcpyHostToDevice, c->stream));
+    PP_CUDA(cudaMalloc(&c->d_groups, sizeof(PPGroup) * num_groups));
+    PP_CUDA(cudaMalloc(&c->d_counter, sizeof(int)));
+    c->frames.resize(num_groups);
+    c->groups.resize(num_groups);
+    c->apf_cap.assign(num_groups, 0);
+    c->d_apf.assign(num_groups, nullptr);
+    float z[3] = {0, 0, 0};
+    for (int g = 0; g < num_groups; g++)
+    {
+        // Grid3D ctor: goal (0,0,0), start (0,0,0) -> grid heading atan2(0,0) = 0
+        pp_host_update_goal(c->model.C, z, z, c->frames[g]);
+        c->groups[g].map = c->d_maps + nn * g;
+        c->groups[g].apf = nullptr;
+        c->groups[g].K = 0;
+        c->groups[g].pad = 0;
+        c->groups[g].frame = c->frames[g].F;
+    }
+    c->groups_dirty = true;
+    PP_CUDA(cudaStreamSynchronize(c->stream));
+    *out = c;
+    return PP_SUCCESS;
+}
+
+void pp_destroy(pp_context* c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    for (float* p : c->d_apf) if (p) cudaFree(p);
+    cudaFree(c->d_maps); cudaFree(c->d_map_tmp); cudaFree(c->d_cell_scratch); cudaFree(c->d_off_xy);
+    cudaFree(c->d_groups); cudaFree(c->d_counter);
+    c->s0.release(); c->s1.release(); c->s2.release(); c->s3.release(); c->s4.release();
+    c->d_queries.release(); c->d_results.release(); c->d_paths.release(); c->d_trace.release();
+    c->wp.release(); c->wp_retry.release(); c->d_qmap.release();
+    cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
+    cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+int pp_get_consts(pp_context* c, pp_consts_info* o)
+{
+    if (!c || !o) return pp_fail(PP_ERR_INVALID, "pp_get_consts: null");
+    const PPConsts& C = c->model.C;
+    o->log_threshold = C.log_thr; o->log_min = C.log_min; o->log_max = C.log_max; o->log_free = C.log_free;
+    o->precision = C.precision; o->r_min = C.r_min; o->ang_step = C.ang_step; o->n2 = C.n2; o->n45 = C.n45;
+    return PP_SUCCESS;
+}
+
+int pp_get_frame(pp_context* c, int g, pp_frame_info* o)
+{
+    int rc = check_group(c, g); if (rc) return rc;
+    const PPHostFrame& f = c->frames[g];
+    o->grid_heading = f.grid_heading;
+    for (int q = 0; q < 3; q++) o->goal_world[q] = f.goal_world[q];
+    o->goal_grid[0] = f.F.goal_x; o->goal_grid[1] = f.F.goal_y; o->goal_grid[2] = f.F.goal_h;
+    o->goal_bin = f.F.goal_bin; o->goal_ci = f.F.goal_ci; o->goal_cj = f.F.goal_cj;
+    o->num_apf = c->groups[g].K;
+    return PP_SUCCESS;
+}
+
+int pp_get_tables(pp_context* c, float* offset_xy, float* offset_heading, float* actions_cost, float* abs_curv)
+{
+    if (!c) return pp_fail(PP_ERR_INVALID, "null context");
+    const PPConsts& C = c->model.C;
+    for (int i = 0; i < C.S; i++)
+    {
+        offset_heading[i] = C.off_heading[i]; actions_cost[i] = C.act_cost3d[i]; abs_curv[i] = C.abs_curv[i];
+        for (int j = 0; j < C.bins; j++)
+        {
+            offset_xy[((size_t)i * C.bins + j) * 2] = c->model.off_xy[((size_t)i * (C.bins + 1) + j) * 2];
+            offset_xy[((size_t)i * C.bins + j) * 2 + 1] = c->model.off_xy[((size_t)i * (C.bins + 1) + j) * 2 + 1];
+        }
+    }
+    return PP_SUCCESS;
+}
+
+int pp_sync(pp_context* c)
+{
+    if (!c) return pp_fail(PP_ERR_INVALID, "null context");
+    PP_CUDA(cudaSetDevice(c->device));
+    PP_CUDA(cudaStreamSynchronize(c->stream));
+    return PP_SUCCESS;
+}
+
+// ---- map -------------------------------------------------------------------------------------------
+int pp_update_goal(pp_context* c, int g, const float* goal3, const float* start3)
+{
+    int rc = check_group(c, g); if (rc) return rc;
+    PP_CUDA(cudaSetDevice(c->device));
+    const PPConsts& C = c->model.C;
+    PPHostFrame prev = c->frames[g];
+    pp_host_update_goal(C, goal3, start3, c->frames[g]);
+    c->groups[g].frame = c->frames[g].F;
+    c->groups_dirty = true;
+    // relocate_obstacles (Grid3D.cpp:169-203): forward scatter, last writer in raster order wins
+    PPRelocDesc d;
+    pp_host_reloc_desc(C, c->frames[g].grid_heading, prev.grid_heading, c->frames[g].goal_world, prev.goal_world, d);
+    size_t nn = nn_of(c);
+    float* map = c->d_maps + nn * g;
+    int blocks = c->sm_count * 8;
+    pp_map_reloc_fill_kernel<<<blocks, 256, 0, c->stream>>>(c->d_cell_scratch, nn);
+    pp_map_reloc_scatter_kernel<<<blocks, 256, 0, c->stream>>>(c->d_cell_scratch, C.N, d);
+    pp_map_reloc_gather_kernel<<<blocks, 256, 0, c->stream>>>(map, c->d_map_tmp, c->d_cell_scratch, nn);
+    c->launches += 3;
+    PP_CUDA(cudaMemcpyAsync(map, c->d_map_tmp, sizeof(float) * nn, cudaMemcpyDeviceToDevice, c->stream));
+    PP_CUDA(cudaGetLastError());
+    return PP_SUCCESS;
+}
+
+int pp_reset(pp_context* c, int g) { return check_group(c, g); }
+
+int pp_update_obstacles_decay(pp_context* c, int g)
+{
+    int rc = check_group(c, g); if (rc) return rc;
+    PP_CUDA(cudaSetDevice(c->device));
+    const PPConsts& C = c->model.C;
+    size_t nn = nn_of(c);
+    size_t want = (nn / 4 + 255) / 256;
+    int blocks = (int)std::min<size_t>(std::max<size_t>(want, 1), (size_t)c->sm_count * 8);
+    pp_map_decay_kernel<<<blocks, 256, 0, c->stream>>>(c->d_maps + nn * g, nn, C.log_free, C.log_min, C.log_max);
+    c->launches += 1;
+    PP_CUDA(cudaGetLastError());
+    return PP_SUCCESS;
+}
+
+int pp_update_obstacles_boxes_2d(pp_context* c, int g, const float* boxes, const float* conf, int n)
+{
+    int rc = check_group(c, g); if (rc) return rc;
+    if (n < 0 || (n > 0 && (!boxes || !conf))) return pp_fail(PP_ERR_INVALID, "boxes: bad arguments");
+    if (n == 0) return PP_SUCCESS;
+    PP_CUDA(cudaSetDevice(c->device));
+    const PPConsts& C = c->model.C;
+    float ch, sh;
+    std::vector<PPBoxDesc> d;
+    pp_host_box_descs(C, c->frames[g], boxes, conf, n, ch, sh, d);
+    // bin boxes (ascending index) into the 32x32 tiles their sample bounding box overlaps
+    int T = (C.N + PP_TILE - 1) / PP_TILE;
+    std::vector<std::vector<int>> bins((size_t)T * T);
+    std::vector<PPBoxDescDev> dd(n);
+    for (int k = 0; k < n; k++)
+    {
+        dd[k].start_i = d[k].start_i; dd[k].start_j = d[k].start_j; dd[k].ni = d[k].ni; dd[k].nj = d[k].nj; dd[k].delta = d[k].delta;
+        if (d[k].lo_i > d[k].hi_i || d[k].lo_j > d[k].hi_j || d[k].ni <= 0 || d[k].nj <= 0) continue;
+        for (int ti = d[k].lo_i / PP_TILE; ti <= d[k].hi_i / PP_TILE; ti++)
+            for (int tj = d[k].lo_j / PP_TILE; tj <= d[k].hi_j / PP_TILE; tj++)
+                bins[(size_t)ti * T + tj].push_back(k);
+    }
+    std::vector<int> tile_ids, tile_off(1, 0), tile_boxes;
+    for (int t = 0; t < T * T; t++)
+        if (!bins[t].empty())
+        {
+            tile_ids.push_back(t);
+            tile_boxes.insert(tile_boxes.end(), bins[t].begin(), bins[t].end());
+            tile_off.push_back((int)tile_boxes.size());
+        }
+    if (tile_ids.empty()) return PP_SUCCESS;
+    PP_CUDA(c->s0.ensure(sizeof(int) * tile_ids.size()));
+    PP_CUDA(c->s1.ensure(sizeof(int) * tile_off.size()));
+    PP_CUDA(c->s2.ensure(sizeof(int) * tile_boxes.size()));
+    PP_CUDA(c->s3.ensure(sizeof(PPBoxDescDev) * dd.size()));
+    PP_CUDA(cudaMemcpyAsync(c->s0.p, tile_ids.data(), sizeof(int) * tile_ids.size(), cudaMemcpyHostToDevice, c->stream));
+    PP_CUDA(cudaMemcpyAsync(c->s1.p, tile_off.data(), sizeof(int) * tile_off.size(), cudaMemcpyHostToDevice, c->stream));
+    PP_CUDA(cudaMemcpyAsync(c->s2.p, tile_boxes.data(), sizeof(int) * tile_boxes.size(), cudaMemcpyHostToDevice, c->stream));
+    PP_CUDA(cudaMemcpyAsync(c->s3.p, dd.data(), sizeof(PPBoxDescDev) * dd.size(), cudaMemcpyHostToDevice, c->stream));
+    pp_map_boxes_kernel<<<(int)tile_ids.size(), 256, 0, c->stream>>>(c->d_maps + nn_of(c) * g, C.N, (const int*)c->s0.p,
+        (const int*)c->s1.p, (const int*)c->s2.p, (const PPBoxDescDev*)c->s3.p, ch, sh, C.log_min, C.log_max, T);
+    c->launches += 1;
+    PP_CUDA(cudaGetLastError());
+    // the pageable host vectors above die at return: make sure the copies have been consumed
+    PP_CUDA(cudaStreamSynchronize(c->stream));
+    return PP_SUCCESS;
+}
+
+int pp_update_obstacles_boxes(pp_context* c, int g, const float* boxes, const float* conf, int n, float apf_added_radius)
+{
+    int rc = check_group(c, g); if (rc) return rc;
+    if (n < 0 || (n > 0 && (!boxes || !conf))) return pp_fail(PP_ERR_INVALID, "boxes: bad arguments");
+    PP_CUDA(cudaSetDevice(c->device));
+    // APF list rebuild, Grid3D.cpp:26-40
+    std::vector<float> apf;
+    pp_host_apf_list(c->model.C, c->frames[g], boxes, n, apf_added_radius, apf);
+    if (n > c->apf_cap[g])
+    {
+        if (c->d_apf[g]) PP_CUDA(cudaFree(c->d_apf[g]));
+        c->d_apf[g] = nullptr;
+        PP_CUDA(cudaMalloc(&c->d_apf[g], sizeof(float) * 3 * n));
+        c->apf_cap[g] = n;
+    }
+    if (n > 0) PP_CUDA(cudaMemcpyAsync(c->d_apf[g], apf.data(), sizeof(float) * 3 * n, cudaMemcpyHostToDevice, c->stream));
+    c->groups[g].apf = c->d_apf[g];
+    c->groups[g].K = n;
+    c->groups_dirty = true;
+    PP_CUDA(cudaStreamSynchronize(c->stream));
+    return pp_update_obstacles_boxes_2d(c, g, boxes, conf, n);
+}
+
+int pp_update_obstacles_lines(pp_context* c, int g, const float* lines, const float* conf, int n, float width)
+{
+    int rc = check_group(c, g); if (rc) return rc;
+    if (n < 0 || (n > 0 && (!lines || !conf))) return pp_fail(PP_ERR_INVALID, "lines: bad arguments");
+    if (n == 0) return PP_SUCCESS;
+    PP_CUDA(cudaSetDevice(c->device));
+    const PPConsts& C = c->model.C;
+    std::vector<PPLineDesc> d;
+    pp_host_line_descs(C, c->frames[g], lines, conf, n, d);
+    PP_CUDA(c->s4.ensure(sizeof(PPLineDesc) * n));
+    PP_CUDA(cudaMemcpyAsync(c->s4.p, d.data(), sizeof(PPLineDesc) * n, cudaMemcpyHostToDevice, c->stream));
+    pp_map_lines_kernel<<<1, 1024, 0, c->stream>>>(c->d_maps + nn_of(c) * g, c->d_cell_scratch, C.N, C.n45, C.n2, C.res,
+                                                  (const PPLineDesc*)c->s4.p, n, width, C.log_min, C.log_max);
+    c->launches += 1;
+    PP_CUDA(cudaGetLastError());
+    PP_CUDA(cudaStreamSynchronize(c->stream));
+    return PP_SUCCESS;
+}
+
+int pp_map_download(pp_context* c, int g, float* out)
+{
+    int rc = check_group(c, g); if (rc) return rc;
+    PP_CUDA(cudaSetDevice(c->device));
+    PP_CUDA(cudaMemcpyAsync(out, c->d_maps + nn_of(c) * g, sizeof(float) * nn_of(c), cudaMemcpyDeviceToHost, c->stream));
+    PP_CUDA(cudaStreamSynchronize(c->stream));
+    return PP_SUCCESS;
+}
+
+int pp_map_upload(pp_context* c, int g, const float* in)
+{
+    int rc = check_group(c, g); if (rc) return rc;
+    PP_CUDA(cudaSetDevice(c->device));
+    PP_CUDA(cudaMemcpyAsync(c->d_maps + nn_of(c) * g, in, sizeof(float) * nn_of(c), cudaMemcpyHostToDevice, c->stream));
+    PP_CUDA(cudaStreamSynchronize(c->stream));
+    return PP_SUCCESS;
+}
+
+void* pp_map_device_ptr(pp_context* c, int g)
+{
+    if (check_group(c, g)) return nullptr;
+    return c->d_maps + nn_of(c) * g;
+}
+
+// ---- host-side start nodes ---------------------------------------------------------------------------
+int pp_set_start_batch(pp_context* c, const pp_query* q, int n, pp_state* out)
+{
+    if (!c || !q || !out) return pp_fail(PP_ERR_INVALID, "pp_set_start_batch: null");
+    for (int k = 0; k < n; k++)
+    {
+        if (q[k].group < 0 || q[k].group >= c->num_groups) return pp_fail(PP_ERR_INVALID, "query group out of range");
+        PPState s = pp_host_set_start(c->model.C, c->frames[q[k].group], q[k].x, q[k].y, q[k].heading, q[k].vel);
+        out[k].x = s.x; out[k].y = s.y; out[k].heading = s.heading; out[k].g = s.g; out[k].f = s.f;
+        out[k].vmin_sqr = s.vmin_sqr; out[k].curvature_index = s.curv; out[k].angle_bin = s.bin; out[k].ci = s.ci; out[k].cj = s.cj;
+    }
+    return PP_SUCCESS;
+}
+
+// ---- stateless batches -------------------------------------------------------------------------------
+static_assert(sizeof(pp_state) == sizeof(PPState), "pp_state layout");
+static_assert(sizeof(pp_pop) == sizeof(PPPop), "pp_pop layout");
+
+static int successors(pp_context* c, int g, const pp_state* in, int n, pp_state* out, int* n_out, int* flags, int expand)
+{
+    int rc = check_group(c, g); if (rc) return rc;
+    if (n <= 0) return PP_SUCCESS;
+    PP_CUDA(cudaSetDevice(c->device));
+    const PPConsts& C = c->model.C;
+    int stride = 2 * C.A + 1;
+    PP_CUDA(c->s0.ensure(sizeof(PPState) * n));
+    PP_CUDA(c->s1.ensure(sizeof(PPState) * (size_t)n * stride));
+    PP_CUDA(c->s2.ensure(sizeof(int) * n));
+    PP_CUDA(c->s3.ensure(sizeof(int) * n));
+    PP_CUDA(cudaMemcpyAsync(c->s0.p, in, sizeof(PPState) * n, cudaMemcpyHostToDevice, c->stream));
+    PP_CUDA(cudaMemsetAsync(c->s1.p, 0, sizeof(PPState) * (size_t)n * stride, c->stream));
+    PPSuccArgs a;
+    a.C = C; a.off_xy = c->d_off_xy; a.G = c->groups[g]; a.in = (const PPState*)c->s0.p; a.n = n; a.expand = expand;
+    a.out = (PPState*)c->s1.p; a.n_out = (int*)c->s2.p; a.flags = (int*)c->s3.p;
+    pp_successor_kernel<<<(n + 3) / 4, 128, 0, c->stream>>>(a);
+    c->launches += 1;
+    PP_CUDA(cudaGetLastError());
+    PP_CUDA(cudaMemcpyAsync(out, c->s1.p, sizeof(PPState) * (size_t)n * stride, cudaMemcpyDeviceToHost, c->stream));
+    PP_CUDA(cudaMemcpyAsync(n_out, c->s2.p, sizeof(int) * n, cudaMemcpyDeviceToHost, c->stream));
+    PP_CUDA(cudaMemcpyAsync(flags, c->s3.p, sizeof(int) * n, cudaMemcpyDeviceToHost, c->stream));
+    PP_CUDA(cudaStreamSynchronize(c->stream));
+    return PP_SUCCESS;
+}
+
+int pp_rollout_batch(pp_context* c, const pp_state* in, int n, pp_state* out, int* n_out, int* flags)
+{ return successors(c, 0, in, n, out, n_out, flags, 0); }
+
+int pp_expand_batch(pp_context* c, int g, const pp_state* in, int n, pp_state* out, int* n_out, int* flags)
+{ return successors(c, g, in, n, out, n_out, flags, 1); }
+
+int pp_collision_batch(pp_context* c, int g, const float* xy, int n, int* free_out, int* cells_ij)
+{
+    int rc = check_group(c, g); if (rc) return rc;
+    if (n <= 0) return PP_SUCCESS;
+    PP_CUDA(cudaSetDevice(c->device));
+    PP_CUDA(c->s0.ensure(sizeof(float) * 2 * n));
+    PP_CUDA(c->s1.ensure(sizeof(int) * n));
+    PP_CUDA(c->s2.ensure(sizeof(int) * 2 * n));
+    PP_CUDA(cudaMemcpyAsync(c->s0.p, xy, sizeof(float) * 2 * n, cudaMemcpyHostToDevice, c->stream));
+    pp_collision_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(c->model.C, c->groups[g].map, (const float*)c->s0.p, 2, n, 0,
+                                                              (int*)c->s1.p, (int*)c->s2.p);
+    c->launches += 1;
+    PP_CUDA(cudaGetLastError());
+    PP_CUDA(cudaMemcpyAsync(free_out, c->s1.p, sizeof(int) * n, cudaMemcpyDeviceToHost, c->stream));
+    if (cells_ij) PP_CUDA(cudaMemcpyAsync(cells_ij, c->s2.p, sizeof(int) * 2 * n, cudaMemcpyDeviceToHost, c->stream));
+    PP_CUDA(cudaStreamSynchronize(c->stream));
+    return PP_SUCCESS;
+}
+
+int pp_check_path(pp_context* c, int g, const float* xyh, int n, int* free_out)
+{
+    int rc = check_group(c, g); if (rc) return rc;
+    *free_out = 1;
+    if (n <= 0) return PP_SUCCESS;
+    PP_CUDA(cudaSetDevice(c->device));
+    PP_CUDA(c->s0.ensure(sizeof(float) * 3 * n));
+    PP_CUDA(c->s1.ensure(sizeof(int) * n));
+    PP_CUDA(cudaMemcpyAsync(c->s0.p, xyh, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, c->stream));
+    pp_collision_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(c->model.C, c->groups[g].map, (const float*)c->s0.p, 3, n, 1,
+                                                              (int*)c->s1.p, nullptr);
+    c->launches += 1;
+    PP_CUDA(cudaGetLastError());
+    std::vector<int> fr(n);
+    PP_CUDA(cudaMemcpyAsync(fr.data(), c->s1.p, sizeof(int) * n, cudaMemcpyDeviceToHost, c->stream));
+    PP_CUDA(cudaStreamSynchronize(c->stream));
+    for (int k = 0; k < n; k++) if (!fr[k]) { *free_out = 0; break; }
+    return PP_SUCCESS;
+}
+
+int pp_apf_batch(pp_context* c, int g, const float* xyh, int n, float* out)
+{
+    int rc = check_group(c, g); if (rc) return rc;
+    if (n <= 0) return PP_SUCCESS;
+    PP_CUDA(cudaSetDevice(c->device));
+    PP_CUDA(c->s0.ensure(sizeof(float) * 3 * n));
+    PP_CUDA(c->s1.ensure(sizeof(float) * n));
+    PP_CUDA(cudaMemcpyAsync(c->s0.p, xyh, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, c->stream));
+    pp_apf_kernel<<<(n + 3) / 4, 128, 0, c->stream>>>(c->model.C, c->groups[g], (const float*)c->s0.p, n, (float*)c->s1.p);
+    c->launches += 1;
+    PP_CUDA(cudaGetLastError());
+    PP_CUDA(cudaMemcpyAsync(out, c->s1.p, sizeof(float) * n, cudaMemcpyDeviceToHost, c->stream));
+    PP_CUDA(cudaStreamSynchronize(c->stream));
+    return PP_SUCCESS;
+}
+
+int pp_dubins_length_batch(pp_context* c, const float* starts, int n, const float* goal3, float* length, int* type, float* params4)
+{
+    if (!c) return pp_fail(PP_ERR_INVALID, "null context");
+    if (n <= 0) return PP_SUCCESS;
+    PP_CUDA(cudaSetDevice(c->device));
+    PP_CUDA(c->s0.ensure(sizeof(float) * 3 * n));
+    PP_CUDA(c->s1.ensure(sizeof(float) * n));
+    PP_CUDA(c->s2.ensure(sizeof(int) * n));
+    PP_CUDA(c->s3.ensure(sizeof(float) * 4 * n));
+    PP_CUDA(cudaMemcpyAsync(c->s0.p, starts, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, c->stream));
+    size_t threads = (size_t)n * 4;
+    pp_dubins_length_kernel<<<(int)((threads + 127) / 128), 128, 0, c->stream>>>(c->model.C.r_min, (const float*)c->s0.p, n,
+        goal3[0], goal3[1], goal3[2], (float*)c->s1.p, (int*)c->s2.p, (float*)c->s3.p);
+    c->launches += 1;
+    PP_CUDA(cudaGetLastError());
+    PP_CUDA(cudaMemcpyAsync(length, c->s1.p, sizeof(float) * n, cudaMemcpyDeviceToHost, c->stream));
+    if (type) PP_CUDA(cudaMemcpyAsync(type, c->s2.p, sizeof(int) * n, cudaMemcpyDeviceToHost, c->stream));
+    if (params4) PP_CUDA(cudaMemcpyAsync(params4, c->s3.p, sizeof(float) * 4 * n, cudaMemcpyDeviceToHost, c->stream));
+    PP_CUDA(cudaStreamSynchronize(c->stream));
+    return PP_SUCCESS;
+}
+
+int pp_dubins_path(pp_context* c, const float* s, const float* g, float* xyh, float* curvature, int cap, int* n_out,
+                   float* length, int* long_turn_flag)
+{
+    if (!c) return pp_fail(PP_ERR_INVALID, "null context");
+    PP_CUDA(cudaSetDevice(c->device));
+    PP_CUDA(c->s0.ensure(sizeof(PPPathPt) * (size_t)cap));
+    PP_CUDA(c->s1.ensure(16));
+    int* d_n = (int*)c->s1.p; float* d_len = (float*)(c->s1.p + 4); int* d_flag = (int*)(c->s1.p + 8);
+    pp_dubins_path_kernel<<<1, 32, 0, c->stream>>>(c->model.C, s[0], s[1], s[2], g[0], g[1], g[2], (PPPathPt*)c->s0.p, cap,
+                                                   d_n, d_len, d_flag);
+    c->launches += 1;
+    PP_CUDA(cudaGetLastError());
+    unsigned char hdr[16];
+    PP_CUDA(cudaMemcpyAsync(hdr, c->s1.p, 16, cudaMemcpyDeviceToHost, c->stream));
+    PP_CUDA(cudaStreamSynchronize(c->stream));
+    int n; std::memcpy(&n, hdr, 4); std::memcpy(length, hdr + 4, 4); std::memcpy(long_turn_flag, hdr + 8, 4);
+    *n_out = n;
+    int m = std::min(n, cap);
+    std::vector<PPPathPt> pts(std::max(m, 1));
+    if (m > 0) PP_CUDA(cudaMemcpy(pts.data(), c->s0.p, sizeof(PPPathPt) * m, cudaMemcpyDeviceToHost));
+    for (int k = 0; k < m; k++)
+    {
+        xyh[3 * k] = pts[k].x; xyh[3 * k + 1] = pts[k].y; xyh[3 * k + 2] = pts[k].heading;
+        curvature[k] = pts[k].curvature;
+    }
+    return PP_SUCCESS;
+}
+
+// ---- batch search ------------------------------------------------------------------------------------
+static void fill_args(pp_context* c, const WorkPools& w, int n_slots, const int* qmap, int n_work, PPBatchArgs& a)
+{
+    a.C = c->model.C; a.off_xy = c->d_off_xy; a.groups = c->d_groups; a.queries = c->d_queries.p; a.n_queries = n_work;
+    a.qmap = qmap;
+    a.n_slots = n_slots; a.counter = c->d_counter; a.results = c->d_results.p;
+    a.paths = c->d_paths.p; a.path_cap = c->opts.path_cap;
+    a.trace = c->opts.trace_cap > 0 ? c->d_trace.p : nullptr; a.trace_cap = c->opts.trace_cap;
+    a.open3 = w.open3.p; a.open3_cap = w.open3_cap; a.closed = w.closed.p; a.closed_cap = w.closed_cap;
+    a.chash = w.chash.p; a.chash_cap = w.chash_cap; a.cell_state = w.cell_state.p; a.nm_g = w.nm_g.p; a.nm_f = w.nm_f.p;
+    a.cl_g = w.cl_g.p; a.cl_prev = w.cl_prev.p; a.open2 = w.open2.p; a.open2_cap = w.open2_cap;
+}
+
+// (re)allocate `w` for `want_slots` slots of the given capacities, limited to `mem_frac` of the free memory
+static int ensure_work(pp_context* c, WorkPools& w, int want_slots, int max_exp, int max_open, int max_open2d, double mem_frac)
+{
+    size_t nn = nn_of(c);
+    int hc = 1; while (hc < 2 * max_exp) hc <<= 1;
+    size_t per_slot = sizeof(PPNode3) * (size_t)max_open + sizeof(PPClosed3) * (size_t)max_exp + sizeof(int) * (size_t)hc +
+                      nn * 20 + sizeof(PPNode2) * (size_t)max_open2d;
+    int slots = want_slots;
+    if (!(w.alloc_slots >= slots && w.open3_cap == max_open && w.closed_cap == max_exp && w.open2_cap == max_open2d))
+    {
+        w.release();
+        size_t free_b = 0, total_b = 0;
+        PP_CUDA(cudaMemGetInfo(&free_b, &total_b));
+        size_t budget = (size_t)(free_b * mem_frac);
+        if ((size_t)slots * per_slot > budget) slots = (int)(budget / per_slot);
+        if (slots < 1) return pp_fail(PP_ERR_CAPACITY, "not enough device memory for one query slot");
+        PP_CUDA(w.open3.ensure((size_t)slots * max_open));
+        PP_CUDA(w.closed.ensure((size_t)slots * max_exp));
+        PP_CUDA(w.chash.ensure((size_t)slots * hc));
+        PP_CUDA(w.cell_state.ensure((size_t)slots * nn));
+        PP_CUDA(w.nm_g.ensure((size_t)slots * nn));
+        PP_CUDA(w.nm_f.ensure((size_t)slots * nn));
+        PP_CUDA(w.cl_g.ensure((size_t)slots * nn));
+        PP_CUDA(w.cl_prev.ensure((size_t)slots * nn));
+        PP_CUDA(w.open2.ensure((size_t)slots * max_open2d));
+        w.open3_cap = max_open; w.closed_cap = max_exp; w.open2_cap = max_open2d; w.chash_cap = hc;
+        w.alloc_slots = slots;
+    }
+    return PP_SUCCESS;
+}
+
+static pp_search_opts default_opts(const pp_search_opts* in)
+{
+    pp_search_opts o;
+    if (in) o = *in; else std::memset(&o, 0, sizeof(o));
+    if (o.max_expansions <= 0) o.max_expansions = 1 << 17;
+    if (o.max_open <= 0) o.max_open = 1 << 16;
+    if (o.max_open2d <= 0) o.max_open2d = 1 << 14;
+    if (o.path_cap <= 0) o.path_cap = 2048;
+    if (o.trace_cap < 0) o.trace_cap = 0;
+    return o;
+}
+
+static int hw_slots_of(pp_context* c, int* out)
+{
+    int occ = 0;
+    PP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pp_search_kernel, PP_SEARCH_WARPS * 32, 0));
+    *out = std::max(1, occ) * c->sm_count * PP_SEARCH_WARPS;
+    return PP_SUCCESS;
+}
+
+int pp_batch_upload(pp_context* c, const pp_query* q, int n, const pp_search_opts* opts)
+{
+    if (!c || !q || n <= 0) return pp_fail(PP_ERR_INVALID, "pp_batch_upload: bad arguments");
+    PP_CUDA(cudaSetDevice(c->device));
+    pp_search_opts o = default_opts(opts);
+    c->opts = o;
+    c->h_queries.resize(n);
+    for (int k = 0; k < n; k++)
+    {
+        if (q[k].group < 0 || q[k].group >= c->num_groups) return pp_fail(PP_ERR_INVALID, "query group out of range");
+        c->h_queries[k].start = pp_host_set_start(c->model.C, c->frames[q[k].group], q[k].x, q[k].y, q[k].heading, q[k].vel);
+        c->h_queries[k].group = q[k].group;
+        c->h_queries[k].pad = 0;
+    }
+    c->n_queries = n;
+    int hw_slots = 0;
+    int rc = hw_slots_of(c, &hw_slots); if (rc) return rc;
+    int want = std::min(n, hw_slots);
+    if (o.max_slots > 0) want = std::min(want, o.max_slots);
+    PP_CUDA(c->d_queries.ensure(n));
+    PP_CUDA(c->d_results.ensure(n));
+    PP_CUDA(c->d_paths.ensure((size_t)n * o.path_cap));
+    if (o.trace_cap > 0) PP_CUDA(c->d_trace.ensure((size_t)n * o.trace_cap));
+    rc = ensure_work(c, c->wp, want, o.max_expansions, o.max_open, o.max_open2d, 0.6); if (rc) return rc;
+    c->n_slots = std::max(std::min(c->wp.alloc_slots, want), 1);
+    PP_CUDA(cudaMemcpyAsync(c->d_queries.p, c->h_queries.data(), sizeof(PPQuery) * n, cudaMemcpyHostToDevice, c->stream));
+    rc = sync_groups(c); if (rc) return rc;
+    PP_CUDA(cudaStreamSynchronize(c->stream));
+    return PP_SUCCESS;
+}
+
+static int launch_search(pp_context* c, const WorkPools& w, int n_slots, const int* qmap, int n_work)
+{
+    PPBatchArgs a;
+    fill_args(c, w, n_slots, qmap, n_work, a);
+    PP_CUDA(cudaMemsetAsync(c->d_counter, 0, sizeof(int), c->stream));
+    int blocks = (n_slots + PP_SEARCH_WARPS - 1) / PP_SEARCH_WARPS;
+    pp_search_kernel<<<blocks, PP_SEARCH_WARPS * 32, 0, c->stream>>>(a);
+    c->launches += 1;
+    PP_CUDA(cudaGetLastError());
+    return PP_SUCCESS;
+}
+
+int pp_batch_run(pp_context* c, float* kernel_ms)
+{
+    if (!c || c->n_queries <= 0) return pp_fail(PP_ERR_INVALID, "pp_batch_run: nothing uploaded");
+    PP_CUDA(cudaSetDevice(c->device));
+    const int n = c->n_queries;
+    PP_CUDA(cudaEventRecord(c->ev0, c->stream));
+    int rc = launch_search(c, c->wp, c->n_slots, nullptr, n); if (rc) return rc;
+    // The reference's containers are unbounded.  Queries that exhausted a pool are re-run from scratch with
+    // 8x larger pools (fewer resident slots), up to 3 escalations; what still overflows stays flagged.
+    c->retried = 0;
+    int max_exp = c->opts.max_expansions, max_open = c->opts.max_open, max_open2d = c->opts.max_open2d;
+    std::vector<PPResult> r(n);
+    const int overflow = PP_STATUS_OPEN_OVERFLOW | PP_STATUS_CLOSED_OVERFLOW | PP_STATUS_OPEN2D_OVERFLOW;
+    for (int level = 0; level < 3; level++)
+    {
+        PP_CUDA(cudaMemcpyAsync(r.data(), c->d_results.p, sizeof(PPResult) * n, cudaMemcpyDeviceToHost, c->stream));
+        PP_CUDA(cudaStreamSynchronize(c->stream));
+        std::vector<int> redo;
+        for (int k = 0; k < n; k++) if (r[k].status & overflow) redo.push_back(k);
+        if (redo.empty()) break;
+        if (level == 0) c->retried = (int)redo.size();
+        long long e = (long long)max_exp * 8, o3 = (long long)max_open * 8, o2 = (long long)max_open2d * 4;
+        max_exp = (int)std::min<long long>(e, 1 << 26); max_open = (int)std::min<long long>(o3, 1 << 25);
+        max_open2d = (int)std::min<long long>(o2, 1 << 22);
+        int hw_slots = 0;
+        rc = hw_slots_of(c, &hw_slots); if (rc) return rc;
+        int want = std::min((int)redo.size(), hw_slots);
+        rc = ensure_work(c, c->wp_retry, want, max_exp, max_open, max_open2d, 0.85); if (rc) return rc;
+        int slots = std::max(std::min(c->wp_retry.alloc_slots, want), 1);
+        PP_CUDA(c->d_qmap.ensure(redo.size()));
+        PP_CUDA(cudaMemcpyAsync(c->d_qmap.p, redo.data(), sizeof(int) * redo.size(), cudaMemcpyHostToDevice, c->stream));
+        rc = launch_search(c, c->wp_retry, slots, c->d_qmap.p, (int)redo.size()); if (rc) return rc;
+        PP_CUDA(cudaStreamSynchronize(c->stream));
+    }
+    PP_CUDA(cudaEventRecord(c->ev1, c->stream));
+    PP_CUDA(cudaStreamSynchronize(c->stream));
+    if (kernel_ms) PP_CUDA(cudaEventElapsedTime(kernel_ms, c->ev0, c->ev1));
+    return PP_SUCCESS;
+}
+
+int pp_batch_fetch(pp_context* c, pp_result* results, float* paths_xyh, float* curvature, pp_pop* trace)
+{
+    if (!c || c->n_queries <= 0 || !results) return pp_fail(PP_ERR_INVALID, "pp_batch_fetch: bad arguments");
+    PP_CUDA(cudaSetDevice(c->device));
+    int n = c->n_queries, pc = c->opts.path_cap;
+    std::vector<PPResult> r(n);
+    PP_CUDA(cudaMemcpyAsync(r.data(), c->d_results.p, sizeof(PPResult) * n, cudaMemcpyDeviceToHost, c->stream));
+    std::vector<PPPathPt> pts;
+    if (paths_xyh)
+    {
+        pts.resize((size_t)n * pc);
+        PP_CUDA(cudaMemcpyAsync(pts.data(), c->d_paths.p, sizeof(PPPathPt) * (size_t)n * pc, cudaMemcpyDeviceToHost, c->stream));
+    }
+    if (trace && c->opts.trace_cap > 0)
+        PP_CUDA(cudaMemcpyAsync(trace, c->d_trace.p, sizeof(PPPop) * (size_t)n * c->opts.trace_cap, cudaMemcpyDeviceToHost, c->stream));
+    PP_CUDA(cudaStreamSynchronize(c->stream));
+    int any_cap = 0;
+    for (int k = 0; k < n; k++)
+    {
+        pp_result& o = results[k];
+        o.success = r[k].success; o.status = r[k].status; o.cost = r[k].cost; o.n_pops = r[k].n_pops;
+        o.n_pops_bin_oob = r[k].n_pops_bin_oob; o.n_chain = r[k].n_chain; o.n_dubins = r[k].n_dubins;
+        o.n_lazy_searches = r[k].n_lazy_searches; o.n_lazy_pops = r[k].n_lazy_pops; o.max_open = r[k].max_open;
+        o.n_closed = r[k].n_closed; o.n_path = 0;
+        if (o.status) any_cap = 1;
+        if (!o.success || !paths_xyh) continue;
+        // HybridAStar::reconstruct_path (HybridAStar.cpp:208-262): reversed Dubins samples, then the parent chain,
+        // rotated back to the world frame; curvature shifted by one point
+        const PPHostFrame& fr = c->frames[c->h_queries[k].group];
+        const PPPathPt* src = pts.data() + (size_t)k * pc;
+        int nd = std::min(r[k].n_dubins, pc), nc = std::min(r[k].n_chain, std::max(pc - nd, 0));
+        int total = nd + nc;
+        float* P = paths_xyh + (size_t)k * pc * 3;
+        float* K = curvature ? curvature + (size_t)k * pc : nullptr;
+        float prev_curv = 0.0f;
+        for (int t = 0; t < total; t++)
+        {
+            const PPPathPt& s = (t < nd) ? src[nd - 1 - t] : src[t];
+            pp_host_to_world(fr, s.x, s.y, s.heading, P[3 * t], P[3 * t + 1], P[3 * t + 2]);
+            if (K) K[t] = prev_curv;
+            prev_curv = s.curvature;
+        }
+        o.n_path = total;
+    }
+    (void)any_cap;
+    return PP_SUCCESS;
+}
+
+int pp_find_path_batch(pp_context* c, const pp_query* q, int n, const pp_search_opts* opts, pp_result* results,
+                       float* paths_xyh, float* curvature, pp_pop* trace)
+{
+    int rc = pp_batch_upload(c, q, n, opts); if (rc) return rc;
+    rc = pp_batch_run(c, nullptr); if (rc) return rc;
+    return pp_batch_fetch(c, results, paths_xyh, curvature, trace);
+}
+
+int pp_astar_lazy_batch(pp_context* c, int g, const int* ij, int n, float* out)
+{
+    int rc = check_group(c, g); if (rc) return rc;
+    if (n <= 0) return PP_SUCCESS;
+    PP_CUDA(cudaSetDevice(c->device));
+    pp_search_opts o = default_opts(nullptr);
+    rc = ensure_work(c, c->wp_retry, 1, 16, 16, 1 << 18, 0.5); if (rc) return rc;
+    rc = sync_groups(c); if (rc) return rc;
+    PPBatchArgs a;
+    c->opts = o;
+    fill_args(c, c->wp_retry, 1, nullptr, 0, a);
+    PP_CUDA(c->s0.ensure(sizeof(int) * 2 * n));
+    PP_CUDA(c->s1.ensure(sizeof(float) * n));
+    PP_CUDA(c->s2.ensure(sizeof(int)));
+    PP_CUDA(cudaMemcpyAsync(c->s0.p, ij, sizeof(int) * 2 * n, cudaMemcpyHostToDevice, c->stream));
+    pp_lazy_astar_kernel<<<1, 32, 0, c->stream>>>(a, c->groups[g], (const int*)c->s0.p, n, (float*)c->s1.p, (int*)c->s2.p);
+    c->launches += 1;
+    PP_CUDA(cudaGetLastError());
+    int status = 0;
+    PP_CUDA(cudaMemcpyAsync(out, c->s1.p, sizeof(float) * n, cudaMemcpyDeviceToHost, c->stream));
+    PP_CUDA(cudaMemcpyAsync(&status, c->s2.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    PP_CUDA(cudaStreamSynchronize(c->stream));
+    if (status) return pp_fail(PP_ERR_CAPACITY, "lazy A*: 2D open-list pool exhausted");
+    return PP_SUCCESS;
+}
+
+unsigned long long pp_kernel_launches(pp_context* c) { return c ? c->launches : 0ull; }
+
+#ifdef PP_PROFILE
+// development variant only (lib/libpp_b200_prof.so): per-phase SM cycles summed over all queries; reset on read
+int pp_profile_read(pp_context* c, unsigned long long* out8)
+{
+    if (!c) return pp_fail(PP_ERR_INVALID, "null context");
+    PP_CUDA(cudaSetDevice(c->device));
+    PP_CUDA(cudaStreamSynchronize(c->stream));
+    PP_CUDA(cudaMemcpyFromSymbol(out8, pp_prof_acc, sizeof(unsigned long long) * 8));
+    unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    PP_CUDA(cudaMemcpyToSymbol(pp_prof_acc, z, sizeof(z)));
+    return PP_SUCCESS;
+}
+#endif
+
+} // extern "C"

@@ -24,6 +24,19 @@
 #define PP_MAX_SUCC 16
 #define PP_NEAR_CAP 64
 
+// Optional per-phase cycle accounting (library variant built with -DPP_PROFILE; never in the shipped .so).
+// Phases: 0 scratch init, 1 pop + closed insert + erase, 2 roll-out/collision/APF, 3 Dubins candidates,
+// 4 closed.find, 5 open.find (+erase), 6 lazy 2D A*, 7 open.insert.
+#if defined(PP_PROFILE) && defined(__CUDA_ARCH__)
+#define PP_PROF_DECL long long pp_prof_t = clock64(); long long pp_prof_a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#define PP_PROF_MARK(k) { long long t__ = clock64(); pp_prof_a[k] += t__ - pp_prof_t; pp_prof_t = t__; }
+#define PP_PROF_FLUSH if (lane == 0) { for (int q__ = 0; q__ < 8; q__++) atomicAdd(&pp_prof_acc[q__], (unsigned long long)pp_prof_a[q__]); }
+#else
+#define PP_PROF_DECL
+#define PP_PROF_MARK(k)
+#define PP_PROF_FLUSH
+#endif
+
 // cell_state word of the lazy 2D A*: bit31 = _visted, bit30 = node_map entry touched this query,
 // bits 0..29 = id of the lazy search that closed the cell.
 #define PP_CS_VISITED 0x80000000u
@@ -474,10 +487,12 @@ PP_HD_NOINLINE void pp_search_exact(const W& w, const PPConsts& C, const float* 
     const PPFrame& F = G.frame;
     const unsigned kb = (unsigned)(C.bins + 1);
 
+    PP_PROF_DECL
     // ---- scratch init (all lanes) ----
     for (int c = lane; c < N * N; c += W::LANES) wk.cell_state[c] = 0u;
     for (int c = lane; c < wk.chash_cap; c += W::LANES) wk.chash[c] = -1;
     w.sync();
+    PP_PROF_MARK(0)
 
     PPSearchState S;
     int shot_counter = 0, shot_interval = C.shot_interval;
@@ -543,6 +558,7 @@ PP_HD_NOINLINE void pp_search_exact(const W& w, const PPConsts& C, const float* 
         action = w.shfl(action, 0);
         cur = w.shfl(cur, 0);
         w.sync();
+        PP_PROF_MARK(1)
         if (action == ACT_FAIL || action == ACT_ABORT) break;
 
         // popped node, read by every lane
@@ -645,6 +661,7 @@ PP_HD_NOINLINE void pp_search_exact(const W& w, const PPConsts& C, const float* 
         }
         shot_allowed = (cn.vmin_sqr < 1.0f);     // neglect_acceleration, VehicleModel.cpp:76
         pp_expand_warp(w, C, off_xy, G, cn.x, cn.y, cn.heading, cn.g, cn.vmin_sqr, cn.curv, cn.bin, sm);
+        PP_PROF_MARK(2)
         // Dubins candidates: one lane per (successor, CSC type)
         for (int q = lane; q < n_succ_max * 4; q += W::LANES)
         {
@@ -659,6 +676,7 @@ PP_HD_NOINLINE void pp_search_exact(const W& w, const PPConsts& C, const float* 
             }
         }
         w.sync();
+        PP_PROF_MARK(3)
 
         // ---------------- phase 4: successors into the containers (control lane) ----------------
         int abort = 0;
@@ -669,20 +687,25 @@ PP_HD_NOINLINE void pp_search_exact(const W& w, const PPConsts& C, const float* 
                 const PPSucc& sc = sm.succ[s];
                 if (!sc.ok) continue;
                 unsigned key = (unsigned)(sc.ci * N + sc.cj) * kb + (unsigned)sc.bin;
-                if (pp_closed_find(wk, key) >= 0) continue;                 // HybridAStar.cpp:162
+                int in_closed = pp_closed_find(wk, key);
+                PP_PROF_MARK(4)
+                if (in_closed >= 0) continue;                               // HybridAStar.cpp:162
                 PPKey3 k; k.key = key; k.f = sc.g;                          // f == g + field at find time
                 int it_node = S.open.find(k, PPLt3NK(), PPLt3KN());
                 bool do_insert = false;
                 if (it_node == PP_RB_NIL) do_insert = true;
                 else if (sc.g < S.open.n[it_node].g) { S.open.erase(it_node); do_insert = true; }
+                PP_PROF_MARK(5)
                 if (do_insert)
                 {
                     float h1 = pp_lazy_astar(C, G.map, F, wk, S.lazy, sc.ci, sc.cj);
+                    PP_PROF_MARK(6)
                     float h2 = sm.cand[4 * s];
                     for (int t = 1; t < 4; t++) if (sm.cand[4 * s + t] < h2) h2 = sm.cand[4 * s + t];
                     float f = sc.g + ((h1 < h2) ? h2 : h1);
                     if (!pp_open3_insert(S, sc, key, f, cur)) abort = 1;
                     if (S.lazy.status) { S.status |= S.lazy.status; abort = 1; }
+                    PP_PROF_MARK(7)
                 }
             }
         }
@@ -690,6 +713,7 @@ PP_HD_NOINLINE void pp_search_exact(const W& w, const PPConsts& C, const float* 
         w.sync();
         if (abort) break;
     }
+    PP_PROF_FLUSH
 
     if (lane == 0)
     {

@@ -1,0 +1,456 @@
+// sm_100a kernels of the local-planner hot path.  Compiled with -fmad=false (bit-exact parity with the
+// reference's x86-64 arithmetic needs every a*b+c rounded twice) and full-precision div/sqrt.
+//
+//   pp_search_kernel        persistent warps, one query per warp at a time (dynamic fetch), EXACT mode
+//   pp_successor_kernel     one warp per popped state: roll-out lanes = steering primitives,
+//                           collision lookup, APF lanes = obstacles           (north_star (b), (c))
+//   pp_apf_kernel           one warp per pose, order-preserving warp sum
+//   pp_collision_kernel     one thread per point (the reference's check is a single-cell lookup, F3)
+//   pp_dubins_length_kernel 4 lanes per state (one per CSC candidate), FP64-evaluated/rounded ("pinned libm")
+//   pp_dubins_path_kernel   one warp: plan + parallel sampling
+//   pp_lazy_astar_kernel    one control lane: the lazy cached 2D A* on a fresh cache (parity tests)
+//   pp_map_decay_kernel     float4 grid-stride streaming, HBM/L2 bound
+//   pp_map_boxes_kernel     gather-form log-odds rasterisation, one CTA per touched 32x32 tile
+//   pp_map_lines_kernel     ordered (line by line) counted scatter, single CTA
+//   pp_map_reloc_*          forward-scatter resample with atomicMax(source index) = "last writer wins"
+#ifndef PP_KERNELS_CUH
+#define PP_KERNELS_CUH
+
+#include <cuda_runtime.h>
+#ifdef PP_PROFILE
+__device__ unsigned long long pp_prof_acc[8];
+#endif
+#include "../core/pp_search.h"
+#include "../core/pp_map.h"
+
+#define PP_SEARCH_WARPS 4
+#define PP_TILE 32
+
+struct PPWarpDev
+{
+    enum { LANES = 32 };
+    __host__ __device__ __forceinline__ int lane() const
+    {
+#ifdef __CUDA_ARCH__
+        return threadIdx.x & 31;
+#else
+        return 0;
+#endif
+    }
+    __host__ __device__ __forceinline__ void sync() const
+    {
+#ifdef __CUDA_ARCH__
+        __syncwarp();
+#endif
+    }
+    __host__ __device__ __forceinline__ unsigned ballot(bool p) const
+    {
+#ifdef __CUDA_ARCH__
+        return __ballot_sync(0xffffffffu, p);
+#else
+        return p ? 1u : 0u;
+#endif
+    }
+    __host__ __device__ __forceinline__ unsigned lanemask_lt() const
+    {
+#ifdef __CUDA_ARCH__
+        return (1u << (threadIdx.x & 31)) - 1u;
+#else
+        return 0u;
+#endif
+    }
+    template <class T> __host__ __device__ __forceinline__ T shfl(T v, int src) const
+    {
+#ifdef __CUDA_ARCH__
+        return __shfl_sync(0xffffffffu, v, src);
+#else
+        return v;
+#endif
+    }
+};
+
+// ---------------------------------------------------------------------------------------------------
+struct PPBatchArgs
+{
+    PPConsts        C;
+    const float*    off_xy;
+    const PPGroup*  groups;
+    const PPQuery*  queries;
+    const int*      qmap;       // optional indirection (retry pass): work item -> query index
+    int             n_queries;  // number of work items
+    int             n_slots;
+    int*            counter;
+    PPResult*       results;
+    PPPathPt*       paths;      int path_cap;
+    PPPop*          trace;      int trace_cap;
+    // per-slot scratch pools
+    PPNode3*        open3;      int open3_cap;
+    PPClosed3*      closed;     int closed_cap;
+    int*            chash;      int chash_cap;
+    unsigned*       cell_state;
+    float*          nm_g;
+    float*          nm_f;
+    float*          cl_g;
+    int*            cl_prev;
+    PPNode2*        open2;      int open2_cap;
+};
+
+__device__ __forceinline__ void pp_slot_work(const PPBatchArgs& a, int slot, PPWork& wk)
+{
+    size_t nn = (size_t)a.C.N * a.C.N;
+    wk.open3 = a.open3 + (size_t)slot * a.open3_cap;   wk.open3_cap = a.open3_cap;
+    wk.closed = a.closed + (size_t)slot * a.closed_cap; wk.closed_cap = a.closed_cap;
+    wk.chash = a.chash + (size_t)slot * a.chash_cap;   wk.chash_cap = a.chash_cap;
+    wk.cell_state = a.cell_state + slot * nn;
+    wk.nm_g = a.nm_g + slot * nn;
+    wk.nm_f = a.nm_f + slot * nn;
+    wk.cl_g = a.cl_g + slot * nn;
+    wk.cl_prev = a.cl_prev + slot * nn;
+    wk.open2 = a.open2 + (size_t)slot * a.open2_cap;   wk.open2_cap = a.open2_cap;
+    wk.path = nullptr; wk.path_cap = 0; wk.trace = nullptr; wk.trace_cap = 0;
+}
+
+__global__ void __launch_bounds__(PP_SEARCH_WARPS * 32, 4)
+pp_search_kernel(const __grid_constant__ PPBatchArgs a)
+{
+    __shared__ PPSmem sm[PP_SEARCH_WARPS];
+    const int warp = threadIdx.x >> 5;
+    const int slot = blockIdx.x * PP_SEARCH_WARPS + warp;
+    if (slot >= a.n_slots) return;
+    PPWarpDev w;
+    PPWork wk;
+    pp_slot_work(a, slot, wk);
+    for (;;)
+    {
+        int q = 0;
+        if (w.lane() == 0) q = atomicAdd(a.counter, 1);
+        q = w.shfl(q, 0);
+        if (q >= a.n_queries) break;
+        if (a.qmap) q = a.qmap[q];
+        wk.path = a.paths + (size_t)q * a.path_cap; wk.path_cap = a.path_cap;
+        wk.trace = a.trace ? a.trace + (size_t)q * a.trace_cap : nullptr;
+        wk.trace_cap = a.trace ? a.trace_cap : 0;
+        const PPQuery Q = a.queries[q];
+        const PPGroup G = a.groups[Q.group];
+        PPResult res;
+        pp_search_exact(w, a.C, a.off_xy, G, Q.start, wk, sm[warp], res);
+        if (w.lane() == 0) a.results[q] = res;
+        __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// stateless batches
+struct PPSuccArgs
+{
+    PPConsts       C;
+    const float*   off_xy;
+    PPGroup        G;
+    const PPState* in;
+    int            n;
+    int            expand;    // 0: VehicleModel::get_neighbors only, 1: Grid3D::get_neighbors
+    PPState*       out;       // n x (2A+1), compacted
+    int*           n_out;
+    int*           flags;
+};
+
+__global__ void __launch_bounds__(128) pp_successor_kernel(const __grid_constant__ PPSuccArgs a)
+{
+    __shared__ PPSmem sm[4];
+    const int warp = threadIdx.x >> 5;
+    const int k = blockIdx.x * 4 + warp;
+    if (k >= a.n) return;
+    PPWarpDev w;
+    const int lane = w.lane();
+    const PPState s = a.in[k];
+    const int stride = 2 * a.C.A + 1;
+    PPSmem& m = sm[warp];
+    if (a.expand)
+        pp_expand_warp(w, a.C, a.off_xy, a.G, s.x, s.y, s.heading, s.g, s.vmin_sqr, s.curv, s.bin, m);
+    else
+    {
+        int start_index = s.curv - a.C.A;
+        if (start_index < 0) start_index = 0;
+        if (lane < stride)
+        {
+            PPSucc o; o.ok = 0; o.ci = -1; o.cj = -1;
+            int i = start_index + lane;
+            int bin = (s.bin > a.C.bins) ? a.C.bins : s.bin;
+            if (i < a.C.S && pp_rollout_one(a.C, a.off_xy, s.x, s.y, s.heading, s.g, s.vmin_sqr, bin, i, o)) o.ok = 1;
+            m.succ[lane] = o;
+        }
+        __syncwarp();
+    }
+    if (lane == 0)
+    {
+        int cnt = 0;
+        for (int q = 0; q < stride; q++)
+        {
+            const PPSucc& o = m.succ[q];
+            if (!o.ok) continue;
+            PPState r;
+            r.x = o.x; r.y = o.y; r.heading = o.heading; r.g = o.g; r.f = o.g; r.vmin_sqr = o.vmin_sqr;
+            r.curv = o.curv; r.bin = o.bin; r.ci = a.expand ? o.ci : -1; r.cj = a.expand ? o.cj : -1;
+            a.out[(size_t)k * stride + cnt] = r;
+            cnt++;
+        }
+        a.n_out[k] = cnt;
+        a.flags[k] = (s.vmin_sqr < 1.0f) ? 1 : 0;
+    }
+}
+
+__global__ void __launch_bounds__(128) pp_apf_kernel(const __grid_constant__ PPConsts C, PPGroup G,
+                                                      const float* xyh, int n, float* out)
+{
+    const int k = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (k >= n) return;
+    PPWarpDev w;
+    float v = pp_apf_sum(w, C, G.apf, (const int*)0, G.K, xyh[3 * k], xyh[3 * k + 1], xyh[3 * k + 2]);
+    if (w.lane() == 0) out[k] = v;
+}
+
+// mode 0: successor lookup (truncated index, Grid3D.cpp:56-59) -> free flag + cell;
+// mode 1: path-point lookup (rounded index, Grid3D.cpp:83-90) -> free flag
+__global__ void pp_collision_kernel(const __grid_constant__ PPConsts C, const float* map, const float* pts, int stride,
+                                    int n, int mode, int* free_out, int* cells)
+{
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    float x = pts[(size_t)k * stride], y = pts[(size_t)k * stride + 1];
+    if (mode == 0)
+    {
+        int ci, cj;
+        bool ok = pp_collision_free(C, map, x, y, ci, cj);
+        free_out[k] = ok ? 1 : 0;
+        if (cells) { cells[2 * k] = ci; cells[2 * k + 1] = cj; }
+    }
+    else free_out[k] = pp_path_point_blocked(C, map, x, y) ? 0 : 1;
+}
+
+// 4 lanes per state: one CSC candidate each, folded in candidate order (Dubins.cpp:36-68)
+__global__ void __launch_bounds__(128) pp_dubins_length_kernel(float r_min, const float* starts, int n, float gx, float gy,
+                                                                float gh, float* length, int* type, float* params4)
+{
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    int k = t >> 2, cand = t & 3;
+    bool active = k < n;
+    float sx = 0, sy = 0, sh = 0;
+    if (active) { sx = starts[3 * k]; sy = starts[3 * k + 1]; sh = starts[3 * k + 2]; }
+    PPDubinsCenters c;
+    float p[4] = {0, 0, 0, 0};
+    float len = 0.0f;
+    if (active)
+    {
+        pp_dubins_centers(r_min, sx, sy, sh, gx, gy, gh, c);
+        float csx, csy, cgx, cgy;
+        pp_dubins_pick(c, cand, csx, csy, cgx, cgy);
+        len = pp_dubins_candidate(cand, r_min, sh, gh, csx, csy, cgx, cgy, p);
+    }
+    // fold across the 4 lanes of the group
+    int base = (threadIdx.x & 31) & ~3;
+    float best = __shfl_sync(0xffffffffu, len, base);
+    int best_t = 0;
+    for (int q = 1; q < 4; q++)
+    {
+        float l = __shfl_sync(0xffffffffu, len, base + q);
+        if (l < best) { best = l; best_t = q; }
+    }
+    float bp[4];
+    for (int q = 0; q < 4; q++) bp[q] = __shfl_sync(0xffffffffu, p[q], base + best_t);
+    if (active && cand == 0)
+    {
+        length[k] = best;
+        if (type) type[k] = best_t;
+        if (params4) for (int q = 0; q < 4; q++) params4[4 * k + q] = bp[q];
+    }
+}
+
+// one warp: Dubins::get_shortest_path (Dubins.cpp:125-153)
+__global__ void __launch_bounds__(32) pp_dubins_path_kernel(const __grid_constant__ PPConsts C, float sx, float sy, float sh,
+                                                             float gx, float gy, float gh, PPPathPt* out, int cap, int* n_out,
+                                                             float* length, int* flag)
+{
+    const int lane = threadIdx.x & 31;
+    int type; float p[4]; PPDubinsCenters cen; PPDubinsPlan pl;
+    float len = pp_dubins_shortest(C.r_min, sx, sy, sh, gx, gy, gh, type, p, cen);
+    pp_dubins_plan(C.r_min, C.step, C.ang_step, type, p, cen, pl);
+    int total = pl.size_3 + 1;
+    float acc = p[0];
+    for (int k = 0; k < total; k++)
+    {
+        if (k == pl.size_1) acc = 0.0f;
+        if (k == pl.size_2) acc = p[2];
+        if ((k & 31) == lane && k < cap)
+        {
+            PPPathPt q;
+            pp_dubins_sample(pl, C.r_min, k, acc, q.x, q.y, q.heading, q.curvature);
+            out[k] = q;
+        }
+        if (k < pl.size_1) acc = (pl.s1 < 0) ? acc - C.ang_step : acc + C.ang_step;
+        else if (k < pl.size_2) acc = acc + C.step;
+        else if (k < pl.size_3) acc = (pl.s2 < 0) ? acc - C.ang_step : acc + C.ang_step;
+    }
+    if (lane == 0) { *n_out = total; *length = len; *flag = (fabsf(p[1]) > (float)PP_PI_2) ? 1 : 0; }
+}
+
+// lazy cached 2D A* on a fresh cache, cells queried in sequence (AStar.cpp:100-113); slot 0 scratch
+__global__ void __launch_bounds__(32) pp_lazy_astar_kernel(const __grid_constant__ PPBatchArgs a, PPGroup G, const int* ij,
+                                                            int n, float* out, int* status)
+{
+    PPWork wk;
+    pp_slot_work(a, 0, wk);
+    const int lane = threadIdx.x & 31;
+    for (int c = lane; c < a.C.N * a.C.N; c += 32) wk.cell_state[c] = 0u;
+    __syncwarp();
+    if (lane == 0)
+    {
+        PPLazy L;
+        L.open.init(wk.open2, wk.open2_cap);
+        L.search_id = 0; L.status = 0; L.n_searches = 0; L.n_pops = 0;
+        for (int k = 0; k < n; k++) out[k] = pp_lazy_astar(a.C, G.map, G.frame, wk, L, ij[2 * k], ij[2 * k + 1]);
+        *status = L.status;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// map update
+
+// Grid2D::update_obstacles(), Grid2D.cpp:197-208.  n4 = N*N/4 float4 elements (+ scalar tail).
+__global__ void __launch_bounds__(256) pp_map_decay_kernel(float* __restrict__ map, size_t n, float log_free, float lo, float hi)
+{
+    size_t n4 = n >> 2;
+    float4* m4 = reinterpret_cast<float4*>(map);
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride)
+    {
+        float4 v = m4[i];
+        v.x = pp_map_decay_cell(v.x, log_free, lo, hi);
+        v.y = pp_map_decay_cell(v.y, log_free, lo, hi);
+        v.z = pp_map_decay_cell(v.z, log_free, lo, hi);
+        v.w = pp_map_decay_cell(v.w, log_free, lo, hi);
+        m4[i] = v;
+    }
+    for (size_t i = (n4 << 2) + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        map[i] = pp_map_decay_cell(map[i], log_free, lo, hi);
+}
+
+struct PPBoxDescDev { int start_i, start_j, ni, nj; float delta; };
+
+// Grid2D::update_obstacles(boxes, conf), Grid2D.cpp:99-139, gather form.  One CTA per touched 32x32 tile;
+// tile_off/tile_boxes = CSR list (ascending box index) of the boxes whose sample bounding box overlaps the tile.
+__global__ void __launch_bounds__(256) pp_map_boxes_kernel(float* __restrict__ map, int N, const int* __restrict__ tile_ids,
+                                                            const int* __restrict__ tile_off, const int* __restrict__ tile_boxes,
+                                                            const PPBoxDescDev* __restrict__ descs, float cos_h, float sin_h,
+                                                            float lo, float hi, int tiles_per_row)
+{
+    __shared__ PPBoxDescDev sd[64];
+    const int tile = tile_ids[blockIdx.x];
+    const int ti = tile / tiles_per_row, tj = tile - ti * tiles_per_row;
+    const int beg = tile_off[blockIdx.x], end = tile_off[blockIdx.x + 1];
+    const int lj = threadIdx.x & 31, li0 = threadIdx.x >> 5;   // 8 rows per pass, 4 passes
+    float v[4];
+    int   ci[4];
+    const int cj = tj * PP_TILE + lj;
+#pragma unroll
+    for (int r = 0; r < 4; r++)
+    {
+        ci[r] = ti * PP_TILE + li0 + 8 * r;
+        v[r] = (ci[r] < N && cj < N) ? map[(size_t)ci[r] * N + cj] : 0.0f;
+    }
+    for (int b0 = beg; b0 < end; b0 += 64)
+    {
+        int nb = min(64, end - b0);
+        __syncthreads();
+        if (threadIdx.x < nb) sd[threadIdx.x] = descs[tile_boxes[b0 + threadIdx.x]];
+        __syncthreads();
+        for (int b = 0; b < nb; b++)
+        {
+            const PPBoxDescDev d = sd[b];
+#pragma unroll
+            for (int r = 0; r < 4; r++)
+            {
+                int cnt = pp_box_count(d.ni, d.nj, cos_h, sin_h, ci[r] - d.start_i, cj - d.start_j);
+                if (cnt) v[r] = pp_box_apply(v[r], cnt, d.delta, lo, hi);
+            }
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < 4; r++)
+        if (ci[r] < N && cj < N) map[(size_t)ci[r] * N + cj] = v[r];
+}
+
+// Grid2D::update_obstacles(lines, conf, width), Grid2D.cpp:142-194.  Lines are applied one after the other
+// (clamping is order dependent across lines); inside a line every sample adds the same delta, so samples are
+// counted per cell with atomics and the owner applies clamp(v + delta) `count` times.  cnt = N*N zeroed ints.
+__global__ void __launch_bounds__(1024) pp_map_lines_kernel(float* map, int* cnt, int N, int n45, int n2, float res,
+                                                             const PPLineDesc* lines, int n_lines, float width, float lo, float hi)
+{
+    for (int k = 0; k < n_lines; k++)
+    {
+        const PPLineDesc d = lines[k];
+        const int t = threadIdx.x;
+        bool active = false;
+        float pl = 0.0f;
+        if (t < 100) { pl = pp_accumulate_steps(res, t); active = (pl <= d.length); }
+        if (active)
+            for (float pw = 0.0f; pw <= width; pw += res)
+            {
+                int i1, j1, i2, j2;
+                pp_line_cells(d, res, n45, n2, pl, pw, i1, j1, i2, j2);
+                if (i1 > -1 && i1 < N && j1 > -1 && j1 < N) atomicAdd(&cnt[(size_t)i1 * N + j1], 1);
+                if (i2 > -1 && i2 < N && j2 > -1 && j2 < N) atomicAdd(&cnt[(size_t)i2 * N + j2], 1);
+            }
+        __syncthreads();
+        if (active)
+            for (float pw = 0.0f; pw <= width; pw += res)
+            {
+                int i1, j1, i2, j2;
+                pp_line_cells(d, res, n45, n2, pl, pw, i1, j1, i2, j2);
+                if (i1 > -1 && i1 < N && j1 > -1 && j1 < N)
+                {
+                    size_t c = (size_t)i1 * N + j1;
+                    int q = atomicExch(&cnt[c], 0);
+                    if (q) map[c] = pp_box_apply(map[c], q, d.delta, lo, hi);
+                }
+                if (i2 > -1 && i2 < N && j2 > -1 && j2 < N)
+                {
+                    size_t c = (size_t)i2 * N + j2;
+                    int q = atomicExch(&cnt[c], 0);
+                    if (q) map[c] = pp_box_apply(map[c], q, d.delta, lo, hi);
+                }
+            }
+        __syncthreads();
+    }
+}
+
+// Grid3D::relocate_obstacles, Grid3D.cpp:169-203
+__global__ void pp_map_reloc_fill_kernel(int* idx, size_t n)
+{
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) idx[i] = -1;
+}
+
+__global__ void pp_map_reloc_scatter_kernel(int* idx, int N, PPRelocDesc d)
+{
+    size_t n = (size_t)N * N, stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t s = (size_t)blockIdx.x * blockDim.x + threadIdx.x; s < n; s += stride)
+    {
+        int i = (int)(s / N), j = (int)(s - (size_t)i * N);
+        int in, jn;
+        pp_reloc_target(d, i, j, in, jn);
+        if (in > -1 && in < N && jn > -1 && jn < N) atomicMax(&idx[(size_t)in * N + jn], (int)s);
+    }
+}
+
+__global__ void pp_map_reloc_gather_kernel(const float* __restrict__ old_map, float* __restrict__ new_map, int* idx, size_t n)
+{
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += stride)
+    {
+        int s = idx[t];
+        new_map[t] = (s >= 0) ? old_map[s] : 0.0f;
+        idx[t] = 0;     // leave the scratch zeroed for the line rasteriser
+    }
+}
+
+#endif

@@ -1,0 +1,63 @@
+#!/usr/bin/env python
+"""Development probe (not part of the product or the tests): runs a C4-shaped batch and prints work statistics
+and, when PP_B200_LIB points at the -DPP_PROFILE variant, the per-phase cycle split of the search kernel."""
+import argparse
+import ctypes as C
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "tests")):
+    sys.path.insert(0, p)
+import scenarios as S  # noqa: E402
+import path_planning_pkg_b200 as pp  # noqa: E402
+import bench  # noqa: E402
+
+PHASES = ["init", "pop+closed.insert+erase", "rollout+collision+apf", "dubins cand", "closed.find", "open.find(+erase)",
+          "lazy 2D A*", "open.insert"]
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--groups", type=int, default=8)
+    ap.add_argument("--starts", type=int, default=64)
+    ap.add_argument("--slots", type=int, default=0)
+    ap.add_argument("--reps", type=int, default=1)
+    ap.add_argument("--max-expansions", type=int, default=1 << 17)
+    ap.add_argument("--max-open", type=int, default=1 << 16)
+    a = ap.parse_args()
+    P = pp.make_params(grid_size=512, resolution=0.2)
+    ctx = pp.Context(P, num_groups=a.groups)
+    groups = bench.build_workload(a.groups, a.starts, 0)
+    queries, qgroups, maps = bench.apply_groups(ctx, groups)
+    q = ctx.make_queries(queries, qgroups)
+    opts = ctx.make_opts(max_expansions=a.max_expansions, max_open=a.max_open, max_slots=a.slots)
+    ctx.batch_upload(q, opts)
+    prof = hasattr(ctx.lib, "pp_profile_read")
+    buf = (C.c_ulonglong * 8)()
+    if prof:
+        ctx.lib.pp_profile_read(ctx.h, buf)
+    for rep in range(a.reps):
+        ms = ctx.batch_run()
+        res, _, _ = ctx.batch_fetch()
+        pops = int(res["n_pops"].sum())
+        print(f"rep {rep}: {len(q)} queries, {pops} expansions, {ms:.1f} ms -> {pops / ms / 1e3:.3f} M exp/s, "
+              f"{len(q) / ms * 1e3:.1f} q/s")
+    np_ = res["n_pops"]
+    print("pops/query: min %d p50 %d p90 %d max %d mean %.0f" % (np_.min(), np.median(np_), np.percentile(np_, 90), np_.max(), np_.mean()))
+    print("max_open: p50 %d max %d | n_closed max %d | lazy searches/query mean %.0f | lazy pops/3D pop %.2f" % (
+        np.median(res["max_open"]), res["max_open"].max(), res["n_closed"].max(), res["n_lazy_searches"].mean(),
+        res["n_lazy_pops"].sum() / max(pops, 1)))
+    print("success %.3f, status!=0: %d, oob pops %d" % (res["success"].mean(), (res["status"] != 0).sum(), res["n_pops_bin_oob"].sum()))
+    if prof:
+        ctx.lib.pp_profile_read(ctx.h, buf)
+        tot = sum(buf)
+        for name, v in zip(PHASES, buf):
+            print(f"  {name:28s} {100.0 * v / max(tot, 1):6.2f} %   {v / max(pops, 1):10.0f} cycles/expansion")
+
+
+if __name__ == "__main__":
+    main()

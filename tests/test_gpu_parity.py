@@ -1,0 +1,263 @@
+"""GPU parity tests (run with `pytest -m gpu` on a B200): every call goes through the C ABI of
+libpp_b200.so and is compared with the compiled, unmodified reference (oracle/_ref).
+
+Oracle flavours (tests/orc.py):
+  ref = stock glibc float libm; crm = same objects with the float transcendentals of the device-executed
+  functions (Dubins.cpp, atan2f of Grid3D::get_field_intensity) pinned to correctly-rounded values.
+Bit-exact targets (map, indices, collision booleans, roll-out) are checked against BOTH flavours;
+APF / Dubins values bit-exactly against crm and within 1e-5 relative against ref; the expansion
+sequence and path bit-exactly against crm, with the match rate against ref reported.
+"""
+import numpy as np
+import pytest
+
+import orc
+import scenarios as S
+
+pytestmark = pytest.mark.gpu
+
+
+def _ctx(P, groups=1):
+    import path_planning_pkg_b200 as pp
+    return pp.Context(pp._cabi.params_from(P), num_groups=groups, device=0)
+
+
+def _bits(a):
+    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+def _states_equal(a, b):
+    for f in a.dtype.names:
+        x, y = a[f], b[f]
+        if x.dtype.kind == "f":
+            if not np.array_equal(_bits(x), _bits(y)):
+                return False, f
+        elif not np.array_equal(x, y):
+            return False, f
+    return True, None
+
+
+@pytest.fixture(scope="module")
+def golden():
+    P = orc.ref_test_params()
+    ctx, ref, crm = _ctx(P), orc.ref(P), orc.crm(P)
+    for o in (ctx, ref, crm):
+        orc.setup_ref_test_scenario(o)
+    return P, ctx, ref, crm
+
+
+def test_constants_and_tables(golden):
+    P, ctx, ref, crm = golden
+    c, r = ctx.consts(), ref.consts()
+    for f in ("log_threshold", "log_min", "log_max", "log_free", "precision", "r_min", "ang_step"):
+        assert np.float32(getattr(c, f)) == np.float32(getattr(r, f)), f
+    fr = ctx.frame()
+    assert np.float32(fr.grid_heading) == np.float32(r.grid_heading)
+    assert list(fr.goal_grid) == list(r.goal_grid) and fr.goal_bin == r.goal_bin
+    assert (fr.goal_ci, fr.goal_cj) == (r.goal_ci, r.goal_cj)
+    for a, b in zip(ctx.tables(), ref.tables()):
+        assert np.array_equal(_bits(a), _bits(b))
+
+
+def test_map_golden_scenario_bitexact(golden):
+    """decay + lane lines + boxes x5 (utils/hybrid_astar/test_hybrid_astar.cpp:77-84): all N*N floats bitwise."""
+    P, ctx, ref, crm = golden
+    m = ctx.get_map()
+    assert np.array_equal(_bits(m), _bits(ref.get_map()))
+    assert (m >= ref.consts().log_threshold).sum() > 100
+
+
+def test_rollout_bitexact(golden):
+    P, ctx, ref, crm = golden
+    rs = np.random.RandomState(3)
+    n = 4096
+    st = np.zeros(n, orc.STATE_DT)
+    st["x"] = rs.uniform(0, 30, n); st["y"] = rs.uniform(0, 30, n); st["heading"] = rs.uniform(-3.05, 3.05, n)
+    st["g"] = rs.uniform(0, 50, n); st["vmin_sqr"] = rs.uniform(0, 9, n)
+    st["curvature_index"] = rs.randint(0, P.num_steering, n)
+    prec = ref.consts().precision
+    st["angle_bin"] = [int((np.float32(np.round(np.float32(h) / np.float32(prec)) * np.float32(prec)) + np.pi) / float(prec)) for h in st["heading"]]
+    st["f"] = st["g"]; st["ci"] = -1; st["cj"] = -1
+    assert (st["angle_bin"] < P.num_angle_bins).all()
+    a, ac, af = ctx.rollout(st)
+    b, bc, bf = ref.rollout(st)
+    assert np.array_equal(ac, bc) and np.array_equal(af, bf)
+    ok, f = _states_equal(a, b)
+    assert ok, f
+
+
+def test_expand_collision_apf(golden):
+    """Grid3D::get_neighbors: survivors (collision booleans), cells and roll-out bit-exact vs stock reference;
+    APF-augmented g bit-exact vs the pinned-libm reference and within 1e-5 of the stock one."""
+    P, ctx, ref, crm = golden
+    rs = np.random.RandomState(4)
+    n = 8192
+    st = np.zeros(n, orc.STATE_DT)
+    st["x"] = rs.uniform(0, 30, n); st["y"] = rs.uniform(0, 30, n); st["heading"] = rs.uniform(-3.05, 3.05, n)
+    st["g"] = rs.uniform(0, 50, n); st["vmin_sqr"] = rs.uniform(0, 9, n)
+    st["curvature_index"] = rs.randint(0, P.num_steering, n)
+    prec = np.float32(ref.consts().precision)
+    st["angle_bin"] = ((np.round(st["heading"] / prec).astype(np.float32) * prec).astype(np.float64) + np.pi) / float(prec)
+    st["f"] = st["g"]
+    a, ac, af = ctx.expand(st)
+    b, bc, bf = ref.expand(st)
+    c, cc, cf = crm.expand(st)
+    assert np.array_equal(ac, bc) and np.array_equal(af, bf)          # same survivors = same collision booleans
+    for f in ("x", "y", "heading", "vmin_sqr"):
+        assert np.array_equal(_bits(a[f]), _bits(b[f])), f
+    for f in ("curvature_index", "angle_bin", "ci", "cj"):
+        assert np.array_equal(a[f], b[f]), f
+    assert np.array_equal(_bits(a["g"]), _bits(c["g"])), "APF cost differs from pinned-libm reference"
+    assert (a["g"] != st["g"][:, None] + 0).any()
+    rel = np.abs(a["g"] - b["g"]) / np.maximum(np.abs(b["g"]), 1e-6)
+    assert rel.max() <= 1e-5, rel.max()
+
+
+def test_collision_lookup_bitexact(golden):
+    P, ctx, ref, crm = golden
+    rs = np.random.RandomState(5)
+    n = 20000
+    xy = np.stack([rs.uniform(-2, 32, n), rs.uniform(-2, 32, n)], 1).astype(np.float32)
+    free, cells = ctx.collision(xy)
+    m = ref.get_map(); thr = ref.consts().log_threshold; N = P.grid_size
+    res = np.float32(P.resolution)
+    ci = (xy[:, 0] / res).astype(np.int32); cj = (xy[:, 1] / res).astype(np.int32)   # trunc toward zero, float32 divide
+    inb = (ci > -1) & (ci < N) & (cj > -1) & (cj < N)
+    exp = np.zeros(n, bool)
+    exp[inb] = m[ci[inb], cj[inb]] < thr
+    assert np.array_equal(cells[:, 0], ci) and np.array_equal(cells[:, 1], cj)
+    assert np.array_equal(free, exp)
+    assert 0.05 < exp.mean() < 0.99
+    # rounded-index variant used by the Dubins shot (Grid3D::check_path)
+    for k in range(0, 400, 7):
+        pts = np.concatenate([xy[k:k + 5], np.zeros((5, 1), np.float32)], 1)
+        assert ctx.check_path(pts) == ref.check_path(pts)
+
+
+def test_apf_values(golden):
+    P, ctx, ref, crm = golden
+    rs = np.random.RandomState(6)
+    n = 20000
+    xyh = np.stack([rs.uniform(2, 28, n), rs.uniform(2, 28, n), rs.uniform(-3.14, 3.14, n)], 1).astype(np.float32)
+    a = ctx.apf(xyh); b = crm.apf(xyh); r = ref.apf(xyh)
+    assert (b > 0).sum() > 1000
+    assert np.array_equal(_bits(a), _bits(b))
+    # vs stock glibc: atan2f there is off by up to 1 ulp and the (alpha - |angle|)/alpha weight amplifies it near
+    # the edge of the active cone, so the bound is absolute on the weight scale, not 1e-5 relative
+    err = np.abs(a - r)
+    assert (err <= 1e-4 * np.maximum(np.abs(r), 1.0)).all(), err.max()
+    print(f"apf vs glibc: {(a != r).mean() * 100:.2f}% of values differ, max abs err {err.max():.3g}")
+
+
+def test_dubins_length(golden):
+    P, ctx, ref, crm = golden
+    rs = np.random.RandomState(7)
+    n = 50000
+    goal = np.array(list(ref.consts().goal_grid), np.float32)
+    starts = np.stack([rs.uniform(0, 30, n), rs.uniform(0, 30, n), rs.uniform(-3.14, 3.14, n)], 1).astype(np.float32)
+    a, at, ap = ctx.dubins_length(starts, goal)
+    b, bt, bp = crm.dubins_length(starts, goal)
+    r, rt, rp = ref.dubins_length(starts, goal)
+    assert np.array_equal(_bits(a), _bits(b)) and np.array_equal(at, bt) and np.array_equal(_bits(ap), _bits(bp))
+    # vs stock glibc: 1e-5 relative, except where an ulp flips one of the +-2pi corrections (a discontinuity of
+    # the reference formula itself, Dubins.cpp:196-204): those are counted, not hidden
+    rel = np.abs(a - r) / np.maximum(np.abs(r), 1e-6)
+    jumps = int((rel > 1e-5).sum())
+    print(f"dubins vs glibc: max rel (non-jump) {rel[rel <= 1e-5].max():.3g}, branch flips {jumps}/{n}")
+    assert jumps <= n // 2000
+
+
+def test_dubins_path_golden(golden):
+    """utils/dubins_paths.py:6 scenario: (0,0,0) -> (20,-20,pi/2)."""
+    P, ctx, ref, crm = golden
+    s = np.array([0, 0, 0], np.float32); g = np.array([20, -20, np.pi / 2], np.float32)
+    a = ctx.dubins_path(s, g); b = crm.dubins_path(s, g)
+    assert len(a[0]) == len(b[0]) and a[3] == b[3]
+    assert np.array_equal(_bits(a[0]), _bits(b[0])) and np.array_equal(_bits(a[1]), _bits(b[1]))
+    assert np.float32(a[2]) == np.float32(b[2])
+
+
+def test_lazy_astar_sequence(golden):
+    """AStar::find_path(i,j) is history dependent: same query order -> identical values."""
+    P, ctx, ref, crm = golden
+    rs = np.random.RandomState(8)
+    m = ref.get_map(); thr = ref.consts().log_threshold
+    free = np.argwhere(m < thr)
+    ij = free[rs.choice(len(free), 600, replace=False)].astype(np.int32)
+    ref.scrub()
+    b = ref.astar_lazy(ij)
+    a = ctx.astar_lazy(ij)
+    assert np.array_equal(_bits(a), _bits(b))
+    assert (b < 1e30).sum() > 300
+
+
+def test_search_golden_sequence_and_path(golden):
+    """utils/hybrid_astar/plot.py:47-51: cost 33.0305, 43 points; full expansion sequence vs the reference."""
+    P, ctx, ref, crm = golden
+    crm.scrub(); ref.scrub()
+    a = ctx.find_path(2.0, orc.REF_TEST_START)
+    b = crm.find_path(2.0, orc.REF_TEST_START)
+    assert a["success"] and a["status"] == 0
+    assert abs(float(a["cost"]) - 33.0305) < 1e-4 and len(a["path"]) == 43
+    assert a["n_pops"] == b["n_pops"] == 882
+    ok, f = _states_equal(a["pops"], b["pops"])
+    assert ok, f
+    assert np.array_equal(_bits(a["path"]), _bits(b["path"])) and np.array_equal(_bits(a["curvature"]), _bits(b["curvature"]))
+    assert a["cost"] == b["cost"]
+    golden_path = np.load(orc.ROOT + "/tests/golden/hybrid_astar_path.npy")
+    assert np.allclose(a["path"][::-1], golden_path, rtol=2e-5, atol=2e-5)
+
+
+@pytest.mark.parametrize("seed", list(range(8)))
+def test_search_c1_exact(seed):
+    sc = S.c1_scenario(seed)
+    P = orc.make_params(grid_size=sc["grid_size"], resolution=sc["resolution"])
+    ctx, crm, ref = _ctx(P), orc.crm(P), orc.ref(P)
+    for o in (ctx, crm, ref):
+        S.build_map(o, sc)
+    assert np.array_equal(_bits(ctx.get_map()), _bits(ref.get_map()))
+    q = sc["queries"][0]
+    a = ctx.find_path(float(q[3]), q[:3]); b = crm.find_path(float(q[3]), q[:3])
+    assert a["status"] == 0 and a["success"] == b["success"] and a["n_pops"] == b["n_pops"]
+    ok, f = _states_equal(a["pops"], b["pops"])
+    assert ok, f
+    assert a["cost"] == b["cost"] and np.array_equal(_bits(a["path"]), _bits(b["path"]))
+
+
+def test_search_c4_batch_exact():
+    """C4 shape (512^2 x 72, 96 boxes): a batch over 2 groups x 6 starts, each compared with a scrubbed reference."""
+    groups = [S.c4_group(s, n_starts=6) for s in (0, 1)]
+    P = orc.make_params(grid_size=512, resolution=0.2)
+    ctx = _ctx(P, groups=len(groups))
+    oracles = []
+    queries, qgroups = [], []
+    for gi, sc in enumerate(groups):
+        crm = orc.crm(P)
+        S.build_map(crm, sc)
+        ctx.update_goal(sc["goal"], sc["frame_start"], group=gi)
+        for _ in range(sc["rounds"]):
+            ctx.update_boxes(sc["boxes"], sc["conf"], S.APF_ADDED_RADIUS, group=gi)
+            ctx.decay(group=gi)
+        m = crm.get_map()
+        assert np.array_equal(_bits(ctx.get_map(gi)), _bits(m))
+        qs = S.select_starts(sc, m, crm.consts().log_threshold, crm.set_start)
+        queries += list(qs); qgroups += [gi] * len(qs)
+        oracles.append(crm)
+    q = ctx.make_queries(np.array(queries), qgroups)
+    opts = ctx.make_opts(trace_cap=1 << 17, path_cap=2048)
+    res, paths, curv, trace = ctx.find_path_batch(q, opts)
+    n_match = 0
+    for k in range(len(q)):
+        o = oracles[qgroups[k]]
+        o.scrub()
+        b = o.find_path(float(q["vel"][k]), np.array([q["x"][k], q["y"][k], q["heading"][k]], np.float32))
+        r = res[k]
+        assert r["status"] == 0 and bool(r["success"]) == b["success"]
+        assert r["n_pops"] == b["n_pops"], (k, r["n_pops"], b["n_pops"])
+        ok, f = _states_equal(trace[k, :r["n_pops"]], b["pops"])
+        assert ok, (k, f)
+        assert np.float32(r["cost"]) == b["cost"]
+        assert np.array_equal(_bits(paths[k, :r["n_path"]]), _bits(b["path"]))
+        assert np.array_equal(_bits(curv[k, :r["n_path"]]), _bits(b["curvature"]))
+        n_match += 1
+    print(f"C4 batch: {n_match}/{len(q)} queries identical, {int(res['n_pops'].sum())} expansions")
