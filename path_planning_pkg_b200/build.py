@@ -65,6 +65,15 @@ def build_cuda_profile(force=False, verbose=True):
     return target
 
 
+def build_cuda_variant(name, defines, force=True, verbose=True):
+    """Development variants for A/B runs on the GPU box: lib/libpp_b200_<name>.so (never loaded by the package)."""
+    os.makedirs(LIB, exist_ok=True)
+    target = os.path.join(LIB, f"libpp_b200_{name}.so")
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    _run([nvcc] + NVCC_FLAGS + [f"-D{d}" for d in defines] + ["-shared", "-o", target, os.path.join(CSRC, "cabi", "pp_cabi.cu")], verbose)
+    return target
+
+
 def build_host(force=False, verbose=True):
     """g++ -> lib/libpath_planning_b200.so (reference-compatible C++ classes over the C ABI)"""
     os.makedirs(LIB, exist_ok=True)

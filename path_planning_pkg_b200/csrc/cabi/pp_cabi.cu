@@ -48,7 +48,7 @@ struct DevBuf
 struct WorkPools
 {
     int alloc_slots = 0, chash_cap = 0, open3_cap = 0, closed_cap = 0, open2_cap = 0;
-    DevBuf<PPNode3> open3; DevBuf<PPClosed3> closed; DevBuf<int> chash;
+    DevBuf<PPNode3> open3; DevBuf<PPClosed3> closed; DevBuf<PPHashSlot> chash;
     DevBuf<unsigned> cell_state; DevBuf<float> nm_g, nm_f, cl_g; DevBuf<int> cl_prev; DevBuf<PPNode2> open2;
     void release()
     {
@@ -566,7 +566,7 @@ static int ensure_work(pp_context* c, WorkPools& w, int want_slots, int max_exp,
 {
     size_t nn = nn_of(c);
     int hc = 1; while (hc < 2 * max_exp) hc <<= 1;
-    size_t per_slot = sizeof(PPNode3) * (size_t)max_open + sizeof(PPClosed3) * (size_t)max_exp + sizeof(int) * (size_t)hc +
+    size_t per_slot = sizeof(PPNode3) * (size_t)max_open + sizeof(PPClosed3) * (size_t)max_exp + sizeof(PPHashSlot) * (size_t)hc +
                       nn * 20 + sizeof(PPNode2) * (size_t)max_open2d;
     int slots = want_slots;
     if (!(w.alloc_slots >= slots && w.open3_cap == max_open && w.closed_cap == max_exp && w.open2_cap == max_open2d))

@@ -13,8 +13,10 @@
 //   decrement        = _Rb_tree_decrement
 // Node 0 of the pool is the header (parent = root, left = leftmost, right = rightmost, red).
 //
-// `Node` must provide int fields parent, left, right, color.  `Less` is a functor
-// bool(const Key&, const Node&) / bool(const Node&, const Key&) supplied by the caller.
+// `Node` must start with a 16-byte aligned PPWalk record `w` = {left, right, f, key} -- everything a
+// walk step needs, fetched with ONE 128-bit load per level -- followed by int fields parent, color and the
+// payload.  The ordering is the reference's for both of its sets (Node3D.h:45-54, Node2D.h:37-41):
+//     a < b  <=>  (a.key != b.key) && (a.f < b.f)       key = cell (2D) or (cell, heading bin) (3D)
 #ifndef PP_RBTREE_H
 #define PP_RBTREE_H
 
@@ -24,6 +26,22 @@
 #define PP_RB_RED 0
 #define PP_RB_BLACK 1
 #define PP_RB_HEADER 0
+
+struct
+#if defined(__CUDACC__) || defined(__GNUC__)
+__attribute__((aligned(16)))
+#endif
+PPWalk
+{
+    int      left, right;
+    float    f;
+    unsigned key;
+};
+
+struct PPKey { unsigned key; float f; };
+
+// the reference's non-strict-weak ordering
+PP_HD bool pp_lt(unsigned ka, float fa, unsigned kb, float fb) { return (ka != kb) && (fa < fb); }
 
 template <class Node>
 struct PPRbTree
@@ -43,14 +61,14 @@ struct PPRbTree
     PP_HD void clear()
     {
         n[PP_RB_HEADER].parent = PP_RB_NIL;
-        n[PP_RB_HEADER].left = PP_RB_HEADER;
-        n[PP_RB_HEADER].right = PP_RB_HEADER;
+        n[PP_RB_HEADER].w.left = PP_RB_HEADER;
+        n[PP_RB_HEADER].w.right = PP_RB_HEADER;
         n[PP_RB_HEADER].color = PP_RB_RED;
         next = 1; free_head = PP_RB_NIL; count = 0;
     }
 
     PP_HD bool empty() const { return count == 0; }
-    PP_HD int  begin() const { return n[PP_RB_HEADER].left; }
+    PP_HD int  begin() const { return n[PP_RB_HEADER].w.left; }
     PP_HD int  root() const { return n[PP_RB_HEADER].parent; }
 
     // returns a free slot or PP_RB_NIL when the pool is exhausted
@@ -65,67 +83,67 @@ struct PPRbTree
 
     PP_HD void rotate_left(int x)
     {
-        int y = n[x].right;
-        n[x].right = n[y].left;
-        if (n[y].left != PP_RB_NIL) n[n[y].left].parent = x;
+        int y = n[x].w.right;
+        n[x].w.right = n[y].w.left;
+        if (n[y].w.left != PP_RB_NIL) n[n[y].w.left].parent = x;
         n[y].parent = n[x].parent;
         if (x == n[PP_RB_HEADER].parent) n[PP_RB_HEADER].parent = y;
-        else if (x == n[n[x].parent].left) n[n[x].parent].left = y;
-        else n[n[x].parent].right = y;
-        n[y].left = x;
+        else if (x == n[n[x].parent].w.left) n[n[x].parent].w.left = y;
+        else n[n[x].parent].w.right = y;
+        n[y].w.left = x;
         n[x].parent = y;
     }
 
     PP_HD void rotate_right(int x)
     {
-        int y = n[x].left;
-        n[x].left = n[y].right;
-        if (n[y].right != PP_RB_NIL) n[n[y].right].parent = x;
+        int y = n[x].w.left;
+        n[x].w.left = n[y].w.right;
+        if (n[y].w.right != PP_RB_NIL) n[n[y].w.right].parent = x;
         n[y].parent = n[x].parent;
         if (x == n[PP_RB_HEADER].parent) n[PP_RB_HEADER].parent = y;
-        else if (x == n[n[x].parent].right) n[n[x].parent].right = y;
-        else n[n[x].parent].left = y;
-        n[y].right = x;
+        else if (x == n[n[x].parent].w.right) n[n[x].parent].w.right = y;
+        else n[n[x].parent].w.left = y;
+        n[y].w.right = x;
         n[x].parent = y;
     }
 
     // _Rb_tree_decrement
-    PP_HD int decrement(int x) const
+    PP_HD_NOINLINE int decrement(int x) const
     {
-        if (x == PP_RB_HEADER) return n[x].right;   // end() -> rightmost
-        if (n[x].left != PP_RB_NIL)
+        if (x == PP_RB_HEADER) return n[x].w.right;   // end() -> rightmost
+        if (n[x].w.left != PP_RB_NIL)
         {
-            int y = n[x].left;
-            while (n[y].right != PP_RB_NIL) y = n[y].right;
+            int y = n[x].w.left;
+            while (n[y].w.right != PP_RB_NIL) y = n[y].w.right;
             return y;
         }
         int y = n[x].parent;
-        while (x == n[y].left) { x = y; y = n[y].parent; }
+        while (x == n[y].w.left) { x = y; y = n[y].parent; }
         return y;
     }
 
     // _Rb_tree_insert_and_rebalance
-    PP_HD void insert_and_rebalance(bool insert_left, int x, int p)
+    PP_HD_NOINLINE void insert_and_rebalance(bool insert_left, int x, int p)
     {
-        n[x].parent = p; n[x].left = PP_RB_NIL; n[x].right = PP_RB_NIL; n[x].color = PP_RB_RED;
+        n[x].parent = p; n[x].w.left = PP_RB_NIL; n[x].w.right = PP_RB_NIL; n[x].color = PP_RB_RED;
         if (insert_left)
         {
-            n[p].left = x;   // also sets leftmost = x when p is the header
-            if (p == PP_RB_HEADER) { n[PP_RB_HEADER].parent = x; n[PP_RB_HEADER].right = x; }
-            else if (p == n[PP_RB_HEADER].left) n[PP_RB_HEADER].left = x;
+            n[p].w.left = x;   // also sets leftmost = x when p is the header
+            if (p == PP_RB_HEADER) { n[PP_RB_HEADER].parent = x; n[PP_RB_HEADER].w.right = x; }
+            else if (p == n[PP_RB_HEADER].w.left) n[PP_RB_HEADER].w.left = x;
         }
         else
         {
-            n[p].right = x;
-            if (p == n[PP_RB_HEADER].right) n[PP_RB_HEADER].right = x;
+            n[p].w.right = x;
+            if (p == n[PP_RB_HEADER].w.right) n[PP_RB_HEADER].w.right = x;
         }
         while (x != n[PP_RB_HEADER].parent && n[n[x].parent].color == PP_RB_RED)
         {
             int xp = n[x].parent;
             int xpp = n[xp].parent;
-            if (xp == n[xpp].left)
+            if (xp == n[xpp].w.left)
             {
-                int y = n[xpp].right;
+                int y = n[xpp].w.right;
                 if (y != PP_RB_NIL && n[y].color == PP_RB_RED)
                 {
                     n[xp].color = PP_RB_BLACK; n[y].color = PP_RB_BLACK; n[xpp].color = PP_RB_RED;
@@ -133,7 +151,7 @@ struct PPRbTree
                 }
                 else
                 {
-                    if (x == n[xp].right) { x = xp; rotate_left(x); }
+                    if (x == n[xp].w.right) { x = xp; rotate_left(x); }
                     n[n[x].parent].color = PP_RB_BLACK;
                     n[xpp].color = PP_RB_RED;
                     rotate_right(xpp);
@@ -141,7 +159,7 @@ struct PPRbTree
             }
             else
             {
-                int y = n[xpp].left;
+                int y = n[xpp].w.left;
                 if (y != PP_RB_NIL && n[y].color == PP_RB_RED)
                 {
                     n[xp].color = PP_RB_BLACK; n[y].color = PP_RB_BLACK; n[xpp].color = PP_RB_RED;
@@ -149,7 +167,7 @@ struct PPRbTree
                 }
                 else
                 {
-                    if (x == n[xp].left) { x = xp; rotate_right(x); }
+                    if (x == n[xp].w.left) { x = xp; rotate_right(x); }
                     n[n[x].parent].color = PP_RB_BLACK;
                     n[xpp].color = PP_RB_RED;
                     rotate_left(xpp);
@@ -161,34 +179,34 @@ struct PPRbTree
     }
 
     // _Rb_tree_rebalance_for_erase; recycles slot z
-    PP_HD void erase(int z)
+    PP_HD_NOINLINE void erase(int z)
     {
         int y = z, x = PP_RB_NIL, x_parent = PP_RB_NIL;
-        if (n[y].left == PP_RB_NIL) x = n[y].right;
-        else if (n[y].right == PP_RB_NIL) x = n[y].left;
+        if (n[y].w.left == PP_RB_NIL) x = n[y].w.right;
+        else if (n[y].w.right == PP_RB_NIL) x = n[y].w.left;
         else
         {
-            y = n[y].right;
-            while (n[y].left != PP_RB_NIL) y = n[y].left;
-            x = n[y].right;
+            y = n[y].w.right;
+            while (n[y].w.left != PP_RB_NIL) y = n[y].w.left;
+            x = n[y].w.right;
         }
         if (y != z)
         {
             // relink y in place of z
-            n[n[z].left].parent = y;
-            n[y].left = n[z].left;
-            if (y != n[z].right)
+            n[n[z].w.left].parent = y;
+            n[y].w.left = n[z].w.left;
+            if (y != n[z].w.right)
             {
                 x_parent = n[y].parent;
                 if (x != PP_RB_NIL) n[x].parent = n[y].parent;
-                n[n[y].parent].left = x;
-                n[y].right = n[z].right;
-                n[n[z].right].parent = y;
+                n[n[y].parent].w.left = x;
+                n[y].w.right = n[z].w.right;
+                n[n[z].w.right].parent = y;
             }
             else x_parent = y;
             if (n[PP_RB_HEADER].parent == z) n[PP_RB_HEADER].parent = y;
-            else if (n[n[z].parent].left == z) n[n[z].parent].left = y;
-            else n[n[z].parent].right = y;
+            else if (n[n[z].parent].w.left == z) n[n[z].parent].w.left = y;
+            else n[n[z].parent].w.right = y;
             n[y].parent = n[z].parent;
             int c = n[y].color; n[y].color = n[z].color; n[z].color = c;
             y = z;
@@ -198,34 +216,34 @@ struct PPRbTree
             x_parent = n[y].parent;
             if (x != PP_RB_NIL) n[x].parent = n[y].parent;
             if (n[PP_RB_HEADER].parent == z) n[PP_RB_HEADER].parent = x;
-            else if (n[n[z].parent].left == z) n[n[z].parent].left = x;
-            else n[n[z].parent].right = x;
-            if (n[PP_RB_HEADER].left == z)
+            else if (n[n[z].parent].w.left == z) n[n[z].parent].w.left = x;
+            else n[n[z].parent].w.right = x;
+            if (n[PP_RB_HEADER].w.left == z)
             {
-                if (n[z].right == PP_RB_NIL) n[PP_RB_HEADER].left = n[z].parent;
-                else { int m = x; while (n[m].left != PP_RB_NIL) m = n[m].left; n[PP_RB_HEADER].left = m; }
+                if (n[z].w.right == PP_RB_NIL) n[PP_RB_HEADER].w.left = n[z].parent;
+                else { int m = x; while (n[m].w.left != PP_RB_NIL) m = n[m].w.left; n[PP_RB_HEADER].w.left = m; }
             }
-            if (n[PP_RB_HEADER].right == z)
+            if (n[PP_RB_HEADER].w.right == z)
             {
-                if (n[z].left == PP_RB_NIL) n[PP_RB_HEADER].right = n[z].parent;
-                else { int m = x; while (n[m].right != PP_RB_NIL) m = n[m].right; n[PP_RB_HEADER].right = m; }
+                if (n[z].w.left == PP_RB_NIL) n[PP_RB_HEADER].w.right = n[z].parent;
+                else { int m = x; while (n[m].w.right != PP_RB_NIL) m = n[m].w.right; n[PP_RB_HEADER].w.right = m; }
             }
         }
         if (n[y].color != PP_RB_RED)
         {
             while (x != n[PP_RB_HEADER].parent && (x == PP_RB_NIL || n[x].color == PP_RB_BLACK))
             {
-                if (x == n[x_parent].left)
+                if (x == n[x_parent].w.left)
                 {
-                    int w = n[x_parent].right;
+                    int w = n[x_parent].w.right;
                     if (n[w].color == PP_RB_RED)
                     {
                         n[w].color = PP_RB_BLACK; n[x_parent].color = PP_RB_RED;
                         rotate_left(x_parent);
-                        w = n[x_parent].right;
+                        w = n[x_parent].w.right;
                     }
-                    if ((n[w].left == PP_RB_NIL || n[n[w].left].color == PP_RB_BLACK) &&
-                        (n[w].right == PP_RB_NIL || n[n[w].right].color == PP_RB_BLACK))
+                    if ((n[w].w.left == PP_RB_NIL || n[n[w].w.left].color == PP_RB_BLACK) &&
+                        (n[w].w.right == PP_RB_NIL || n[n[w].w.right].color == PP_RB_BLACK))
                     {
                         n[w].color = PP_RB_RED;
                         x = x_parent;
@@ -233,31 +251,31 @@ struct PPRbTree
                     }
                     else
                     {
-                        if (n[w].right == PP_RB_NIL || n[n[w].right].color == PP_RB_BLACK)
+                        if (n[w].w.right == PP_RB_NIL || n[n[w].w.right].color == PP_RB_BLACK)
                         {
-                            n[n[w].left].color = PP_RB_BLACK;
+                            n[n[w].w.left].color = PP_RB_BLACK;
                             n[w].color = PP_RB_RED;
                             rotate_right(w);
-                            w = n[x_parent].right;
+                            w = n[x_parent].w.right;
                         }
                         n[w].color = n[x_parent].color;
                         n[x_parent].color = PP_RB_BLACK;
-                        if (n[w].right != PP_RB_NIL) n[n[w].right].color = PP_RB_BLACK;
+                        if (n[w].w.right != PP_RB_NIL) n[n[w].w.right].color = PP_RB_BLACK;
                         rotate_left(x_parent);
                         break;
                     }
                 }
                 else
                 {
-                    int w = n[x_parent].left;
+                    int w = n[x_parent].w.left;
                     if (n[w].color == PP_RB_RED)
                     {
                         n[w].color = PP_RB_BLACK; n[x_parent].color = PP_RB_RED;
                         rotate_right(x_parent);
-                        w = n[x_parent].left;
+                        w = n[x_parent].w.left;
                     }
-                    if ((n[w].right == PP_RB_NIL || n[n[w].right].color == PP_RB_BLACK) &&
-                        (n[w].left == PP_RB_NIL || n[n[w].left].color == PP_RB_BLACK))
+                    if ((n[w].w.right == PP_RB_NIL || n[n[w].w.right].color == PP_RB_BLACK) &&
+                        (n[w].w.left == PP_RB_NIL || n[n[w].w.left].color == PP_RB_BLACK))
                     {
                         n[w].color = PP_RB_RED;
                         x = x_parent;
@@ -265,16 +283,16 @@ struct PPRbTree
                     }
                     else
                     {
-                        if (n[w].left == PP_RB_NIL || n[n[w].left].color == PP_RB_BLACK)
+                        if (n[w].w.left == PP_RB_NIL || n[n[w].w.left].color == PP_RB_BLACK)
                         {
-                            n[n[w].right].color = PP_RB_BLACK;
+                            n[n[w].w.right].color = PP_RB_BLACK;
                             n[w].color = PP_RB_RED;
                             rotate_left(w);
-                            w = n[x_parent].left;
+                            w = n[x_parent].w.left;
                         }
                         n[w].color = n[x_parent].color;
                         n[x_parent].color = PP_RB_BLACK;
-                        if (n[w].left != PP_RB_NIL) n[n[w].left].color = PP_RB_BLACK;
+                        if (n[w].w.left != PP_RB_NIL) n[n[w].w.left].color = PP_RB_BLACK;
                         rotate_right(x_parent);
                         break;
                     }
@@ -287,54 +305,55 @@ struct PPRbTree
         {
             // libstdc++ leaves header.left/right == header when the tree becomes empty
             n[PP_RB_HEADER].parent = PP_RB_NIL;
-            n[PP_RB_HEADER].left = PP_RB_HEADER;
-            n[PP_RB_HEADER].right = PP_RB_HEADER;
+            n[PP_RB_HEADER].w.left = PP_RB_HEADER;
+            n[PP_RB_HEADER].w.right = PP_RB_HEADER;
         }
         release(z);
     }
 
-    // std::set::find(k): lower-bound walk, then reject when k < *j.  lt_nk(node, key), lt_kn(key, node).
-    template <class Key, class LtNK, class LtKN>
-    PP_HD int find(const Key& k, LtNK lt_nk, LtKN lt_kn) const
+    // std::set::find(k): lower-bound walk, then reject when k < *j.
+    PP_HD_NOINLINE int find(const PPKey& k) const
     {
         int x = n[PP_RB_HEADER].parent, y = PP_RB_HEADER;
+        PPWalk yw; yw.left = 0; yw.right = 0; yw.f = 0.0f; yw.key = 0u;
         while (x != PP_RB_NIL)
         {
-            if (!lt_nk(n[x], k)) { y = x; x = n[x].left; }
-            else x = n[x].right;
+            const PPWalk r = n[x].w;                       // one 128-bit load per level
+            if (!pp_lt(r.key, r.f, k.key, k.f)) { y = x; yw = r; x = r.left; }
+            else x = r.right;
         }
-        if (y == PP_RB_HEADER || lt_kn(k, n[y])) return PP_RB_NIL;
+        if (y == PP_RB_HEADER || pp_lt(k.key, k.f, yw.key, yw.f)) return PP_RB_NIL;
         return y;
     }
 
     // std::set::insert(v) position search (_M_get_insert_unique_pos).  Returns true when the key must be
     // inserted under parent `p` (left child iff `left`); false when an equivalent element exists.
-    template <class Key, class LtNK, class LtKN>
-    PP_HD bool insert_pos(const Key& k, LtNK lt_nk, LtKN lt_kn, int& p, bool& left) const
+    PP_HD_NOINLINE bool insert_pos(const PPKey& k, int& p, bool& left) const
     {
         int x = n[PP_RB_HEADER].parent, y = PP_RB_HEADER;
         bool comp = true;
         while (x != PP_RB_NIL)
         {
+            const PPWalk r = n[x].w;
             y = x;
-            comp = lt_kn(k, n[x]);
-            x = comp ? n[x].left : n[x].right;
+            comp = pp_lt(k.key, k.f, r.key, r.f);
+            x = comp ? r.left : r.right;
         }
         int j = y;
         if (comp)
         {
-            if (j == n[PP_RB_HEADER].left)   // j == begin()
+            if (j == n[PP_RB_HEADER].w.left)   // j == begin(): insert to the left of the leftmost (or into an empty tree)
             {
-                p = y; left = true;          // _M_insert_: p == header or k < p
-                left = (y == PP_RB_HEADER) || lt_kn(k, n[y]);
+                p = y; left = true;            // _M_insert_: p == header, or k < p (== comp, which is true here)
                 return true;
             }
             j = decrement(j);
         }
-        if (lt_nk(n[j], k))
+        const PPWalk jw = n[j].w;
+        if (pp_lt(jw.key, jw.f, k.key, k.f))
         {
             p = y;
-            left = (y == PP_RB_HEADER) || lt_kn(k, n[y]);
+            left = (y == PP_RB_HEADER) || comp;   // _M_insert_ re-evaluates k < p, which is `comp` of the last step
             return true;
         }
         return false;

@@ -43,24 +43,23 @@
 #define PP_CS_TOUCHED 0x40000000u
 #define PP_CS_STAMP   0x3fffffffu
 
-struct PPNode3   // 3D open-list entry: links + key in the first 32 B sector (all a tree walk reads)
+struct PPNode3   // 3D open-list entry, 64 B; w = everything a tree walk reads (one 128-bit load)
 {
-    int      parent, left, right, color;
-    float    f;
-    unsigned key;        // (ci*N + cj)*(bins+1) + bin
+    PPWalk   w;          // left, right, f, key = (ci*N + cj)*(bins+1) + bin
+    int      parent, color;
     float    g, x;
     float    y, heading, vmin_sqr;
-    int      curv, prev, bin;
+    int      curv;
+    int      prev, bin;
     int      pad0, pad1;
 };
 
 struct PPNode2   // 2D open-list entry (copy of a Node2D at insertion time), 32 B
 {
-    int   parent, left, right, color;
-    float f;
-    int   cell;
-    float g;
-    int   prev;          // cell of the closed parent, -1 = none
+    PPWalk   w;          // left, right, f, key = cell
+    int      parent, color;
+    float    g;
+    int      prev;       // cell of the closed parent, -1 = none
 };
 
 struct PPClosed3
@@ -70,6 +69,8 @@ struct PPClosed3
     unsigned key;
     int      prev;       // index of the parent in the closed log, -1 = none
 };
+
+struct PPHashSlot { unsigned key; int idx; };   // closed-set hash slot: key + index into the closed log (-1 = empty)
 
 struct PPPathPt { float x, y, heading, curvature; };
 
@@ -94,7 +95,7 @@ struct PPWork
 {
     PPNode3*   open3;      int open3_cap;
     PPClosed3* closed;     int closed_cap;
-    int*       chash;      int chash_cap;     // power of two
+    PPHashSlot* chash;     int chash_cap;     // power of two
     unsigned*  cell_state;                    // N*N
     float*     nm_g;                          // N*N  node_map[i][j]._cost_g
     float*     nm_f;                          // N*N  node_map[i][j]._cost_f
@@ -124,13 +125,7 @@ struct PPWarpSerial
 };
 
 // ---------------------------------------------------------------------------------------------------
-// comparators of the reference (Node3D.h:39-54, Node2D.h:27-41)
-struct PPKey3 { unsigned key; float f; };
-struct PPLt3NK { PP_HD bool operator()(const PPNode3& a, const PPKey3& b) const { return (a.key != b.key) && (a.f < b.f); } };
-struct PPLt3KN { PP_HD bool operator()(const PPKey3& a, const PPNode3& b) const { return (a.key != b.key) && (a.f < b.f); } };
-struct PPKey2 { int cell; float f; };
-struct PPLt2NK { PP_HD bool operator()(const PPNode2& a, const PPKey2& b) const { return (a.cell != b.cell) && (a.f < b.f); } };
-struct PPLt2KN { PP_HD bool operator()(const PPKey2& a, const PPNode2& b) const { return (a.cell != b.cell) && (a.f < b.f); } };
+// (the comparators of the reference, Node3D.h:39-54 / Node2D.h:27-41, live in pp_rbtree.h: pp_lt)
 
 // Euclidean 2D heuristic, Grid2D.cpp:303-316 (recomputed instead of stored: 2 muls, 1 add, 1 sqrt)
 PP_HD float pp_h2d(const PPConsts& C, int i, int j)
@@ -160,7 +155,7 @@ PP_HD void pp_lazy_touch(const PPConsts& C, PPWork& wk, int cell)
 }
 
 // AStar::update_visted + Grid2D::update_costs (AStar.cpp:209-218, Grid2D.cpp:219-227)
-PP_HD void pp_lazy_update_visited(const PPConsts& C, PPWork& wk, float total, int last_cell)
+PP_HD_NOINLINE void pp_lazy_update_visited(const PPConsts& C, PPWork& wk, float total, int last_cell)
 {
     int c = last_cell;
     while (c >= 0)
@@ -172,15 +167,15 @@ PP_HD void pp_lazy_update_visited(const PPConsts& C, PPWork& wk, float total, in
     }
 }
 
-PP_HD bool pp_lazy_insert(PPLazy& L, int cell, float g, float f, int prev)
+PP_HD_NOINLINE bool pp_lazy_insert(PPLazy& L, int cell, float g, float f, int prev)
 {
-    PPKey2 k; k.cell = cell; k.f = f;
+    PPKey k; k.key = (unsigned)cell; k.f = f;
     int p; bool left;
-    if (!L.open.insert_pos(k, PPLt2NK(), PPLt2KN(), p, left)) return true;   // silently dropped (F5)
+    if (!L.open.insert_pos(k, p, left)) return true;   // silently dropped (F5)
     int s = L.open.alloc();
     if (s == PP_RB_NIL) { L.status |= PP_STATUS_OPEN2D_OVERFLOW; return false; }
     PPNode2& n = L.open.n[s];
-    n.f = f; n.cell = cell; n.g = g; n.prev = prev;
+    n.w.f = f; n.w.key = (unsigned)cell; n.g = g; n.prev = prev;
     L.open.insert_and_rebalance(left, s, p);
     return true;
 }
@@ -210,7 +205,7 @@ PP_HD_NOINLINE float pp_lazy_astar(const PPConsts& C, const float* map, const PP
     while (!L.open.empty())
     {
         int it = L.open.begin();
-        int c = L.open.n[it].cell;
+        int c = (int)L.open.n[it].w.key;
         float cg;
         unsigned cs = wk.cell_state[c];
         if ((cs & PP_CS_STAMP) == sid) cg = wk.cl_g[c];   // re-pop: unordered_set::insert returns the old copy
@@ -257,8 +252,8 @@ PP_HD_NOINLINE float pp_lazy_astar(const PPConsts& C, const float* map, const PP
             }
             if ((ns & PP_CS_STAMP) == sid) continue;    // in the closed set of this search
             pp_lazy_touch(C, wk, nb);
-            PPKey2 k; k.cell = nb; k.f = wk.nm_f[nb];    // node_map's current (possibly stale) f
-            int it_node = L.open.find(k, PPLt2NK(), PPLt2KN());
+            PPKey k; k.key = (unsigned)nb; k.f = wk.nm_f[nb];    // node_map's current (possibly stale) f
+            int it_node = L.open.find(k);
             float newg = cg + w;
             if (it_node == PP_RB_NIL)
             {
@@ -323,7 +318,7 @@ PP_HD bool pp_path_point_blocked(const PPConsts& C, const float* map, float x, f
 }
 
 // one obstacle's term of Grid3D::get_field_intensity (Grid3D.cpp:209-223)
-PP_HD float pp_apf_term(const PPConsts& C, float ox, float oy, float radius, float x, float y, float heading)
+PP_HD_NOINLINE float pp_apf_term(const PPConsts& C, float ox, float oy, float radius, float x, float y, float heading)
 {
     float dx = ox - x, dy = oy - y;
     float distance = pp_hypotf(dx, dy);
@@ -341,7 +336,7 @@ PP_HD float pp_apf_term(const PPConsts& C, float ox, float oy, float radius, flo
 // idx == nullptr): std::accumulate from T(0) in obstacle order (Grid3D.cpp:226).  Zero terms are skipped
 // (x + 0 == x), non-zero terms are added one by one in index order.
 template <class W>
-PP_HD float pp_apf_sum(const W& w, const PPConsts& C, const float* apf, const int* idx, int n,
+PP_HD_NOINLINE float pp_apf_sum(const W& w, const PPConsts& C, const float* apf, const int* idx, int n,
                        float x, float y, float heading)
 {
     float acc = 0.0f;
@@ -374,7 +369,7 @@ PP_HD float pp_apf_sum(const W& w, const PPConsts& C, const float* apf, const in
 // (one lane per steering primitive) + bounds/collision lookup + APF cost (lanes over obstacles).
 // Results in sm.succ[0 .. 2A] (ok = 0 for pruned / colliding primitives); g includes the field cost.
 template <class W>
-PP_HD void pp_expand_warp(const W& w, const PPConsts& C, const float* off_xy, const PPGroup& G,
+PP_HD_NOINLINE void pp_expand_warp(const W& w, const PPConsts& C, const float* off_xy, const PPGroup& G,
                           float px, float py, float ph, float pg, float pv2, int pcurv, int pbin, PPSmem& sm)
 {
     const int lane = w.lane();
@@ -446,9 +441,9 @@ PP_HD int pp_closed_find(const PPWork& wk, unsigned key)
     unsigned h = pp_hash_key(key) & mask;
     for (;;)
     {
-        int s = wk.chash[h];
-        if (s < 0) return -1;
-        if (wk.closed[s].key == key) return s;
+        const PPHashSlot s = wk.chash[h];      // one 8-byte load answers both "empty?" and "same key?"
+        if (s.idx < 0) return -1;
+        if (s.key == key) return s.idx;
         h = (h + 1) & mask;
     }
 }
@@ -457,20 +452,21 @@ PP_HD void pp_closed_link(PPWork& wk, unsigned key, int idx)
 {
     unsigned mask = (unsigned)wk.chash_cap - 1u;
     unsigned h = pp_hash_key(key) & mask;
-    while (wk.chash[h] >= 0) h = (h + 1) & mask;
-    wk.chash[h] = idx;
+    while (wk.chash[h].idx >= 0) h = (h + 1) & mask;
+    PPHashSlot s; s.key = key; s.idx = idx;
+    wk.chash[h] = s;
 }
 
 // returns false when the pool is exhausted
-PP_HD bool pp_open3_insert(PPSearchState& S, const PPSucc& s, unsigned key, float f, int prev)
+PP_HD_NOINLINE bool pp_open3_insert(PPSearchState& S, const PPSucc& s, unsigned key, float f, int prev)
 {
-    PPKey3 k; k.key = key; k.f = f;
+    PPKey k; k.key = key; k.f = f;
     int p; bool left;
-    if (!S.open.insert_pos(k, PPLt3NK(), PPLt3KN(), p, left)) return true;   // equal-f drop (F5)
+    if (!S.open.insert_pos(k, p, left)) return true;   // equal-f drop (F5)
     int slot = S.open.alloc();
     if (slot == PP_RB_NIL) { S.status |= PP_STATUS_OPEN_OVERFLOW; return false; }
     PPNode3& n = S.open.n[slot];
-    n.f = f; n.key = key; n.g = s.g; n.x = s.x; n.y = s.y; n.heading = s.heading;
+    n.w.f = f; n.w.key = key; n.g = s.g; n.x = s.x; n.y = s.y; n.heading = s.heading;
     n.vmin_sqr = s.vmin_sqr; n.curv = s.curv; n.prev = prev; n.bin = s.bin;
     S.open.insert_and_rebalance(left, slot, p);
     if (S.open.count > S.max_open) S.max_open = S.open.count;
@@ -490,7 +486,7 @@ PP_HD_NOINLINE void pp_search_exact(const W& w, const PPConsts& C, const float* 
     PP_PROF_DECL
     // ---- scratch init (all lanes) ----
     for (int c = lane; c < N * N; c += W::LANES) wk.cell_state[c] = 0u;
-    for (int c = lane; c < wk.chash_cap; c += W::LANES) wk.chash[c] = -1;
+    for (int c = lane; c < wk.chash_cap; c += W::LANES) { PPHashSlot e; e.key = 0xffffffffu; e.idx = -1; wk.chash[c] = e; }
     w.sync();
     PP_PROF_MARK(0)
 
@@ -529,7 +525,7 @@ PP_HD_NOINLINE void pp_search_exact(const W& w, const PPConsts& C, const float* 
             {
                 int it = S.open.begin();
                 const PPNode3& n = S.open.n[it];
-                cur = pp_closed_find(wk, n.key);       // _closed_set.insert(*it).first
+                cur = pp_closed_find(wk, n.w.key);     // _closed_set.insert(*it).first
                 if (cur < 0)
                 {
                     if (S.n_closed >= wk.closed_cap) { S.status |= PP_STATUS_CLOSED_OVERFLOW; action = ACT_ABORT; }
@@ -537,9 +533,9 @@ PP_HD_NOINLINE void pp_search_exact(const W& w, const PPConsts& C, const float* 
                     {
                         cur = S.n_closed++;
                         PPClosed3& c = wk.closed[cur];
-                        c.x = n.x; c.y = n.y; c.heading = n.heading; c.g = n.g; c.f = n.f; c.vmin_sqr = n.vmin_sqr;
-                        c.curv = n.curv; c.bin = n.bin; c.key = n.key; c.prev = n.prev;
-                        pp_closed_link(wk, n.key, cur);
+                        c.x = n.x; c.y = n.y; c.heading = n.heading; c.g = n.g; c.f = n.w.f; c.vmin_sqr = n.vmin_sqr;
+                        c.curv = n.curv; c.bin = n.bin; c.key = n.w.key; c.prev = n.prev;
+                        pp_closed_link(wk, n.w.key, cur);
                     }
                 }
                 if (action != ACT_ABORT)
@@ -690,8 +686,8 @@ PP_HD_NOINLINE void pp_search_exact(const W& w, const PPConsts& C, const float* 
                 int in_closed = pp_closed_find(wk, key);
                 PP_PROF_MARK(4)
                 if (in_closed >= 0) continue;                               // HybridAStar.cpp:162
-                PPKey3 k; k.key = key; k.f = sc.g;                          // f == g + field at find time
-                int it_node = S.open.find(k, PPLt3NK(), PPLt3KN());
+                PPKey k; k.key = key; k.f = sc.g;                           // f == g + field at find time
+                int it_node = S.open.find(k);
                 bool do_insert = false;
                 if (it_node == PP_RB_NIL) do_insert = true;
                 else if (sc.g < S.open.n[it_node].g) { S.open.erase(it_node); do_insert = true; }

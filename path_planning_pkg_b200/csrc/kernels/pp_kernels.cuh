@@ -24,6 +24,9 @@ __device__ unsigned long long pp_prof_acc[8];
 #include "../core/pp_map.h"
 
 #define PP_SEARCH_WARPS 4
+#ifndef PP_SEARCH_MIN_BLOCKS
+#define PP_SEARCH_MIN_BLOCKS 4     // resident CTAs per SM the register allocation is tuned for (x4 warps)
+#endif
 #define PP_TILE 32
 
 struct PPWarpDev
@@ -86,7 +89,7 @@ struct PPBatchArgs
     // per-slot scratch pools
     PPNode3*        open3;      int open3_cap;
     PPClosed3*      closed;     int closed_cap;
-    int*            chash;      int chash_cap;
+    PPHashSlot*     chash;      int chash_cap;
     unsigned*       cell_state;
     float*          nm_g;
     float*          nm_f;
@@ -110,7 +113,7 @@ __device__ __forceinline__ void pp_slot_work(const PPBatchArgs& a, int slot, PPW
     wk.path = nullptr; wk.path_cap = 0; wk.trace = nullptr; wk.trace_cap = 0;
 }
 
-__global__ void __launch_bounds__(PP_SEARCH_WARPS * 32, 4)
+__global__ void __launch_bounds__(PP_SEARCH_WARPS * 32, PP_SEARCH_MIN_BLOCKS)
 pp_search_kernel(const __grid_constant__ PPBatchArgs a)
 {
     __shared__ PPSmem sm[PP_SEARCH_WARPS];

@@ -27,7 +27,7 @@ namespace
         // search scratch
         std::vector<PPNode3> open3;
         std::vector<PPClosed3> closed;
-        std::vector<int> chash;
+        std::vector<PPHashSlot> chash;
         std::vector<unsigned> cell_state;
         std::vector<float> nm_g, nm_f, cl_g;
         std::vector<int> cl_prev;
