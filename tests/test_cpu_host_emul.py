@@ -1,0 +1,173 @@
+"""CPU tests of the PRODUCT's device core compiled for one host lane (tests/cpp/host_emul.cpp, test-only
+harness): the code the CUDA kernels execute -- libstdc++-exact red-black tree, lazy cached 2D A*, search
+loop, Dubins, APF, rasteriser arithmetic -- against the oracles, bit for bit.  No GPU involved; the GPU tests
+(test_gpu_parity.py) check the same things through the kernels.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import orc
+import scenarios as S
+
+EMU_SO = os.path.join(orc.ROOT, "tests", "cpp", "bin", "libpp_host_emul.so")
+
+
+def _bits(a):
+    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+@pytest.fixture(scope="module")
+def emu_lib(built):
+    return C.CDLL(EMU_SO)
+
+
+def _emu(lib, P):
+    return orc.Oracle(lib, "emu", P)
+
+
+def _pinned(P):
+    """Oracle with the device's float-transcendental definition: compiled reference (crm flavour) when present."""
+    return orc.crm(P) if orc.have_ref() else None
+
+
+def test_constants_tables_map(emu_lib):
+    P = orc.ref_test_params()
+    e, o = _emu(emu_lib, P), orc.port(P)
+    for x in (e, o):
+        orc.setup_ref_test_scenario(x)
+    ce, co = e.consts(), o.consts()
+    for f, _ in orc.Consts._fields_:
+        a, b = getattr(ce, f), getattr(co, f)
+        if hasattr(a, "__len__"):
+            a, b = list(a), list(b)
+        assert a == b, f
+    for a, b in zip(e.tables(), o.tables()):
+        assert np.array_equal(_bits(a), _bits(b))
+    assert np.array_equal(_bits(e.apf_list()), _bits(o.apf_list()))
+    assert np.array_equal(_bits(e.get_map()), _bits(o.get_map()))      # gather-form rasteriser == reference scatter
+
+
+def test_map_gather_equals_scatter_rotated_frames(emu_lib):
+    """Box rasterisation in gather form (per-cell sample counting) on rotated frames, several rounds with decay."""
+    rs = np.random.RandomState(5)
+    for trial in range(4):
+        P = orc.make_params(grid_size=160, resolution=0.25)
+        e, o = _emu(emu_lib, P), orc.port(P)
+        goal = np.array([rs.uniform(10, 30), rs.uniform(-20, 20), 0.3], np.float32)
+        n = 40
+        boxes = np.stack([rs.uniform(-5, 35, n), rs.uniform(-25, 25, n), rs.uniform(0.3, 5, n), rs.uniform(0.3, 5, n)], 1).astype(np.float32)
+        conf = rs.uniform(0.55, 0.99, n).astype(np.float32)
+        for x in (e, o):
+            x.update_goal(goal, [0, 0, 0])
+            for _ in range(3):
+                x.update_boxes_2d(boxes, conf)
+                x.decay()
+        assert np.array_equal(_bits(e.get_map()), _bits(o.get_map())), trial
+
+
+def test_empty_and_degenerate_inputs(emu_lib):
+    P = orc.make_params(grid_size=64, resolution=0.5)
+    e, o = _emu(emu_lib, P), orc.port(P)
+    for x in (e, o):
+        x.update_goal([10, 0, 0], [0, 0, 0])
+        x.update_boxes_2d(np.zeros((0, 4), np.float32), np.zeros(0, np.float32))          # empty list
+        x.update_boxes_2d(np.array([[1000, 1000, 2, 2]], np.float32), np.array([0.9], np.float32))   # fully outside
+        x.update_boxes_2d(np.array([[5, 0, 0.01, 0.01]], np.float32), np.array([0.9], np.float32))   # smaller than a cell
+        x.update_boxes_2d(np.array([[-20, 0, 30, 3]], np.float32), np.array([0.8], np.float32))      # clipped by the border
+        x.decay()
+    assert np.array_equal(_bits(e.get_map()), _bits(o.get_map()))
+
+
+@pytest.mark.skipif(not orc.have_ref(), reason="needs the pinned-libm compiled reference")
+def test_search_golden_bitexact(emu_lib):
+    P = orc.ref_test_params()
+    e, o = _emu(emu_lib, P), _pinned(P)
+    for x in (e, o):
+        orc.setup_ref_test_scenario(x)
+    a = e.find_path(2.0, orc.REF_TEST_START); b = o.find_path(2.0, orc.REF_TEST_START)
+    assert a["n_pops"] == b["n_pops"] == 882 and np.array_equal(a["pops"], b["pops"])
+    assert a["cost"] == b["cost"]
+    assert np.array_equal(_bits(a["path"]), _bits(b["path"])) and np.array_equal(_bits(a["curvature"]), _bits(b["curvature"]))
+
+
+@pytest.mark.skipif(not orc.have_ref(), reason="needs the pinned-libm compiled reference")
+@pytest.mark.parametrize("seed", [0, 1, 2, 6, 10])
+def test_search_c1_bitexact(emu_lib, seed):
+    sc = S.c1_scenario(seed)
+    P = orc.make_params(grid_size=sc["grid_size"], resolution=sc["resolution"])
+    e, o = _emu(emu_lib, P), _pinned(P)
+    for x in (e, o):
+        S.build_map(x, sc)
+    q = sc["queries"][0]
+    a = e.find_path(float(q[3]), q[:3]); b = o.find_path(float(q[3]), q[:3])
+    assert np.array_equal(a["pops"], b["pops"]) and a["cost"] == b["cost"]
+    assert np.array_equal(_bits(a["path"]), _bits(b["path"]))
+
+
+@pytest.mark.skipif(not orc.have_ref(), reason="needs the pinned-libm compiled reference")
+def test_search_c4_bitexact(emu_lib):
+    sc = S.c4_group(0, n_starts=3)
+    P = orc.make_params(grid_size=512, resolution=0.2)
+    e, o = _emu(emu_lib, P), _pinned(P)
+    for x in (e, o):
+        S.build_map(x, sc)
+    n = 0
+    for q in S.select_starts(sc, o.get_map(), o.consts().log_threshold, o.set_start):
+        o.scrub()
+        a = e.find_path(float(q[3]), q[:3]); b = o.find_path(float(q[3]), q[:3])
+        if b["n_pops_bin_oob"]:
+            continue
+        n += 1
+        assert a["n_pops"] == b["n_pops"] and np.array_equal(a["pops"], b["pops"])
+        assert np.array_equal(_bits(a["path"]), _bits(b["path"])) and a["cost"] == b["cost"]
+    assert n >= 1
+
+
+def test_lazy_astar_history_dependence(emu_lib):
+    """The lazy cached A*  returns query-order dependent values; the emulation follows the same order."""
+    P = orc.ref_test_params()
+    e, o = _emu(emu_lib, P), orc.port(P)
+    for x in (e, o):
+        orc.setup_ref_test_scenario(x)
+    rs = np.random.RandomState(2)
+    free = np.argwhere(o.get_map() < o.consts().log_threshold)
+    ij = free[rs.choice(len(free), 500, replace=False)].astype(np.int32)
+    for order in (ij, ij[::-1].copy()):
+        e.scrub(); o.scrub()
+        assert np.array_equal(_bits(e.astar_lazy(order)), _bits(o.astar_lazy(order)))
+        ve, ge, fe = e.astar_dump(); vo, go, fo = o.astar_dump()
+        assert np.array_equal(ve, vo) and np.array_equal(_bits(fe), _bits(fo))
+
+
+def test_stateless_pieces_vs_port(emu_lib):
+    """Roll-out, collision survivors and cells bit-exact; APF / Dubins within 1e-5 of the stock-libm port
+    (bit-exactness of those against the pinned-libm reference is covered by the search tests above)."""
+    P = orc.ref_test_params()
+    e, o = _emu(emu_lib, P), orc.port(P)
+    for x in (e, o):
+        orc.setup_ref_test_scenario(x)
+    rs = np.random.RandomState(3)
+    n = 3000
+    st = np.zeros(n, orc.STATE_DT)
+    st["x"] = rs.uniform(0, 30, n); st["y"] = rs.uniform(0, 30, n); st["heading"] = rs.uniform(-3.05, 3.05, n)
+    st["g"] = rs.uniform(0, 50, n); st["vmin_sqr"] = rs.uniform(0, 9, n); st["f"] = st["g"]
+    st["curvature_index"] = rs.randint(0, P.num_steering, n)
+    prec = np.float32(o.consts().precision)
+    st["angle_bin"] = ((np.round(st["heading"] / prec).astype(np.float32) * prec).astype(np.float64) + np.pi) / float(prec)
+    a, ac, af = e.rollout(st); b, bc, bf = o.rollout(st)
+    assert np.array_equal(ac, bc) and np.array_equal(af, bf) and a.tobytes() == b.tobytes()
+    a, ac, af = e.expand(st); b, bc, bf = o.expand(st)
+    assert np.array_equal(ac, bc)
+    for f in ("x", "y", "heading", "vmin_sqr"):
+        assert np.array_equal(_bits(a[f]), _bits(b[f])), f
+    for f in ("curvature_index", "angle_bin", "ci", "cj"):
+        assert np.array_equal(a[f], b[f]), f
+    assert np.abs(a["g"] - b["g"]).max() <= 1e-4
+    goal = np.array(list(o.consts().goal_grid), np.float32)
+    xyh = np.stack([st["x"], st["y"], st["heading"]], 1)
+    la, ta, _ = e.dubins_length(xyh, goal); lb, tb, _ = o.dubins_length(xyh, goal)
+    rel = np.abs(la - lb) / np.maximum(lb, 1e-6)
+    assert (rel > 1e-5).sum() <= 3        # +-2pi branch flips at an ulp (discontinuity of the reference formula)
