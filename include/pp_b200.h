@@ -184,6 +184,12 @@ int  pp_dubins_path(pp_context* ctx, const float* start3, const float* goal3, fl
                     int* n_out, float* length, int* long_turn_flag);
 /* AStar::find_path(i, j) (lib/AStar.cpp:100-113) called in sequence on a fresh cache for n cells */
 int  pp_astar_lazy_batch(pp_context* ctx, int group, const int* ij, int n, float* out);
+/* same, continuing on the cache left by the previous call (AStar::find_path between two AStar::reset(), lib/AStar.cpp:56-60) */
+int  pp_astar_lazy_continue(pp_context* ctx, int group, const int* ij, int n, float* out);
+/* Dubins::Dubins(r_min, step_size) (lib/Dubins.cpp:7-16) for a stand-alone Dubins<T> handle */
+int  pp_override_dubins(pp_context* ctx, float r_min, float step_size);
+/* Grid2D::clear_obstacles (lib/Grid2D.cpp:211-216) */
+int  pp_clear_obstacles(pp_context* ctx, int group);
 
 /* ---- the search: HybridAStar::find_path (lib/HybridAStar.cpp:68-88) for a batch of queries ---- */
 /* paths: n x path_cap x (x, y, heading) world frame in the reference's order (goal -> start);

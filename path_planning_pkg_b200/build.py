@@ -85,7 +85,8 @@ def build_host(force=False, verbose=True):
     srcs = _sources(CSRC, os.path.join(ROOT, "include"))
     if force or _newer(target, srcs):
         cxx = os.environ.get("CXX", "g++")
-        _run([cxx] + CXX_FLAGS + ["-I", os.path.join(ROOT, "include"), "-I", os.path.join(ROOT, "include", "path_planning_pkg"),
+        _run([cxx] + CXX_FLAGS + ["-DSTORE_GRID_AS_REFERENCE",   # as the reference's CMakeLists.txt:128
+                                  "-I", os.path.join(ROOT, "include"), "-I", os.path.join(ROOT, "include", "path_planning_pkg"),
                                   "-shared", "-o", target] + cpps +
              ["-L", LIB, "-lpp_b200", "-Wl,-rpath,$ORIGIN"], verbose)
     return target
@@ -104,6 +105,31 @@ def build_host_emul(force=False, verbose=True):
     return target
 
 
+def build_cpp_tests(force=False, verbose=True, reference="/root/reference"):
+    """g++ -> tests/cpp/bin/api_driver (C++ API test driver) and, when the reference tree is present,
+    tests/cpp/bin/local_planner_linkcheck = the reference's UNMODIFIED src/local_planner.cpp compiled against this repo's
+    headers (with ROS stub headers) and linked against libpath_planning_b200.so."""
+    out_dir = os.path.join(ROOT, "tests", "cpp", "bin")
+    os.makedirs(out_dir, exist_ok=True)
+    cxx = os.environ.get("CXX", "g++")
+    inc = os.path.join(ROOT, "include", "path_planning_pkg")
+    link = ["-L", LIB, "-lpath_planning_b200", "-lpp_b200", "-Wl,-rpath,$ORIGIN/../../../path_planning_pkg_b200/lib"]
+    built = []
+    drv = os.path.join(ROOT, "tests", "cpp", "api_driver.cpp")
+    target = os.path.join(out_dir, "api_driver")
+    if force or _newer(target, _sources(CSRC, os.path.join(ROOT, "include")) + [drv]):
+        _run([cxx, "-std=c++14", "-O1", "-DSTORE_GRID_AS_REFERENCE", "-I", inc, drv, "-o", target] + link, verbose)
+    built.append(target)
+    lp = os.path.join(reference, "src", "local_planner.cpp")
+    if os.path.exists(lp):
+        target = os.path.join(out_dir, "local_planner_linkcheck")
+        if force or _newer(target, _sources(CSRC, os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "ros_stubs")) + [lp]):
+            _run([cxx, "-std=c++14", "-O1", "-DSTORE_GRID_AS_REFERENCE", "-I", os.path.join(ROOT, "tests", "ros_stubs"), "-I", inc,
+                  "-I", os.path.join(reference, "src"), lp, "-o", target] + link, verbose)
+        built.append(target)
+    return built
+
+
 def build_oracle(verbose=True):
     """make -C oracle: CPU restatement + (when /root/reference is present) the compiled reference"""
     cmd = ["make", "-C", os.path.join(ROOT, "oracle"), "all"]
@@ -116,6 +142,7 @@ def build_all(force=False, verbose=True):
     build_cuda(force, verbose)
     build_host(force, verbose)
     build_host_emul(force, verbose)
+    build_cpp_tests(force, verbose)
     build_oracle(verbose)
 
 

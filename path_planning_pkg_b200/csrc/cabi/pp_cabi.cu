@@ -92,6 +92,9 @@ struct pp_context
     int n_slots = 0;
     WorkPools wp;          // first pass: every query, moderate capacities
     WorkPools wp_retry;    // queries that hit a capacity are re-run here with 8x larger pools (the reference is unbounded)
+    WorkPools wp_lazy;     // persistent cache of the stand-alone lazy 2D A* (AStar<T> handle)
+    unsigned* d_lazy_sid = nullptr;
+    int lazy_group = -1;
     DevBuf<int> d_qmap;
     int retried = 0;       // queries re-run in the last pp_batch_run
     unsigned long long launches = 0;      // kernels launched by this context
@@ -156,6 +159,8 @@ int pp_create(const pp_params* params, int device, int num_groups, pp_context** 
     PP_CUDA(cudaMemcpyAsync(c->d_off_xy, c->model.off_xy.data(), sizeof(float) * c->model.off_xy.size(), cudaMemcpyHostToDevice, c->stream));
     PP_CUDA(cudaMalloc(&c->d_groups, sizeof(PPGroup) * num_groups));
     PP_CUDA(cudaMalloc(&c->d_counter, sizeof(int)));
+    PP_CUDA(cudaMalloc(&c->d_lazy_sid, sizeof(unsigned)));
+    PP_CUDA(cudaMemsetAsync(c->d_lazy_sid, 0, sizeof(unsigned), c->stream));
     c->frames.resize(num_groups);
     c->groups.resize(num_groups);
     c->apf_cap.assign(num_groups, 0);
@@ -187,7 +192,8 @@ void pp_destroy(pp_context* c)
     cudaFree(c->d_groups); cudaFree(c->d_counter);
     c->s0.release(); c->s1.release(); c->s2.release(); c->s3.release(); c->s4.release();
     c->d_queries.release(); c->d_results.release(); c->d_paths.release(); c->d_trace.release();
-    c->wp.release(); c->wp_retry.release(); c->d_qmap.release();
+    c->wp.release(); c->wp_retry.release(); c->wp_lazy.release(); c->d_qmap.release();
+    cudaFree(c->d_lazy_sid);
     cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
     cudaStreamDestroy(c->stream);
     delete c;
@@ -751,22 +757,25 @@ int pp_find_path_batch(pp_context* c, const pp_query* q, int n, const pp_search_
     return pp_batch_fetch(c, results, paths_xyh, curvature, trace);
 }
 
-int pp_astar_lazy_batch(pp_context* c, int g, const int* ij, int n, float* out)
+static int lazy_run(pp_context* c, int g, const int* ij, int n, float* out, int restart)
 {
     int rc = check_group(c, g); if (rc) return rc;
     if (n <= 0) return PP_SUCCESS;
     PP_CUDA(cudaSetDevice(c->device));
     pp_search_opts o = default_opts(nullptr);
-    rc = ensure_work(c, c->wp_retry, 1, 16, 16, 1 << 18, 0.5); if (rc) return rc;
+    if (c->wp_lazy.alloc_slots < 1 || c->lazy_group != g) restart = 1;      // no cache yet (or another planner's)
+    rc = ensure_work(c, c->wp_lazy, 1, 16, 16, 1 << 18, 0.5); if (rc) return rc;
+    c->lazy_group = g;
     rc = sync_groups(c); if (rc) return rc;
     PPBatchArgs a;
     c->opts = o;
-    fill_args(c, c->wp_retry, 1, nullptr, 0, a);
+    fill_args(c, c->wp_lazy, 1, nullptr, 0, a);
     PP_CUDA(c->s0.ensure(sizeof(int) * 2 * n));
     PP_CUDA(c->s1.ensure(sizeof(float) * n));
     PP_CUDA(c->s2.ensure(sizeof(int)));
     PP_CUDA(cudaMemcpyAsync(c->s0.p, ij, sizeof(int) * 2 * n, cudaMemcpyHostToDevice, c->stream));
-    pp_lazy_astar_kernel<<<1, 32, 0, c->stream>>>(a, c->groups[g], (const int*)c->s0.p, n, (float*)c->s1.p, (int*)c->s2.p);
+    pp_lazy_astar_kernel<<<1, 32, 0, c->stream>>>(a, c->groups[g], (const int*)c->s0.p, n, (float*)c->s1.p, (int*)c->s2.p,
+                                                 restart, c->d_lazy_sid);
     c->launches += 1;
     PP_CUDA(cudaGetLastError());
     int status = 0;
@@ -774,6 +783,26 @@ int pp_astar_lazy_batch(pp_context* c, int g, const int* ij, int n, float* out)
     PP_CUDA(cudaMemcpyAsync(&status, c->s2.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     PP_CUDA(cudaStreamSynchronize(c->stream));
     if (status) return pp_fail(PP_ERR_CAPACITY, "lazy A*: 2D open-list pool exhausted");
+    return PP_SUCCESS;
+}
+
+int pp_astar_lazy_batch(pp_context* c, int g, const int* ij, int n, float* out) { return lazy_run(c, g, ij, n, out, 1); }
+int pp_astar_lazy_continue(pp_context* c, int g, const int* ij, int n, float* out) { return lazy_run(c, g, ij, n, out, 0); }
+
+int pp_override_dubins(pp_context* c, float r_min, float step_size)
+{
+    if (!c || !(r_min > 0.0f) || !(step_size > 0.0f)) return pp_fail(PP_ERR_INVALID, "pp_override_dubins: bad arguments");
+    c->model.C.r_min = r_min;                     // Dubins::Dubins(r_min, step_size), Dubins.cpp:7-16
+    c->model.C.step = step_size;
+    c->model.C.ang_step = step_size / r_min;
+    return PP_SUCCESS;
+}
+
+int pp_clear_obstacles(pp_context* c, int g)
+{
+    int rc = check_group(c, g); if (rc) return rc;
+    PP_CUDA(cudaSetDevice(c->device));
+    PP_CUDA(cudaMemsetAsync(c->d_maps + nn_of(c) * g, 0, sizeof(float) * nn_of(c), c->stream));
     return PP_SUCCESS;
 }
 

@@ -298,20 +298,22 @@ __global__ void __launch_bounds__(32) pp_dubins_path_kernel(const __grid_constan
 
 // lazy cached 2D A* on a fresh cache, cells queried in sequence (AStar.cpp:100-113); slot 0 scratch
 __global__ void __launch_bounds__(32) pp_lazy_astar_kernel(const __grid_constant__ PPBatchArgs a, PPGroup G, const int* ij,
-                                                            int n, float* out, int* status)
+                                                            int n, float* out, int* status, int restart, unsigned* sid_io)
 {
     PPWork wk;
     pp_slot_work(a, 0, wk);
     const int lane = threadIdx.x & 31;
-    for (int c = lane; c < a.C.N * a.C.N; c += 32) wk.cell_state[c] = 0u;
+    if (restart)      // AStar::reset() / fresh planner: nothing visited, node costs back to g = 0, f = h
+        for (int c = lane; c < a.C.N * a.C.N; c += 32) wk.cell_state[c] = 0u;
     __syncwarp();
     if (lane == 0)
     {
         PPLazy L;
         L.open.init(wk.open2, wk.open2_cap);
-        L.search_id = 0; L.status = 0; L.n_searches = 0; L.n_pops = 0;
+        L.search_id = restart ? 0u : *sid_io; L.status = 0; L.n_searches = 0; L.n_pops = 0;
         for (int k = 0; k < n; k++) out[k] = pp_lazy_astar(a.C, G.map, G.frame, wk, L, ij[2 * k], ij[2 * k + 1]);
         *status = L.status;
+        *sid_io = L.search_id;
     }
 }
 

@@ -1,0 +1,43 @@
+"""CPU test of the drop-in boundary: the reference's UNMODIFIED src/local_planner.cpp compiles against
+this repo's include/path_planning_pkg/*.h (plus ROS stub headers, tests/ros_stubs) and links against
+libpath_planning_b200.so with no unresolved planning:: symbol.  Needs the reference tree, so it runs where
+/root/reference exists; the C++ API driver must build everywhere."""
+import os
+import subprocess
+
+import pytest
+
+import orc
+
+REF_LP = "/root/reference/src/local_planner.cpp"
+
+
+@pytest.fixture(scope="module")
+def bins():
+    from path_planning_pkg_b200 import build
+    build.build_cuda(verbose=False)
+    build.build_host(verbose=False)
+    return build.build_cpp_tests(verbose=False)
+
+
+def test_api_driver_builds(bins):
+    assert os.path.exists(bins[0])
+    out = subprocess.run(["ldd", bins[0]], capture_output=True, text=True).stdout
+    assert "libpath_planning_b200.so" in out and "libpp_b200.so" in out and "not found" not in out
+
+
+@pytest.mark.skipif(not os.path.exists(REF_LP), reason="reference tree not present")
+def test_unmodified_local_planner_links(bins):
+    exe = [b for b in bins if b.endswith("local_planner_linkcheck")]
+    assert exe and os.path.exists(exe[0])
+    und = subprocess.run(["nm", "-C", "-u", exe[0]], capture_output=True, text=True).stdout
+    need = [l.split(" U ")[1] for l in und.split("\n") if " U planning::" in l]
+    assert any("HybridAStar<float>::find_path" in s for s in need)
+    lib = os.path.join(orc.ROOT, "path_planning_pkg_b200", "lib", "libpath_planning_b200.so")
+    have = subprocess.run(["nm", "-C", "-D", "--defined-only", lib], capture_output=True, text=True).stdout
+    missing = [s for s in need if s not in have]
+    assert not missing, missing
+    # every class the caller instantiates exists for float and double, like the reference's explicit instantiations
+    for cls in ("HybridAStar", "VelocityGenerator", "PedestrianHandler"):
+        for t in ("float", "double"):
+            assert f"planning::{cls}<{t}>::" in have
