@@ -39,14 +39,21 @@ PP_HD void pp_dubins_pick(const PPDubinsCenters& c, int type, float& csx, float&
     cgx = g_right ? c.grx : c.glx; cgy = g_right ? c.gry : c.gly;
 }
 
-// One candidate: get_params_{rsr,rsl,lsr,lsl} (Dubins.cpp:180-323).  p[4] = {start angle, delta on the
-// start circle, start angle on the goal circle, delta on the goal circle}.  Returns the path length
-// (NaN for RSL/LSR when the centres are closer than 2r).
-PP_HD_NOINLINE float pp_dubins_candidate(int type, float r, float sh, float gh,
-                                float csx, float csy, float cgx, float cgy, float p[4])
+// Pure-float tail of get_params_{rsr,rsl,lsr,lsl} (Dubins.cpp:180-323) once the transcendentals are known:
+//   theta = atan2f(dc) for every type; for RSL / LSR additionally ac = acosf(2r/dist) and the sin / cos of
+//   theta_t1 (= +-ac + theta) and of p[2] (= theta_t1 -+ pi).  Splitting it this way lets a warp evaluate the
+//   transcendentals of all (successor, type) pairs in three parallel stages instead of ten in sequence.
+// p[4] = {start angle, delta on the start circle, start angle on the goal circle, delta on the goal circle}.
+PP_HD float pp_dubins_theta_t1(int type, float ac, float theta) { return (type == PP_RSL) ? ac + theta : -ac + theta; }
+PP_HD float pp_dubins_p2(int type, float theta_t1)
+{
+    return (type == PP_RSL) ? (float)((double)theta_t1 - PP_PI) : (float)((double)theta_t1 + PP_PI);
+}
+
+PP_HD float pp_dubins_finish(int type, float r, float sh, float gh, float csx, float csy, float cgx, float cgy,
+                             float theta, float ac, float cos_t1, float sin_t1, float cos_p2, float sin_p2, float p[4])
 {
     float dcx = cgx - csx, dcy = cgy - csy;
-    float theta = pp_atan2f(dcy, dcx);
     if (type == PP_RSR)
     {
         p[0] = (float)(PP_PI_2 + (double)sh);
@@ -73,14 +80,11 @@ PP_HD_NOINLINE float pp_dubins_candidate(int type, float r, float sh, float gh,
         float dist_st = sqrtf(dcx * dcx + dcy * dcy);
         return dist_st + r * (p[1] + p[3]);
     }
-    float dist = sqrtf(dcx * dcx + dcy * dcy);
-    float ac = pp_acosf(2 * r / dist);
-    float theta_t1;
+    float theta_t1 = pp_dubins_theta_t1(type, ac, theta);
+    p[2] = pp_dubins_p2(type, theta_t1);
     if (type == PP_RSL)
     {
         p[0] = (float)(PP_PI_2 + (double)sh);
-        theta_t1 = ac + theta;
-        p[2] = (float)((double)theta_t1 - PP_PI);
         float theta_g = (float)(-PP_PI_2 + (double)gh);
         p[1] = theta_t1 - p[0];
         if (p[1] > 0) p[1] = (float)((double)p[1] - 2 * PP_PI);
@@ -90,22 +94,45 @@ PP_HD_NOINLINE float pp_dubins_candidate(int type, float r, float sh, float gh,
     else // PP_LSR
     {
         p[0] = (float)(-PP_PI_2 + (double)sh);
-        theta_t1 = -ac + theta;
-        p[2] = (float)((double)theta_t1 + PP_PI);
         float theta_g = (float)(PP_PI_2 + (double)gh);
         p[1] = theta_t1 - p[0];
         if (p[1] < 0) p[1] = (float)((double)p[1] + 2 * PP_PI);
         p[3] = theta_g - p[2];
         if (p[3] > 0) p[3] = (float)((double)p[3] - 2 * PP_PI);
     }
-    float ssx = csx + r * pp_cosf(theta_t1);
-    float ssy = csy + r * pp_sinf(theta_t1);
-    float esx = cgx + r * pp_cosf(p[2]);
-    float esy = cgy + r * pp_sinf(p[2]);
+    float ssx = csx + r * cos_t1;
+    float ssy = csy + r * sin_t1;
+    float esx = cgx + r * cos_p2;
+    float esy = cgy + r * sin_p2;
     float dx = esx - ssx, dy = esy - ssy;
     float dist_st = sqrtf(dx * dx + dy * dy);
     if (type == PP_RSL) return dist_st + r * (-p[1] + p[3]);
     return dist_st + r * (p[1] - p[3]);
+}
+
+// acosf(2 r / dist) of the RSL / LSR candidates (NaN when the circle centres are closer than 2r)
+PP_HD float pp_dubins_acos_arg(float r, float csx, float csy, float cgx, float cgy)
+{
+    float dcx = cgx - csx, dcy = cgy - csy;
+    float dist = sqrtf(dcx * dcx + dcy * dcy);
+    return 2 * r / dist;
+}
+
+// One candidate, all of it on the calling thread (stateless kernels, the Dubins shot).  Returns the path length
+// (NaN for RSL/LSR when the centres are closer than 2r).
+PP_HD_NOINLINE float pp_dubins_candidate(int type, float r, float sh, float gh,
+                                         float csx, float csy, float cgx, float cgy, float p[4])
+{
+    float theta = pp_atan2f(cgy - csy, cgx - csx);
+    float ac = 0.0f, c1 = 0.0f, s1 = 0.0f, c2 = 0.0f, s2 = 0.0f;
+    if (type == PP_RSL || type == PP_LSR)
+    {
+        ac = pp_acosf(pp_dubins_acos_arg(r, csx, csy, cgx, cgy));
+        float t1 = pp_dubins_theta_t1(type, ac, theta);
+        float p2 = pp_dubins_p2(type, t1);
+        c1 = pp_cosf(t1); s1 = pp_sinf(t1); c2 = pp_cosf(p2); s2 = pp_sinf(p2);
+    }
+    return pp_dubins_finish(type, r, sh, gh, csx, csy, cgx, cgy, theta, ac, c1, s1, c2, s2, p);
 }
 
 // Sequential fold of the four candidates, Dubins.cpp:36-68.

@@ -109,9 +109,18 @@ struct PPWork
 struct PPSmem   // per-warp staging area (shared memory on the device)
 {
     PPSucc succ[PP_MAX_SUCC];
-    float  cand[PP_MAX_SUCC * 4];
+    float  cand[PP_MAX_SUCC * 4];        // Dubins candidate lengths [successor][type] (also APF accumulators)
     int    near_idx[PP_NEAR_CAP];
+    // staged Dubins evaluation (pp_dubins_h2_warp)
+    float  d_centre[PP_MAX_SUCC * 4];    // start circle centres per successor: right x, y, left x, y
+    float  d_theta[PP_MAX_SUCC * 4];     // atan2f of the centre offset per (successor, type)
+    float  d_acos[PP_MAX_SUCC * 2];      // acosf(2r/dist) per (successor, RSL | LSR)
+    float  d_sin[PP_MAX_SUCC * 4];       // sin / cos of theta_t1 and p2 per (successor, RSL | LSR)
+    float  d_cos[PP_MAX_SUCC * 4];
 };
+
+// goal-side constants of the Dubins heuristic, evaluated once per query
+struct PPDubinsGoal { float grx, gry, glx, gly; };
 
 // ---- lane policy for a single host thread (tests only); the device policy lives in pp_kernels.cu ----
 struct PPWarpSerial
@@ -409,15 +418,119 @@ PP_HD_NOINLINE void pp_expand_warp(const W& w, const PPConsts& C, const float* o
     }
     const bool near_overflow = (n_near > PP_NEAR_CAP);
     w.sync();
-    // APF per surviving successor, added to g (and f), Grid3D.cpp:61-63
-    for (int s = 0; s < n_succ_max; s++)
+    // APF of the surviving successors, added to g (and f), Grid3D.cpp:61-63
+    if (near_overflow)
     {
-        if (!sm.succ[s].ok) continue;
-        float sx = sm.succ[s].x, sy = sm.succ[s].y, sh = sm.succ[s].heading;
-        float field = near_overflow ? pp_apf_sum(w, C, G.apf, (const int*)0, G.K, sx, sy, sh)
-                                    : pp_apf_sum(w, C, G.apf, sm.near_idx, n_near, sx, sy, sh);
+        // rare: more obstacles in reach than the staging list holds -> one successor at a time over the full list
+        for (int s = 0; s < n_succ_max; s++)
+        {
+            if (!sm.succ[s].ok) continue;
+            float field = pp_apf_sum(w, C, G.apf, (const int*)0, G.K, sm.succ[s].x, sm.succ[s].y, sm.succ[s].heading);
+            w.sync();
+            if (lane == 0) sm.succ[s].g = sm.succ[s].g + field;
+        }
+    }
+    else if (n_near > 0)
+    {
+        // one lane per (successor, near obstacle) pair, successor-major so that a successor's terms are met in
+        // obstacle order; sm.cand[s] accumulates successor s's field (std::accumulate order, Grid3D.cpp:226)
+        for (int s = lane; s < n_succ_max; s += W::LANES) sm.cand[s] = 0.0f;
         w.sync();
-        if (lane == 0) sm.succ[s].g = sm.succ[s].g + field;
+        const int n_pairs = n_succ_max * n_near;
+        for (int base = 0; base < n_pairs; base += W::LANES)
+        {
+            int q = base + lane;
+            float term = 0.0f;
+            int s = 0;
+            if (q < n_pairs)
+            {
+                s = q / n_near;
+                if (sm.succ[s].ok)
+                {
+                    int k = sm.near_idx[q - s * n_near];
+                    float ox = G.apf[3 * k], oy = G.apf[3 * k + 1], r = G.apf[3 * k + 2];
+                    float sx = sm.succ[s].x, sy = sm.succ[s].y;
+                    float dx = ox - sx, dy = oy - sy, lim = r * 1.001f + 1e-3f;   // cheap conservative reject
+                    if (dx * dx + dy * dy <= lim * lim) term = pp_apf_term(C, ox, oy, r, sx, sy, sm.succ[s].heading);
+                }
+            }
+            unsigned m = w.ballot(term != 0.0f);
+            while (m)       // non-zero terms one by one, in pair order; zero terms are skipped (x + 0 == x)
+            {
+                int src = 0;
+                unsigned t = m;
+                while (!(t & 1u)) { t >>= 1; src++; }
+                float tv = w.shfl(term, src);
+                int ts = w.shfl(s, src);
+                if (lane == 0) sm.cand[ts] = sm.cand[ts] + tv;
+                m &= m - 1;
+            }
+        }
+        w.sync();
+        for (int s = lane; s < n_succ_max; s += W::LANES)
+            if (sm.succ[s].ok) sm.succ[s].g = sm.succ[s].g + sm.cand[s];
+    }
+    w.sync();
+}
+
+// Dubins lengths of all (successor, CSC type) pairs of one expansion -> sm.cand[4*s + type]
+// (Dubins::get_shortest_path_length, Dubins.cpp:19-69, evaluated for every surviving successor).  The ~10
+// dependent float transcendentals of one candidate are spread over the warp in three parallel stages:
+//   A  lanes = successors           : sin, cos of the successor heading -> start circle centres
+//   B  lanes = (succ, type) + (succ, RSL|LSR) : atan2f of the centre offset  ||  acosf(2r/dist)
+//   C  lanes = (succ, RSL|LSR, theta_t1|p2)   : sin, cos of the two tangent angles
+//   D  lanes = (succ, type)         : float-only tail (pp_dubins_finish)
+template <class W>
+PP_HD_NOINLINE void pp_dubins_h2_warp(const W& w, const PPConsts& C, const PPFrame& F, const PPDubinsGoal& gc, PPSmem& sm)
+{
+    const int lane = w.lane();
+    const int n = 2 * C.A + 1;
+    const float r = C.r_min;
+    for (int s = lane; s < n; s += W::LANES)                                   // stage A
+        if (sm.succ[s].ok)
+        {
+            float sn = pp_sinf(sm.succ[s].heading), cs = pp_cosf(sm.succ[s].heading);
+            sm.d_centre[4 * s] = sm.succ[s].x + r * sn;     sm.d_centre[4 * s + 1] = sm.succ[s].y - r * cs;
+            sm.d_centre[4 * s + 2] = sm.succ[s].x - r * sn; sm.d_centre[4 * s + 3] = sm.succ[s].y + r * cs;
+        }
+    w.sync();
+    for (int q = lane; q < 6 * n; q += W::LANES)                               // stage B
+    {
+        int s, type;
+        if (q < 4 * n) { s = q >> 2; type = q & 3; } else { int e = q - 4 * n; s = e >> 1; type = 1 + (e & 1); }
+        if (!sm.succ[s].ok) continue;
+        bool s_right = (type == PP_RSR) || (type == PP_RSL), g_right = (type == PP_RSR) || (type == PP_LSR);
+        float csx = s_right ? sm.d_centre[4 * s] : sm.d_centre[4 * s + 2], csy = s_right ? sm.d_centre[4 * s + 1] : sm.d_centre[4 * s + 3];
+        float cgx = g_right ? gc.grx : gc.glx, cgy = g_right ? gc.gry : gc.gly;
+        if (q < 4 * n) sm.d_theta[q] = pp_atan2f(cgy - csy, cgx - csx);
+        else sm.d_acos[q - 4 * n] = pp_acosf(pp_dubins_acos_arg(r, csx, csy, cgx, cgy));
+    }
+    w.sync();
+    for (int q = lane; q < 4 * n; q += W::LANES)                               // stage C
+    {
+        int s = q >> 2, type = 1 + ((q >> 1) & 1), which = q & 1;
+        if (!sm.succ[s].ok) continue;
+        float t1 = pp_dubins_theta_t1(type, sm.d_acos[2 * s + (type - 1)], sm.d_theta[4 * s + type]);
+        float ang = which ? pp_dubins_p2(type, t1) : t1;
+        sm.d_sin[q] = pp_sinf(ang);
+        sm.d_cos[q] = pp_cosf(ang);
+    }
+    w.sync();
+    for (int q = lane; q < 4 * n; q += W::LANES)                               // stage D
+    {
+        int s = q >> 2, type = q & 3;
+        if (!sm.succ[s].ok) continue;
+        bool s_right = (type == PP_RSR) || (type == PP_RSL), g_right = (type == PP_RSR) || (type == PP_LSR);
+        float csx = s_right ? sm.d_centre[4 * s] : sm.d_centre[4 * s + 2], csy = s_right ? sm.d_centre[4 * s + 1] : sm.d_centre[4 * s + 3];
+        float cgx = g_right ? gc.grx : gc.glx, cgy = g_right ? gc.gry : gc.gly;
+        float ac = 0.0f, c1 = 0.0f, s1 = 0.0f, c2 = 0.0f, s2 = 0.0f, p[4];
+        if (type == PP_RSL || type == PP_LSR)
+        {
+            int e = 4 * s + 2 * (type - 1);
+            ac = sm.d_acos[2 * s + (type - 1)];
+            c1 = sm.d_cos[e]; s1 = sm.d_sin[e]; c2 = sm.d_cos[e + 1]; s2 = sm.d_sin[e + 1];
+        }
+        sm.cand[q] = pp_dubins_finish(type, r, sm.succ[s].heading, F.goal_h, csx, csy, cgx, cgy, sm.d_theta[q], ac, c1, s1, c2, s2, p);
     }
     w.sync();
 }
@@ -513,6 +626,14 @@ PP_HD_NOINLINE void pp_search_exact(const W& w, const PPConsts& C, const float* 
 
     const int n_succ_max = 2 * C.A + 1;
     enum { ACT_EXPAND = 0, ACT_FAIL = 1, ACT_GOAL = 2, ACT_SHOT = 3, ACT_ABORT = 4 };
+
+    // goal circle centres (Dubins.cpp:29-33): the same for every heuristic evaluation of this query
+    PPDubinsGoal gc;
+    {
+        float sg = pp_sinf(F.goal_h), cg = pp_cosf(F.goal_h);
+        gc.grx = F.goal_x + C.r_min * sg; gc.gry = F.goal_y - C.r_min * cg;
+        gc.glx = F.goal_x - C.r_min * sg; gc.gly = F.goal_y + C.r_min * cg;
+    }
 
     for (;;)
     {
@@ -658,20 +779,18 @@ PP_HD_NOINLINE void pp_search_exact(const W& w, const PPConsts& C, const float* 
         shot_allowed = (cn.vmin_sqr < 1.0f);     // neglect_acceleration, VehicleModel.cpp:76
         pp_expand_warp(w, C, off_xy, G, cn.x, cn.y, cn.heading, cn.g, cn.vmin_sqr, cn.curv, cn.bin, sm);
         PP_PROF_MARK(2)
-        // Dubins candidates: one lane per (successor, CSC type)
-        for (int q = lane; q < n_succ_max * 4; q += W::LANES)
-        {
-            int s = q >> 2, type = q & 3;
+        // closed-set membership of all successors at once (one probe per lane; the closed set only changes at a
+        // pop, so this equals the per-successor `_closed_set.find(node)` of HybridAStar.cpp:162); members drop out
+        for (int s = lane; s < n_succ_max; s += W::LANES)
             if (sm.succ[s].ok)
             {
-                PPDubinsCenters cen;
-                pp_dubins_centers(C.r_min, sm.succ[s].x, sm.succ[s].y, sm.succ[s].heading, F.goal_x, F.goal_y, F.goal_h, cen);
-                float csx, csy, cgx, cgy, pp[4];
-                pp_dubins_pick(cen, type, csx, csy, cgx, cgy);
-                sm.cand[q] = pp_dubins_candidate(type, C.r_min, sm.succ[s].heading, F.goal_h, csx, csy, cgx, cgy, pp);
+                unsigned key = (unsigned)(sm.succ[s].ci * N + sm.succ[s].cj) * kb + (unsigned)sm.succ[s].bin;
+                if (pp_closed_find(wk, key) >= 0) sm.succ[s].ok = 0;
             }
-        }
         w.sync();
+        PP_PROF_MARK(4)
+        // Dubins candidates of every surviving successor, transcendentals spread over the warp in stages
+        pp_dubins_h2_warp(w, C, F, gc, sm);
         PP_PROF_MARK(3)
 
         // ---------------- phase 4: successors into the containers (control lane) ----------------
@@ -683,9 +802,6 @@ PP_HD_NOINLINE void pp_search_exact(const W& w, const PPConsts& C, const float* 
                 const PPSucc& sc = sm.succ[s];
                 if (!sc.ok) continue;
                 unsigned key = (unsigned)(sc.ci * N + sc.cj) * kb + (unsigned)sc.bin;
-                int in_closed = pp_closed_find(wk, key);
-                PP_PROF_MARK(4)
-                if (in_closed >= 0) continue;                               // HybridAStar.cpp:162
                 PPKey k; k.key = key; k.f = sc.g;                           // f == g + field at find time
                 int it_node = S.open.find(k);
                 bool do_insert = false;
