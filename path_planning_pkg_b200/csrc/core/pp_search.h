@@ -237,31 +237,54 @@ PP_HD_NOINLINE float pp_lazy_astar(const PPConsts& C, const float* map, const PP
         }
 
         // Grid2D::get_neighbors (Grid2D.cpp:72-96): all valid neighbours first, in action order
-        int   nb_cell[8];
-        float nb_cost[8];
-        int   nn = 0;
-        for (int k = 0; k < C.n_act2d; k++)
+        // The 8 neighbours are distinct cells whose per-cell words nobody else touches while this node is expanded,
+        // so the map value, cell_state and node_map f of all of them are fetched up front as 24 independent loads
+        // (one memory round trip instead of 24 dependent ones); they are consumed in action order below.
+        int      nb_all[8];
+        float    nb_map[8], nb_f[8];
+        unsigned nb_cs[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++)
         {
             int i = pi + C.act_di[k], j = pj + C.act_dj[k];
-            if (i > -1 && i < N && j > -1 && j < N && map[i * N + j] < C.log_thr)
-            {
-                nb_cell[nn] = i * N + j; nb_cost[nn] = C.act_cost[k]; nn++;
-            }
+            nb_all[k] = (k < C.n_act2d && i > -1 && i < N && j > -1 && j < N) ? i * N + j : -1;
         }
+#pragma unroll
+        for (int k = 0; k < 8; k++)
+        {
+            int a = nb_all[k] < 0 ? c : nb_all[k];          // harmless in-bounds address for the masked-out slots
+            nb_map[k] = map[a]; nb_cs[k] = wk.cell_state[a]; nb_f[k] = wk.nm_f[a];
+        }
+        int      nb_cell[8];
+        float    nb_cost[8], nb_nmf[8];
+        unsigned nb_state[8];
+        int      nn = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++)
+            if (nb_all[k] >= 0 && nb_map[k] < C.log_thr)
+            {
+                nb_cell[nn] = nb_all[k]; nb_cost[nn] = C.act_cost[k]; nb_state[nn] = nb_cs[k]; nb_nmf[nn] = nb_f[k]; nn++;
+            }
         for (int q = 0; q < nn; q++)
         {
             int nb = nb_cell[q];
             float w = nb_cost[q];
-            unsigned ns = wk.cell_state[nb];
+            unsigned ns = nb_state[q];
             if (ns & PP_CS_VISITED)
             {
-                float total = wk.nm_f[nb] + cg + w;
+                float total = nb_nmf[q] + cg + w;
                 pp_lazy_update_visited(C, wk, total, c);
                 return total;
             }
             if ((ns & PP_CS_STAMP) == sid) continue;    // in the closed set of this search
-            pp_lazy_touch(C, wk, nb);
-            PPKey k; k.key = (unsigned)nb; k.f = wk.nm_f[nb];    // node_map's current (possibly stale) f
+            float cur_f = nb_nmf[q];
+            if (!(ns & PP_CS_TOUCHED))                  // pp_lazy_touch: first use this query -> g = 0, f = h
+            {
+                cur_f = pp_h2d(C, nb / N, nb % N);
+                wk.nm_g[nb] = 0.0f; wk.nm_f[nb] = cur_f;
+                wk.cell_state[nb] = ns | PP_CS_TOUCHED;
+            }
+            PPKey k; k.key = (unsigned)nb; k.f = cur_f;          // node_map's current (possibly stale) f
             int it_node = L.open.find(k);
             float newg = cg + w;
             if (it_node == PP_RB_NIL)
