@@ -191,6 +191,16 @@ int  pp_override_dubins(pp_context* ctx, float r_min, float step_size);
 /* Grid2D::clear_obstacles (lib/Grid2D.cpp:211-216) */
 int  pp_clear_obstacles(pp_context* ctx, int group);
 
+/* ---- heuristic fields (north_star (d), (e); BASELINE config C3) ---- */
+/* 2D holonomic-with-obstacles distance-to-goal field over Grid2D (same metric as lib/Grid2D.cpp:32-58, :72-96: 8- or 4-connected,
+ * step costs res*sqrt(di^2+dj^2), cells >= threshold blocked) by block-tiled Bellman relaxation; FLT_MAX = unreachable.  This is the
+ * exact distance field, NOT the order-dependent value of AStar::find_path (lib/AStar.cpp:100-186).
+ * out_nn may be NULL (result stays on the device for the throughput search modes). */
+int  pp_heuristic_field_2d(pp_context* ctx, int group, float* out_nn, int* sweeps, float* kernel_ms);
+/* h(i, j, b) = max(h2d(i, j), Dubins length from pose (i*res, j*res, -pi + b*precision) to the goal) for every state of the grid
+ * (Dubins::get_shortest_path_length, lib/Dubins.cpp:19-69, FP32 SIMT); out_nnb = N*N*bins floats or NULL. */
+int  pp_heuristic_field_3d(pp_context* ctx, int group, int use_h2d, float* out_nnb, float* kernel_ms);
+
 /* ---- the search: HybridAStar::find_path (lib/HybridAStar.cpp:68-88) for a batch of queries ---- */
 /* paths: n x path_cap x (x, y, heading) world frame in the reference's order (goal -> start);
  * curvature: n x path_cap; trace: n x trace_cap pops (may be NULL). */
@@ -202,6 +212,9 @@ int  pp_batch_run(pp_context* ctx, float* kernel_ms);
 int  pp_batch_fetch(pp_context* ctx, pp_result* results, float* paths_xyh, float* curvature, pp_pop* trace);
 /* number of CUDA kernels this context has launched so far (bench.py's gpu_launches) */
 unsigned long long pp_kernel_launches(pp_context* ctx);
+/* CUDA-event bracket on the context's stream (for measuring the asynchronous map / field calls in between) */
+int  pp_timer_begin(pp_context* ctx);
+int  pp_timer_end(pp_context* ctx, float* ms);
 
 #ifdef __cplusplus
 }

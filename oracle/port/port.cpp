@@ -680,6 +680,39 @@ void port_astar_dump(void* hv, unsigned char* visited, float* g, float* f)
     if (f) std::memcpy(f, P.nm_f.data(), nn * 4);
 }
 
+// Exact 2D distance-to-goal field in double precision (Dijkstra) over the metric of Grid2D (Grid2D.cpp:32-58, :72-96):
+// oracle for the device wavefront field (north_star (e)).  NOT the value AStar::find_path returns.
+// out[i*N + j] = distance, or a negative value when unreachable.
+void port_field2d(void* hv, double* out)
+{
+    Port& P = *static_cast<Port*>(hv);
+    const int N = P.N;
+    std::vector<double> d((size_t)N * N, -1.0);
+    typedef std::pair<double, int> QE;
+    std::vector<QE> heap;
+    auto cmp = [](const QE& a, const QE& b) { return a.first > b.first; };
+    int goal = P.n45 * N + P.n2;
+    d[goal] = 0.0;
+    heap.push_back(QE(0.0, goal));
+    while (!heap.empty())
+    {
+        std::pop_heap(heap.begin(), heap.end(), cmp);
+        QE e = heap.back(); heap.pop_back();
+        if (e.first > d[e.second]) continue;
+        int ui = e.second / N, uj = e.second % N;
+        for (size_t k = 0; k < P.actions.size(); k++)
+        {
+            int i = ui + P.actions[k].first, j = uj + P.actions[k].second;
+            if (i < 0 || i >= N || j < 0 || j >= N) continue;
+            if (!(P.map[(size_t)i * N + j] < P.log_thr)) continue;
+            double nd = e.first + (double)P.actions_cost[k];
+            int v = i * N + j;
+            if (d[v] < 0.0 || nd < d[v]) { d[v] = nd; heap.push_back(QE(nd, v)); std::push_heap(heap.begin(), heap.end(), cmp); }
+        }
+    }
+    std::memcpy(out, d.data(), sizeof(double) * d.size());
+}
+
 // HybridAStar::find_path + hybrid_a_star_search + reconstruct_path, HybridAStar.cpp:68-88, :93-199, :208-262
 void port_find_path(void* hv, float vel, const float* s, orc_result* res, float* path_xyh, float* curv, int path_cap,
                     orc_pop* pops, int pop_cap)

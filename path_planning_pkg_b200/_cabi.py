@@ -331,3 +331,20 @@ class Context:
         return dict(success=bool(r["success"]), cost=np.float32(r["cost"]), path=paths[0, :n].copy(),
                     curvature=curv[0, :n].copy(), pops=trace[0, :min(int(r["n_pops"]), pop_cap)].copy(),
                     n_pops=int(r["n_pops"]), n_pops_bin_oob=int(r["n_pops_bin_oob"]), status=int(r["status"]), raw=r)
+
+    # ---- heuristic fields ----
+    def field2d(self, group=0, download=True):
+        """pp_heuristic_field_2d: exact 2D distance-to-goal field (FLT_MAX = unreachable); returns (field|None, sweeps, ms)."""
+        out = np.empty((self.N, self.N), np.float32) if download else None
+        sw = C.c_int(); ms = C.c_float()
+        self._chk(self.lib.pp_heuristic_field_2d(self.h, C.c_int(group), _p(out) if download else None, C.byref(sw), C.byref(ms)))
+        return out, sw.value, ms.value
+
+    def field3d(self, group=0, use_h2d=True, download=True):
+        """pp_heuristic_field_3d: max(h2d, Dubins) for every (i, j, heading bin); returns (field|None, ms)."""
+        B = self.params.num_angle_bins
+        out = np.empty((self.N, self.N, B), np.float32) if download else None
+        ms = C.c_float()
+        self._chk(self.lib.pp_heuristic_field_3d(self.h, C.c_int(group), C.c_int(1 if use_h2d else 0),
+                                                 _p(out) if download else None, C.byref(ms)))
+        return out, ms.value

@@ -50,8 +50,21 @@ def build_cuda(force=False, verbose=True, extra=()):
     srcs = _sources(CSRC, os.path.join(ROOT, "include"))
     if force or _newer(target, srcs):
         nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
-        _run([nvcc] + NVCC_FLAGS + list(extra) + ["-shared", "-o", target, os.path.join(CSRC, "cabi", "pp_cabi.cu")], verbose)
+        _nvcc_link(nvcc, list(extra), target, verbose)
     return target
+
+
+def _nvcc_link(nvcc, defines, target, verbose):
+    """pp_cabi.cu (bit-exact arithmetic: -fmad=false) + pp_fields.cu (tolerance-bound field kernels: FMA on) -> one .so"""
+    obj_dir = os.path.join(LIB, "obj")
+    os.makedirs(obj_dir, exist_ok=True)
+    tag = os.path.basename(target).replace(".so", "")
+    o1 = os.path.join(obj_dir, tag + "_cabi.o")
+    o2 = os.path.join(obj_dir, tag + "_fields.o")
+    _run([nvcc] + NVCC_FLAGS + defines + ["-c", "-o", o1, os.path.join(CSRC, "cabi", "pp_cabi.cu")], verbose)
+    fields_flags = [f for f in NVCC_FLAGS if f != "-fmad=false"]
+    _run([nvcc] + fields_flags + defines + ["-c", "-o", o2, os.path.join(CSRC, "kernels", "pp_fields.cu")], verbose)
+    _run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-cudart", "static", "-o", target, o1, o2], verbose)
 
 
 def build_cuda_profile(force=False, verbose=True):
@@ -61,7 +74,7 @@ def build_cuda_profile(force=False, verbose=True):
     srcs = _sources(CSRC, os.path.join(ROOT, "include"))
     if force or _newer(target, srcs):
         nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
-        _run([nvcc] + NVCC_FLAGS + ["-DPP_PROFILE", "-shared", "-o", target, os.path.join(CSRC, "cabi", "pp_cabi.cu")], verbose)
+        _nvcc_link(nvcc, ["-DPP_PROFILE"], target, verbose)
     return target
 
 
@@ -70,7 +83,7 @@ def build_cuda_variant(name, defines, force=True, verbose=True):
     os.makedirs(LIB, exist_ok=True)
     target = os.path.join(LIB, f"libpp_b200_{name}.so")
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
-    _run([nvcc] + NVCC_FLAGS + [f"-D{d}" for d in defines] + ["-shared", "-o", target, os.path.join(CSRC, "cabi", "pp_cabi.cu")], verbose)
+    _nvcc_link(nvcc, [f"-D{d}" for d in defines], target, verbose)
     return target
 
 

@@ -10,6 +10,7 @@
 
 #include "../kernels/pp_kernels.cuh"
 #include "../host/pp_host.h"
+#include "../kernels/pp_fields.h"
 #include "../../../include/pp_b200.h"
 
 static thread_local std::string g_last_error;
@@ -95,6 +96,10 @@ struct pp_context
     WorkPools wp_lazy;     // persistent cache of the stand-alone lazy 2D A* (AStar<T> handle)
     unsigned* d_lazy_sid = nullptr;
     int lazy_group = -1;
+    // heuristic fields (throughput modes / C3)
+    DevBuf<float> d_field2d;              // num_groups x N*N, filled per group on demand
+    std::vector<char> field2d_valid;
+    DevBuf<unsigned> d_f2d_work; DevBuf<unsigned char> d_f2d_flags; DevBuf<float> d_dubins_field;
     DevBuf<int> d_qmap;
     int retried = 0;       // queries re-run in the last pp_batch_run
     unsigned long long launches = 0;      // kernels launched by this context
@@ -194,6 +199,7 @@ void pp_destroy(pp_context* c)
     c->d_queries.release(); c->d_results.release(); c->d_paths.release(); c->d_trace.release();
     c->wp.release(); c->wp_retry.release(); c->wp_lazy.release(); c->d_qmap.release();
     cudaFree(c->d_lazy_sid);
+    c->d_field2d.release(); c->d_f2d_work.release(); c->d_f2d_flags.release(); c->d_dubins_field.release();
     cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
     cudaStreamDestroy(c->stream);
     delete c;
@@ -806,7 +812,90 @@ int pp_clear_obstacles(pp_context* c, int g)
     return PP_SUCCESS;
 }
 
+// ---- heuristic fields ------------------------------------------------------------------------------------
+static int field2d_run(pp_context* c, int g, int* sweeps, float* ms)
+{
+    const PPConsts& C = c->model.C;
+    size_t nn = nn_of(c);
+    int T = (C.N + 31) / 32;
+    PP_CUDA(c->d_field2d.ensure(nn * c->num_groups));
+    if ((int)c->field2d_valid.size() != c->num_groups) c->field2d_valid.assign(c->num_groups, 0);
+    PP_CUDA(c->d_f2d_work.ensure(nn));
+    PP_CUDA(c->d_f2d_flags.ensure((size_t)2 * T * T));
+    float diag = C.n_act2d == 8 ? C.act_cost[1] : 0.0f;
+    PP_CUDA(cudaEventRecord(c->ev0, c->stream));
+    int sw = 0;
+    int e = pp_launch_field2d(c->stream, c->groups[g].map, C.N, C.log_thr, C.act_cost[0], diag, C.n_act2d == 8 ? 1 : 0,
+                              c->frames[g].F.goal_ci, c->frames[g].F.goal_cj, c->d_f2d_work.p, c->d_f2d_flags.p, c->d_counter,
+                              c->d_field2d.p + nn * g, c->sm_count, &sw, &c->launches);
+    if (e != 0) return pp_fail(PP_ERR_CUDA, std::string("field2d: ") + cudaGetErrorString((cudaError_t)e));
+    PP_CUDA(cudaEventRecord(c->ev1, c->stream));
+    PP_CUDA(cudaStreamSynchronize(c->stream));
+    if (ms) PP_CUDA(cudaEventElapsedTime(ms, c->ev0, c->ev1));
+    if (sweeps) *sweeps = sw;
+    c->field2d_valid[g] = 1;
+    return PP_SUCCESS;
+}
+
+int pp_heuristic_field_2d(pp_context* c, int g, float* out_nn, int* sweeps, float* ms)
+{
+    int rc = check_group(c, g); if (rc) return rc;
+    PP_CUDA(cudaSetDevice(c->device));
+    rc = field2d_run(c, g, sweeps, ms); if (rc) return rc;
+    if (out_nn)
+    {
+        PP_CUDA(cudaMemcpyAsync(out_nn, c->d_field2d.p + nn_of(c) * g, sizeof(float) * nn_of(c), cudaMemcpyDeviceToHost, c->stream));
+        PP_CUDA(cudaStreamSynchronize(c->stream));
+    }
+    return PP_SUCCESS;
+}
+
+int pp_heuristic_field_3d(pp_context* c, int g, int use_h2d, float* out_nnb, float* ms)
+{
+    int rc = check_group(c, g); if (rc) return rc;
+    PP_CUDA(cudaSetDevice(c->device));
+    const PPConsts& C = c->model.C;
+    size_t nn = nn_of(c), total = nn * C.bins;
+    if (use_h2d && ((int)c->field2d_valid.size() != c->num_groups || !c->field2d_valid[g]))
+    { rc = field2d_run(c, g, nullptr, nullptr); if (rc) return rc; }
+    PP_CUDA(c->d_dubins_field.ensure(total));
+    const PPFrame& F = c->frames[g].F;
+    PP_CUDA(cudaEventRecord(c->ev0, c->stream));
+    int e = pp_launch_dubins_field(c->stream, use_h2d ? c->d_field2d.p + nn * g : nullptr, c->d_dubins_field.p, C.N, C.bins, C.res,
+                                   C.precision, C.r_min, F.goal_x, F.goal_y, F.goal_h, c->sm_count, &c->launches);
+    if (e != 0) return pp_fail(PP_ERR_CUDA, std::string("dubins field: ") + cudaGetErrorString((cudaError_t)e));
+    PP_CUDA(cudaEventRecord(c->ev1, c->stream));
+    PP_CUDA(cudaStreamSynchronize(c->stream));
+    if (ms) PP_CUDA(cudaEventElapsedTime(ms, c->ev0, c->ev1));
+    if (out_nnb)
+    {
+        PP_CUDA(cudaMemcpyAsync(out_nnb, c->d_dubins_field.p, sizeof(float) * total, cudaMemcpyDeviceToHost, c->stream));
+        PP_CUDA(cudaStreamSynchronize(c->stream));
+    }
+    return PP_SUCCESS;
+}
+
 unsigned long long pp_kernel_launches(pp_context* c) { return c ? c->launches : 0ull; }
+
+// CUDA-event bracket on the context's stream (the stream every kernel of this context is launched on)
+int pp_timer_begin(pp_context* c)
+{
+    if (!c) return pp_fail(PP_ERR_INVALID, "null context");
+    PP_CUDA(cudaSetDevice(c->device));
+    PP_CUDA(cudaStreamSynchronize(c->stream));
+    PP_CUDA(cudaEventRecord(c->ev0, c->stream));
+    return PP_SUCCESS;
+}
+
+int pp_timer_end(pp_context* c, float* ms)
+{
+    if (!c || !ms) return pp_fail(PP_ERR_INVALID, "null argument");
+    PP_CUDA(cudaSetDevice(c->device));
+    PP_CUDA(cudaEventRecord(c->ev1, c->stream));
+    PP_CUDA(cudaStreamSynchronize(c->stream));
+    PP_CUDA(cudaEventElapsedTime(ms, c->ev0, c->ev1));
+    return PP_SUCCESS;
+}
 
 #ifdef PP_PROFILE
 // development variant only (lib/libpp_b200_prof.so): per-phase SM cycles summed over all queries; reset on read

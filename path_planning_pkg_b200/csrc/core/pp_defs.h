@@ -15,9 +15,11 @@
 #if defined(__CUDACC__)
 #define PP_HD __host__ __device__ __forceinline__
 #define PP_HD_NOINLINE __host__ __device__ __noinline__
+#define PP_HD_NOINLINE_FN static __host__ __device__ __noinline__   /* free functions: one copy per translation unit */
 #else
 #define PP_HD inline
 #define PP_HD_NOINLINE inline
+#define PP_HD_NOINLINE_FN inline
 #endif
 
 #define PP_MAX_STEER 16

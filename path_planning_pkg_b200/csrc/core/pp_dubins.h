@@ -120,7 +120,7 @@ PP_HD float pp_dubins_acos_arg(float r, float csx, float csy, float cgx, float c
 
 // One candidate, all of it on the calling thread (stateless kernels, the Dubins shot).  Returns the path length
 // (NaN for RSL/LSR when the centres are closer than 2r).
-PP_HD_NOINLINE float pp_dubins_candidate(int type, float r, float sh, float gh,
+PP_HD_NOINLINE_FN float pp_dubins_candidate(int type, float r, float sh, float gh,
                                          float csx, float csy, float cgx, float cgy, float p[4])
 {
     float theta = pp_atan2f(cgy - csy, cgx - csx);
@@ -136,7 +136,7 @@ PP_HD_NOINLINE float pp_dubins_candidate(int type, float r, float sh, float gh,
 }
 
 // Sequential fold of the four candidates, Dubins.cpp:36-68.
-PP_HD_NOINLINE float pp_dubins_shortest(float r, float sx, float sy, float sh, float gx, float gy, float gh,
+PP_HD_NOINLINE_FN float pp_dubins_shortest(float r, float sx, float sy, float sh, float gx, float gy, float gh,
                                int& best_type, float best_p[4], PPDubinsCenters& c)
 {
     pp_dubins_centers(r, sx, sy, sh, gx, gy, gh, c);
@@ -169,7 +169,7 @@ struct PPDubinsPlan
     float curvature;            // 1 / r_min
 };
 
-PP_HD_NOINLINE void pp_dubins_plan(float r, float step, float ang_step, int type, const float p[4],
+PP_HD_NOINLINE_FN void pp_dubins_plan(float r, float step, float ang_step, int type, const float p[4],
                           const PPDubinsCenters& c, PPDubinsPlan& pl)
 {
     pl.type = type;
@@ -197,7 +197,7 @@ PP_HD_NOINLINE void pp_dubins_plan(float r, float step, float ang_step, int type
 
 // Sample k of the plan.  `acc` is the float accumulator of the segment the sample lies on:
 // theta (arcs; p0 -/+ k*ang_step accumulated one step at a time) or dist (straight; k*step likewise).
-PP_HD_NOINLINE void pp_dubins_sample(const PPDubinsPlan& pl, float r, int k, float acc,
+PP_HD_NOINLINE_FN void pp_dubins_sample(const PPDubinsPlan& pl, float r, int k, float acc,
                             float& x, float& y, float& heading, float& curvature)
 {
     if (k < pl.size_1)

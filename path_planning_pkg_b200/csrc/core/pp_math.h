@@ -15,10 +15,10 @@
 #define PP_PI    3.14159265358979323846   /* M_PI   */
 #define PP_PI_2  1.57079632679489661923   /* M_PI_2 */
 
-PP_HD_NOINLINE float pp_sinf(float x) { return (float)sin((double)x); }
-PP_HD_NOINLINE float pp_cosf(float x) { return (float)cos((double)x); }
-PP_HD_NOINLINE float pp_atan2f(float y, float x) { return (float)atan2((double)y, (double)x); }
-PP_HD_NOINLINE float pp_acosf(float x) { return (float)acos((double)x); }
+PP_HD_NOINLINE_FN float pp_sinf(float x) { return (float)sin((double)x); }
+PP_HD_NOINLINE_FN float pp_cosf(float x) { return (float)cos((double)x); }
+PP_HD_NOINLINE_FN float pp_atan2f(float y, float x) { return (float)atan2((double)y, (double)x); }
+PP_HD_NOINLINE_FN float pp_acosf(float x) { return (float)acos((double)x); }
 
 // glibc hypotf == (float)sqrt((double)x*x + (double)y*y) (checked on 2e8 random pairs)
 PP_HD float pp_hypotf(float x, float y)
@@ -31,7 +31,7 @@ PP_HD float pp_hypotf(float x, float y)
 // double, correction in double rounded to float.
 // fmod(a, 2*pi) bit-exactly, without the generic (slow, iterative) fmod for the arguments that occur:
 // |a| < 2pi -> a; 2pi <= |a| < 4pi -> a -/+ 2pi, exact by Sterbenz' lemma; otherwise the library fmod.
-PP_HD_NOINLINE double pp_fmod_2pi_slow(double a) { return fmod(a, 2 * PP_PI); }
+PP_HD_NOINLINE_FN double pp_fmod_2pi_slow(double a) { return fmod(a, 2 * PP_PI); }
 PP_HD double pp_fmod_2pi(double a)
 {
     double m = fabs(a);

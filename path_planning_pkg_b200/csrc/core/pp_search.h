@@ -164,7 +164,7 @@ PP_HD void pp_lazy_touch(const PPConsts& C, PPWork& wk, int cell)
 }
 
 // AStar::update_visted + Grid2D::update_costs (AStar.cpp:209-218, Grid2D.cpp:219-227)
-PP_HD_NOINLINE void pp_lazy_update_visited(const PPConsts& C, PPWork& wk, float total, int last_cell)
+PP_HD_NOINLINE_FN void pp_lazy_update_visited(const PPConsts& C, PPWork& wk, float total, int last_cell)
 {
     int c = last_cell;
     while (c >= 0)
@@ -176,7 +176,7 @@ PP_HD_NOINLINE void pp_lazy_update_visited(const PPConsts& C, PPWork& wk, float 
     }
 }
 
-PP_HD_NOINLINE bool pp_lazy_insert(PPLazy& L, int cell, float g, float f, int prev)
+PP_HD_NOINLINE_FN bool pp_lazy_insert(PPLazy& L, int cell, float g, float f, int prev)
 {
     PPKey k; k.key = (unsigned)cell; k.f = f;
     int p; bool left;
@@ -191,7 +191,7 @@ PP_HD_NOINLINE bool pp_lazy_insert(PPLazy& L, int cell, float g, float f, int pr
 
 // AStar::find_path(i, j) + a_star_search (AStar.cpp:100-113, :118-186) on per-query scratch that
 // starts in the freshly-constructed state (g = 0, f = Euclidean h, nothing visited).
-PP_HD_NOINLINE float pp_lazy_astar(const PPConsts& C, const float* map, const PPFrame& F, PPWork& wk,
+PP_HD_NOINLINE_FN float pp_lazy_astar(const PPConsts& C, const float* map, const PPFrame& F, PPWork& wk,
                                    PPLazy& L, int ci, int cj)
 {
     const int N = C.N;
@@ -350,7 +350,7 @@ PP_HD bool pp_path_point_blocked(const PPConsts& C, const float* map, float x, f
 }
 
 // one obstacle's term of Grid3D::get_field_intensity (Grid3D.cpp:209-223)
-PP_HD_NOINLINE float pp_apf_term(const PPConsts& C, float ox, float oy, float radius, float x, float y, float heading)
+PP_HD_NOINLINE_FN float pp_apf_term(const PPConsts& C, float ox, float oy, float radius, float x, float y, float heading)
 {
     float dx = ox - x, dy = oy - y;
     float distance = pp_hypotf(dx, dy);
@@ -368,7 +368,7 @@ PP_HD_NOINLINE float pp_apf_term(const PPConsts& C, float ox, float oy, float ra
 // idx == nullptr): std::accumulate from T(0) in obstacle order (Grid3D.cpp:226).  Zero terms are skipped
 // (x + 0 == x), non-zero terms are added one by one in index order.
 template <class W>
-PP_HD_NOINLINE float pp_apf_sum(const W& w, const PPConsts& C, const float* apf, const int* idx, int n,
+PP_HD_NOINLINE_FN float pp_apf_sum(const W& w, const PPConsts& C, const float* apf, const int* idx, int n,
                        float x, float y, float heading)
 {
     float acc = 0.0f;
@@ -401,7 +401,7 @@ PP_HD_NOINLINE float pp_apf_sum(const W& w, const PPConsts& C, const float* apf,
 // (one lane per steering primitive) + bounds/collision lookup + APF cost (lanes over obstacles).
 // Results in sm.succ[0 .. 2A] (ok = 0 for pruned / colliding primitives); g includes the field cost.
 template <class W>
-PP_HD_NOINLINE void pp_expand_warp(const W& w, const PPConsts& C, const float* off_xy, const PPGroup& G,
+PP_HD_NOINLINE_FN void pp_expand_warp(const W& w, const PPConsts& C, const float* off_xy, const PPGroup& G,
                           float px, float py, float ph, float pg, float pv2, int pcurv, int pbin, PPSmem& sm)
 {
     const int lane = w.lane();
@@ -504,7 +504,7 @@ PP_HD_NOINLINE void pp_expand_warp(const W& w, const PPConsts& C, const float* o
 //   C  lanes = (succ, RSL|LSR, theta_t1|p2)   : sin, cos of the two tangent angles
 //   D  lanes = (succ, type)         : float-only tail (pp_dubins_finish)
 template <class W>
-PP_HD_NOINLINE void pp_dubins_h2_warp(const W& w, const PPConsts& C, const PPFrame& F, const PPDubinsGoal& gc, PPSmem& sm)
+PP_HD_NOINLINE_FN void pp_dubins_h2_warp(const W& w, const PPConsts& C, const PPFrame& F, const PPDubinsGoal& gc, PPSmem& sm)
 {
     const int lane = w.lane();
     const int n = 2 * C.A + 1;
@@ -594,7 +594,7 @@ PP_HD void pp_closed_link(PPWork& wk, unsigned key, int idx)
 }
 
 // returns false when the pool is exhausted
-PP_HD_NOINLINE bool pp_open3_insert(PPSearchState& S, const PPSucc& s, unsigned key, float f, int prev)
+PP_HD_NOINLINE_FN bool pp_open3_insert(PPSearchState& S, const PPSucc& s, unsigned key, float f, int prev)
 {
     PPKey k; k.key = key; k.f = f;
     int p; bool left;
@@ -611,7 +611,7 @@ PP_HD_NOINLINE bool pp_open3_insert(PPSearchState& S, const PPSucc& s, unsigned 
 
 // The search.  All lanes of the warp call it with identical arguments.
 template <class W>
-PP_HD_NOINLINE void pp_search_exact(const W& w, const PPConsts& C, const float* off_xy, const PPGroup& G,
+PP_HD_NOINLINE_FN void pp_search_exact(const W& w, const PPConsts& C, const float* off_xy, const PPGroup& G,
                                     const PPState& start, PPWork& wk, PPSmem& sm, PPResult& res)
 {
     const int lane = w.lane();

@@ -1,0 +1,107 @@
+#!/usr/bin/env python
+"""Kernel-level measurements for BASELINE configs C2 (map update at 2048^2, 256 boxes) and C3 (2D field + Dubins field
+sweep over 2048^2 x 72), with roofline fractions against MEASURED_PEAKS.json.  One JSON line per kernel.
+(The contract benchmark is bench.py; this script supplies the per-kernel numbers quoted in DESIGN.md / profiles/.)"""
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "tests")):
+    sys.path.insert(0, p)
+import scenarios as S  # noqa: E402
+import path_planning_pkg_b200 as pp  # noqa: E402
+
+
+def peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"], "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+def timed(ctx, fn, reps):
+    ms = C.c_float()
+    fn()
+    ctx.sync()
+    ctx.lib.pp_timer_begin(ctx.h)
+    for _ in range(reps):
+        fn()
+    ctx.lib.pp_timer_end(ctx.h, C.byref(ms))
+    return ms.value / reps
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--n", type=int, default=2048)
+    ap.add_argument("--reps", type=int, default=20)
+    ap.add_argument("--cpu", action="store_true", help="also time the reference (oracle/_ref) on one host core")
+    a = ap.parse_args()
+    peak, src = peaks()
+    sc = S.c2_scenario(grid_size=a.n)
+    P = pp.make_params(grid_size=a.n, resolution=sc["resolution"])
+    ctx = pp.Context(P, num_groups=1)
+    ctx.update_goal(sc["goal"], sc["frame_start"])
+    nn = a.n * a.n
+    out = []
+
+    # C2: decay (pure streaming: 4 B read + 4 B write per cell)
+    ms = timed(ctx, lambda: ctx.decay(), a.reps)
+    gbs = 8.0 * nn / (ms * 1e-3) / 1e9
+    out.append(dict(kernel="pp_map_decay_kernel", config=f"C2 decay {a.n}^2", ms=ms, algorithmic_bytes=8 * nn, achieved_gbs=gbs, peak_gbs=peak,
+                    frac=gbs / peak, peak_source=src, note="16 MiB map is L2 resident on B200 (126 MB L2): can exceed the HBM roofline"))
+    # C2: boxes (host prologue + H2D of descriptors + gather kernel + sync, as one call)
+    ctx.set_map(np.zeros((a.n, a.n), np.float32))
+    ms = timed(ctx, lambda: ctx.update_boxes_2d(sc["boxes"], sc["conf"]), max(a.reps // 4, 3))
+    ctx.set_map(np.zeros((a.n, a.n), np.float32))
+    ctx.update_boxes_2d(sc["boxes"], sc["conf"])
+    touched = int((ctx.get_map() != 0).sum())
+    alg = 8 * touched + 20 * len(sc["boxes"])
+    out.append(dict(kernel="pp_map_boxes_kernel (+host prologue, H2D, sync)", config=f"C2 {len(sc['boxes'])} boxes into {a.n}^2", ms=ms,
+                    distinct_cells=touched, algorithmic_bytes=alg, achieved_gbs=alg / (ms * 1e-3) / 1e9, peak_gbs=peak,
+                    frac=alg / (ms * 1e-3) / 1e9 / peak, note="launch/latency bound: ~0.5 MB of useful traffic per call (SURVEY H4)"))
+    # three C2 rounds so the field kernels see the C2 map
+    ctx.set_map(np.zeros((a.n, a.n), np.float32))
+    for _ in range(sc["rounds"]):
+        ctx.update_boxes(sc["boxes"], sc["conf"], S.APF_ADDED_RADIUS)
+        ctx.decay()
+    # C3: 2D field
+    f, sweeps, ms = ctx.field2d(download=True)
+    f, sweeps, ms = ctx.field2d(download=False)
+    alg = 8 * nn
+    out.append(dict(kernel="pp_field2d_sweep_kernel (all sweeps)", config=f"C3 2D field {a.n}^2", ms=ms, sweeps=sweeps,
+                    algorithmic_bytes_per_sweep=alg, achieved_gbs=alg * sweeps / (ms * 1e-3) / 1e9, peak_gbs=peak,
+                    frac=alg * sweeps / (ms * 1e-3) / 1e9 / peak,
+                    note="upper bound on traffic: inactive tiles are skipped, so real traffic per sweep is far below 8 B/cell"))
+    # C3: Dubins field sweep (mandatory write: 4 B per state)
+    _, ms = ctx.field3d(use_h2d=True, download=False)
+    _, ms = ctx.field3d(use_h2d=True, download=False)
+    states = nn * 72
+    flops = 485.0 * states
+    out.append(dict(kernel="pp_dubins_field_kernel", config=f"C3 Dubins sweep {a.n}^2 x 72", ms=ms, states=states,
+                    states_per_s=states / (ms * 1e-3), write_gbs=4.0 * states / (ms * 1e-3) / 1e9, write_frac_of_hbm=4.0 * states / (ms * 1e-3) / 1e9 / peak,
+                    fp32_tflops_est=flops / (ms * 1e-3) / 1e12, fp32_peak_tflops_derived=74.4, fp32_frac=flops / (ms * 1e-3) / 1e12 / 74.4,
+                    note="485 FP32 op/state is SURVEY 8d's estimate (125 basic + 18 transcendentals x 20); FP32 peak derived, not measured"))
+    if a.cpu:
+        import orc
+        o = orc.ref(orc.make_params(grid_size=a.n, resolution=sc["resolution"])) if orc.have_ref() else orc.port(orc.make_params(grid_size=a.n, resolution=sc["resolution"]))
+        o.update_goal(sc["goal"], sc["frame_start"])
+        t = time.perf_counter(); o.update_boxes_2d(sc["boxes"], sc["conf"]); tb = time.perf_counter() - t
+        t = time.perf_counter(); o.decay(); td = time.perf_counter() - t
+        goal = np.array(list(o.consts().goal_grid), np.float32)
+        m = 200000
+        starts = np.random.RandomState(0).uniform(0, a.n * sc["resolution"], (m, 3)).astype(np.float32)
+        t = time.perf_counter(); o.dubins_length(starts, goal); tdu = (time.perf_counter() - t) / m
+        out.append(dict(kernel="cpu reference, 1 core", boxes_ms=tb * 1e3, decay_ms=td * 1e3, dubins_ns_per_state=tdu * 1e9,
+                        dubins_sweep_extrapolated_s=tdu * states))
+    for o in out:
+        print(json.dumps(o), flush=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -291,3 +291,10 @@ def setup_ref_test_scenario(o):
         o.decay()
         o.update_lines(REF_TEST_LINES, np.full(4, 0.6, np.float32), 1.25)
         o.update_boxes(REF_TEST_BOXES, np.full(3, 0.75, np.float32), 2.5)
+
+
+def field2d(o):
+    """Double-precision Dijkstra distance-to-goal field of the port oracle (negative = unreachable)."""
+    out = np.empty((o.N, o.N), np.float64)
+    o._fn("field2d")(o.h, _fp(out))
+    return out
