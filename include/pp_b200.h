@@ -123,7 +123,12 @@ typedef struct pp_search_opts
     int path_cap;            /* path points per query in the output arrays */
     int trace_cap;           /* pops recorded per query (0 = no trace) */
     int max_slots;           /* resident query slots (0 = auto from free memory) */
+    int mode;                /* PP_MODE_EXACT (0, reference-identical single pop) or PP_MODE_KPOP (1) */
+    int kpop;                /* pops per iteration in PP_MODE_KPOP, 1..32 (0 = 32) */
 } pp_search_opts;
+
+#define PP_MODE_EXACT 0
+#define PP_MODE_KPOP 1
 
 typedef struct pp_context pp_context;
 

@@ -20,6 +20,7 @@
 #include <algorithm>
 #include <limits>
 #include <numeric>
+#include <tuple>
 
 #include "../oracle_api.h"
 
@@ -162,6 +163,15 @@ void build(Port& P, const orc_params& p)
 
 float clampv(const Port& P, float v) { return std::max(std::min(v, P.log_max), P.log_min); }
 
+// libm flavour of the functions the B200 build executes on the device (Dubins.cpp, atan2f of Grid3D::get_field_intensity):
+// 0 = platform libm like the reference; 1 = "pinned": evaluate in double, round once to float (see oracle/cr_math.c).
+// With flavour 1 this restatement equals oracle/_ref/libref_oracle_crm.so.
+static bool g_pinned_libm = false;
+static inline float m_sin(float x) { return g_pinned_libm ? (float)std::sin((double)x) : std::sin(x); }
+static inline float m_cos(float x) { return g_pinned_libm ? (float)std::cos((double)x) : std::cos(x); }
+static inline float m_atan2(float y, float x) { return g_pinned_libm ? (float)std::atan2((double)y, (double)x) : std::atan2(y, x); }
+static inline float m_acos(float x) { return g_pinned_libm ? (float)std::acos((double)x) : std::acos(x); }
+
 // ---- Dubins ------------------------------------------------------------------------------------------
 struct DubRes { float len; int type; float p[4]; float c[8]; };   // c = srx sry slx sly grx gry glx gly
 
@@ -169,7 +179,7 @@ float dub_cand(const Port& P, int type, float sh, float gh, float csx, float csy
 {
     const float r = P.r_min;
     float dcx = cgx - csx, dcy = cgy - csy;
-    float theta = std::atan2(dcy, dcx);
+    float theta = m_atan2(dcy, dcx);
     if (type == 0)        // get_params_rsr, Dubins.cpp:180-210
     {
         p[0] = M_PI_2 + sh; float t1 = M_PI_2 + theta; p[2] = t1; float tg = M_PI_2 + gh;
@@ -190,18 +200,18 @@ float dub_cand(const Port& P, int type, float sh, float gh, float csx, float csy
     float t1;
     if (type == 1)        // get_params_rsl, Dubins.cpp:212-250
     {
-        p[0] = M_PI_2 + sh; t1 = std::acos(2 * r / dist) + theta; p[2] = t1 - M_PI; float tg = -M_PI_2 + gh;
+        p[0] = M_PI_2 + sh; t1 = m_acos(2 * r / dist) + theta; p[2] = t1 - M_PI; float tg = -M_PI_2 + gh;
         p[1] = t1 - p[0]; if (p[1] > 0) p[1] -= 2 * M_PI;
         p[3] = tg - p[2]; if (p[3] < 0) p[3] += 2 * M_PI;
     }
     else                  // get_params_lsr, Dubins.cpp:252-291
     {
-        p[0] = -M_PI_2 + sh; t1 = -std::acos(2 * r / dist) + theta; p[2] = t1 + M_PI; float tg = M_PI_2 + gh;
+        p[0] = -M_PI_2 + sh; t1 = -m_acos(2 * r / dist) + theta; p[2] = t1 + M_PI; float tg = M_PI_2 + gh;
         p[1] = t1 - p[0]; if (p[1] < 0) p[1] += 2 * M_PI;
         p[3] = tg - p[2]; if (p[3] > 0) p[3] -= 2 * M_PI;
     }
-    float ssx = csx + r * std::cos(t1), ssy = csy + r * std::sin(t1);
-    float esx = cgx + r * std::cos(p[2]), esy = cgy + r * std::sin(p[2]);
+    float ssx = csx + r * m_cos(t1), ssy = csy + r * m_sin(t1);
+    float esx = cgx + r * m_cos(p[2]), esy = cgy + r * m_sin(p[2]);
     float dx = esx - ssx, dy = esy - ssy;
     float d = std::sqrt(dx * dx + dy * dy);
     return (type == 1) ? d + r * (-p[1] + p[3]) : d + r * (p[1] - p[3]);
@@ -211,10 +221,10 @@ DubRes dub_shortest(const Port& P, const float* s, const float* g)    // Dubins.
 {
     DubRes R;
     const float r = P.r_min;
-    R.c[0] = s[0] + r * std::sin(s[2]); R.c[1] = s[1] - r * std::cos(s[2]);
-    R.c[2] = s[0] - r * std::sin(s[2]); R.c[3] = s[1] + r * std::cos(s[2]);
-    R.c[4] = g[0] + r * std::sin(g[2]); R.c[5] = g[1] - r * std::cos(g[2]);
-    R.c[6] = g[0] - r * std::sin(g[2]); R.c[7] = g[1] + r * std::cos(g[2]);
+    R.c[0] = s[0] + r * m_sin(s[2]); R.c[1] = s[1] - r * m_cos(s[2]);
+    R.c[2] = s[0] - r * m_sin(s[2]); R.c[3] = s[1] + r * m_cos(s[2]);
+    R.c[4] = g[0] + r * m_sin(g[2]); R.c[5] = g[1] - r * m_cos(g[2]);
+    R.c[6] = g[0] - r * m_sin(g[2]); R.c[7] = g[1] + r * m_cos(g[2]);
     const int cs[4] = {0, 0, 2, 2}, cg[4] = {4, 6, 4, 6};       // RSR, RSL, LSR, LSL centre pairs
     for (int t = 0; t < 4; t++)
     {
@@ -232,8 +242,8 @@ void dub_sample(const Port& P, const DubRes& R, std::vector<float>& xyh, std::ve
     const int cs[4] = {0, 0, 2, 2}, cg[4] = {4, 6, 4, 6};
     float csx = R.c[cs[R.type]], csy = R.c[cs[R.type] + 1], cgx = R.c[cg[R.type]], cgy = R.c[cg[R.type] + 1];
     bool r1 = (R.type == 0 || R.type == 1), r2 = (R.type == 0 || R.type == 2);   // right first / second arc
-    float ssx = csx + r * std::cos(R.p[0] + R.p[1]), ssy = csy + r * std::sin(R.p[0] + R.p[1]);
-    float esx = cgx + r * std::cos(R.p[2]), esy = cgy + r * std::sin(R.p[2]);
+    float ssx = csx + r * m_cos(R.p[0] + R.p[1]), ssy = csy + r * m_sin(R.p[0] + R.p[1]);
+    float esx = cgx + r * m_cos(R.p[2]), esy = cgy + r * m_sin(R.p[2]);
     float dx = esx - ssx, dy = esy - ssy;
     float len_st = std::sqrt(dx * dx + dy * dy);
     int size_1 = static_cast<int>(std::floor((r1 ? -R.p[1] : R.p[1]) / P.ang_step));
@@ -243,13 +253,13 @@ void dub_sample(const Port& P, const DubRes& R, std::vector<float>& xyh, std::ve
     float theta = R.p[0], kappa = 1 / r;
     for (int i = 0; i < size_1; i++)
     {
-        xyh[3 * i] = csx + r * std::cos(theta); xyh[3 * i + 1] = csy + r * std::sin(theta);
+        xyh[3 * i] = csx + r * m_cos(theta); xyh[3 * i + 1] = csy + r * m_sin(theta);
         xyh[3 * i + 2] = r1 ? wrap_pi_d(theta - M_PI_2) : wrap_pi_d(theta + M_PI_2);
         curv[i] = kappa;
         if (r1) theta -= P.ang_step; else theta += P.ang_step;
     }
-    theta = std::atan2(dy, dx);
-    float ct = std::cos(theta), st = std::sin(theta), dist = 0.0f;
+    theta = m_atan2(dy, dx);
+    float ct = m_cos(theta), st = m_sin(theta), dist = 0.0f;
     for (int i = size_1; i < size_2; i++)
     {
         xyh[3 * i] = ssx + dist * ct; xyh[3 * i + 1] = ssy + dist * st; xyh[3 * i + 2] = theta; curv[i] = 0.0f;
@@ -258,12 +268,12 @@ void dub_sample(const Port& P, const DubRes& R, std::vector<float>& xyh, std::ve
     theta = R.p[2];
     for (int i = size_2; i < size_3; i++)
     {
-        xyh[3 * i] = cgx + r * std::cos(theta); xyh[3 * i + 1] = cgy + r * std::sin(theta);
+        xyh[3 * i] = cgx + r * m_cos(theta); xyh[3 * i + 1] = cgy + r * m_sin(theta);
         xyh[3 * i + 2] = r2 ? wrap_pi_d(theta - M_PI_2) : wrap_pi_d(theta + M_PI_2);
         curv[i] = kappa;
         if (r2) theta -= P.ang_step; else theta += P.ang_step;
     }
-    xyh[3 * size_3] = cgx + r * std::cos(R.p[2] + R.p[3]); xyh[3 * size_3 + 1] = cgy + r * std::sin(R.p[2] + R.p[3]);
+    xyh[3 * size_3] = cgx + r * m_cos(R.p[2] + R.p[3]); xyh[3 * size_3 + 1] = cgy + r * m_sin(R.p[2] + R.p[3]);
     xyh[3 * size_3 + 2] = r2 ? wrap_pi_d(R.p[2] + R.p[3] - M_PI_2) : wrap_pi_d(R.p[2] + R.p[3] + M_PI_2);
     curv[size_3] = 0.0f;
 }
@@ -307,7 +317,7 @@ float field(const Port& P, float x, float y, float h)
     {
         float ox = P.apf[3 * k], oy = P.apf[3 * k + 1], rad = P.apf[3 * k + 2];
         float distance = std::hypot(ox - x, oy - y);
-        float angle = std::abs(wrap_pi_f(h - std::atan2(oy - y, ox - x)));
+        float angle = std::abs(wrap_pi_f(h - m_atan2(oy - y, ox - x)));
         angle = std::max(P.apf_alpha - angle, 0.0f);
         float fp = 0;
         if (distance < rad)
@@ -832,3 +842,5 @@ void port_find_path(void* hv, float vel, const float* s, orc_result* res, float*
     res->n_path = n;
 }
 }   // extern "C"
+
+#include "kpop.inc"

@@ -44,7 +44,8 @@ class FrameInfo(C.Structure):
 
 class SearchOpts(C.Structure):
     _fields_ = [("max_expansions", C.c_int), ("max_open", C.c_int), ("max_open2d", C.c_int),
-                ("path_cap", C.c_int), ("trace_cap", C.c_int), ("max_slots", C.c_int)]
+                ("path_cap", C.c_int), ("trace_cap", C.c_int), ("max_slots", C.c_int),
+                ("mode", C.c_int), ("kpop", C.c_int)]
 
 
 STATE_DT = np.dtype([("x", "f4"), ("y", "f4"), ("heading", "f4"), ("g", "f4"), ("f", "f4"),
@@ -281,8 +282,9 @@ class Context:
         return q
 
     @staticmethod
-    def make_opts(max_expansions=0, max_open=0, max_open2d=0, path_cap=0, trace_cap=0, max_slots=0):
-        return SearchOpts(max_expansions, max_open, max_open2d, path_cap, trace_cap, max_slots)
+    def make_opts(max_expansions=0, max_open=0, max_open2d=0, path_cap=0, trace_cap=0, max_slots=0, mode=0, kpop=0):
+        """mode 0 = EXACT (reference-identical), 1 = KPOP (k pops per iteration, exact 2D field heuristic)."""
+        return SearchOpts(max_expansions, max_open, max_open2d, path_cap, trace_cap, max_slots, mode, kpop)
 
     def find_path_batch(self, queries, opts=None, want_paths=True):
         """pp_find_path_batch with host buffers: H2D of the queries and D2H of results/paths inside the call."""

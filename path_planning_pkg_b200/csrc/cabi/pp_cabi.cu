@@ -96,6 +96,11 @@ struct pp_context
     WorkPools wp_lazy;     // persistent cache of the stand-alone lazy 2D A* (AStar<T> handle)
     unsigned* d_lazy_sid = nullptr;
     int lazy_group = -1;
+    // K-POP mode pools (per slot): node log, hash table, LSM queue arena + merge scratch
+    struct KPools { int alloc_slots = 0, nodes_cap = 0, table_cap = 0, levels = 0; size_t arena_cap = 0, tmp_cap = 0;
+                    DevBuf<PPKNode> nodes; DevBuf<PPKSlot> table; DevBuf<PPKEntry> arena, tmp_a, tmp_b;
+                    void release() { nodes.release(); table.release(); arena.release(); tmp_a.release(); tmp_b.release(); alloc_slots = 0; } };
+    KPools kp, kp_retry;
     // heuristic fields (throughput modes / C3)
     DevBuf<float> d_field2d;              // num_groups x N*N, filled per group on demand
     std::vector<char> field2d_valid;
@@ -113,6 +118,11 @@ static int sync_groups(pp_context* c)
     PP_CUDA(cudaMemcpyAsync(c->d_groups, c->groups.data(), sizeof(PPGroup) * c->num_groups, cudaMemcpyHostToDevice, c->stream));
     c->groups_dirty = false;
     return PP_SUCCESS;
+}
+
+static void map_changed(pp_context* c, int g)
+{
+    if (g >= 0 && g < (int)c->field2d_valid.size()) c->field2d_valid[g] = 0;
 }
 
 static int check_group(pp_context* c, int g)
@@ -199,6 +209,7 @@ void pp_destroy(pp_context* c)
     c->d_queries.release(); c->d_results.release(); c->d_paths.release(); c->d_trace.release();
     c->wp.release(); c->wp_retry.release(); c->wp_lazy.release(); c->d_qmap.release();
     cudaFree(c->d_lazy_sid);
+    c->kp.release(); c->kp_retry.release();
     c->d_field2d.release(); c->d_f2d_work.release(); c->d_f2d_flags.release(); c->d_dubins_field.release();
     cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
     cudaStreamDestroy(c->stream);
@@ -254,6 +265,7 @@ int pp_sync(pp_context* c)
 int pp_update_goal(pp_context* c, int g, const float* goal3, const float* start3)
 {
     int rc = check_group(c, g); if (rc) return rc;
+    map_changed(c, g);
     PP_CUDA(cudaSetDevice(c->device));
     const PPConsts& C = c->model.C;
     PPHostFrame prev = c->frames[g];
@@ -280,6 +292,7 @@ int pp_reset(pp_context* c, int g) { return check_group(c, g); }
 int pp_update_obstacles_decay(pp_context* c, int g)
 {
     int rc = check_group(c, g); if (rc) return rc;
+    map_changed(c, g);
     PP_CUDA(cudaSetDevice(c->device));
     const PPConsts& C = c->model.C;
     size_t nn = nn_of(c);
@@ -294,6 +307,7 @@ int pp_update_obstacles_decay(pp_context* c, int g)
 int pp_update_obstacles_boxes_2d(pp_context* c, int g, const float* boxes, const float* conf, int n)
 {
     int rc = check_group(c, g); if (rc) return rc;
+    map_changed(c, g);
     if (n < 0 || (n > 0 && (!boxes || !conf))) return pp_fail(PP_ERR_INVALID, "boxes: bad arguments");
     if (n == 0) return PP_SUCCESS;
     PP_CUDA(cudaSetDevice(c->device));
@@ -365,6 +379,7 @@ int pp_update_obstacles_boxes(pp_context* c, int g, const float* boxes, const fl
 int pp_update_obstacles_lines(pp_context* c, int g, const float* lines, const float* conf, int n, float width)
 {
     int rc = check_group(c, g); if (rc) return rc;
+    map_changed(c, g);
     if (n < 0 || (n > 0 && (!lines || !conf))) return pp_fail(PP_ERR_INVALID, "lines: bad arguments");
     if (n == 0) return PP_SUCCESS;
     PP_CUDA(cudaSetDevice(c->device));
@@ -393,6 +408,7 @@ int pp_map_download(pp_context* c, int g, float* out)
 int pp_map_upload(pp_context* c, int g, const float* in)
 {
     int rc = check_group(c, g); if (rc) return rc;
+    map_changed(c, g);
     PP_CUDA(cudaSetDevice(c->device));
     PP_CUDA(cudaMemcpyAsync(c->d_maps + nn_of(c) * g, in, sizeof(float) * nn_of(c), cudaMemcpyHostToDevice, c->stream));
     PP_CUDA(cudaStreamSynchronize(c->stream));
@@ -613,6 +629,8 @@ static pp_search_opts default_opts(const pp_search_opts* in)
     if (o.max_open2d <= 0) o.max_open2d = 1 << 14;
     if (o.path_cap <= 0) o.path_cap = 2048;
     if (o.trace_cap < 0) o.trace_cap = 0;
+    if (o.mode != PP_MODE_KPOP) o.mode = PP_MODE_EXACT;
+    if (o.kpop <= 0 || o.kpop > PP_K_MAXPOP) o.kpop = PP_K_MAXPOP;
     return o;
 }
 
@@ -621,6 +639,65 @@ static int hw_slots_of(pp_context* c, int* out)
     int occ = 0;
     PP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pp_search_kernel, PP_SEARCH_WARPS * 32, 0));
     *out = std::max(1, occ) * c->sm_count * PP_SEARCH_WARPS;
+    return PP_SUCCESS;
+}
+
+static int field2d_run(pp_context* c, int g, int* sweeps, float* ms);
+
+// ---- K-POP pools / launch ----------------------------------------------------------------------------
+static int kpop_levels_for(int nodes_cap)
+{
+    int levels = 1;
+    while ((size_t)PP_K_RUN0 * (((size_t)1 << levels) - 1) < (size_t)nodes_cap + PP_K_RUN0 && levels < PP_K_LEVELS) levels++;
+    return levels;
+}
+
+static int ensure_kpop(pp_context* c, pp_context::KPools& k, int want_slots, int nodes_cap, double mem_frac)
+{
+    int tc = 1; while (tc < 2 * nodes_cap) tc <<= 1;
+    int levels = kpop_levels_for(nodes_cap);
+    size_t arena_cap = (size_t)PP_K_RUN0 * (((size_t)1 << levels) - 1), tmp_cap = (size_t)nodes_cap + 2 * PP_K_RUN0;
+    size_t per_slot = sizeof(PPKNode) * (size_t)nodes_cap + sizeof(PPKSlot) * (size_t)tc + sizeof(PPKEntry) * (arena_cap + 2 * tmp_cap);
+    int slots = want_slots;
+    if (!(k.alloc_slots >= slots && k.nodes_cap == nodes_cap))
+    {
+        k.release();
+        size_t free_b = 0, total_b = 0;
+        PP_CUDA(cudaMemGetInfo(&free_b, &total_b));
+        size_t budget = (size_t)(free_b * mem_frac);
+        if ((size_t)slots * per_slot > budget) slots = (int)(budget / per_slot);
+        if (slots < 1) return pp_fail(PP_ERR_CAPACITY, "not enough device memory for one K-POP query slot");
+        PP_CUDA(k.nodes.ensure((size_t)slots * nodes_cap));
+        PP_CUDA(k.table.ensure((size_t)slots * tc));
+        PP_CUDA(k.arena.ensure((size_t)slots * arena_cap));
+        PP_CUDA(k.tmp_a.ensure((size_t)slots * tmp_cap));
+        PP_CUDA(k.tmp_b.ensure((size_t)slots * tmp_cap));
+        k.nodes_cap = nodes_cap; k.table_cap = tc; k.levels = levels; k.arena_cap = arena_cap; k.tmp_cap = tmp_cap; k.alloc_slots = slots;
+    }
+    return PP_SUCCESS;
+}
+
+static int kpop_hw_slots(pp_context* c, int* out)
+{
+    int occ = 0;
+    PP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pp_kpop_kernel, 32, 0));
+    *out = std::max(1, occ) * c->sm_count;
+    return PP_SUCCESS;
+}
+
+static int launch_kpop(pp_context* c, const pp_context::KPools& k, int n_slots, const int* qmap, int n_work)
+{
+    PPKpopArgs a;
+    a.C = c->model.C; a.off_xy = c->d_off_xy; a.groups = c->d_groups; a.field2d = c->d_field2d.p; a.queries = c->d_queries.p;
+    a.qmap = qmap; a.n_queries = n_work; a.n_slots = n_slots; a.kpop = c->opts.kpop; a.counter = c->d_counter; a.results = c->d_results.p;
+    a.paths = c->d_paths.p; a.path_cap = c->opts.path_cap;
+    a.trace = c->opts.trace_cap > 0 ? c->d_trace.p : nullptr; a.trace_cap = c->opts.trace_cap;
+    a.nodes = k.nodes.p; a.nodes_cap = k.nodes_cap; a.table = k.table.p; a.table_cap = k.table_cap;
+    a.arena = k.arena.p; a.arena_cap = k.arena_cap; a.tmp_a = k.tmp_a.p; a.tmp_b = k.tmp_b.p; a.tmp_cap = k.tmp_cap; a.lsm_levels = k.levels;
+    PP_CUDA(cudaMemsetAsync(c->d_counter, 0, sizeof(int), c->stream));
+    pp_kpop_kernel<<<n_slots, 32, 0, c->stream>>>(a);
+    c->launches += 1;
+    PP_CUDA(cudaGetLastError());
     return PP_SUCCESS;
 }
 
@@ -647,8 +724,27 @@ int pp_batch_upload(pp_context* c, const pp_query* q, int n, const pp_search_opt
     PP_CUDA(c->d_results.ensure(n));
     PP_CUDA(c->d_paths.ensure((size_t)n * o.path_cap));
     if (o.trace_cap > 0) PP_CUDA(c->d_trace.ensure((size_t)n * o.trace_cap));
-    rc = ensure_work(c, c->wp, want, o.max_expansions, o.max_open, o.max_open2d, 0.6); if (rc) return rc;
-    c->n_slots = std::max(std::min(c->wp.alloc_slots, want), 1);
+    if (o.mode == PP_MODE_KPOP)
+    {
+        if (2 * c->model.C.A + 1 > PP_K_MAXSUCC) return pp_fail(PP_ERR_INVALID, "K-POP mode supports at most 8 successors per node (num_actions <= 3)");
+        // the exact 2D distance field of every group the batch touches (recomputed only after a map / goal change)
+        size_t nn_ = nn_of(c);
+        PP_CUDA(c->d_field2d.ensure(nn_ * c->num_groups));
+        if ((int)c->field2d_valid.size() != c->num_groups) c->field2d_valid.assign(c->num_groups, 0);
+        for (int k = 0; k < n; k++)
+            if (!c->field2d_valid[q[k].group]) { rc = field2d_run(c, q[k].group, nullptr, nullptr); if (rc) return rc; }
+        rc = kpop_hw_slots(c, &hw_slots); if (rc) return rc;
+        want = std::min(n, hw_slots);
+        if (o.max_slots > 0) want = std::min(want, o.max_slots);
+        int nodes_cap = std::max(o.max_expansions, 4096);
+        rc = ensure_kpop(c, c->kp, want, nodes_cap, 0.6); if (rc) return rc;
+        c->n_slots = std::max(std::min(c->kp.alloc_slots, want), 1);
+    }
+    else
+    {
+        rc = ensure_work(c, c->wp, want, o.max_expansions, o.max_open, o.max_open2d, 0.6); if (rc) return rc;
+        c->n_slots = std::max(std::min(c->wp.alloc_slots, want), 1);
+    }
     PP_CUDA(cudaMemcpyAsync(c->d_queries.p, c->h_queries.data(), sizeof(PPQuery) * n, cudaMemcpyHostToDevice, c->stream));
     rc = sync_groups(c); if (rc) return rc;
     PP_CUDA(cudaStreamSynchronize(c->stream));
@@ -673,7 +769,9 @@ int pp_batch_run(pp_context* c, float* kernel_ms)
     PP_CUDA(cudaSetDevice(c->device));
     const int n = c->n_queries;
     PP_CUDA(cudaEventRecord(c->ev0, c->stream));
-    int rc = launch_search(c, c->wp, c->n_slots, nullptr, n); if (rc) return rc;
+    const bool kmode = (c->opts.mode == PP_MODE_KPOP);
+    int rc = kmode ? launch_kpop(c, c->kp, c->n_slots, nullptr, n) : launch_search(c, c->wp, c->n_slots, nullptr, n);
+    if (rc) return rc;
     // The reference's containers are unbounded.  Queries that exhausted a pool are re-run from scratch with
     // 8x larger pools (fewer resident slots), up to 3 escalations; what still overflows stays flagged.
     c->retried = 0;
@@ -692,13 +790,22 @@ int pp_batch_run(pp_context* c, float* kernel_ms)
         max_exp = (int)std::min<long long>(e, 1 << 26); max_open = (int)std::min<long long>(o3, 1 << 25);
         max_open2d = (int)std::min<long long>(o2, 1 << 22);
         int hw_slots = 0;
-        rc = hw_slots_of(c, &hw_slots); if (rc) return rc;
+        rc = kmode ? kpop_hw_slots(c, &hw_slots) : hw_slots_of(c, &hw_slots); if (rc) return rc;
         int want = std::min((int)redo.size(), hw_slots);
-        rc = ensure_work(c, c->wp_retry, want, max_exp, max_open, max_open2d, 0.85); if (rc) return rc;
-        int slots = std::max(std::min(c->wp_retry.alloc_slots, want), 1);
         PP_CUDA(c->d_qmap.ensure(redo.size()));
         PP_CUDA(cudaMemcpyAsync(c->d_qmap.p, redo.data(), sizeof(int) * redo.size(), cudaMemcpyHostToDevice, c->stream));
-        rc = launch_search(c, c->wp_retry, slots, c->d_qmap.p, (int)redo.size()); if (rc) return rc;
+        if (kmode)
+        {
+            rc = ensure_kpop(c, c->kp_retry, want, max_exp, 0.85); if (rc) return rc;
+            int slots = std::max(std::min(c->kp_retry.alloc_slots, want), 1);
+            rc = launch_kpop(c, c->kp_retry, slots, c->d_qmap.p, (int)redo.size()); if (rc) return rc;
+        }
+        else
+        {
+            rc = ensure_work(c, c->wp_retry, want, max_exp, max_open, max_open2d, 0.85); if (rc) return rc;
+            int slots = std::max(std::min(c->wp_retry.alloc_slots, want), 1);
+            rc = launch_search(c, c->wp_retry, slots, c->d_qmap.p, (int)redo.size()); if (rc) return rc;
+        }
         PP_CUDA(cudaStreamSynchronize(c->stream));
     }
     PP_CUDA(cudaEventRecord(c->ev1, c->stream));
@@ -807,6 +914,7 @@ int pp_override_dubins(pp_context* c, float r_min, float step_size)
 int pp_clear_obstacles(pp_context* c, int g)
 {
     int rc = check_group(c, g); if (rc) return rc;
+    map_changed(c, g);
     PP_CUDA(cudaSetDevice(c->device));
     PP_CUDA(cudaMemsetAsync(c->d_maps + nn_of(c) * g, 0, sizeof(float) * nn_of(c), c->stream));
     return PP_SUCCESS;

@@ -1,0 +1,567 @@
+// K-POP search mode: up to k <= 32 nodes popped and expanded per iteration by one warp, on a warp-parallel
+// priority queue, with the exact 2D distance field as the holonomic heuristic.
+//
+// This is NEW semantics (north_star: "optionally k pops per iteration within one query"; SURVEY.md §7 mode
+// definitions): the reference's equal-f drops (F5) and its order-dependent lazy 2D A* (F4) are replaced by clean rules
+// that parallelise, so results differ from the reference (typically a few % lower cost with 4-7x fewer expansions).
+// The rules are stated in oracle/port/kpop.inc (CPU restatement); this file must reproduce that restatement bit
+// for bit -- pop sequence, cost, path.  Summary:
+//   open list = total order (f, key, idx), lazy deletion, best-g-wins per key; an iteration takes the min(k, |open|)
+//   smallest entries, the valid ones are the pops (rank order), all closed at once; goal / Dubins shot decided in rank
+//   order; every pop expands every steering primitive of its window -> candidates c = rank*(2A+1) + a; per key the
+//   smallest pack(g, order = iteration*1024 + c) wins, also against the key's recorded best; winners get node indices in
+//   c order and f = g + max(h1[cell], Dubins).
+//
+// Data structures (per query slot, global memory), all driven by the 32 lanes together:
+//   nodes[]   append-only log of generated nodes (parent links are log indices)
+//   table[]   open-addressing hash (key -> best pack, best node, closed bit); candidates race with atomicMin(pack):
+//             the winner is the minimum, independent of thread order => deterministic
+//   LSM queue sorted runs in levels of capacity 256 << level (log-structured merge): a batch of new entries is
+//             bitonic-sorted in shared memory and merged down the levels with warp merge-path merges; the k smallest are
+//             found by ranking the first k entries of every run against each other (binary searches in shared memory)
+#ifndef PP_KPOP_H
+#define PP_KPOP_H
+
+#include "pp_search.h"
+
+#define PP_K_MAXPOP 32
+#define PP_K_MAXSUCC 8                                  // (2A+1) supported by this mode
+#define PP_K_MAXCAND (PP_K_MAXPOP * PP_K_MAXSUCC)        // 256
+#define PP_K_LEVELS 14                                   // LSM levels: capacity 256 << level
+#define PP_K_RUN0 256
+#define PP_K_NONE 0x7fffffffu
+#define PP_K_CLOSED 0x80000000u
+#define PP_K_EMPTY 0xffffffffu
+
+struct PPKEntry { float f; unsigned key; unsigned idx; unsigned pad; };               // 16 B queue entry
+struct PPKNode { float x, y, heading, g, v2, f; int curv, bin, cell, parent; unsigned key; int pad; };   // 48 B
+struct PPKSlot { unsigned key; unsigned node; unsigned long long pack; };             // 16 B hash slot
+struct PPKCand { float x, y, heading, g, v2; int curv_bin_ok; int cell; int slot; unsigned long long pack; };   // 40 B
+
+struct PPKWork
+{
+    PPKNode*  nodes;   int nodes_cap;
+    PPKSlot*  table;   int table_cap;          // power of two
+    PPKEntry* arena;                           // level l at offset PP_K_RUN0 * ((1 << l) - 1), PP_K_LEVELS levels used up to lsm_levels
+    PPKEntry* tmp_a;   PPKEntry* tmp_b;        // merge scratch, each nodes_cap + PP_K_RUN0 entries
+    int       lsm_levels;
+    const float* h1;                           // N*N exact 2D distance field of the query's group
+    PPPathPt* path;    int path_cap;
+    PPPop*    trace;   int trace_cap;
+};
+
+struct PPKSmem
+{
+    union
+    {
+        PPKCand  cand[PP_K_MAXCAND];                       // expansion
+        PPKEntry sel[PP_K_LEVELS * PP_K_MAXPOP];           // pop selection: first k entries of every run
+        PPKEntry batch[PP_K_MAXCAND];                      // new queue entries of this iteration
+    } u;
+    PPKEntry popped[PP_K_MAXPOP];
+    PPKNode  parents[PP_K_MAXPOP];                         // copies of this iteration's pops, by rank
+    int      pop_idx[PP_K_MAXPOP];                         // their node indices
+    int      head[PP_K_LEVELS], size[PP_K_LEVELS];         // live range [head, size) of every level's run
+    int      taken[PP_K_LEVELS];
+};
+
+PP_HD bool pp_kless(const PPKEntry& a, const PPKEntry& b)
+{
+    if (a.f != b.f) return a.f < b.f;
+    if (a.key != b.key) return a.key < b.key;
+    return a.idx < b.idx;
+}
+PP_HD unsigned pp_fbits(float v)
+{
+    union { float f; unsigned u; } c; c.f = v; return c.u;
+}
+PP_HD PPKEntry pp_kinf()
+{
+    PPKEntry e; e.f = INFINITY; e.key = 0xffffffffu; e.idx = 0xffffffffu; e.pad = 0; return e;
+}
+
+// ---- atomics (device) / plain (single host lane) ----------------------------------------------------------------
+PP_HD unsigned pp_atomic_cas_u32(unsigned* p, unsigned expect, unsigned val)
+{
+#ifdef __CUDA_ARCH__
+    return atomicCAS(p, expect, val);
+#else
+    unsigned old = *p; if (old == expect) *p = val; return old;
+#endif
+}
+PP_HD void pp_atomic_min_u64(unsigned long long* p, unsigned long long val)
+{
+#ifdef __CUDA_ARCH__
+    atomicMin(p, val);
+#else
+    if (val < *p) *p = val;
+#endif
+}
+PP_HD void pp_fence()
+{
+#ifdef __CUDA_ARCH__
+    __threadfence_block();
+#endif
+}
+
+// ---- hash table -----------------------------------------------------------------------------------------------------
+PP_HD int pp_ktable_find(const PPKWork& wk, unsigned key)
+{
+    unsigned mask = (unsigned)wk.table_cap - 1u, h = pp_hash_key(key) & mask;
+    for (;;)
+    {
+        unsigned k = wk.table[h].key;
+        if (k == key) return (int)h;
+        if (k == PP_K_EMPTY) return -1;
+        h = (h + 1) & mask;
+    }
+}
+PP_HD int pp_ktable_find_or_insert(PPKWork& wk, unsigned key)
+{
+    unsigned mask = (unsigned)wk.table_cap - 1u, h = pp_hash_key(key) & mask;
+    for (;;)
+    {
+        unsigned k = wk.table[h].key;
+        if (k == key) return (int)h;
+        if (k == PP_K_EMPTY)
+        {
+            unsigned old = pp_atomic_cas_u32(&wk.table[h].key, PP_K_EMPTY, key);
+            if (old == PP_K_EMPTY || old == key) return (int)h;
+        }
+        h = (h + 1) & mask;
+    }
+}
+
+// ---- warp sort of n (power of two, <= PP_K_MAXCAND) entries in shared memory ------------------------------------------
+template <class W>
+PP_HD void pp_kbitonic(const W& w, PPKEntry* s, int n)
+{
+    for (int k = 2; k <= n; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1)
+        {
+            for (int t = w.lane(); t < n; t += W::LANES)
+            {
+                int x = t ^ j;
+                if (x > t)
+                {
+                    bool asc = ((t & k) == 0);
+                    PPKEntry a = s[t], b = s[x];
+                    if (pp_kless(b, a) == asc) { s[t] = b; s[x] = a; }
+                }
+            }
+            w.sync();
+        }
+}
+
+// ---- warp merge of two sorted runs (merge path): dst[0 .. na+nb) ------------------------------------------------------
+template <class W>
+PP_HD void pp_kmerge(const W& w, const PPKEntry* A, int na, const PPKEntry* B, int nb, PPKEntry* dst)
+{
+    const int total = na + nb;
+    const int seg = (total + W::LANES - 1) / W::LANES;
+    int d0 = w.lane() * seg; if (d0 > total) d0 = total;
+    int d1 = d0 + seg; if (d1 > total) d1 = total;
+    // number of A elements among the first d0 outputs
+    int lo = d0 - nb; if (lo < 0) lo = 0;
+    int hi = d0 < na ? d0 : na;
+    while (lo < hi)
+    {
+        int mid = (lo + hi) >> 1;
+        if (pp_kless(B[d0 - 1 - mid], A[mid])) hi = mid; else lo = mid + 1;
+    }
+    int i = lo, j = d0 - lo;
+    for (int o = d0; o < d1; o++)
+    {
+        bool take_a = (j >= nb) || (i < na && !pp_kless(B[j], A[i]));
+        dst[o] = take_a ? A[i] : B[j];
+        if (take_a) i++; else j++;
+    }
+    w.sync();
+}
+
+template <class W>
+PP_HD void pp_kcopy(const W& w, const PPKEntry* src, PPKEntry* dst, int n)
+{
+    for (int t = w.lane(); t < n; t += W::LANES) dst[t] = src[t];
+    w.sync();
+}
+
+PP_HD PPKEntry* pp_klevel(const PPKWork& wk, int l) { return wk.arena + (size_t)PP_K_RUN0 * (((size_t)1 << l) - 1); }
+
+// insert a sorted batch (shared memory, m <= PP_K_MAXCAND entries); false = queue capacity exhausted
+template <class W>
+PP_HD bool pp_klsm_insert(const W& w, PPKWork& wk, PPKSmem& sm, const PPKEntry* batch, int m)
+{
+    const PPKEntry* carry = batch;
+    int carry_n = m;
+    PPKEntry* t0 = wk.tmp_a; PPKEntry* t1 = wk.tmp_b;
+    for (int l = 0; l < wk.lsm_levels; l++)
+    {
+        int cnt = sm.size[l] - sm.head[l];
+        PPKEntry* L = pp_klevel(wk, l);
+        if (cnt == 0)
+        {
+            pp_kcopy(w, carry, L, carry_n);
+            if (w.lane() == 0) { sm.head[l] = 0; sm.size[l] = carry_n; }
+            w.sync();
+            return true;
+        }
+        pp_kmerge(w, L + sm.head[l], cnt, carry, carry_n, t0);
+        if (w.lane() == 0) { sm.head[l] = 0; sm.size[l] = 0; }
+        w.sync();
+        carry = t0; carry_n += cnt;
+        PPKEntry* t = t0; t0 = t1; t1 = t;
+    }
+    return false;
+}
+
+// the min(k, total) smallest entries -> sm.popped[0 .. n) in ascending order; returns n
+template <class W>
+PP_HD int pp_klsm_pop(const W& w, PPKWork& wk, PPKSmem& sm, int k)
+{
+    const int lane = w.lane();
+    const int nl = wk.lsm_levels;
+    // stage the first k entries of every run (padded with +inf)
+    for (int t = lane; t < nl * PP_K_MAXPOP; t += W::LANES)
+    {
+        int l = t / PP_K_MAXPOP, p = t - l * PP_K_MAXPOP;
+        int at = sm.head[l] + p;
+        sm.u.sel[t] = (p < k && at < sm.size[l]) ? pp_klevel(wk, l)[at] : pp_kinf();
+    }
+    for (int t = lane; t < PP_K_LEVELS; t += W::LANES) sm.taken[t] = 0;
+    for (int t = lane; t < PP_K_MAXPOP; t += W::LANES) sm.popped[t] = pp_kinf();
+    w.sync();
+    // rank every staged entry among all staged entries; ranks < k are the result.  The entries taken from a run form
+    // a prefix of it, so counting them per run gives the new heads.
+    for (int t = lane; t < nl * PP_K_MAXPOP; t += W::LANES)
+    {
+        const PPKEntry e = sm.u.sel[t];
+        if (e.idx == 0xffffffffu) continue;
+        int l = t / PP_K_MAXPOP, p = t - l * PP_K_MAXPOP;
+        int rank = p;
+        for (int l2 = 0; l2 < nl && rank < k; l2++)
+        {
+            if (l2 == l) continue;
+            const PPKEntry* r = sm.u.sel + l2 * PP_K_MAXPOP;
+            int lo = 0, hi = PP_K_MAXPOP;                       // first position whose entry is not less than e
+            while (lo < hi) { int mid = (lo + hi) >> 1; if (pp_kless(r[mid], e)) lo = mid + 1; else hi = mid; }
+            rank += lo;
+        }
+        if (rank < k)
+        {
+            sm.popped[rank] = e;
+#ifdef __CUDA_ARCH__
+            atomicAdd(&sm.taken[l], 1);
+#else
+            sm.taken[l]++;
+#endif
+        }
+    }
+    w.sync();
+    int n = 0;
+    for (int t = 0; t < k; t++) if (sm.popped[t].idx != 0xffffffffu) n++;
+    for (int t = lane; t < nl; t += W::LANES) sm.head[t] += sm.taken[t];
+    w.sync();
+    return n;
+}
+
+// Dubins length with the sequential candidate fold (Dubins.cpp:19-69), pinned libm; goal circle centres precomputed
+PP_HD float pp_kdubins(const PPConsts& C, const PPFrame& F, const PPDubinsGoal& gc, float x, float y, float h)
+{
+    const float r = C.r_min;
+    float sn = pp_sinf(h), cs = pp_cosf(h);
+    float srx = x + r * sn, sry = y - r * cs, slx = x - r * sn, sly = y + r * cs;
+    float best = 0.0f;
+    for (int type = 0; type < 4; type++)
+    {
+        bool s_right = (type == PP_RSR) || (type == PP_RSL), g_right = (type == PP_RSR) || (type == PP_LSR);
+        float p[4];
+        float len = pp_dubins_candidate(type, r, h, F.goal_h, s_right ? srx : slx, s_right ? sry : sly,
+                                        g_right ? gc.grx : gc.glx, g_right ? gc.gry : gc.gly, p);
+        if (type == 0 || len < best) best = len;
+    }
+    return best;
+}
+
+// The Dubins shot (HybridAStar.cpp:129-149): all lanes; returns true when accepted; samples in path[0 .. n_dubins)
+template <class W>
+PP_HD bool pp_try_shot(const W& w, const PPConsts& C, const float* map, const PPFrame& F, float x, float y, float h,
+                       PPPathPt* path, int path_cap, float& len_out, int& n_dubins, int& overflow)
+{
+    int type; float p[4]; PPDubinsCenters cen; PPDubinsPlan pl;
+    float len = pp_dubins_shortest(C.r_min, x, y, h, F.goal_x, F.goal_y, F.goal_h, type, p, cen);
+    if (fabsf(p[1]) > (float)PP_PI_2) return false;                       // Dubins.cpp:152
+    pp_dubins_plan(C.r_min, C.step, C.ang_step, type, p, cen, pl);
+    const int total = pl.size_3 + 1;
+    bool blocked = false, over = false;
+    float acc = p[0];
+    for (int k = 0; k < total; k++)
+    {
+        if (k == pl.size_1) acc = 0.0f;
+        if (k == pl.size_2) acc = p[2];
+        if ((k % W::LANES) == w.lane())
+        {
+            float sx, sy, sh, kappa;
+            pp_dubins_sample(pl, C.r_min, k, acc, sx, sy, sh, kappa);
+            if (pp_path_point_blocked(C, map, sx, sy)) blocked = true;
+            if (k < path_cap) { PPPathPt& q = path[k]; q.x = sx; q.y = sy; q.heading = sh; q.curvature = kappa; }
+            else over = true;
+        }
+        if (k < pl.size_1) acc = (pl.s1 < 0) ? acc - C.ang_step : acc + C.ang_step;
+        else if (k < pl.size_2) acc = acc + C.step;
+        else if (k < pl.size_3) acc = (pl.s2 < 0) ? acc - C.ang_step : acc + C.ang_step;
+    }
+    if (w.ballot(blocked) != 0u) return false;
+    overflow = (w.ballot(over) != 0u) ? 1 : 0;
+    len_out = len; n_dubins = total;
+    return true;
+}
+
+// ---- the search ---------------------------------------------------------------------------------------------------------
+template <class W>
+PP_HD_NOINLINE void pp_search_kpop(const W& w, const PPConsts& C, const float* off_xy, const PPGroup& G, const PPState& start,
+                                   int kpop, PPKWork& wk, PPKSmem& sm, PPResult& res)
+{
+    const int lane = w.lane();
+    const int N = C.N;
+    const PPFrame& F = G.frame;
+    const unsigned kb = (unsigned)(C.bins + 1);
+    const int n_succ = 2 * C.A + 1;
+    const unsigned goal_cell = (unsigned)(F.goal_ci * N + F.goal_cj);
+
+    // ---- init ----
+    for (int t = lane; t < wk.table_cap; t += W::LANES)
+    {
+        PPKSlot e; e.key = PP_K_EMPTY; e.node = PP_K_NONE; e.pack = ~0ull; wk.table[t] = e;
+    }
+    for (int t = lane; t < PP_K_LEVELS; t += W::LANES) { sm.head[t] = 0; sm.size[t] = 0; sm.taken[t] = 0; }
+    w.sync();
+    PPDubinsGoal gc;
+    {
+        float sg = pp_sinf(F.goal_h), cg = pp_cosf(F.goal_h);
+        gc.grx = F.goal_x + C.r_min * sg; gc.gry = F.goal_y - C.r_min * cg;
+        gc.glx = F.goal_x - C.r_min * sg; gc.gly = F.goal_y + C.r_min * cg;
+    }
+    int n_nodes = 1;
+    if (lane == 0)
+    {
+        PPKNode n0;
+        n0.x = start.x; n0.y = start.y; n0.heading = start.heading; n0.g = 0.0f; n0.v2 = start.vmin_sqr; n0.f = start.f;
+        n0.curv = start.curv; n0.bin = start.bin; n0.cell = start.ci * N + start.cj; n0.parent = -1;
+        n0.key = (unsigned)n0.cell * kb + (unsigned)start.bin; n0.pad = 0;
+        wk.nodes[0] = n0;
+        int slot = pp_ktable_find_or_insert(wk, n0.key);
+        wk.table[slot].node = 0u;
+        wk.table[slot].pack = ((unsigned long long)pp_fbits(0.0f) << 32);
+        PPKEntry e; e.f = n0.f; e.key = n0.key; e.idx = 0u; e.pad = 0;
+        pp_klevel(wk, 0)[0] = e;
+        sm.head[0] = 0; sm.size[0] = 1;
+    }
+    w.sync();
+
+    int counter = 0, interval = C.shot_interval;
+    int n_pops = 0, n_oob = 0, status = 0, success = 0, n_chain = 0, n_dubins = 0, terminal = -1;
+    float cost = FLT_MAX;
+
+    for (unsigned it = 1;; it++)
+    {
+        // ---- pop the k smallest entries ----
+        const int nb = pp_klsm_pop(w, wk, sm, kpop);
+        if (nb == 0) break;                                                     // open list exhausted: failure
+        // validity (lazy deletion), ranks, closing, goal / shot candidates -- in rank (= queue) order
+        int n_valid = 0, r_g = -1, r_s = -1;
+        for (int base = 0; base < nb; base += W::LANES)
+        {
+            const int b = base + lane;
+            bool valid = false, is_goal = false, slow = false, oob = false;
+            PPKEntry me = pp_kinf();
+            int slot = -1;
+            if (b < nb)
+            {
+                me = sm.popped[b];
+                slot = pp_ktable_find(wk, me.key);
+                valid = (slot >= 0) && (wk.table[slot].node == me.idx);          // closed or superseded => mismatch
+            }
+            const unsigned vm = w.ballot(valid);
+            int rank = n_valid;
+            { unsigned below = vm & w.lanemask_lt(); while (below) { rank++; below &= below - 1; } }
+            if (valid)
+            {
+                wk.table[slot].node = me.idx | PP_K_CLOSED;
+                const PPKNode nd = wk.nodes[me.idx];
+                sm.parents[rank] = nd;
+                sm.pop_idx[rank] = (int)me.idx;
+                is_goal = ((unsigned)nd.cell == goal_cell);
+                slow = (nd.v2 < 1.0f);
+                oob = (nd.bin >= C.bins);
+                if (wk.trace && (n_pops + rank) < wk.trace_cap)
+                {
+                    PPPop& t = wk.trace[n_pops + rank];
+                    t.ci = nd.cell / N; t.cj = nd.cell % N; t.bin = nd.bin; t.x = nd.x; t.y = nd.y; t.heading = nd.heading; t.g = nd.g; t.f = nd.f;
+                }
+            }
+            const unsigned gm = w.ballot(is_goal), sl = w.ballot(slow), om = w.ballot(oob);
+            if (r_g < 0 && gm)                                                   // first goal pop
+            {
+                int src = 0; { unsigned t = gm; while (!(t & 1u)) { t >>= 1; src++; } }
+                r_g = n_valid; { unsigned bl = vm & ((src == 0) ? 0u : (0xffffffffu >> (32 - src))); while (bl) { r_g++; bl &= bl - 1; } }
+            }
+            if (r_s < 0)                                                         // shot counter over the slow pops
+            {
+                int ns = 0; { unsigned t = sl; while (t) { ns++; t &= t - 1; } }
+                const int need = interval - counter;
+                if (need >= 1 && need <= ns)
+                {
+                    unsigned t = sl; int src = 0;
+                    for (int q = 1; q < need; q++) t &= t - 1;                   // drop the first need-1 slow pops
+                    while (!(t & 1u)) { t >>= 1; src++; }
+                    r_s = n_valid; { unsigned bl = vm & ((src == 0) ? 0u : (0xffffffffu >> (32 - src))); while (bl) { r_s++; bl &= bl - 1; } }
+                    counter = interval;
+                }
+                else counter += ns;
+            }
+            { unsigned t = om; while (t) { n_oob++; t &= t - 1; } }
+            { unsigned t = vm; while (t) { n_valid++; t &= t - 1; } }
+            w.sync();
+        }
+        if (n_valid == 0) continue;
+        n_pops += n_valid;
+
+        // ---- goal / shot, rank ordered ----
+        if (r_g >= 0 && (r_s < 0 || r_g < r_s)) { success = 1; terminal = sm.pop_idx[r_g]; cost = sm.parents[r_g].g; break; }
+        if (r_s >= 0)
+        {
+            const PPKNode nd = sm.parents[r_s];
+            float len = 0.0f; int ovf = 0;
+            if (pp_try_shot(w, C, G.map, F, nd.x, nd.y, nd.heading, wk.path, wk.path_cap, len, n_dubins, ovf))
+            {
+                if (ovf) status |= PP_STATUS_PATH_OVERFLOW;
+                success = 1; cost = nd.g + len; terminal = nd.parent;
+                if (terminal < 0) status |= PP_STATUS_NULL_TERMINAL;
+                break;
+            }
+            n_dubins = 0;
+            counter = 0;
+            int ni = interval - C.shot_decay;
+            interval = (ni < 50) ? 50 : ni;
+            if (r_g >= 0) { success = 1; terminal = sm.pop_idx[r_g]; cost = sm.parents[r_g].g; break; }
+        }
+        if (n_nodes + n_valid * n_succ > wk.nodes_cap) { status |= PP_STATUS_CLOSED_OVERFLOW; break; }
+
+        // ---- expansion: candidate c = rank * n_succ + a ----
+        const int n_cand = n_valid * n_succ;
+        for (int c = lane; c < n_cand; c += W::LANES)
+        {
+            const int r = c / n_succ, a = c - r * n_succ;
+            const PPKNode& pn = sm.parents[r];
+            PPKCand cd; cd.curv_bin_ok = 0; cd.slot = -1; cd.pack = ~0ull; cd.cell = 0;
+            cd.x = cd.y = cd.heading = cd.g = cd.v2 = 0.0f;
+            int start_index = pn.curv - C.A; if (start_index < 0) start_index = 0;
+            const int i = start_index + a;
+            PPSucc o; o.ok = 0;
+            const int pbin = (pn.bin > C.bins) ? C.bins : pn.bin;
+            if (i < C.S && pp_rollout_one(C, off_xy, pn.x, pn.y, pn.heading, pn.g, pn.v2, pbin, i, o) &&
+                pp_collision_free(C, G.map, o.x, o.y, o.ci, o.cj))
+            {
+                // APF: std::accumulate over the obstacles in order (Grid3D.cpp:226)
+                float field = 0.0f;
+                for (int q = 0; q < G.K; q++)
+                {
+                    float ox = G.apf[3 * q], oy = G.apf[3 * q + 1], rad = G.apf[3 * q + 2];
+                    float dx = ox - o.x, dy = oy - o.y, lim = rad * 1.001f + 1e-3f;
+                    if (dx * dx + dy * dy <= lim * lim)
+                    {
+                        float term = pp_apf_term(C, ox, oy, rad, o.x, o.y, o.heading);
+                        if (term != 0.0f) field = field + term;
+                    }
+                }
+                const float g = o.g + field;
+                const int cell = o.ci * N + o.cj;
+                const unsigned key = (unsigned)cell * kb + (unsigned)o.bin;
+                const int sl2 = pp_ktable_find_or_insert(wk, key);
+                if (!(wk.table[sl2].node & PP_K_CLOSED))
+                {
+                    cd.x = o.x; cd.y = o.y; cd.heading = o.heading; cd.g = g; cd.v2 = o.vmin_sqr;
+                    cd.curv_bin_ok = (o.curv & 0xff) | ((o.bin & 0xff) << 8) | (1 << 16);
+                    cd.cell = cell; cd.slot = sl2;
+                    cd.pack = ((unsigned long long)pp_fbits(g) << 32) | (unsigned long long)(it * 1024u + (unsigned)c);
+                    pp_atomic_min_u64(&wk.table[sl2].pack, cd.pack);
+                }
+            }
+            sm.u.cand[c] = cd;
+        }
+        pp_fence();
+        w.sync();
+
+        // ---- winners in c order -> nodes, queue entries ----
+        int n_new = 0;
+        for (int base = 0; base < n_cand; base += W::LANES)
+        {
+            const int c = base + lane;
+            bool win = false;
+            PPKCand cd;
+            if (c < n_cand)
+            {
+                cd = sm.u.cand[c];
+                win = ((cd.curv_bin_ok >> 16) & 1) && (wk.table[cd.slot].pack == cd.pack);
+            }
+            unsigned wm = w.ballot(win);
+            int pos = n_new;
+            { unsigned below = wm & w.lanemask_lt(); while (below) { pos++; below &= below - 1; } }
+            PPKEntry e = pp_kinf();
+            if (win)
+            {
+                const int r = c / n_succ;
+                const int idx = n_nodes + pos;
+                const float h2 = pp_kdubins(C, F, gc, cd.x, cd.y, cd.heading);
+                const float h1 = wk.h1[cd.cell];
+                PPKNode nd;
+                nd.x = cd.x; nd.y = cd.y; nd.heading = cd.heading; nd.g = cd.g; nd.v2 = cd.v2;
+                nd.f = cd.g + ((h1 < h2) ? h2 : h1);
+                nd.curv = cd.curv_bin_ok & 0xff; nd.bin = (cd.curv_bin_ok >> 8) & 0xff; nd.cell = cd.cell;
+                nd.parent = sm.pop_idx[r];
+                nd.key = (unsigned)cd.cell * kb + (unsigned)nd.bin; nd.pad = 0;
+                wk.nodes[idx] = nd;
+                wk.table[cd.slot].node = (unsigned)idx;
+                e.f = nd.f; e.key = nd.key; e.idx = (unsigned)idx; e.pad = 0;
+            }
+            w.sync();
+            // the candidate staging area is reused for the batch: safe, candidate `c` is consumed before batch[pos <= c] is written
+            if (win) sm.u.batch[pos] = e;
+            { unsigned t = wm; while (t) { n_new++; t &= t - 1; } }
+            w.sync();
+        }
+        n_nodes += n_new;
+        if (n_new > 0)
+        {
+            int n_pad = 1; while (n_pad < n_new) n_pad <<= 1;
+            for (int t = n_new + lane; t < n_pad; t += W::LANES) sm.u.batch[t] = pp_kinf();
+            w.sync();
+            pp_kbitonic(w, sm.u.batch, n_pad);
+            if (!pp_klsm_insert(w, wk, sm, sm.u.batch, n_new)) { status |= PP_STATUS_OPEN_OVERFLOW; break; }
+        }
+    }
+
+    // ---- path: [dubins samples (already in wk.path[0 .. n_dubins)) | parent chain terminal -> start] ----
+    if (lane == 0)
+    {
+        if (success)
+            for (int c = terminal; c >= 0; c = wk.nodes[c].parent)
+            {
+                int at = n_dubins + n_chain;
+                if (at < wk.path_cap)
+                {
+                    PPPathPt& q = wk.path[at];
+                    q.x = wk.nodes[c].x; q.y = wk.nodes[c].y; q.heading = wk.nodes[c].heading;
+                    q.curvature = C.abs_curv[wk.nodes[c].curv];
+                }
+                else status |= PP_STATUS_PATH_OVERFLOW;
+                n_chain++;
+            }
+        res.success = success; res.status = status; res.cost = cost; res.n_pops = n_pops; res.n_pops_bin_oob = n_oob;
+        res.n_chain = n_chain; res.n_dubins = n_dubins; res.n_lazy_searches = 0; res.n_lazy_pops = 0; res.max_open = 0;
+        res.n_closed = n_nodes; res.pad = 0;
+    }
+}
+
+#endif

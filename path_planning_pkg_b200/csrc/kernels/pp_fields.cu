@@ -33,15 +33,12 @@ __device__ __forceinline__ double f2d_value(unsigned ab, double c1, double c2)
 __global__ void pp_field2d_init_kernel(unsigned* __restrict__ field, unsigned char* __restrict__ tile_active, int N, int T,
                                        int goal_i, int goal_j)
 {
+    // the goal cell is the source even when it is marked occupied (the reference never tests the start cell of a search)
     size_t n = (size_t)N * N, stride = (size_t)gridDim.x * blockDim.x;
-    for (size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x; c < n; c += stride) field[c] = F2D_UNREACHED;
-    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < (size_t)2 * T * T; t += stride) tile_active[t] = 0;
-    if (blockIdx.x == 0 && threadIdx.x == 0)
-    {
-        // the goal cell is the source even when it is marked occupied (the reference never tests the start cell of a search)
-        field[(size_t)goal_i * N + goal_j] = 0u;
-        tile_active[(goal_i / F2D_TILE) * T + goal_j / F2D_TILE] = 1;
-    }
+    const size_t goal = (size_t)goal_i * N + goal_j, goal_tile = (size_t)(goal_i / F2D_TILE) * T + goal_j / F2D_TILE;
+    for (size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x; c < n; c += stride) field[c] = (c == goal) ? 0u : F2D_UNREACHED;
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < (size_t)2 * T * T; t += stride)
+        tile_active[t] = (t == goal_tile) ? 1 : 0;
 }
 
 // One global sweep.  active_in / active_out: per-tile flags of the previous / next sweep.

@@ -21,6 +21,7 @@
 __device__ unsigned long long pp_prof_acc[8];
 #endif
 #include "../core/pp_search.h"
+#include "../core/pp_kpop.h"
 #include "../core/pp_map.h"
 
 #define PP_SEARCH_WARPS 4
@@ -137,6 +138,64 @@ pp_search_kernel(const __grid_constant__ PPBatchArgs a)
         const PPGroup G = a.groups[Q.group];
         PPResult res;
         pp_search_exact(w, a.C, a.off_xy, G, Q.start, wk, sm[warp], res);
+        if (w.lane() == 0) a.results[q] = res;
+        __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K-POP mode: one warp (= one CTA of 32 threads) per query at a time; see csrc/core/pp_kpop.h
+struct PPKpopArgs
+{
+    PPConsts        C;
+    const float*    off_xy;
+    const PPGroup*  groups;
+    const float*    field2d;    // num_groups x N*N exact 2D distance fields
+    const PPQuery*  queries;
+    const int*      qmap;
+    int             n_queries;
+    int             n_slots;
+    int             kpop;
+    int*            counter;
+    PPResult*       results;
+    PPPathPt*       paths;      int path_cap;
+    PPPop*          trace;      int trace_cap;
+    // per-slot pools
+    PPKNode*        nodes;      int nodes_cap;
+    PPKSlot*        table;      int table_cap;
+    PPKEntry*       arena;      size_t arena_cap;
+    PPKEntry*       tmp_a;      PPKEntry* tmp_b;   size_t tmp_cap;
+    int             lsm_levels;
+};
+
+__global__ void __launch_bounds__(32) pp_kpop_kernel(const __grid_constant__ PPKpopArgs a)
+{
+    __shared__ PPKSmem sm;
+    const int slot = blockIdx.x;
+    if (slot >= a.n_slots) return;
+    PPWarpDev w;
+    PPKWork wk;
+    wk.nodes = a.nodes + (size_t)slot * a.nodes_cap;   wk.nodes_cap = a.nodes_cap;
+    wk.table = a.table + (size_t)slot * a.table_cap;   wk.table_cap = a.table_cap;
+    wk.arena = a.arena + (size_t)slot * a.arena_cap;
+    wk.tmp_a = a.tmp_a + (size_t)slot * a.tmp_cap;     wk.tmp_b = a.tmp_b + (size_t)slot * a.tmp_cap;
+    wk.lsm_levels = a.lsm_levels;
+    const size_t nn = (size_t)a.C.N * a.C.N;
+    for (;;)
+    {
+        int q = 0;
+        if (w.lane() == 0) q = atomicAdd(a.counter, 1);
+        q = w.shfl(q, 0);
+        if (q >= a.n_queries) break;
+        if (a.qmap) q = a.qmap[q];
+        const PPQuery Q = a.queries[q];
+        const PPGroup G = a.groups[Q.group];
+        wk.h1 = a.field2d + nn * Q.group;
+        wk.path = a.paths + (size_t)q * a.path_cap; wk.path_cap = a.path_cap;
+        wk.trace = a.trace ? a.trace + (size_t)q * a.trace_cap : nullptr;
+        wk.trace_cap = a.trace ? a.trace_cap : 0;
+        PPResult res;
+        pp_search_kpop(w, a.C, a.off_xy, G, Q.start, a.kpop, wk, sm, res);
         if (w.lane() == 0) a.results[q] = res;
         __syncwarp();
     }

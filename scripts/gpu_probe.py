@@ -28,13 +28,15 @@ def main():
     ap.add_argument("--reps", type=int, default=1)
     ap.add_argument("--max-expansions", type=int, default=1 << 17)
     ap.add_argument("--max-open", type=int, default=1 << 16)
+    ap.add_argument("--mode", type=int, default=0)
+    ap.add_argument("--k", type=int, default=32)
     a = ap.parse_args()
     P = pp.make_params(grid_size=512, resolution=0.2)
     ctx = pp.Context(P, num_groups=a.groups)
     groups = bench.build_workload(a.groups, a.starts, 0)
     queries, qgroups, maps = bench.apply_groups(ctx, groups)
     q = ctx.make_queries(queries, qgroups)
-    opts = ctx.make_opts(max_expansions=a.max_expansions, max_open=a.max_open, max_slots=a.slots)
+    opts = ctx.make_opts(max_expansions=a.max_expansions, max_open=a.max_open, max_slots=a.slots, mode=a.mode, kpop=a.k)
     ctx.batch_upload(q, opts)
     prof = hasattr(ctx.lib, "pp_profile_read")
     buf = (C.c_ulonglong * 8)()

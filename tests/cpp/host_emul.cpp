@@ -11,6 +11,7 @@
 #include <memory>
 
 #include "../../path_planning_pkg_b200/csrc/core/pp_search.h"
+#include "../../path_planning_pkg_b200/csrc/core/pp_kpop.h"
 #include "../../path_planning_pkg_b200/csrc/core/pp_map.h"
 #include "../../path_planning_pkg_b200/csrc/host/pp_host.h"
 #include "../../oracle/oracle_api.h"
@@ -359,6 +360,49 @@ void emu_find_path(void* h, float vel, const float* s, orc_result* res, float* p
             pp_host_to_world(e->fr, seq[k].x, seq[k].y, seq[k].heading, wx, wy, wh);
             path_xyh[3 * k] = wx; path_xyh[3 * k + 1] = wy; path_xyh[3 * k + 2] = wh;
             curv[k] = (k == 0) ? 0.0f : seq[k - 1].curvature;   // curvature shifted by one (HybridAStar.cpp:212, :261)
+        }
+    }
+    res->n_path = n;
+}
+
+// K-POP mode on one host lane (same signature as port_find_path_kpop); h1_field = 2D distance field, N*N floats
+void emu_find_path_kpop(void* h, float vel, const float* s, int k, const float* h1_field, int max_nodes, orc_result* res,
+                        float* path_xyh, float* curv, int path_cap, orc_pop* pops, int pop_cap)
+{
+    Emu* e = static_cast<Emu*>(h);
+    const PPConsts& C = e->m.C;
+    PPKWork wk;
+    std::vector<PPKNode> nodes(max_nodes);
+    int tc = 1; while (tc < 2 * max_nodes) tc <<= 1;
+    std::vector<PPKSlot> table(tc);
+    int levels = 1; while ((PP_K_RUN0 * ((1 << levels) - 1)) < max_nodes + PP_K_RUN0 && levels < PP_K_LEVELS) levels++;
+    std::vector<PPKEntry> arena((size_t)PP_K_RUN0 * ((1 << levels) - 1)), ta(max_nodes + 2 * PP_K_RUN0), tb(max_nodes + 2 * PP_K_RUN0);
+    std::vector<PPPathPt> path(4096);
+    wk.nodes = nodes.data(); wk.nodes_cap = max_nodes; wk.table = table.data(); wk.table_cap = tc;
+    wk.arena = arena.data(); wk.tmp_a = ta.data(); wk.tmp_b = tb.data(); wk.lsm_levels = levels; wk.h1 = h1_field;
+    wk.path = path.data(); wk.path_cap = (int)path.size();
+    wk.trace = reinterpret_cast<PPPop*>(pops); wk.trace_cap = pops ? pop_cap : 0;
+    PPState st = pp_host_set_start(C, e->fr, s[0], s[1], s[2], vel);
+    PPGroup G = group_of(e);
+    std::unique_ptr<PPKSmem> sm(new PPKSmem());
+    PPResult r;
+    PPWarpSerial w;
+    pp_search_kpop(w, C, e->m.off_xy.data(), G, st, k, wk, *sm, r);
+    res->success = r.success; res->cost = r.cost; res->n_pops = r.n_pops; res->n_pops_bin_oob = r.n_pops_bin_oob;
+    if (r.status) std::fprintf(stderr, "emu_find_path_kpop: status %d\n", r.status);
+    int n = 0;
+    if (r.success)
+    {
+        std::vector<PPPathPt> seq;
+        for (int q = r.n_dubins - 1; q >= 0; q--) seq.push_back(wk.path[q]);
+        for (int q = 0; q < r.n_chain; q++) seq.push_back(wk.path[r.n_dubins + q]);
+        n = (int)seq.size();
+        for (int q = 0; q < n && q < path_cap; q++)
+        {
+            float wx, wy, wh;
+            pp_host_to_world(e->fr, seq[q].x, seq[q].y, seq[q].heading, wx, wy, wh);
+            path_xyh[3 * q] = wx; path_xyh[3 * q + 1] = wy; path_xyh[3 * q + 2] = wh;
+            curv[q] = (q == 0) ? 0.0f : seq[q - 1].curvature;
         }
     }
     res->n_path = n;

@@ -42,7 +42,7 @@ def test_struct_layouts_match_native(lib):
     assert C.sizeof(pp._cabi.Params) == C.sizeof(orc.Params) == 19 * 4 + 2 * 16 * 4
     assert pp._cabi.STATE_DT.itemsize == 40 and pp._cabi.POP_DT.itemsize == 32
     assert pp._cabi.QUERY_DT.itemsize == 20 and pp._cabi.RESULT_DT.itemsize == 48
-    assert C.sizeof(pp._cabi.SearchOpts) == 24
+    assert C.sizeof(pp._cabi.SearchOpts) == 32
 
 
 def test_no_cpu_fallback(lib):

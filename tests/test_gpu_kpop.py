@@ -1,0 +1,116 @@
+"""GPU parity tests of the K-POP search mode (new semantics: k pops per iteration on a warp-parallel queue, exact 2D
+field heuristic).  Oracle = the CPU restatement of the same rules (oracle/port/kpop.inc), fed with the device's own 2D
+field; the bar is bit-identical pop sequence, cost and path.  The deviation from the unmodified reference (single-pop,
+lazy heuristic, equal-f drops) is printed, not asserted: K-POP does not claim reference costs."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import orc
+import scenarios as S
+
+pytestmark = pytest.mark.gpu
+
+
+def _ctx(P, groups=1):
+    import path_planning_pkg_b200 as pp
+    return pp.Context(pp._cabi.params_from(P), num_groups=groups, device=0)
+
+
+def _bits(a):
+    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+def port_kpop(o, vel, start, k, h1, max_nodes=1 << 21, pop_cap=1 << 21, path_cap=1 << 13):
+    s = np.asarray(start, np.float32); res = orc.Result()
+    path = np.empty((path_cap, 3), np.float32); cv = np.empty(path_cap, np.float32)
+    pops = np.zeros(pop_cap, orc.POP_DT); h1 = np.ascontiguousarray(h1, np.float32)
+    o._fn("find_path_kpop")(o.h, C.c_float(vel), orc._fp(s), C.c_int(k), orc._fp(h1), C.c_int(max_nodes), C.byref(res),
+                            orc._fp(path), orc._fp(cv), C.c_int(path_cap), orc._fp(pops), C.c_int(pop_cap))
+    n = min(res.n_path, path_cap)
+    return dict(success=bool(res.success), cost=np.float32(res.cost), path=path[:n].copy(), curvature=cv[:n].copy(),
+                pops=pops[:min(res.n_pops, pop_cap)].copy(), n_pops=res.n_pops)
+
+
+def _same(a_res, a_trace, a_path, a_curv, b):
+    n = int(a_res["n_pops"])
+    assert bool(a_res["success"]) == b["success"]
+    assert n == b["n_pops"], (n, b["n_pops"])
+    for f in orc.POP_DT.names:
+        x, y = a_trace[:n][f], b["pops"][f]
+        assert np.array_equal(x.view(np.uint32) if x.dtype.kind == "f" else x, y.view(np.uint32) if y.dtype.kind == "f" else y), f
+    assert np.float32(a_res["cost"]) == b["cost"]
+    m = int(a_res["n_path"])
+    assert np.array_equal(_bits(a_path[:m]), _bits(b["path"])) and np.array_equal(_bits(a_curv[:m]), _bits(b["curvature"]))
+
+
+@pytest.mark.parametrize("k", [1, 5, 32])
+def test_kpop_golden_scenario(k):
+    P = orc.ref_test_params()
+    ctx, port = _ctx(P), orc.port(P)
+    for o in (ctx, port):
+        orc.setup_ref_test_scenario(o)
+    h1, _, _ = ctx.field2d()
+    q = ctx.make_queries([[18.0, 18.0, np.pi / 2, 2.0]], [0])
+    opts = ctx.make_opts(trace_cap=1 << 16, path_cap=4096, mode=1, kpop=k)
+    res, paths, curv, trace = ctx.find_path_batch(q, opts)
+    assert res[0]["status"] == 0
+    b = port_kpop(port, 2.0, orc.REF_TEST_START, k, h1)
+    _same(res[0], trace[0], paths[0], curv[0], b)
+    ref = port.find_path(2.0, orc.REF_TEST_START)
+    print(f"k={k}: cost {float(res[0]['cost']):.4f} / {int(res[0]['n_pops'])} pops   (reference single-pop: {float(ref['cost']):.4f} / {ref['n_pops']})")
+
+
+def test_kpop_c4_batch():
+    groups = [S.c4_group(s, n_starts=8) for s in (0, 5)]
+    P = orc.make_params(grid_size=512, resolution=0.2)
+    ctx = _ctx(P, groups=len(groups))
+    ports, queries, qg = [], [], []
+    for gi, sc in enumerate(groups):
+        port = orc.port(P)
+        S.build_map(port, sc)
+        ctx.update_goal(sc["goal"], sc["frame_start"], group=gi)
+        for _ in range(sc["rounds"]):
+            ctx.update_boxes(sc["boxes"], sc["conf"], S.APF_ADDED_RADIUS, group=gi)
+            ctx.decay(group=gi)
+        qs = S.select_starts(sc, port.get_map(), port.consts().log_threshold, port.set_start)
+        queries += list(qs); qg += [gi] * len(qs); ports.append(port)
+    q = ctx.make_queries(np.array(queries), qg)
+    for k in (32, 4):
+        opts = ctx.make_opts(trace_cap=1 << 17, path_cap=2048, mode=1, kpop=k)
+        res, paths, curv, trace = ctx.find_path_batch(q, opts)
+        fields = [ctx.field2d(g)[0] for g in range(len(groups))]
+        dev = []
+        for i in range(len(q)):
+            assert res[i]["status"] == 0
+            b = port_kpop(ports[qg[i]], float(q["vel"][i]), [q["x"][i], q["y"][i], q["heading"][i]], k, fields[qg[i]])
+            _same(res[i], trace[i], paths[i], curv[i], b)
+            ports[qg[i]].scrub()
+            r = ports[qg[i]].find_path(float(q["vel"][i]), [q["x"][i], q["y"][i], q["heading"][i]])
+            if r["success"] and res[i]["success"]:
+                dev.append((float(res[i]["cost"]) / float(r["cost"]) - 1, int(res[i]["n_pops"]) / max(r["n_pops"], 1)))
+        dev = np.array(dev)
+        print(f"k={k}: {len(q)} queries identical to the K-POP restatement; vs reference single-pop: cost "
+              f"{dev[:, 0].min() * 100:+.1f}% .. {dev[:, 0].max() * 100:+.1f}%, expansions x{np.median(dev[:, 1]):.2f} (median)")
+
+
+def test_kpop_unreachable_goal_fails_cleanly():
+    """A start walled in by an obstacle ring: the open list runs dry -> {max, false} like the reference."""
+    P = orc.make_params(grid_size=120, resolution=0.25)
+    ctx, port = _ctx(P), orc.port(P)
+    ring = []
+    for a in np.linspace(0, 2 * np.pi, 28, endpoint=False):
+        ring.append([3.0 + 4.0 * np.cos(a), 4.0 * np.sin(a), 1.2, 1.2])
+    ring = np.array(ring, np.float32)
+    for o in (ctx, port):
+        o.update_goal([20, 2, 0.0], [0, 0, 0])
+        for _ in range(3):
+            o.update_boxes(ring, np.full(len(ring), 0.9, np.float32), 1.0)
+    h1, _, _ = ctx.field2d()
+    q = ctx.make_queries([[3.0, 0.0, 0.0, 1.0]], [0])
+    res, paths, curv, trace = ctx.find_path_batch(q, ctx.make_opts(trace_cap=1 << 17, mode=1, kpop=32))
+    b = port_kpop(port, 1.0, [3.0, 0.0, 0.0], 32, h1)
+    assert not b["success"] and not res[0]["success"] and res[0]["status"] == 0
+    assert int(res[0]["n_pops"]) == b["n_pops"] and b["n_pops"] > 100
+    assert np.float32(res[0]["cost"]) == np.finfo(np.float32).max
