@@ -171,3 +171,50 @@ def test_stateless_pieces_vs_port(emu_lib):
     la, ta, _ = e.dubins_length(xyh, goal); lb, tb, _ = o.dubins_length(xyh, goal)
     rel = np.abs(la - lb) / np.maximum(lb, 1e-6)
     assert (rel > 1e-5).sum() <= 3        # +-2pi branch flips at an ulp (discontinuity of the reference formula)
+
+
+def _kpop(o, vel, start, k, h1, max_nodes=1 << 20, pop_cap=1 << 20, path_cap=1 << 13):
+    s = np.asarray(start, np.float32); res = orc.Result()
+    path = np.empty((path_cap, 3), np.float32); cv = np.empty(path_cap, np.float32)
+    pops = np.zeros(pop_cap, orc.POP_DT); h1 = np.ascontiguousarray(h1, np.float32)
+    o._fn("find_path_kpop")(o.h, C.c_float(vel), orc._fp(s), C.c_int(k), orc._fp(h1), C.c_int(max_nodes), C.byref(res),
+                            orc._fp(path), orc._fp(cv), C.c_int(path_cap), orc._fp(pops), C.c_int(pop_cap))
+    n = min(res.n_path, path_cap)
+    return dict(success=bool(res.success), cost=np.float32(res.cost), path=path[:n].copy(), curvature=cv[:n].copy(),
+                pops=pops[:min(res.n_pops, pop_cap)].copy(), n_pops=res.n_pops, oob=res.n_pops_bin_oob)
+
+
+def _h1(o):
+    d = orc.field2d(o)
+    return np.where(d < 0, np.finfo(np.float32).max, d).astype(np.float32)
+
+
+@pytest.mark.parametrize("k", [1, 3, 32])
+def test_kpop_core_vs_restatement(emu_lib, k):
+    """K-POP mode: the device core on one host lane (LSM queue, hash table, dedup) == the CPU restatement of the rules
+    (oracle/port/kpop.inc), bit for bit: pop sequence with every g / f, cost, path, curvature."""
+    P = orc.ref_test_params()
+    e, o = _emu(emu_lib, P), orc.port(P)
+    for x in (e, o):
+        orc.setup_ref_test_scenario(x)
+    h1 = _h1(o)
+    a = _kpop(o, 2.0, orc.REF_TEST_START, k, h1); b = _kpop(e, 2.0, orc.REF_TEST_START, k, h1)
+    assert a["success"] and a["n_pops"] == b["n_pops"] and np.array_equal(a["pops"], b["pops"])
+    assert a["cost"] == b["cost"] and np.array_equal(_bits(a["path"]), _bits(b["path"]))
+    assert np.array_equal(_bits(a["curvature"]), _bits(b["curvature"]))
+
+
+def test_kpop_core_c4_and_backward_start(emu_lib):
+    sc = S.c4_group(0, n_starts=2)
+    P = orc.make_params(grid_size=512, resolution=0.2)
+    e, o = _emu(emu_lib, P), orc.port(P)
+    for x in (e, o):
+        S.build_map(x, sc)
+    h1 = _h1(o)
+    starts = list(S.select_starts(sc, o.get_map(), o.consts().log_threshold, o.set_start)) + [np.array([0.0, 0.0, 2.95, 2.0], np.float32)]
+    for q in starts:
+        for k in (32, 8):
+            a = _kpop(o, float(q[3]), q[:3], k, h1); b = _kpop(e, float(q[3]), q[:3], k, h1)
+            assert a["success"] == b["success"] and a["n_pops"] == b["n_pops"] and a["oob"] == b["oob"]
+            assert np.array_equal(a["pops"], b["pops"]) and a["cost"] == b["cost"]
+            assert np.array_equal(_bits(a["path"]), _bits(b["path"]))
