@@ -3,6 +3,7 @@
 // every entry point that computes launches a kernel on the context's stream.
 #include <cuda_runtime.h>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -72,6 +73,7 @@ struct pp_context
     std::vector<PPGroup> groups;          // host mirror of d_groups
     std::vector<int> apf_cap;             // allocated obstacles per group
     std::vector<float*> d_apf;            // per group
+    std::vector<DevBuf<int>> d_bin_off, d_bin_idx;   // per group: spatial index of the APF list
     float* d_maps = nullptr;              // num_groups x N*N
     float* d_map_tmp = nullptr;           // N*N (relocation double buffer)
     int*   d_cell_scratch = nullptr;      // N*N ints (relocation indices / line sample counts), kept zeroed
@@ -105,7 +107,7 @@ struct pp_context
     DevBuf<float> d_field2d;              // num_groups x N*N, filled per group on demand
     std::vector<char> field2d_valid;
     DevBuf<unsigned> d_f2d_work; DevBuf<unsigned char> d_f2d_flags; DevBuf<float> d_dubins_field;
-    DevBuf<int> d_qmap;
+    DevBuf<int> d_qmap, d_order;
     int retried = 0;       // queries re-run in the last pp_batch_run
     unsigned long long launches = 0;      // kernels launched by this context
 };
@@ -180,6 +182,7 @@ int pp_create(const pp_params* params, int device, int num_groups, pp_context** 
     c->groups.resize(num_groups);
     c->apf_cap.assign(num_groups, 0);
     c->d_apf.assign(num_groups, nullptr);
+    c->d_bin_off.resize(num_groups); c->d_bin_idx.resize(num_groups);
     float z[3] = {0, 0, 0};
     for (int g = 0; g < num_groups; g++)
     {
@@ -188,6 +191,7 @@ int pp_create(const pp_params* params, int device, int num_groups, pp_context** 
         c->groups[g].map = c->d_maps + nn * g;
         c->groups[g].apf = nullptr;
         c->groups[g].K = 0;
+        c->groups[g].bin_shift = 0; c->groups[g].bin_n = 0; c->groups[g].bin_off = nullptr; c->groups[g].bin_idx = nullptr;
         c->groups[g].pad = 0;
         c->groups[g].frame = c->frames[g].F;
     }
@@ -203,11 +207,13 @@ void pp_destroy(pp_context* c)
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     for (float* p : c->d_apf) if (p) cudaFree(p);
+    for (auto& b : c->d_bin_off) b.release();
+    for (auto& b : c->d_bin_idx) b.release();
     cudaFree(c->d_maps); cudaFree(c->d_map_tmp); cudaFree(c->d_cell_scratch); cudaFree(c->d_off_xy);
     cudaFree(c->d_groups); cudaFree(c->d_counter);
     c->s0.release(); c->s1.release(); c->s2.release(); c->s3.release(); c->s4.release();
     c->d_queries.release(); c->d_results.release(); c->d_paths.release(); c->d_trace.release();
-    c->wp.release(); c->wp_retry.release(); c->wp_lazy.release(); c->d_qmap.release();
+    c->wp.release(); c->wp_retry.release(); c->wp_lazy.release(); c->d_qmap.release(); c->d_order.release();
     cudaFree(c->d_lazy_sid);
     c->kp.release(); c->kp_retry.release();
     c->d_field2d.release(); c->d_f2d_work.release(); c->d_f2d_flags.release(); c->d_dubins_field.release();
@@ -371,6 +377,19 @@ int pp_update_obstacles_boxes(pp_context* c, int g, const float* boxes, const fl
     if (n > 0) PP_CUDA(cudaMemcpyAsync(c->d_apf[g], apf.data(), sizeof(float) * 3 * n, cudaMemcpyHostToDevice, c->stream));
     c->groups[g].apf = c->d_apf[g];
     c->groups[g].K = n;
+    {
+        std::vector<int> off, idx;
+        int bin_n = 0;
+        const int shift = 4;
+        pp_host_apf_bins(c->model.C, apf, n, shift, bin_n, off, idx);
+        PP_CUDA(c->d_bin_off[g].ensure(off.size()));
+        PP_CUDA(c->d_bin_idx[g].ensure(std::max<size_t>(idx.size(), 1)));
+        PP_CUDA(cudaMemcpyAsync(c->d_bin_off[g].p, off.data(), sizeof(int) * off.size(), cudaMemcpyHostToDevice, c->stream));
+        if (!idx.empty()) PP_CUDA(cudaMemcpyAsync(c->d_bin_idx[g].p, idx.data(), sizeof(int) * idx.size(), cudaMemcpyHostToDevice, c->stream));
+        PP_CUDA(cudaStreamSynchronize(c->stream));
+        c->groups[g].bin_shift = shift; c->groups[g].bin_n = bin_n;
+        c->groups[g].bin_off = c->d_bin_off[g].p; c->groups[g].bin_idx = c->d_bin_idx[g].p;
+    }
     c->groups_dirty = true;
     PP_CUDA(cudaStreamSynchronize(c->stream));
     return pp_update_obstacles_boxes_2d(c, g, boxes, conf, n);
@@ -647,8 +666,9 @@ static int field2d_run(pp_context* c, int g, int* sweeps, float* ms);
 // ---- K-POP pools / launch ----------------------------------------------------------------------------
 static int kpop_levels_for(int nodes_cap)
 {
+    // the top level alone must hold every live entry (see pp_klsm_insert)
     int levels = 1;
-    while ((size_t)PP_K_RUN0 * (((size_t)1 << levels) - 1) < (size_t)nodes_cap + PP_K_RUN0 && levels < PP_K_LEVELS) levels++;
+    while (((size_t)PP_K_RUN0 << (levels - 1)) < (size_t)nodes_cap + PP_K_RUN0 && levels < PP_K_LEVELS) levels++;
     return levels;
 }
 
@@ -677,10 +697,28 @@ static int ensure_kpop(pp_context* c, pp_context::KPools& k, int want_slots, int
     return PP_SUCCESS;
 }
 
+// warps cooperating on one K-POP query (CTA size / 32): 4 unless PP_B200_KPOP_WARPS says 1, 2 or 8 (tuning knob)
+static int kpop_warps()
+{
+    static int nw = 0;
+    if (nw == 0)
+    {
+        nw = 4;
+        if (const char* e = std::getenv("PP_B200_KPOP_WARPS")) { int v = std::atoi(e); if (v == 1 || v == 2 || v == 4 || v == 8) nw = v; }
+    }
+    return nw;
+}
+
 static int kpop_hw_slots(pp_context* c, int* out)
 {
     int occ = 0;
-    PP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pp_kpop_kernel, 32, 0));
+    switch (kpop_warps())
+    {
+        case 1:  PP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pp_kpop_kernel<1>, 32, 0)); break;
+        case 2:  PP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pp_kpop_kernel<2>, 64, 0)); break;
+        case 8:  PP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pp_kpop_kernel<8>, 256, 0)); break;
+        default: PP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pp_kpop_kernel<4>, 128, 0)); break;
+    }
     *out = std::max(1, occ) * c->sm_count;
     return PP_SUCCESS;
 }
@@ -694,8 +732,23 @@ static int launch_kpop(pp_context* c, const pp_context::KPools& k, int n_slots, 
     a.trace = c->opts.trace_cap > 0 ? c->d_trace.p : nullptr; a.trace_cap = c->opts.trace_cap;
     a.nodes = k.nodes.p; a.nodes_cap = k.nodes_cap; a.table = k.table.p; a.table_cap = k.table_cap;
     a.arena = k.arena.p; a.arena_cap = k.arena_cap; a.tmp_a = k.tmp_a.p; a.tmp_b = k.tmp_b.p; a.tmp_cap = k.tmp_cap; a.lsm_levels = k.levels;
+    // longest-expected-first fetch order when the batch is larger than the resident slots
+    a.order = nullptr;
+    if (n_work > n_slots && n_work <= (1 << 16))
+    {
+        PP_CUDA(c->d_order.ensure((size_t)n_work));
+        pp_kpop_order_kernel<<<(n_work + 255) / 256, 256, 0, c->stream>>>(a.queries, qmap, n_work, a.field2d, a.C.N, c->d_order.p);
+        c->launches += 1;
+        a.order = c->d_order.p;
+    }
     PP_CUDA(cudaMemsetAsync(c->d_counter, 0, sizeof(int), c->stream));
-    pp_kpop_kernel<<<n_slots, 32, 0, c->stream>>>(a);
+    switch (kpop_warps())
+    {
+        case 1:  pp_kpop_kernel<1><<<n_slots, 32, 0, c->stream>>>(a); break;
+        case 2:  pp_kpop_kernel<2><<<n_slots, 64, 0, c->stream>>>(a); break;
+        case 8:  pp_kpop_kernel<8><<<n_slots, 256, 0, c->stream>>>(a); break;
+        default: pp_kpop_kernel<4><<<n_slots, 128, 0, c->stream>>>(a); break;
+    }
     c->launches += 1;
     PP_CUDA(cudaGetLastError());
     return PP_SUCCESS;
@@ -736,7 +789,8 @@ int pp_batch_upload(pp_context* c, const pp_query* q, int n, const pp_search_opt
         rc = kpop_hw_slots(c, &hw_slots); if (rc) return rc;
         want = std::min(n, hw_slots);
         if (o.max_slots > 0) want = std::min(want, o.max_slots);
-        int nodes_cap = std::max(o.max_expansions, 4096);
+        // generated nodes, not expansions, fill the K-POP pools: about 1.5-4 per expansion
+        int nodes_cap = (int)std::min<long long>(std::max(2ll * o.max_expansions, 4096ll), 1ll << 26);
         rc = ensure_kpop(c, c->kp, want, nodes_cap, 0.6); if (rc) return rc;
         c->n_slots = std::max(std::min(c->kp.alloc_slots, want), 1);
     }
@@ -776,6 +830,7 @@ int pp_batch_run(pp_context* c, float* kernel_ms)
     // 8x larger pools (fewer resident slots), up to 3 escalations; what still overflows stays flagged.
     c->retried = 0;
     int max_exp = c->opts.max_expansions, max_open = c->opts.max_open, max_open2d = c->opts.max_open2d;
+    long long kp_nodes = c->kp.nodes_cap;
     std::vector<PPResult> r(n);
     const int overflow = PP_STATUS_OPEN_OVERFLOW | PP_STATUS_CLOSED_OVERFLOW | PP_STATUS_OPEN2D_OVERFLOW;
     for (int level = 0; level < 3; level++)
@@ -796,7 +851,8 @@ int pp_batch_run(pp_context* c, float* kernel_ms)
         PP_CUDA(cudaMemcpyAsync(c->d_qmap.p, redo.data(), sizeof(int) * redo.size(), cudaMemcpyHostToDevice, c->stream));
         if (kmode)
         {
-            rc = ensure_kpop(c, c->kp_retry, want, max_exp, 0.85); if (rc) return rc;
+            kp_nodes = std::min<long long>(kp_nodes * 8, 1ll << 24);
+            rc = ensure_kpop(c, c->kp_retry, want, (int)kp_nodes, 0.85); if (rc) return rc;
             int slots = std::max(std::min(c->kp_retry.alloc_slots, want), 1);
             rc = launch_kpop(c, c->kp_retry, slots, c->d_qmap.p, (int)redo.size()); if (rc) return rc;
         }

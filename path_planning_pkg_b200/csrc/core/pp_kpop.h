@@ -27,7 +27,7 @@
 #define PP_K_MAXPOP 32
 #define PP_K_MAXSUCC 8                                  // (2A+1) supported by this mode
 #define PP_K_MAXCAND (PP_K_MAXPOP * PP_K_MAXSUCC)        // 256
-#define PP_K_LEVELS 14                                   // LSM levels: capacity 256 << level
+#define PP_K_LEVELS 16                                   // LSM levels: capacity 256 << level
 #define PP_K_RUN0 256
 #define PP_K_NONE 0x7fffffffu
 #define PP_K_CLOSED 0x80000000u
@@ -56,13 +56,17 @@ struct PPKSmem
     {
         PPKCand  cand[PP_K_MAXCAND];                       // expansion
         PPKEntry sel[PP_K_LEVELS * PP_K_MAXPOP];           // pop selection: first k entries of every run
-        PPKEntry batch[PP_K_MAXCAND];                      // new queue entries of this iteration
+        struct { PPKEntry batch[PP_K_MAXCAND]; PPKEntry sorted[PP_K_MAXCAND]; } q;   // new queue entries of this iteration
     } u;
     PPKEntry popped[PP_K_MAXPOP];
     PPKNode  parents[PP_K_MAXPOP];                         // copies of this iteration's pops, by rank
     int      pop_idx[PP_K_MAXPOP];                         // their node indices
     int      head[PP_K_LEVELS], size[PP_K_LEVELS];         // live range [head, size) of every level's run
     int      taken[PP_K_LEVELS];
+    unsigned short wlist[PP_K_MAXCAND];                    // candidate index of the t-th winner
+    float    shot[4][5];                                   // Dubins shot: (length, p[0..3]) of the four candidates
+    int      bc[8];                                        // values decided by ballot group 0, broadcast to the CTA
+    int      scan[32];                                     // per-warp counts of W::scan_count
 };
 
 PP_HD bool pp_kless(const PPKEntry& a, const PPKEntry& b)
@@ -132,25 +136,19 @@ PP_HD int pp_ktable_find_or_insert(PPKWork& wk, unsigned key)
     }
 }
 
-// ---- warp sort of n (power of two, <= PP_K_MAXCAND) entries in shared memory ------------------------------------------
+// ---- sort of n <= PP_K_MAXCAND entries, shared memory src -> dst: every lane ranks its entries against all others (the
+// order is total, so the ranks are a permutation); no barrier inside, unlike a sorting network ---------------------------
 template <class W>
-PP_HD void pp_kbitonic(const W& w, PPKEntry* s, int n)
+PP_HD void pp_kranksort(const W& w, const PPKEntry* src, PPKEntry* dst, int n)
 {
-    for (int k = 2; k <= n; k <<= 1)
-        for (int j = k >> 1; j > 0; j >>= 1)
-        {
-            for (int t = w.lane(); t < n; t += W::LANES)
-            {
-                int x = t ^ j;
-                if (x > t)
-                {
-                    bool asc = ((t & k) == 0);
-                    PPKEntry a = s[t], b = s[x];
-                    if (pp_kless(b, a) == asc) { s[t] = b; s[x] = a; }
-                }
-            }
-            w.sync();
-        }
+    for (int t = w.lane(); t < n; t += W::LANES)
+    {
+        const PPKEntry e = src[t];
+        int rank = 0;
+        for (int j = 0; j < n; j++) rank += pp_kless(src[j], e) ? 1 : 0;
+        dst[rank] = e;
+    }
+    w.sync();
 }
 
 // ---- warp merge of two sorted runs (merge path): dst[0 .. na+nb) ------------------------------------------------------
@@ -188,7 +186,10 @@ PP_HD void pp_kcopy(const W& w, const PPKEntry* src, PPKEntry* dst, int n)
 
 PP_HD PPKEntry* pp_klevel(const PPKWork& wk, int l) { return wk.arena + (size_t)PP_K_RUN0 * (((size_t)1 << l) - 1); }
 
-// insert a sorted batch (shared memory, m <= PP_K_MAXCAND entries); false = queue capacity exhausted
+// insert a sorted batch (shared memory, m <= PP_K_MAXCAND entries); false = queue capacity exhausted.
+// The carry walks down the levels: it settles in the first level that can hold it together with that level's live run
+// (merged), otherwise it absorbs the run and moves on.  carry <= capacity(l) holds at every level, so the queue only
+// overflows when the live entries exceed the top level's capacity (sized >= nodes_cap by the host).
 template <class W>
 PP_HD bool pp_klsm_insert(const W& w, PPKWork& wk, PPKSmem& sm, const PPKEntry* batch, int m)
 {
@@ -197,7 +198,8 @@ PP_HD bool pp_klsm_insert(const W& w, PPKWork& wk, PPKSmem& sm, const PPKEntry* 
     PPKEntry* t0 = wk.tmp_a; PPKEntry* t1 = wk.tmp_b;
     for (int l = 0; l < wk.lsm_levels; l++)
     {
-        int cnt = sm.size[l] - sm.head[l];
+        const int cnt = sm.size[l] - sm.head[l];
+        const int cap = PP_K_RUN0 << l;
         PPKEntry* L = pp_klevel(wk, l);
         if (cnt == 0)
         {
@@ -207,9 +209,17 @@ PP_HD bool pp_klsm_insert(const W& w, PPKWork& wk, PPKSmem& sm, const PPKEntry* 
             return true;
         }
         pp_kmerge(w, L + sm.head[l], cnt, carry, carry_n, t0);
+        carry_n += cnt;
+        if (carry_n <= cap)
+        {
+            pp_kcopy(w, t0, L, carry_n);
+            if (w.lane() == 0) { sm.head[l] = 0; sm.size[l] = carry_n; }
+            w.sync();
+            return true;
+        }
         if (w.lane() == 0) { sm.head[l] = 0; sm.size[l] = 0; }
         w.sync();
-        carry = t0; carry_n += cnt;
+        carry = t0;
         PPKEntry* t = t0; t0 = t1; t1 = t;
     }
     return false;
@@ -221,28 +231,33 @@ PP_HD int pp_klsm_pop(const W& w, PPKWork& wk, PPKSmem& sm, int k)
 {
     const int lane = w.lane();
     const int nl = wk.lsm_levels;
-    // stage the first k entries of every run (padded with +inf)
-    for (int t = lane; t < nl * PP_K_MAXPOP; t += W::LANES)
+    // compact list of the non-empty runs (identical on every lane): usually 3-5 of the levels hold a run
+    int lv[PP_K_LEVELS];
+    int nr = 0;
+    for (int l = 0; l < nl; l++) if (sm.size[l] > sm.head[l]) lv[nr++] = l;
+    for (int t = lane; t < PP_K_LEVELS; t += W::LANES) sm.taken[t] = 0;
+    for (int t = lane; t < PP_K_MAXPOP; t += W::LANES) sm.popped[t] = pp_kinf();
+    if (nr == 0) { w.sync(); return 0; }
+    // stage the first k entries of every non-empty run (padded with +inf)
+    for (int t = lane; t < nr * PP_K_MAXPOP; t += W::LANES)
     {
-        int l = t / PP_K_MAXPOP, p = t - l * PP_K_MAXPOP;
+        int c = t / PP_K_MAXPOP, p = t - c * PP_K_MAXPOP, l = lv[c];
         int at = sm.head[l] + p;
         sm.u.sel[t] = (p < k && at < sm.size[l]) ? pp_klevel(wk, l)[at] : pp_kinf();
     }
-    for (int t = lane; t < PP_K_LEVELS; t += W::LANES) sm.taken[t] = 0;
-    for (int t = lane; t < PP_K_MAXPOP; t += W::LANES) sm.popped[t] = pp_kinf();
     w.sync();
     // rank every staged entry among all staged entries; ranks < k are the result.  The entries taken from a run form
     // a prefix of it, so counting them per run gives the new heads.
-    for (int t = lane; t < nl * PP_K_MAXPOP; t += W::LANES)
+    for (int t = lane; t < nr * PP_K_MAXPOP; t += W::LANES)
     {
         const PPKEntry e = sm.u.sel[t];
         if (e.idx == 0xffffffffu) continue;
-        int l = t / PP_K_MAXPOP, p = t - l * PP_K_MAXPOP;
+        int c = t / PP_K_MAXPOP, p = t - c * PP_K_MAXPOP;
         int rank = p;
-        for (int l2 = 0; l2 < nl && rank < k; l2++)
+        for (int c2 = 0; c2 < nr && rank < k; c2++)
         {
-            if (l2 == l) continue;
-            const PPKEntry* r = sm.u.sel + l2 * PP_K_MAXPOP;
+            if (c2 == c) continue;
+            const PPKEntry* r = sm.u.sel + c2 * PP_K_MAXPOP;
             int lo = 0, hi = PP_K_MAXPOP;                       // first position whose entry is not less than e
             while (lo < hi) { int mid = (lo + hi) >> 1; if (pp_kless(r[mid], e)) lo = mid + 1; else hi = mid; }
             rank += lo;
@@ -251,15 +266,15 @@ PP_HD int pp_klsm_pop(const W& w, PPKWork& wk, PPKSmem& sm, int k)
         {
             sm.popped[rank] = e;
 #ifdef __CUDA_ARCH__
-            atomicAdd(&sm.taken[l], 1);
+            atomicAdd(&sm.taken[lv[c]], 1);
 #else
-            sm.taken[l]++;
+            sm.taken[lv[c]]++;
 #endif
         }
     }
     w.sync();
     int n = 0;
-    for (int t = 0; t < k; t++) if (sm.popped[t].idx != 0xffffffffu) n++;
+    for (int c = 0; c < nr; c++) n += sm.taken[lv[c]];
     for (int t = lane; t < nl; t += W::LANES) sm.head[t] += sm.taken[t];
     w.sync();
     return n;
@@ -283,36 +298,80 @@ PP_HD float pp_kdubins(const PPConsts& C, const PPFrame& F, const PPDubinsGoal& 
     return best;
 }
 
-// The Dubins shot (HybridAStar.cpp:129-149): all lanes; returns true when accepted; samples in path[0 .. n_dubins)
+// The Dubins shot (HybridAStar.cpp:129-149): all lanes; returns true when accepted; samples in path[0 .. n_dubins).
+// The sample positions come from float accumulators advanced one step at a time (Dubins.cpp:351-386): that chain is
+// inherently sequential, so one lane runs it as three tight loops into `accb` (shared memory) and the 32 lanes then
+// evaluate the samples (sin / cos, collision lookup) in parallel.
 template <class W>
 PP_HD bool pp_try_shot(const W& w, const PPConsts& C, const float* map, const PPFrame& F, float x, float y, float h,
-                       PPPathPt* path, int path_cap, float& len_out, int& n_dubins, int& overflow)
+                       PPPathPt* path, int path_cap, float* accb, int acc_cap, int* scratch, float (*shot)[5], float& len_out, int& n_dubins,
+                       int& overflow)
 {
-    int type; float p[4]; PPDubinsCenters cen; PPDubinsPlan pl;
-    float len = pp_dubins_shortest(C.r_min, x, y, h, F.goal_x, F.goal_y, F.goal_h, type, p, cen);
+    int type = PP_RSR; float p[4]; PPDubinsCenters cen; PPDubinsPlan pl;
+    // the four candidates on four lanes, then the sequential fold of Dubins.cpp:36-68 on every lane
+    pp_dubins_centers(C.r_min, x, y, h, F.goal_x, F.goal_y, F.goal_h, cen);
+    for (int t = w.lane(); t < 4; t += W::LANES)
+    {
+        float csx, csy, cgx, cgy, pc[4];
+        pp_dubins_pick(cen, t, csx, csy, cgx, cgy);
+        shot[t][0] = pp_dubins_candidate(t, C.r_min, h, F.goal_h, csx, csy, cgx, cgy, pc);
+        shot[t][1] = pc[0]; shot[t][2] = pc[1]; shot[t][3] = pc[2]; shot[t][4] = pc[3];
+    }
+    w.sync();
+    float len = 0.0f;
+    for (int t = 0; t < 4; t++)
+        if (t == 0 || shot[t][0] < len) { len = shot[t][0]; type = t; p[0] = shot[t][1]; p[1] = shot[t][2]; p[2] = shot[t][3]; p[3] = shot[t][4]; }
+    w.sync();
     if (fabsf(p[1]) > (float)PP_PI_2) return false;                       // Dubins.cpp:152
     pp_dubins_plan(C.r_min, C.step, C.ang_step, type, p, cen, pl);
     const int total = pl.size_3 + 1;
     bool blocked = false, over = false;
-    float acc = p[0];
-    for (int k = 0; k < total; k++)
+    if (total <= acc_cap)
     {
-        if (k == pl.size_1) acc = 0.0f;
-        if (k == pl.size_2) acc = p[2];
-        if ((k % W::LANES) == w.lane())
+        if (w.lane() == 0)
+        {
+            float a = p[0];
+            const float d1 = (pl.s1 < 0) ? -C.ang_step : C.ang_step, d3 = (pl.s2 < 0) ? -C.ang_step : C.ang_step;
+            for (int k = 0; k < pl.size_1; k++) { accb[k] = a; a = a + d1; }          // a - s == a + (-s) exactly
+            a = 0.0f;
+            for (int k = pl.size_1; k < pl.size_2; k++) { accb[k] = a; a = a + C.step; }
+            a = p[2];
+            for (int k = pl.size_2; k < pl.size_3; k++) { accb[k] = a; a = a + d3; }
+            accb[pl.size_3] = 0.0f;
+        }
+        w.sync();
+        for (int k = w.lane(); k < total; k += W::LANES)
         {
             float sx, sy, sh, kappa;
-            pp_dubins_sample(pl, C.r_min, k, acc, sx, sy, sh, kappa);
+            pp_dubins_sample(pl, C.r_min, k, accb[k], sx, sy, sh, kappa);
             if (pp_path_point_blocked(C, map, sx, sy)) blocked = true;
             if (k < path_cap) { PPPathPt& q = path[k]; q.x = sx; q.y = sy; q.heading = sh; q.curvature = kappa; }
             else over = true;
         }
-        if (k < pl.size_1) acc = (pl.s1 < 0) ? acc - C.ang_step : acc + C.ang_step;
-        else if (k < pl.size_2) acc = acc + C.step;
-        else if (k < pl.size_3) acc = (pl.s2 < 0) ? acc - C.ang_step : acc + C.ang_step;
+        w.sync();
     }
-    if (w.ballot(blocked) != 0u) return false;
-    overflow = (w.ballot(over) != 0u) ? 1 : 0;
+    else
+    {
+        float acc = p[0];
+        for (int k = 0; k < total; k++)
+        {
+            if (k == pl.size_1) acc = 0.0f;
+            if (k == pl.size_2) acc = p[2];
+            if ((k % W::LANES) == w.lane())
+            {
+                float sx, sy, sh, kappa;
+                pp_dubins_sample(pl, C.r_min, k, acc, sx, sy, sh, kappa);
+                if (pp_path_point_blocked(C, map, sx, sy)) blocked = true;
+                if (k < path_cap) { PPPathPt& q = path[k]; q.x = sx; q.y = sy; q.heading = sh; q.curvature = kappa; }
+                else over = true;
+            }
+            if (k < pl.size_1) acc = (pl.s1 < 0) ? acc - C.ang_step : acc + C.ang_step;
+            else if (k < pl.size_2) acc = acc + C.step;
+            else if (k < pl.size_3) acc = (pl.s2 < 0) ? acc - C.ang_step : acc + C.ang_step;
+        }
+    }
+    if (w.any(blocked, scratch)) return false;
+    overflow = w.any(over, scratch) ? 1 : 0;
     len_out = len; n_dubins = total;
     return true;
 }
@@ -360,70 +419,82 @@ PP_HD_NOINLINE void pp_search_kpop(const W& w, const PPConsts& C, const float* o
     w.sync();
 
     int counter = 0, interval = C.shot_interval;
-    int n_pops = 0, n_oob = 0, status = 0, success = 0, n_chain = 0, n_dubins = 0, terminal = -1;
+    PP_PROF_DECL
+    PP_PROF_MARK(0)
+    int n_pops = 0, n_oob = 0, status = 0, success = 0, n_chain = 0, n_dubins = 0, terminal = -1, n_iter = 0, n_popped = 0;
     float cost = FLT_MAX;
 
     for (unsigned it = 1;; it++)
     {
         // ---- pop the k smallest entries ----
         const int nb = pp_klsm_pop(w, wk, sm, kpop);
+        PP_PROF_MARK(1)
         if (nb == 0) break;                                                     // open list exhausted: failure
+        n_iter++; n_popped += nb;
         // validity (lazy deletion), ranks, closing, goal / shot candidates -- in rank (= queue) order
         int n_valid = 0, r_g = -1, r_s = -1;
-        for (int base = 0; base < nb; base += W::LANES)
+        if (w.warp() == 0)                                                       // ballot group 0 decides, then broadcasts
         {
-            const int b = base + lane;
-            bool valid = false, is_goal = false, slow = false, oob = false;
-            PPKEntry me = pp_kinf();
-            int slot = -1;
-            if (b < nb)
+            const int wl = w.wlane();
+            for (int base = 0; base < nb; base += W::BW)
             {
-                me = sm.popped[b];
-                slot = pp_ktable_find(wk, me.key);
-                valid = (slot >= 0) && (wk.table[slot].node == me.idx);          // closed or superseded => mismatch
-            }
-            const unsigned vm = w.ballot(valid);
-            int rank = n_valid;
-            { unsigned below = vm & w.lanemask_lt(); while (below) { rank++; below &= below - 1; } }
-            if (valid)
-            {
-                wk.table[slot].node = me.idx | PP_K_CLOSED;
-                const PPKNode nd = wk.nodes[me.idx];
-                sm.parents[rank] = nd;
-                sm.pop_idx[rank] = (int)me.idx;
-                is_goal = ((unsigned)nd.cell == goal_cell);
-                slow = (nd.v2 < 1.0f);
-                oob = (nd.bin >= C.bins);
-                if (wk.trace && (n_pops + rank) < wk.trace_cap)
+                const int b = base + wl;
+                bool valid = false, is_goal = false, slow = false, oob = false;
+                PPKEntry me = pp_kinf();
+                int slot = -1;
+                if (b < nb)
                 {
-                    PPPop& t = wk.trace[n_pops + rank];
-                    t.ci = nd.cell / N; t.cj = nd.cell % N; t.bin = nd.bin; t.x = nd.x; t.y = nd.y; t.heading = nd.heading; t.g = nd.g; t.f = nd.f;
+                    me = sm.popped[b];
+                    slot = pp_ktable_find(wk, me.key);
+                    valid = (slot >= 0) && (wk.table[slot].node == me.idx);      // closed or superseded => mismatch
                 }
-            }
-            const unsigned gm = w.ballot(is_goal), sl = w.ballot(slow), om = w.ballot(oob);
-            if (r_g < 0 && gm)                                                   // first goal pop
-            {
-                int src = 0; { unsigned t = gm; while (!(t & 1u)) { t >>= 1; src++; } }
-                r_g = n_valid; { unsigned bl = vm & ((src == 0) ? 0u : (0xffffffffu >> (32 - src))); while (bl) { r_g++; bl &= bl - 1; } }
-            }
-            if (r_s < 0)                                                         // shot counter over the slow pops
-            {
-                int ns = 0; { unsigned t = sl; while (t) { ns++; t &= t - 1; } }
-                const int need = interval - counter;
-                if (need >= 1 && need <= ns)
+                const unsigned vm = w.ballot(valid);
+                int rank = n_valid;
+                { unsigned below = vm & w.lanemask_lt(); while (below) { rank++; below &= below - 1; } }
+                if (valid)
                 {
-                    unsigned t = sl; int src = 0;
-                    for (int q = 1; q < need; q++) t &= t - 1;                   // drop the first need-1 slow pops
-                    while (!(t & 1u)) { t >>= 1; src++; }
-                    r_s = n_valid; { unsigned bl = vm & ((src == 0) ? 0u : (0xffffffffu >> (32 - src))); while (bl) { r_s++; bl &= bl - 1; } }
-                    counter = interval;
+                    wk.table[slot].node = me.idx | PP_K_CLOSED;
+                    const PPKNode nd = wk.nodes[me.idx];
+                    sm.parents[rank] = nd;
+                    sm.pop_idx[rank] = (int)me.idx;
+                    is_goal = ((unsigned)nd.cell == goal_cell);
+                    slow = (nd.v2 < 1.0f);
+                    oob = (nd.bin >= C.bins);
+                    if (wk.trace && (n_pops + rank) < wk.trace_cap)
+                    {
+                        PPPop& t = wk.trace[n_pops + rank];
+                        t.ci = nd.cell / N; t.cj = nd.cell % N; t.bin = nd.bin; t.x = nd.x; t.y = nd.y; t.heading = nd.heading; t.g = nd.g; t.f = nd.f;
+                    }
                 }
-                else counter += ns;
+                const unsigned gm = w.ballot(is_goal), sl = w.ballot(slow), om = w.ballot(oob);
+                if (r_g < 0 && gm)                                               // first goal pop
+                {
+                    int src = 0; { unsigned t = gm; while (!(t & 1u)) { t >>= 1; src++; } }
+                    r_g = n_valid; { unsigned bl = vm & ((src == 0) ? 0u : (0xffffffffu >> (32 - src))); while (bl) { r_g++; bl &= bl - 1; } }
+                }
+                if (r_s < 0)                                                     // shot counter over the slow pops
+                {
+                    int ns = 0; { unsigned t = sl; while (t) { ns++; t &= t - 1; } }
+                    const int need = interval - counter;
+                    if (need >= 1 && need <= ns)
+                    {
+                        unsigned t = sl; int src = 0;
+                        for (int q = 1; q < need; q++) t &= t - 1;               // drop the first need-1 slow pops
+                        while (!(t & 1u)) { t >>= 1; src++; }
+                        r_s = n_valid; { unsigned bl = vm & ((src == 0) ? 0u : (0xffffffffu >> (32 - src))); while (bl) { r_s++; bl &= bl - 1; } }
+                        counter = interval;
+                    }
+                    else counter += ns;
+                }
+                { unsigned t = om; while (t) { n_oob++; t &= t - 1; } }
+                { unsigned t = vm; while (t) { n_valid++; t &= t - 1; } }
+                w.wsync();
             }
-            { unsigned t = om; while (t) { n_oob++; t &= t - 1; } }
-            { unsigned t = vm; while (t) { n_valid++; t &= t - 1; } }
-            w.sync();
+            if (wl == 0) { sm.bc[0] = n_valid; sm.bc[1] = r_g; sm.bc[2] = r_s; sm.bc[3] = counter; sm.bc[4] = n_oob; }
         }
+        w.sync();
+        n_valid = sm.bc[0]; r_g = sm.bc[1]; r_s = sm.bc[2]; counter = sm.bc[3]; n_oob = sm.bc[4];
+        w.sync();
         if (n_valid == 0) continue;
         n_pops += n_valid;
 
@@ -433,7 +504,8 @@ PP_HD_NOINLINE void pp_search_kpop(const W& w, const PPConsts& C, const float* o
         {
             const PPKNode nd = sm.parents[r_s];
             float len = 0.0f; int ovf = 0;
-            if (pp_try_shot(w, C, G.map, F, nd.x, nd.y, nd.heading, wk.path, wk.path_cap, len, n_dubins, ovf))
+            if (pp_try_shot(w, C, G.map, F, nd.x, nd.y, nd.heading, wk.path, wk.path_cap, reinterpret_cast<float*>(&sm.u),
+                            (int)(sizeof(sm.u) / sizeof(float)), sm.scan, sm.shot, len, n_dubins, ovf))
             {
                 if (ovf) status |= PP_STATUS_PATH_OVERFLOW;
                 success = 1; cost = nd.g + len; terminal = nd.parent;
@@ -448,6 +520,7 @@ PP_HD_NOINLINE void pp_search_kpop(const W& w, const PPConsts& C, const float* o
         }
         if (n_nodes + n_valid * n_succ > wk.nodes_cap) { status |= PP_STATUS_CLOSED_OVERFLOW; break; }
 
+        PP_PROF_MARK(2)
         // ---- expansion: candidate c = rank * n_succ + a ----
         const int n_cand = n_valid * n_succ;
         for (int c = lane; c < n_cand; c += W::LANES)
@@ -465,8 +538,15 @@ PP_HD_NOINLINE void pp_search_kpop(const W& w, const PPConsts& C, const float* o
             {
                 // APF: std::accumulate over the obstacles in order (Grid3D.cpp:226)
                 float field = 0.0f;
-                for (int q = 0; q < G.K; q++)
+                int q_lo = 0, q_hi = G.K;                                   // the successor's bin of the APF index, if any
+                if (G.bin_off)
                 {
+                    const int bb = (o.ci >> G.bin_shift) * G.bin_n + (o.cj >> G.bin_shift);
+                    q_lo = G.bin_off[bb]; q_hi = G.bin_off[bb + 1];
+                }
+                for (int qq = q_lo; qq < q_hi; qq++)
+                {
+                    const int q = G.bin_off ? G.bin_idx[qq] : qq;
                     float ox = G.apf[3 * q], oy = G.apf[3 * q + 1], rad = G.apf[3 * q + 2];
                     float dx = ox - o.x, dy = oy - o.y, lim = rad * 1.001f + 1e-3f;
                     if (dx * dx + dy * dy <= lim * lim)
@@ -493,26 +573,37 @@ PP_HD_NOINLINE void pp_search_kpop(const W& w, const PPConsts& C, const float* o
         pp_fence();
         w.sync();
 
+        PP_PROF_MARK(3)
         // ---- winners in c order -> nodes, queue entries ----
         int n_new = 0;
         for (int base = 0; base < n_cand; base += W::LANES)
         {
             const int c = base + lane;
             bool win = false;
-            PPKCand cd;
             if (c < n_cand)
             {
-                cd = sm.u.cand[c];
+                const PPKCand& cd = sm.u.cand[c];
                 win = ((cd.curv_bin_ok >> 16) & 1) && (wk.table[cd.slot].pack == cd.pack);
             }
-            unsigned wm = w.ballot(win);
-            int pos = n_new;
-            { unsigned below = wm & w.lanemask_lt(); while (below) { pos++; below &= below - 1; } }
+            int n_win = 0;
+            const int pos = n_new + w.scan_count(win, sm.scan, n_win);
+            if (win) sm.wlist[pos] = (unsigned short)c;
+            n_new += n_win;
+        }
+        w.sync();
+        // the t-th winner becomes node n_nodes + t; the work (Dubins length) is spread evenly over the lanes.  The
+        // candidate staging area is reused for the batch: winner t reads cand[c >= t] before batch[t] is written, and
+        // the winners of later rounds sit at higher addresses than anything written so far (16 t < 40 c).
+        for (int base = 0; base < n_new; base += W::LANES)
+        {
+            const int t = base + lane;
             PPKEntry e = pp_kinf();
-            if (win)
+            if (t < n_new)
             {
+                const int c = sm.wlist[t];
+                const PPKCand cd = sm.u.cand[c];
                 const int r = c / n_succ;
-                const int idx = n_nodes + pos;
+                const int idx = n_nodes + t;
                 const float h2 = pp_kdubins(C, F, gc, cd.x, cd.y, cd.heading);
                 const float h1 = wk.h1[cd.cell];
                 PPKNode nd;
@@ -526,22 +617,20 @@ PP_HD_NOINLINE void pp_search_kpop(const W& w, const PPConsts& C, const float* o
                 e.f = nd.f; e.key = nd.key; e.idx = (unsigned)idx; e.pad = 0;
             }
             w.sync();
-            // the candidate staging area is reused for the batch: safe, candidate `c` is consumed before batch[pos <= c] is written
-            if (win) sm.u.batch[pos] = e;
-            { unsigned t = wm; while (t) { n_new++; t &= t - 1; } }
+            if (t < n_new) sm.u.q.batch[t] = e;
             w.sync();
         }
         n_nodes += n_new;
+        PP_PROF_MARK(4)
         if (n_new > 0)
         {
-            int n_pad = 1; while (n_pad < n_new) n_pad <<= 1;
-            for (int t = n_new + lane; t < n_pad; t += W::LANES) sm.u.batch[t] = pp_kinf();
-            w.sync();
-            pp_kbitonic(w, sm.u.batch, n_pad);
-            if (!pp_klsm_insert(w, wk, sm, sm.u.batch, n_new)) { status |= PP_STATUS_OPEN_OVERFLOW; break; }
+            pp_kranksort(w, sm.u.q.batch, sm.u.q.sorted, n_new);
+            if (!pp_klsm_insert(w, wk, sm, sm.u.q.sorted, n_new)) { status |= PP_STATUS_OPEN_OVERFLOW; break; }
         }
+        PP_PROF_MARK(5)
     }
 
+    PP_PROF_FLUSH
     // ---- path: [dubins samples (already in wk.path[0 .. n_dubins)) | parent chain terminal -> start] ----
     if (lane == 0)
     {
@@ -559,7 +648,10 @@ PP_HD_NOINLINE void pp_search_kpop(const W& w, const PPConsts& C, const float* o
                 n_chain++;
             }
         res.success = success; res.status = status; res.cost = cost; res.n_pops = n_pops; res.n_pops_bin_oob = n_oob;
-        res.n_chain = n_chain; res.n_dubins = n_dubins; res.n_lazy_searches = 0; res.n_lazy_pops = 0; res.max_open = 0;
+        res.n_chain = n_chain; res.n_dubins = n_dubins;
+        res.n_lazy_searches = n_iter;      // K-POP: iterations
+        res.n_lazy_pops = n_popped;        // K-POP: queue entries taken (valid + stale)
+        res.max_open = 0;
         res.n_closed = n_nodes; res.pad = 0;
     }
 }

@@ -86,7 +86,11 @@ struct PPGroup
     const float* map;    // N*N log-odds, map[i*N + j]  (i along grid x)
     const float* apf;    // K x (x, y, radius) in grid-frame metres (Grid3D.cpp:22-44)
     int          K;
+    int          bin_shift;   // spatial index of the APF list: square bins of (1 << bin_shift) cells, bin_n per side
+    int          bin_n;
     int          pad;
+    const int*   bin_off;     // bin_n*bin_n + 1 offsets into bin_idx, nullptr = no index (scan all K)
+    const int*   bin_idx;     // per bin: ascending indices of the obstacles whose disc can reach the bin
     PPFrame      frame;
 };
 
@@ -125,12 +129,18 @@ struct PPDubinsGoal { float grx, gry, glx, gly; };
 // ---- lane policy for a single host thread (tests only); the device policy lives in pp_kernels.cu ----
 struct PPWarpSerial
 {
-    enum { LANES = 1 };
+    enum { LANES = 1, BW = 1 };                      // BW: width of one ballot group (a hardware warp)
     PP_HD int lane() const { return 0; }
+    PP_HD int wlane() const { return 0; }            // lane inside its ballot group
+    PP_HD int warp() const { return 0; }             // index of the ballot group
     PP_HD void sync() const {}
+    PP_HD void wsync() const {}
     PP_HD unsigned ballot(bool p) const { return p ? 1u : 0u; }
     PP_HD unsigned lanemask_lt() const { return 0u; }
     template <class T> PP_HD T shfl(T v, int) const { return v; }
+    PP_HD bool any(bool p, int*) const { return p; }
+    // exclusive count of `p` over the lanes below this one, `total` over all lanes
+    PP_HD int scan_count(bool p, int*, int& total) const { total = p ? 1 : 0; return 0; }
 };
 
 // ---------------------------------------------------------------------------------------------------

@@ -195,6 +195,51 @@ inline void pp_host_apf_list(const PPConsts& C, const PPHostFrame& fr, const flo
     }
 }
 
+// Conservative spatial index of the APF list (not in the reference, which scans every obstacle for every successor,
+// Grid3D.cpp:203-226): the grid is cut into square bins of (1 << shift) cells; a bin lists, in ascending obstacle
+// order, every obstacle whose influence disc (radius + one cell of slack for the float cell rounding) touches the bin.
+// An obstacle outside a pose's bin list is at least its radius away, i.e. its term is exactly zero, so summing the
+// listed obstacles in order reproduces the full std::accumulate.
+inline void pp_host_apf_bins(const PPConsts& C, const std::vector<float>& apf, int n, int shift, int& bin_n,
+                             std::vector<int>& off, std::vector<int>& idx)
+{
+    const int B = 1 << shift;
+    bin_n = (C.N + B - 1) >> shift;
+    const double w = (double)B * (double)C.res;
+    off.assign((size_t)bin_n * bin_n + 1, 0);
+    idx.clear();
+    for (int pass = 0; pass < 2; pass++)
+    {
+        std::vector<int> fill;
+        if (pass == 1)
+        {
+            long long acc = 0;
+            for (size_t b = 0; b + 1 < off.size(); b++) { long long c = off[b]; off[b] = (int)acc; acc += c; }
+            off[off.size() - 1] = (int)acc;
+            idx.assign((size_t)acc, 0);
+            fill.assign(off.begin(), off.end() - 1);
+        }
+        for (int k = 0; k < n; k++)
+        {
+            const double ox = apf[3 * k], oy = apf[3 * k + 1];
+            const double reach = (double)apf[3 * k + 2] * 1.001 + 1.5 * (double)C.res + 1e-3;
+            int i0 = (int)std::floor((ox - reach) / w), i1 = (int)std::floor((ox + reach) / w);
+            int j0 = (int)std::floor((oy - reach) / w), j1 = (int)std::floor((oy + reach) / w);
+            i0 = std::max(i0, 0); j0 = std::max(j0, 0); i1 = std::min(i1, bin_n - 1); j1 = std::min(j1, bin_n - 1);
+            for (int bi = i0; bi <= i1; bi++)
+                for (int bj = j0; bj <= j1; bj++)
+                {
+                    // distance from the obstacle centre to the bin rectangle
+                    double dx = std::max(std::max(bi * w - ox, ox - (bi + 1) * w), 0.0);
+                    double dy = std::max(std::max(bj * w - oy, oy - (bj + 1) * w), 0.0);
+                    if (dx * dx + dy * dy > reach * reach) continue;
+                    size_t b = (size_t)bi * bin_n + bj;
+                    if (pass == 0) off[b]++; else idx[fill[b]++] = k;
+                }
+        }
+    }
+}
+
 // Per-box rasterisation descriptor, the scalar prologue of Grid2D::update_obstacles (Grid2D.cpp:102-122).
 struct PPBoxDesc
 {

@@ -73,6 +73,40 @@ struct PPWarpDev
     }
 };
 
+// The K-POP mode runs one query on a CTA of NW warps: LANES = 32*NW cooperating lanes, ballots per hardware warp.
+template <int NW>
+struct PPBlockDev
+{
+    enum { LANES = 32 * NW, BW = 32 };
+    __device__ __forceinline__ int lane() const { return threadIdx.x; }
+    __device__ __forceinline__ int wlane() const { return threadIdx.x & 31; }
+    __device__ __forceinline__ int warp() const { return threadIdx.x >> 5; }
+    __device__ __forceinline__ void sync() const { if (NW == 1) __syncwarp(); else __syncthreads(); }
+    __device__ __forceinline__ void wsync() const { __syncwarp(); }
+    __device__ __forceinline__ unsigned ballot(bool p) const { return __ballot_sync(0xffffffffu, p); }
+    __device__ __forceinline__ unsigned lanemask_lt() const { return (1u << (threadIdx.x & 31)) - 1u; }
+    template <class T> __device__ __forceinline__ T shfl(T v, int src) const { return __shfl_sync(0xffffffffu, v, src); }
+    __device__ __forceinline__ bool any(bool p, int* scratch) const
+    {
+        if (NW == 1) return __ballot_sync(0xffffffffu, p) != 0u;
+        return __syncthreads_or(p ? 1 : 0) != 0;
+    }
+    __device__ __forceinline__ int scan_count(bool p, int* scratch, int& total) const
+    {
+        const unsigned m = __ballot_sync(0xffffffffu, p);
+        int pos = __popc(m & lanemask_lt());
+        if (NW == 1) { total = __popc(m); return pos; }
+        if (wlane() == 0) scratch[warp()] = __popc(m);
+        __syncthreads();
+        int t = 0;
+#pragma unroll
+        for (int k = 0; k < NW; k++) { int v = scratch[k]; if (k < warp()) pos += v; t += v; }
+        __syncthreads();
+        total = t;
+        return pos;
+    }
+};
+
 // ---------------------------------------------------------------------------------------------------
 struct PPBatchArgs
 {
@@ -153,6 +187,7 @@ struct PPKpopArgs
     const float*    field2d;    // num_groups x N*N exact 2D distance fields
     const PPQuery*  queries;
     const int*      qmap;
+    const int*      order;      // optional launch order of the work items (pp_kpop_order_kernel)
     int             n_queries;
     int             n_slots;
     int             kpop;
@@ -168,12 +203,14 @@ struct PPKpopArgs
     int             lsm_levels;
 };
 
-__global__ void __launch_bounds__(32) pp_kpop_kernel(const __grid_constant__ PPKpopArgs a)
+template <int NW>
+__global__ void __launch_bounds__(32 * NW) pp_kpop_kernel(const __grid_constant__ PPKpopArgs a)
 {
     __shared__ PPKSmem sm;
+    __shared__ int s_q;
     const int slot = blockIdx.x;
     if (slot >= a.n_slots) return;
-    PPWarpDev w;
+    PPBlockDev<NW> w;
     PPKWork wk;
     wk.nodes = a.nodes + (size_t)slot * a.nodes_cap;   wk.nodes_cap = a.nodes_cap;
     wk.table = a.table + (size_t)slot * a.table_cap;   wk.table_cap = a.table_cap;
@@ -183,10 +220,12 @@ __global__ void __launch_bounds__(32) pp_kpop_kernel(const __grid_constant__ PPK
     const size_t nn = (size_t)a.C.N * a.C.N;
     for (;;)
     {
-        int q = 0;
-        if (w.lane() == 0) q = atomicAdd(a.counter, 1);
-        q = w.shfl(q, 0);
+        if (w.lane() == 0) s_q = atomicAdd(a.counter, 1);
+        w.sync();
+        int q = s_q;
+        w.sync();
         if (q >= a.n_queries) break;
+        if (a.order) q = a.order[q];
         if (a.qmap) q = a.qmap[q];
         const PPQuery Q = a.queries[q];
         const PPGroup G = a.groups[Q.group];
@@ -195,10 +234,42 @@ __global__ void __launch_bounds__(32) pp_kpop_kernel(const __grid_constant__ PPK
         wk.trace = a.trace ? a.trace + (size_t)q * a.trace_cap : nullptr;
         wk.trace_cap = a.trace ? a.trace_cap : 0;
         PPResult res;
+#ifdef PP_PROFILE
+        unsigned long long t_begin; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_begin));
+#endif
         pp_search_kpop(w, a.C, a.off_xy, G, Q.start, a.kpop, wk, sm, res);
+#ifdef PP_PROFILE
+        unsigned long long t_end; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end));
+        res.max_open = (int)((t_begin / 1000ull) & 0x7fffffffull); res.n_pops_bin_oob = (int)((t_end / 1000ull) & 0x7fffffffull);   // us
+#endif
         if (w.lane() == 0) a.results[q] = res;
-        __syncwarp();
+        w.sync();
     }
+}
+
+// Longest-expected-first launch order of a K-POP batch: rank the work items by the exact 2D distance of their start
+// cell (descending; ties by index).  Only the order in which the resident slots fetch queries changes -- every query
+// is independent, results are unaffected -- but the batch no longer ends on a long query that was fetched last.
+__global__ void __launch_bounds__(256) pp_kpop_order_kernel(const PPQuery* queries, const int* qmap, int n, const float* field2d,
+                                                            int N, int* order)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const size_t nn = (size_t)N * N;
+    const PPQuery Qi = queries[qmap ? qmap[i] : i];
+    const bool in_i = Qi.start.ci >= 0 && Qi.start.ci < N && Qi.start.cj >= 0 && Qi.start.cj < N;
+    float ki = in_i ? field2d[nn * Qi.group + (size_t)Qi.start.ci * N + Qi.start.cj] : 0.0f;
+    if (!(ki < 3.0e38f)) ki = 0.0f;                                   // unreachable: ends at once
+    int rank = 0;
+    for (int j = 0; j < n; j++)
+    {
+        const PPQuery Qj = queries[qmap ? qmap[j] : j];
+        const bool in_j = Qj.start.ci >= 0 && Qj.start.ci < N && Qj.start.cj >= 0 && Qj.start.cj < N;
+        float kj = in_j ? field2d[nn * Qj.group + (size_t)Qj.start.ci * N + Qj.start.cj] : 0.0f;
+        if (!(kj < 3.0e38f)) kj = 0.0f;
+        rank += (kj > ki || (kj == ki && j < i)) ? 1 : 0;
+    }
+    order[rank] = i;
 }
 
 // ---------------------------------------------------------------------------------------------------

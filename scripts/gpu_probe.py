@@ -18,6 +18,8 @@ import bench  # noqa: E402
 
 PHASES = ["init", "pop+closed.insert+erase", "rollout+collision+apf", "dubins cand", "closed.find", "open.find(+erase)",
           "lazy 2D A*", "open.insert"]
+KPHASES = ["init", "queue pop (select k)", "validate+close+goal/shot", "expand: rollout+collision+apf+hash", "winners: dubins+node write",
+           "sort + LSM insert", "-", "-"]
 
 
 def main():
@@ -54,10 +56,30 @@ def main():
         np.median(res["max_open"]), res["max_open"].max(), res["n_closed"].max(), res["n_lazy_searches"].mean(),
         res["n_lazy_pops"].sum() / max(pops, 1)))
     print("success %.3f, status!=0: %d, oob pops %d" % (res["success"].mean(), (res["status"] != 0).sum(), res["n_pops_bin_oob"].sum()))
+    if a.mode == 1:
+        it = res["n_lazy_searches"].astype(np.float64); tk = res["n_lazy_pops"].astype(np.float64)
+        print("kpop: iterations/query mean %.0f max %d | valid pops per iteration %.2f | entries taken per iteration %.2f | nodes max %d" % (
+            it.mean(), it.max(), np_.sum() / it.sum(), tk.sum() / it.sum(), res["n_closed"].max()))
+        order = np.argsort(-np_)[:5]
+        print("longest queries: pops", np_[order], "iterations", res["n_lazy_searches"][order], "success", res["success"][order])
+    if prof and a.mode == 1:
+        t0 = res["max_open"].astype(np.int64); t1 = res["n_pops_bin_oob"].astype(np.int64)
+        base = t0.min(); t0 -= base; t1 -= base
+        dur = np.maximum(t1 - t0, 1); its = res["n_lazy_searches"].astype(np.float64)
+        print("timeline (us): last start %d, last end %d; queries ending in the last 10%% of the batch: %d" % (
+            t0.max(), t1.max(), (t1 > 0.9 * t1.max()).sum()))
+        edges = np.linspace(0, t1.max(), 11)
+        for lo, hi in zip(edges[:-1], edges[1:]):
+            m = (t0 < hi) & (t1 > lo)                      # queries alive in this window
+            sel = (t0 >= lo) & (t0 < hi) & (its > 50)
+            rate = (dur[sel] / its[sel]).mean() if sel.any() else float("nan")
+            print("  window %7.0f-%7.0f us: alive %4d, started %4d, mean us/iteration of those started here %.1f" % (lo, hi, m.sum(), ((t0 >= lo) & (t0 < hi)).sum(), rate))
+        order = np.argsort(-t1)[:5]
+        print("  last finishers: start", t0[order], "end", t1[order], "iterations", res["n_lazy_searches"][order])
     if prof:
         ctx.lib.pp_profile_read(ctx.h, buf)
         tot = sum(buf)
-        for name, v in zip(PHASES, buf):
+        for name, v in zip(KPHASES if a.mode == 1 else PHASES, buf):
             print(f"  {name:28s} {100.0 * v / max(tot, 1):6.2f} %   {v / max(pops, 1):10.0f} cycles/expansion")
 
 

@@ -9,6 +9,7 @@
 #include <cstring>
 #include <cstdio>
 #include <memory>
+#include <cstdlib>
 
 #include "../../path_planning_pkg_b200/csrc/core/pp_search.h"
 #include "../../path_planning_pkg_b200/csrc/core/pp_kpop.h"
@@ -34,6 +35,7 @@ namespace
         std::vector<int> cl_prev;
         std::vector<PPNode2> open2;
         std::vector<PPPathPt> path;
+        std::vector<int> bin_off, bin_idx; int bin_n = 0;
         PPLazy lazy;               // persistent lazy-A* state for emu_astar_lazy_batch
         bool lazy_init = false;
     };
@@ -45,6 +47,9 @@ namespace
         g.apf = e->apf.empty() ? nullptr : e->apf.data();
         g.K = (int)(e->apf.size() / 3);
         g.pad = 0;
+        g.bin_shift = 4; g.bin_n = e->bin_n;
+        g.bin_off = e->bin_off.empty() ? nullptr : e->bin_off.data();
+        g.bin_idx = e->bin_idx.data();
         g.frame = e->fr.F;
         return g;
     }
@@ -126,6 +131,7 @@ void emu_update_boxes(void* h, const float* boxes, const float* conf, int n, flo
 {
     Emu* e = static_cast<Emu*>(h);
     pp_host_apf_list(e->m.C, e->fr, boxes, n, apf_added_radius, e->apf);
+    pp_host_apf_bins(e->m.C, e->apf, n, 4, e->bin_n, e->bin_off, e->bin_idx);
     emu_update_boxes_2d(h, boxes, conf, n);
 }
 
@@ -390,6 +396,7 @@ void emu_find_path_kpop(void* h, float vel, const float* s, int k, const float* 
     pp_search_kpop(w, C, e->m.off_xy.data(), G, st, k, wk, *sm, r);
     res->success = r.success; res->cost = r.cost; res->n_pops = r.n_pops; res->n_pops_bin_oob = r.n_pops_bin_oob;
     if (r.status) std::fprintf(stderr, "emu_find_path_kpop: status %d\n", r.status);
+    if (std::getenv("PP_EMU_VERBOSE")) std::fprintf(stderr, "kpop k=%d: pops %d iterations %d entries taken %d nodes %d\n", k, r.n_pops, r.n_lazy_searches, r.n_lazy_pops, r.n_closed);
     int n = 0;
     if (r.success)
     {
