@@ -184,6 +184,9 @@ int  pp_check_path(pp_context* ctx, int group, const float* xyh, int n, int* fre
 /* Dubins::get_shortest_path_length (lib/Dubins.cpp:19-69) for n starts and one goal */
 int  pp_dubins_length_batch(pp_context* ctx, const float* starts_xyh, int n, const float* goal3, float* length,
                             int* type, float* params4);
+/* the same length, every operation in FP32 (one thread per start; the heuristic flavour the K-POP mode uses): within
+   1e-5 relative of Dubins::get_shortest_path_length (lib/Dubins.cpp:19-69) */
+int  pp_dubins_length_fp32_batch(pp_context* ctx, const float* starts_xyh, int n, const float* goal3, float* length);
 /* Dubins::get_shortest_path (lib/Dubins.cpp:125-153): returns sample count in *n_out */
 int  pp_dubins_path(pp_context* ctx, const float* start3, const float* goal3, float* xyh, float* curvature, int cap,
                     int* n_out, float* length, int* long_turn_flag);

@@ -166,11 +166,15 @@ float clampv(const Port& P, float v) { return std::max(std::min(v, P.log_max), P
 // libm flavour of the functions the B200 build executes on the device (Dubins.cpp, atan2f of Grid3D::get_field_intensity):
 // 0 = platform libm like the reference; 1 = "pinned": evaluate in double, round once to float (see oracle/cr_math.c).
 // With flavour 1 this restatement equals oracle/_ref/libref_oracle_crm.so.
+// K-POP mode only (new semantics): flavour 2 = the FP32 functions of fmath.inc for the heuristic Dubins length and the APF term.
+#include "fmath.inc"
 static bool g_pinned_libm = false;
-static inline float m_sin(float x) { return g_pinned_libm ? (float)std::sin((double)x) : std::sin(x); }
-static inline float m_cos(float x) { return g_pinned_libm ? (float)std::cos((double)x) : std::cos(x); }
-static inline float m_atan2(float y, float x) { return g_pinned_libm ? (float)std::atan2((double)y, (double)x) : std::atan2(y, x); }
-static inline float m_acos(float x) { return g_pinned_libm ? (float)std::acos((double)x) : std::acos(x); }
+static bool g_fast_libm = false;
+struct FastLibmScope { bool saved; FastLibmScope() : saved(g_fast_libm) { g_fast_libm = true; } ~FastLibmScope() { g_fast_libm = saved; } };
+static inline float m_sin(float x) { return g_fast_libm ? fm::sin(x) : g_pinned_libm ? (float)std::sin((double)x) : std::sin(x); }
+static inline float m_cos(float x) { return g_fast_libm ? fm::cos(x) : g_pinned_libm ? (float)std::cos((double)x) : std::cos(x); }
+static inline float m_atan2(float y, float x) { return g_fast_libm ? fm::atan2(y, x) : g_pinned_libm ? (float)std::atan2((double)y, (double)x) : std::atan2(y, x); }
+static inline float m_acos(float x) { return g_fast_libm ? fm::acos(x) : g_pinned_libm ? (float)std::acos((double)x) : std::acos(x); }
 
 // ---- Dubins ------------------------------------------------------------------------------------------
 struct DubRes { float len; int type; float p[4]; float c[8]; };   // c = srx sry slx sly grx gry glx gly
@@ -316,6 +320,21 @@ float field(const Port& P, float x, float y, float h)
     for (size_t k = 0; k < P.apf.size() / 3; k++)
     {
         float ox = P.apf[3 * k], oy = P.apf[3 * k + 1], rad = P.apf[3 * k + 2];
+        if (g_fast_libm)                          // K-POP: the same term in FP32 throughout
+        {
+            float dx = ox - x, dy = oy - y;
+            float dist = std::sqrt(dx * dx + dy * dy);
+            if (dist < rad)
+            {
+                float ang = std::abs(wrap_pi_f(h - fm::atan2(dy, dx)));
+                ang = std::max(P.apf_alpha - ang, 0.0f);
+                float d = 1.0f / dist - 1.0f / rad;
+                float fp = P.apf_k * (d * d);
+                fp = fp * ang / P.apf_alpha;
+                acc = acc + fp;
+            }
+            continue;
+        }
         float distance = std::hypot(ox - x, oy - y);
         float angle = std::abs(wrap_pi_f(h - m_atan2(oy - y, ox - x)));
         angle = std::max(P.apf_alpha - angle, 0.0f);

@@ -258,6 +258,12 @@ class Context:
         self._chk(self.lib.pp_dubins_length_batch(self.h, _p(starts), C.c_int(n), _p(goal), _p(ln), _p(ty), _p(pr)))
         return ln, ty, pr
 
+    def dubins_length_fp32(self, starts, goal):
+        starts = np.ascontiguousarray(starts, np.float32); goal = np.asarray(goal, np.float32)
+        ln = np.empty(len(starts), np.float32)
+        self._chk(self.lib.pp_dubins_length_fp32_batch(self.h, _p(starts), C.c_int(len(starts)), _p(goal), _p(ln)))
+        return ln
+
     def dubins_path(self, start, goal, cap=4096):
         s = np.asarray(start, np.float32); g = np.asarray(goal, np.float32)
         xyh = np.empty((cap, 3), np.float32); cv = np.empty(cap, np.float32)

@@ -567,6 +567,25 @@ int pp_dubins_length_batch(pp_context* c, const float* starts, int n, const floa
     return PP_SUCCESS;
 }
 
+int pp_dubins_length_fp32_batch(pp_context* c, const float* starts, int n, const float* goal3, float* length)
+{
+    if (!c) return pp_fail(PP_ERR_INVALID, "null context");
+    if (n <= 0) return PP_SUCCESS;
+    if (!starts || !goal3 || !length) return pp_fail(PP_ERR_INVALID, "pp_dubins_length_fp32_batch: bad arguments");
+    PP_CUDA(cudaSetDevice(c->device));
+    PP_CUDA(c->s0.ensure(sizeof(float) * 3 * (size_t)n));
+    PP_CUDA(c->s1.ensure(sizeof(float) * (size_t)n));
+    PP_CUDA(cudaMemcpyAsync(c->s0.p, starts, sizeof(float) * 3 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    int blocks = std::min((n + 255) / 256, c->sm_count * 8);
+    pp_dubins_length_fp32_kernel<<<blocks, 256, 0, c->stream>>>(c->model.C, (const float*)c->s0.p, n, goal3[0], goal3[1], goal3[2],
+                                                                (float*)c->s1.p);
+    c->launches += 1;
+    PP_CUDA(cudaGetLastError());
+    PP_CUDA(cudaMemcpyAsync(length, c->s1.p, sizeof(float) * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+    PP_CUDA(cudaStreamSynchronize(c->stream));
+    return PP_SUCCESS;
+}
+
 int pp_dubins_path(pp_context* c, const float* s, const float* g, float* xyh, float* curvature, int cap, int* n_out,
                    float* length, int* long_turn_flag)
 {
@@ -886,7 +905,6 @@ int pp_batch_fetch(pp_context* c, pp_result* results, float* paths_xyh, float* c
     if (trace && c->opts.trace_cap > 0)
         PP_CUDA(cudaMemcpyAsync(trace, c->d_trace.p, sizeof(PPPop) * (size_t)n * c->opts.trace_cap, cudaMemcpyDeviceToHost, c->stream));
     PP_CUDA(cudaStreamSynchronize(c->stream));
-    int any_cap = 0;
     for (int k = 0; k < n; k++)
     {
         pp_result& o = results[k];
@@ -894,7 +912,6 @@ int pp_batch_fetch(pp_context* c, pp_result* results, float* paths_xyh, float* c
         o.n_pops_bin_oob = r[k].n_pops_bin_oob; o.n_chain = r[k].n_chain; o.n_dubins = r[k].n_dubins;
         o.n_lazy_searches = r[k].n_lazy_searches; o.n_lazy_pops = r[k].n_lazy_pops; o.max_open = r[k].max_open;
         o.n_closed = r[k].n_closed; o.n_path = 0;
-        if (o.status) any_cap = 1;
         if (!o.success || !paths_xyh) continue;
         // HybridAStar::reconstruct_path (HybridAStar.cpp:208-262): reversed Dubins samples, then the parent chain,
         // rotated back to the world frame; curvature shifted by one point
@@ -914,7 +931,6 @@ int pp_batch_fetch(pp_context* c, pp_result* results, float* paths_xyh, float* c
         }
         o.n_path = total;
     }
-    (void)any_cap;
     return PP_SUCCESS;
 }
 

@@ -23,6 +23,7 @@
 #define PP_KPOP_H
 
 #include "pp_search.h"
+#include "pp_fmath.h"
 
 #define PP_K_MAXPOP 32
 #define PP_K_MAXSUCC 8                                  // (2A+1) supported by this mode
@@ -109,28 +110,41 @@ PP_HD void pp_fence()
 }
 
 // ---- hash table -----------------------------------------------------------------------------------------------------
-PP_HD int pp_ktable_find(const PPKWork& wk, unsigned key)
+// (key, node) of a slot with one 8-byte load: they share the slot's first half
+PP_HD void pp_kslot_load(const PPKSlot* s, unsigned& key, unsigned& node)
+{
+#ifdef __CUDA_ARCH__
+    const uint2 v = *reinterpret_cast<const uint2*>(s);
+    key = v.x; node = v.y;
+#else
+    key = s->key; node = s->node;
+#endif
+}
+PP_HD int pp_ktable_find(const PPKWork& wk, unsigned key, unsigned& node)
 {
     unsigned mask = (unsigned)wk.table_cap - 1u, h = pp_hash_key(key) & mask;
     for (;;)
     {
-        unsigned k = wk.table[h].key;
+        unsigned k;
+        pp_kslot_load(wk.table + h, k, node);
         if (k == key) return (int)h;
         if (k == PP_K_EMPTY) return -1;
         h = (h + 1) & mask;
     }
 }
-PP_HD int pp_ktable_find_or_insert(PPKWork& wk, unsigned key)
+// `node` = the slot's node word; a key inserted by this call (or concurrently, in the same expansion phase) has none yet
+PP_HD int pp_ktable_find_or_insert(PPKWork& wk, unsigned key, unsigned& node)
 {
     unsigned mask = (unsigned)wk.table_cap - 1u, h = pp_hash_key(key) & mask;
     for (;;)
     {
-        unsigned k = wk.table[h].key;
+        unsigned k;
+        pp_kslot_load(wk.table + h, k, node);
         if (k == key) return (int)h;
         if (k == PP_K_EMPTY)
         {
             unsigned old = pp_atomic_cas_u32(&wk.table[h].key, PP_K_EMPTY, key);
-            if (old == PP_K_EMPTY || old == key) return (int)h;
+            if (old == PP_K_EMPTY || old == key) { node = PP_K_NONE; return (int)h; }
         }
         h = (h + 1) & mask;
     }
@@ -280,22 +294,53 @@ PP_HD int pp_klsm_pop(const W& w, PPKWork& wk, PPKSmem& sm, int k)
     return n;
 }
 
-// Dubins length with the sequential candidate fold (Dubins.cpp:19-69), pinned libm; goal circle centres precomputed
+// Heuristic Dubins length: the sequential candidate fold of Dubins.cpp:19-69 with the float tail of the reference
+// (pp_dubins_finish) and the transcendentals in FP32 (pp_fmath.h); goal circle centres precomputed the same way.
+PP_HD float pp_kdubins_cand(int type, float r, float sh, float gh, float csx, float csy, float cgx, float cgy)
+{
+    float p[4];
+    const float theta = pp_fm_atan2(cgy - csy, cgx - csx);
+    float ac = 0.0f, c1 = 0.0f, s1 = 0.0f, c2 = 0.0f, s2 = 0.0f;
+    if (type == PP_RSL || type == PP_LSR)
+    {
+        ac = pp_fm_acos(pp_dubins_acos_arg(r, csx, csy, cgx, cgy));
+        const float t1 = pp_dubins_theta_t1(type, ac, theta);
+        const float p2 = pp_dubins_p2(type, t1);
+        pp_fm_sincos(t1, s1, c1);
+        pp_fm_sincos(p2, s2, c2);
+    }
+    return pp_dubins_finish(type, r, sh, gh, csx, csy, cgx, cgy, theta, ac, c1, s1, c2, s2, p);
+}
 PP_HD float pp_kdubins(const PPConsts& C, const PPFrame& F, const PPDubinsGoal& gc, float x, float y, float h)
 {
     const float r = C.r_min;
-    float sn = pp_sinf(h), cs = pp_cosf(h);
+    float sn, cs;
+    pp_fm_sincos(h, sn, cs);
     float srx = x + r * sn, sry = y - r * cs, slx = x - r * sn, sly = y + r * cs;
     float best = 0.0f;
     for (int type = 0; type < 4; type++)
     {
         bool s_right = (type == PP_RSR) || (type == PP_RSL), g_right = (type == PP_RSR) || (type == PP_LSR);
-        float p[4];
-        float len = pp_dubins_candidate(type, r, h, F.goal_h, s_right ? srx : slx, s_right ? sry : sly,
-                                        g_right ? gc.grx : gc.glx, g_right ? gc.gry : gc.gly, p);
+        float len = pp_kdubins_cand(type, r, h, F.goal_h, s_right ? srx : slx, s_right ? sry : sly,
+                                    g_right ? gc.grx : gc.glx, g_right ? gc.gry : gc.gly);
         if (type == 0 || len < best) best = len;
     }
     return best;
+}
+
+// One obstacle's APF term (Grid3D.cpp:209-223) in FP32 throughout -- the K-POP flavour of pp_apf_term
+PP_HD float pp_kapf_term(const PPConsts& C, float ox, float oy, float radius, float x, float y, float heading)
+{
+    const float dx = ox - x, dy = oy - y;
+    const float dist = sqrtf(dx * dx + dy * dy);
+    if (!(dist < radius)) return 0.0f;
+    float ang = fabsf(pp_wrap_pi(heading - pp_fm_atan2(dy, dx)));
+    const float a = C.apf_alpha - ang;
+    ang = (a < 0.0f) ? 0.0f : a;
+    const float d = 1.0f / dist - 1.0f / radius;
+    float fp = C.apf_k * (d * d);
+    fp = fp * ang / C.apf_alpha;
+    return fp;
 }
 
 // The Dubins shot (HybridAStar.cpp:129-149): all lanes; returns true when accepted; samples in path[0 .. n_dubins).
@@ -340,15 +385,20 @@ PP_HD bool pp_try_shot(const W& w, const PPConsts& C, const float* map, const PP
             accb[pl.size_3] = 0.0f;
         }
         w.sync();
-        for (int k = w.lane(); k < total; k += W::LANES)
+        // a blocked sample anywhere rejects the shot: stop after the first round of samples that saw one
+        for (int base = 0; base < total; base += W::LANES)
         {
-            float sx, sy, sh, kappa;
-            pp_dubins_sample(pl, C.r_min, k, accb[k], sx, sy, sh, kappa);
-            if (pp_path_point_blocked(C, map, sx, sy)) blocked = true;
-            if (k < path_cap) { PPPathPt& q = path[k]; q.x = sx; q.y = sy; q.heading = sh; q.curvature = kappa; }
-            else over = true;
+            const int k = base + w.lane();
+            if (k < total)
+            {
+                float sx, sy, sh, kappa;
+                pp_dubins_sample(pl, C.r_min, k, accb[k], sx, sy, sh, kappa);
+                if (pp_path_point_blocked(C, map, sx, sy)) blocked = true;
+                if (k < path_cap) { PPPathPt& q = path[k]; q.x = sx; q.y = sy; q.heading = sh; q.curvature = kappa; }
+                else over = true;
+            }
+            if (w.any(blocked, scratch)) return false;
         }
-        w.sync();
     }
     else
     {
@@ -397,7 +447,8 @@ PP_HD_NOINLINE void pp_search_kpop(const W& w, const PPConsts& C, const float* o
     w.sync();
     PPDubinsGoal gc;
     {
-        float sg = pp_sinf(F.goal_h), cg = pp_cosf(F.goal_h);
+        float sg, cg;
+        pp_fm_sincos(F.goal_h, sg, cg);
         gc.grx = F.goal_x + C.r_min * sg; gc.gry = F.goal_y - C.r_min * cg;
         gc.glx = F.goal_x - C.r_min * sg; gc.gly = F.goal_y + C.r_min * cg;
     }
@@ -409,7 +460,8 @@ PP_HD_NOINLINE void pp_search_kpop(const W& w, const PPConsts& C, const float* o
         n0.curv = start.curv; n0.bin = start.bin; n0.cell = start.ci * N + start.cj; n0.parent = -1;
         n0.key = (unsigned)n0.cell * kb + (unsigned)start.bin; n0.pad = 0;
         wk.nodes[0] = n0;
-        int slot = pp_ktable_find_or_insert(wk, n0.key);
+        unsigned nw0;
+        int slot = pp_ktable_find_or_insert(wk, n0.key, nw0);
         wk.table[slot].node = 0u;
         wk.table[slot].pack = ((unsigned long long)pp_fbits(0.0f) << 32);
         PPKEntry e; e.f = n0.f; e.key = n0.key; e.idx = 0u; e.pad = 0;
@@ -445,8 +497,9 @@ PP_HD_NOINLINE void pp_search_kpop(const W& w, const PPConsts& C, const float* o
                 if (b < nb)
                 {
                     me = sm.popped[b];
-                    slot = pp_ktable_find(wk, me.key);
-                    valid = (slot >= 0) && (wk.table[slot].node == me.idx);      // closed or superseded => mismatch
+                    unsigned nw = 0u;
+                    slot = pp_ktable_find(wk, me.key, nw);
+                    valid = (slot >= 0) && (nw == me.idx);                       // closed or superseded => mismatch
                 }
                 const unsigned vm = w.ballot(valid);
                 int rank = n_valid;
@@ -498,6 +551,7 @@ PP_HD_NOINLINE void pp_search_kpop(const W& w, const PPConsts& C, const float* o
         if (n_valid == 0) continue;
         n_pops += n_valid;
 
+        PP_PROF_MARK(2)
         // ---- goal / shot, rank ordered ----
         if (r_g >= 0 && (r_s < 0 || r_g < r_s)) { success = 1; terminal = sm.pop_idx[r_g]; cost = sm.parents[r_g].g; break; }
         if (r_s >= 0)
@@ -520,7 +574,7 @@ PP_HD_NOINLINE void pp_search_kpop(const W& w, const PPConsts& C, const float* o
         }
         if (n_nodes + n_valid * n_succ > wk.nodes_cap) { status |= PP_STATUS_CLOSED_OVERFLOW; break; }
 
-        PP_PROF_MARK(2)
+        PP_PROF_MARK(6)
         // ---- expansion: candidate c = rank * n_succ + a ----
         const int n_cand = n_valid * n_succ;
         for (int c = lane; c < n_cand; c += W::LANES)
@@ -551,15 +605,16 @@ PP_HD_NOINLINE void pp_search_kpop(const W& w, const PPConsts& C, const float* o
                     float dx = ox - o.x, dy = oy - o.y, lim = rad * 1.001f + 1e-3f;
                     if (dx * dx + dy * dy <= lim * lim)
                     {
-                        float term = pp_apf_term(C, ox, oy, rad, o.x, o.y, o.heading);
+                        float term = pp_kapf_term(C, ox, oy, rad, o.x, o.y, o.heading);
                         if (term != 0.0f) field = field + term;
                     }
                 }
                 const float g = o.g + field;
                 const int cell = o.ci * N + o.cj;
                 const unsigned key = (unsigned)cell * kb + (unsigned)o.bin;
-                const int sl2 = pp_ktable_find_or_insert(wk, key);
-                if (!(wk.table[sl2].node & PP_K_CLOSED))
+                unsigned nw = 0u;
+                const int sl2 = pp_ktable_find_or_insert(wk, key, nw);
+                if (!(nw & PP_K_CLOSED))
                 {
                     cd.x = o.x; cd.y = o.y; cd.heading = o.heading; cd.g = g; cd.v2 = o.vmin_sqr;
                     cd.curv_bin_ok = (o.curv & 0xff) | ((o.bin & 0xff) << 8) | (1 << 16);

@@ -361,6 +361,20 @@ __global__ void pp_collision_kernel(const __grid_constant__ PPConsts C, const fl
 }
 
 // 4 lanes per state: one CSC candidate each, folded in candidate order (Dubins.cpp:36-68)
+// FP32 SIMT Dubins heuristic (north_star (d)), one thread per start: the flavour the K-POP mode evaluates per node
+__global__ void __launch_bounds__(256) pp_dubins_length_fp32_kernel(const __grid_constant__ PPConsts C, const float* starts, int n,
+                                                                     float gx, float gy, float gh, float* length)
+{
+    PPFrame F; F.goal_x = gx; F.goal_y = gy; F.goal_h = gh; F.goal_ci = F.goal_cj = F.goal_bin = 0;
+    PPDubinsGoal gc;
+    float sg, cg;
+    pp_fm_sincos(gh, sg, cg);
+    gc.grx = gx + C.r_min * sg; gc.gry = gy - C.r_min * cg;
+    gc.glx = gx - C.r_min * sg; gc.gly = gy + C.r_min * cg;
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x)
+        length[k] = pp_kdubins(C, F, gc, starts[3 * k], starts[3 * k + 1], starts[3 * k + 2]);
+}
+
 __global__ void __launch_bounds__(128) pp_dubins_length_kernel(float r_min, const float* starts, int n, float gx, float gy,
                                                                 float gh, float* length, int* type, float* params4)
 {

@@ -18,8 +18,8 @@ import bench  # noqa: E402
 
 PHASES = ["init", "pop+closed.insert+erase", "rollout+collision+apf", "dubins cand", "closed.find", "open.find(+erase)",
           "lazy 2D A*", "open.insert"]
-KPHASES = ["init", "queue pop (select k)", "validate+close+goal/shot", "expand: rollout+collision+apf+hash", "winners: dubins+node write",
-           "sort + LSM insert", "-", "-"]
+KPHASES = ["init", "queue pop (select k)", "validate+close", "expand: rollout+collision+apf+hash", "winners: dubins+node write",
+           "sort + LSM insert", "goal / dubins shot", "-"]
 
 
 def main():

@@ -192,3 +192,27 @@ def test_relocation_port_vs_reference():
         o.update_goal([22, 9, -0.1], [1.5, 0.4, 0.1])
     assert (b.get_map() != 0).sum() > 50
     assert np.array_equal(_bits(a.get_map()), _bits(b.get_map()))
+
+
+def test_fp32_dubins_restatement_close_to_reference():
+    """oracle/port/fmath.inc (libm mode 2, the K-POP heuristic flavour): Dubins lengths within 1e-5 relative of the
+    unmodified reference, except at the +-2pi branch flips of the reference formula (counted)."""
+    P = orc.ref_test_params()
+    ref, port = orc.ref(P), orc.port(P)
+    for o in (ref, port):
+        orc.setup_ref_test_scenario(o)
+    rs = np.random.RandomState(5)
+    n = 100000
+    goal = np.array(list(ref.consts().goal_grid), np.float32)
+    starts = np.stack([rs.uniform(0, 30, n), rs.uniform(0, 30, n), rs.uniform(-3.14, 3.14, n)], 1).astype(np.float32)
+    r, _, _ = ref.dubins_length(starts, goal)
+    port.lib.port_set_libm(2)
+    try:
+        a, _, _ = port.dubins_length(starts, goal)
+    finally:
+        port.lib.port_set_libm(0)
+    rel = np.abs(a - r) / np.maximum(np.abs(r), 1e-6)
+    jumps = int((rel > 1e-5).sum())
+    assert jumps <= n // 2000, jumps
+    assert rel[rel <= 1e-5].max() < 1e-5
+    print(f"fp32 restatement vs reference: max rel {rel[rel <= 1e-5].max():.3g}, flips {jumps}/{n}")

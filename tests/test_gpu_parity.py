@@ -167,6 +167,30 @@ def test_dubins_length(golden):
     assert jumps <= n // 2000
 
 
+def test_dubins_length_fp32(golden):
+    """FP32 SIMT flavour (K-POP heuristic): bit-identical to its CPU restatement (oracle/port/fmath.inc, libm mode 2) and
+    within 1e-5 relative of the reference's lengths (north_star), branch flips of the +-2pi corrections counted."""
+    P, ctx, ref, crm = golden
+    port = orc.port(P)
+    orc.setup_ref_test_scenario(port)
+    rs = np.random.RandomState(11)
+    n = 200000
+    goal = np.array(list(ref.consts().goal_grid), np.float32)
+    starts = np.stack([rs.uniform(0, 30, n), rs.uniform(0, 30, n), rs.uniform(-3.14, 3.14, n)], 1).astype(np.float32)
+    a = ctx.dubins_length_fp32(starts, goal)
+    port.lib.port_set_libm(2)
+    try:
+        b, _, _ = port.dubins_length(starts, goal)
+    finally:
+        port.lib.port_set_libm(0)
+    assert np.array_equal(_bits(a), _bits(b))
+    r, _, _ = ref.dubins_length(starts, goal)
+    rel = np.abs(a - r) / np.maximum(np.abs(r), 1e-6)
+    jumps = int((rel > 1e-5).sum())
+    print(f"fp32 dubins vs reference: max rel (non-jump) {rel[rel <= 1e-5].max():.3g}, branch flips {jumps}/{n}")
+    assert jumps <= n // 2000
+
+
 def test_dubins_path_golden(golden):
     """utils/dubins_paths.py:6 scenario: (0,0,0) -> (20,-20,pi/2)."""
     P, ctx, ref, crm = golden
