@@ -145,6 +145,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=1, help="timed end-to-end steps (each is a full batch)")
     ap.add_argument("--no-kpop", action="store_true", help="skip the additional K-POP(32) throughput measurement")
+    ap.add_argument("--no-kpop-large", action="store_true", help="skip the K-POP(32) measurement on the C5-sized batch")
+    ap.add_argument("--large-starts", type=int, default=1024, help="starts per group of the C5-sized K-POP batch")
     args = ap.parse_args()
     rank, local_rank, world = dist_env()
     n_threads = os.cpu_count() or 1
@@ -289,27 +291,74 @@ def main():
     # reference's; reported beside the headline, never instead of it) ----
     kpop_info = None
     if not args.no_kpop:
-        kopts = ctx.make_opts(max_expansions=1 << 16, path_cap=2048, max_slots=args.max_slots, mode=1, kpop=32)
+        kopts = ctx.make_opts(max_expansions=1 << 17, path_cap=2048, max_slots=args.max_slots, mode=1, kpop=32)
         ctx.batch_upload(q, kopts)
+        ksteps = max(args.steps, 5)
         for _ in range(args.warmup):
             ctx.batch_run()
         barrier()
-        kms = [ctx.batch_run() for _ in range(args.steps)]
+        kl0 = ctx.kernel_launches()
+        kms = [ctx.batch_run() for _ in range(ksteps)]
         barrier()
+        k_launches = ctx.kernel_launches() - kl0
         kres, _, _ = ctx.batch_fetch()
+        # end to end through the C ABI, host buffers, same as the exact-mode e2e above
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(ksteps):
+            rc = lib.pp_find_path_batch(ctx.h, C.c_void_p(hq.data_ptr()), C.c_int(nq), C.byref(kopts), C.c_void_p(hres.data_ptr()),
+                                        C.c_void_p(hpath.data_ptr()), C.c_void_p(hcurv.data_ptr()), None)
+            if rc != 0:
+                raise RuntimeError(lib.pp_last_error().decode())
+        barrier()
+        ke2e = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
         kt = torch.tensor([float(np.sum(kms))], dtype=torch.float64, device="cuda")
-        kp = torch.tensor([float(kres["n_pops"].sum()) * args.steps], dtype=torch.float64, device="cuda")
+        kp = torch.tensor([float(kres["n_pops"].sum()) * ksteps], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(kt, op=dist.ReduceOp.MAX)
+            dist.all_reduce(ke2e, op=dist.ReduceOp.MAX)
             dist.all_reduce(kp, op=dist.ReduceOp.SUM)
         both = (res["success"] == 1) & (kres["success"] == 1)
         ratio = kres["cost"][both] / res["cost"][both] - 1.0
+        kq = all_q / args.steps * ksteps
         kpop_info = {"k": 32, "expansions_per_s": float(kp.item()) / (float(kt.item()) * 1e-3),
-                     "queries_per_s": all_q / (float(kt.item()) * 1e-3), "ms_per_step": float(kt.item()) / args.steps,
+                     "queries_per_s": kq / (float(kt.item()) * 1e-3), "ms_per_step": float(kt.item()) / ksteps, "steps": ksteps,
+                     "e2e": {"expansions_per_s": float(kp.item()) / float(ke2e.item()), "queries_per_s": kq / float(ke2e.item())},
+                     "gpu_launches": int(k_launches),
                      "expansions_per_step": int(kres["n_pops"].sum()), "success_rate": float(kres["success"].mean()),
                      "cost_vs_exact_mode": {"median": float(np.median(ratio)), "min": float(ratio.min()), "max": float(ratio.max())},
                      "note": "k pops per iteration, exact 2D field heuristic, no equal-f drops; bit-identical to its CPU restatement "
                              "(oracle/port/kpop.inc), NOT to the reference (SURVEY F4/F5)"}
+
+        # the same mode on a C5-sized batch (BASELINE configs[4]: 65536 queries, k-pop = 32): 1024 starts on each of the
+        # groups already on the device; device-resident timing only
+        if not args.no_kpop_large:
+            big_q, big_g = [], []
+            thr = ctx.consts().log_threshold
+            for gi in range(args.groups):
+                cand = S.c4_group(rank * args.groups + gi, n_starts=args.large_starts, grid_size=N_GRID, resolution=RES)["start_candidates"]
+                st = ctx.set_start(ctx.make_queries(cand, [gi] * len(cand)))
+                free = maps[gi][st["ci"], st["cj"]] < thr
+                sel = cand[free][:args.large_starts]
+                big_q.append(sel); big_g += [gi] * len(sel)
+            bq = ctx.make_queries(np.concatenate(big_q), np.array(big_g, np.int32))
+            bopts = ctx.make_opts(max_expansions=1 << 17, path_cap=1024, max_slots=args.max_slots, mode=1, kpop=32)
+            ctx.batch_upload(bq, bopts)
+            for _ in range(args.warmup):
+                ctx.batch_run()
+            barrier()
+            bms = [ctx.batch_run() for _ in range(ksteps)]
+            barrier()
+            bres, _, _ = ctx.batch_fetch(want_paths=False)
+            bt = torch.tensor([float(np.sum(bms))], dtype=torch.float64, device="cuda")
+            bp = torch.tensor([float(bres["n_pops"].sum()) * ksteps, float(len(bq)) * ksteps], dtype=torch.float64, device="cuda")
+            if world > 1:
+                dist.all_reduce(bt, op=dist.ReduceOp.MAX)
+                dist.all_reduce(bp, op=dist.ReduceOp.SUM)
+            kpop_info["c5_batch"] = {"queries_per_gpu": int(len(bq)), "expansions_per_s": float(bp[0].item()) / (float(bt.item()) * 1e-3),
+                                     "queries_per_s": float(bp[1].item()) / (float(bt.item()) * 1e-3),
+                                     "ms_per_step": float(bt.item()) / ksteps, "success_rate": float(bres["success"].mean()),
+                                     "capacity_flags": int((bres["status"] != 0).sum())}
 
     # single-query latency (p50) on the first 16 queries, one at a time through the same ABI
     lat = []

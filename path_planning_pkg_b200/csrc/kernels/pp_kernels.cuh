@@ -203,8 +203,11 @@ struct PPKpopArgs
     int             lsm_levels;
 };
 
+#ifndef PP_KPOP_MIN_BLOCKS
+#define PP_KPOP_MIN_BLOCKS 6      // 80 registers: 6 CTAs x 4 warps per SM measured best on large batches
+#endif
 template <int NW>
-__global__ void __launch_bounds__(32 * NW) pp_kpop_kernel(const __grid_constant__ PPKpopArgs a)
+__global__ void __launch_bounds__(32 * NW, PP_KPOP_MIN_BLOCKS) pp_kpop_kernel(const __grid_constant__ PPKpopArgs a)
 {
     __shared__ PPKSmem sm;
     __shared__ int s_q;
