@@ -87,6 +87,13 @@ def main():
                     states_per_s=states / (ms * 1e-3), write_gbs=4.0 * states / (ms * 1e-3) / 1e9, write_frac_of_hbm=4.0 * states / (ms * 1e-3) / 1e9 / peak,
                     fp32_tflops_est=flops / (ms * 1e-3) / 1e12, fp32_peak_tflops_derived=74.4, fp32_frac=flops / (ms * 1e-3) / 1e12 / 74.4,
                     note="485 FP32 op/state is SURVEY 8d's estimate (125 basic + 18 transcendentals x 20); FP32 peak derived, not measured"))
+    # FP32 SIMT Dubins length per state (K-POP heuristic flavour), through the C ABI (H2D 12 B + D2H 4 B per state included)
+    m = 1 << 22
+    starts = np.random.RandomState(0).uniform(0, a.n * sc["resolution"], (m, 3)).astype(np.float32)
+    goal = np.array(list(ctx.frame().goal_grid), np.float32)
+    ms = timed(ctx, lambda: ctx.dubins_length_fp32(starts, goal), 3)
+    out.append(dict(kernel="pp_dubins_length_fp32_kernel (+H2D 12 B, D2H 4 B per state, pageable host memory)", config=f"{m} states",
+                    ms=ms, states_per_s=m / (ms * 1e-3)))
     if a.cpu:
         import orc
         o = orc.ref(orc.make_params(grid_size=a.n, resolution=sc["resolution"])) if orc.have_ref() else orc.port(orc.make_params(grid_size=a.n, resolution=sc["resolution"]))
