@@ -4,8 +4,9 @@
 One "step" = one pass of the hot path over one batch: 64 (map, goal) groups x 64 start poses = 4096
 independent HybridAStar::find_path queries on 512 x 512 x 72 maps with 96 box obstacles each (SURVEY.md
 §8d C4), EXACT single-pop mode (expansion sequence identical to the reference).  With --gpus N every rank
-runs its own 4096-query batch on its own groups (weak scaling, no data-path collective; the maps are
-rasterised on rank 0's schedule and NCCL-broadcast, timed separately as `map_broadcast_ms`).
+runs the same 4096-query batch (weak scaling, no data-path collective; every rank rasterises its maps itself,
+the NCCL map broadcast is timed separately as `map_broadcast_ms`).  --workload c5 runs BASELINE configs[4]
+(65 536 queries sharded by group, K-POP(32), strong scaling).
 
   value : node expansions / s, whole job, inputs resident in HBM, kernel timed with CUDA events
   e2e   : the same through pp_find_path_batch with pinned HOST buffers (H2D queries, D2H results+paths)
@@ -130,6 +131,105 @@ def cpu_reference_run(groups, queries, qgroups, maps, sample_idx, n_threads):
     return secs, pops, cost, succ
 
 
+def run_c5(args, rank, local_rank, world):
+    """BASELINE configs[4] / SURVEY §8d C5: 65 536 queries = 1 024 (map, goal) groups x 64 starts, sharded by group
+    round-robin over the ranks (STRONG scaling: the total is fixed), K-POP(32) mode.  Every rank rasterises the maps of
+    its own groups (the bit-exact kernel makes replicas identical); the NCCL map broadcast is timed separately."""
+    import torch
+    import torch.distributed as dist
+    import path_planning_pkg_b200 as pp
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    total_groups = args.c5_groups
+    mine = list(range(rank, total_groups, world))
+    P = pp.make_params(grid_size=N_GRID, resolution=RES)
+    ctx = pp.Context(P, num_groups=len(mine), device=local_rank)
+    groups = [S.c4_group(g, n_starts=args.starts, grid_size=N_GRID, resolution=RES) for g in mine]
+    t0 = time.time()
+    queries, qgroups, _ = apply_groups(ctx, groups)
+    map_build_s = time.time() - t0
+    map_bcast_ms = None
+    if world > 1:
+        scratch = torch.empty(N_GRID * N_GRID, dtype=torch.float32, device="cuda")
+        torch.cuda.synchronize(); dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(8):
+            dist.broadcast(scratch, src=0)
+        e1.record(); torch.cuda.synchronize()
+        map_bcast_ms = e0.elapsed_time(e1) / 8
+    q = ctx.make_queries(queries, qgroups)
+    nq = len(q)
+    pc = 1024
+    opts = ctx.make_opts(max_expansions=1 << 17, path_cap=pc, max_slots=args.max_slots, mode=1, kpop=32)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ctx.sync()
+
+    ctx.batch_upload(q, opts)
+    for _ in range(args.warmup):
+        ctx.batch_run()
+    sampler = ClockSampler(local_rank); sampler.start()
+    barrier()
+    l0 = ctx.kernel_launches()
+    ms = [ctx.batch_run() for _ in range(args.steps)]
+    barrier()
+    clocks = sampler.finish()
+    launches = ctx.kernel_launches() - l0
+    res, _, _ = ctx.batch_fetch()
+    pops = int(res["n_pops"].sum())
+    # end to end: host buffers in, results + paths out
+    hq = torch.from_numpy(q.view(np.uint8).copy()).pin_memory()
+    hres = torch.zeros(nq * pp._cabi.RESULT_DT.itemsize, dtype=torch.uint8).pin_memory()
+    hpath = torch.zeros(nq * pc * 3, dtype=torch.float32).pin_memory()
+    hcurv = torch.zeros(nq * pc, dtype=torch.float32).pin_memory()
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        rc = ctx.lib.pp_find_path_batch(ctx.h, C.c_void_p(hq.data_ptr()), C.c_int(nq), C.byref(opts), C.c_void_p(hres.data_ptr()),
+                                        C.c_void_p(hpath.data_ptr()), C.c_void_p(hcurv.data_ptr()), None)
+        if rc != 0:
+            raise RuntimeError(ctx.lib.pp_last_error().decode())
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([float(np.sum(ms)), e2e_s], dtype=torch.float64, device="cuda")
+    cnt = torch.tensor([float(pops), float(nq), float(res["success"].sum()), float((res["status"] != 0).sum())], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+    if rank == 0:
+        max_ms, e2e_max = float(t[0].item()), float(t[1].item())
+        all_pops, all_q, all_succ, all_flags = [float(v) for v in cnt.tolist()]
+        peak, peak_src = peaks()
+        achieved = all_pops / world * ALGO_BYTES_PER_EXPANSION / (max_ms / args.steps * 1e-3) / 1e9
+        line = {"metric": "hybrid_astar_node_expansions_per_s", "value": all_pops * args.steps / (max_ms * 1e-3), "unit": "expansions/s",
+                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": max_ms / args.steps, "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "queries_per_s": all_q * args.steps / (max_ms * 1e-3), "expansions_per_step": int(all_pops), "queries_per_step": int(all_q),
+                "success_rate": all_succ / all_q, "capacity_flags": int(all_flags),
+                "config": {"workload": f"C5: {total_groups} groups x {args.starts} starts = {int(all_q)} Hybrid A* queries in total, sharded by group over "
+                                       f"{world} GPU(s), {N_GRID}x{N_GRID}x72, 96 boxes/group, K-POP(32) mode (own semantics, DESIGN.md section 9)",
+                           "l2": "per-query pools are tens of GB per step, far larger than the 126 MB L2",
+                           "map_build_s": map_build_s, "map_broadcast_ms": map_bcast_ms},
+                "e2e": {"value": all_pops * e2e_steps / e2e_max, "unit": "expansions/s", "queries_per_s": all_q * e2e_steps / e2e_max,
+                        "h2d_bytes_per_step": int(q.nbytes) * world,
+                        "d2h_bytes_per_step": int(hres.numel() + hpath.numel() * 4 + hcurv.numel() * 4) * world},
+                "gpu_launches": int(launches),
+                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                             "kernel": "pp_kpop_kernel<4>", "peak_source": peak_src,
+                             "note": "latency / barrier bound (DESIGN.md section 9); algorithmic bytes = 312 B/expansion (SURVEY 8d)"},
+                "clocks": clocks}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -147,8 +247,12 @@ def main():
     ap.add_argument("--no-kpop", action="store_true", help="skip the additional K-POP(32) throughput measurement")
     ap.add_argument("--no-kpop-large", action="store_true", help="skip the K-POP(32) measurement on the C5-sized batch")
     ap.add_argument("--large-starts", type=int, default=1024, help="starts per group of the C5-sized K-POP batch")
+    ap.add_argument("--workload", default="c4", choices=["c4", "c5"], help="c4: EXACT-mode headline (default); c5: 65 536 queries, K-POP(32), strong scaling")
+    ap.add_argument("--c5-groups", type=int, default=1024)
     args = ap.parse_args()
     rank, local_rank, world = dist_env()
+    if args.workload == "c5" and args.impl == "b200":
+        return run_c5(args, rank, local_rank, world)
     n_threads = os.cpu_count() or 1
     workload = (f"C4: {args.groups} groups x {args.starts} starts = {args.groups * args.starts} Hybrid A* queries per GPU, "
                 f"{N_GRID}x{N_GRID}x72, 96 boxes/group, launch-default params, EXACT single-pop mode")
@@ -200,7 +304,10 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     P = pp.make_params(grid_size=N_GRID, resolution=RES)
     ctx = pp.Context(P, num_groups=args.groups, device=local_rank)
-    groups = build_workload(args.groups, args.starts, rank * args.groups)
+    # Weak scaling: every rank runs the SAME 4096-query batch (same seeds).  The step time of this batch is the latency of
+    # its single longest query; per-rank batches of different seeds would turn the max-over-ranks
+    # time into an extreme-value statistic of that one query instead of a measurement of scaling.
+    groups = build_workload(args.groups, args.starts, 0)
     t0 = time.time()
     queries, qgroups, maps = apply_groups(ctx, groups)
     map_build_s = time.time() - t0
@@ -330,13 +437,19 @@ def main():
                      "note": "k pops per iteration, exact 2D field heuristic, no equal-f drops; bit-identical to its CPU restatement "
                              "(oracle/port/kpop.inc), NOT to the reference (SURVEY F4/F5)"}
 
+        klat = []
+        for k in range(min(16, nq)):
+            t1 = time.perf_counter()
+            ctx.find_path_batch(q[k:k + 1], ctx.make_opts(max_expansions=1 << 17, path_cap=pc, max_slots=1, mode=1, kpop=32))
+            klat.append((time.perf_counter() - t1) * 1e3)
+        kpop_info["p50_single_query_ms"] = float(np.median(klat))
         # the same mode on a C5-sized batch (BASELINE configs[4]: 65536 queries, k-pop = 32): 1024 starts on each of the
         # groups already on the device; device-resident timing only
         if not args.no_kpop_large:
             big_q, big_g = [], []
             thr = ctx.consts().log_threshold
             for gi in range(args.groups):
-                cand = S.c4_group(rank * args.groups + gi, n_starts=args.large_starts, grid_size=N_GRID, resolution=RES)["start_candidates"]
+                cand = S.c4_group(gi, n_starts=args.large_starts, grid_size=N_GRID, resolution=RES)["start_candidates"]
                 st = ctx.set_start(ctx.make_queries(cand, [gi] * len(cand)))
                 free = maps[gi][st["ci"], st["cj"]] < thr
                 sel = cand[free][:args.large_starts]
@@ -385,6 +498,7 @@ def main():
         "success_rate": float(res["success"].mean()), "capacity_flags": int((res["status"] != 0).sum()),
         "expansions_bin_oob": int(res["n_pops_bin_oob"].sum()),
         "config": {"workload": workload, "slots": int(opts.max_slots) or "auto",
+                   "per_rank_batch": "identical on every rank (same seeds): the step is bound by the batch's single longest query",
                    "l2": "per-query scratch (open/closed sets, lazy-A* cache) is tens of GB per step, far larger than the 126 MB L2",
                    "map_build_s": map_build_s, "map_broadcast_ms": map_bcast_ms},
         "e2e": {"value": e2e_value, "unit": "expansions/s", "h2d_bytes_per_step": int(q.nbytes),

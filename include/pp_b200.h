@@ -99,10 +99,19 @@ typedef struct pp_query
     int   group;
 } pp_query;
 
+/* pp_result.status bits: which per-query capacity was still exhausted after the automatic retries (0 = none) */
+#ifndef PP_STATUS_OPEN_OVERFLOW
+#define PP_STATUS_OPEN_OVERFLOW 1     /* open-list pool (EXACT) / queue (K-POP) exhausted */
+#define PP_STATUS_CLOSED_OVERFLOW 2   /* expansion cap (EXACT closed log) / node log (K-POP) reached */
+#define PP_STATUS_OPEN2D_OVERFLOW 4   /* 2D open-list pool of the lazy heuristic exhausted */
+#define PP_STATUS_PATH_OVERFLOW 8     /* path_cap too small: the returned path is truncated */
+#define PP_STATUS_NULL_TERMINAL 16    /* the reference would dereference a null _prev here (Dubins shot from the start node) */
+#endif
+
 typedef struct pp_result
 {
     int   success;
-    int   status;            /* 0 or PP_STATUS_* capacity bits (pp_defs.h) */
+    int   status;            /* 0 or PP_STATUS_* bits */
     float cost;
     int   n_pops;            /* node expansions */
     int   n_pops_bin_oob;    /* expansions in heading bin == num_angle_bins (undefined in the reference) */

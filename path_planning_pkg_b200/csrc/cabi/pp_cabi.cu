@@ -708,6 +708,7 @@ static int ensure_kpop(pp_context* c, pp_context::KPools& k, int want_slots, int
         if (slots < 1) return pp_fail(PP_ERR_CAPACITY, "not enough device memory for one K-POP query slot");
         PP_CUDA(k.nodes.ensure((size_t)slots * nodes_cap));
         PP_CUDA(k.table.ensure((size_t)slots * tc));
+        PP_CUDA(cudaMemsetAsync(k.table.p, 0xFF, sizeof(PPKSlot) * (size_t)slots * tc, c->stream));   // all-ones = empty (pp_kpop.h)
         PP_CUDA(k.arena.ensure((size_t)slots * arena_cap));
         PP_CUDA(k.tmp_a.ensure((size_t)slots * tmp_cap));
         PP_CUDA(k.tmp_b.ensure((size_t)slots * tmp_cap));

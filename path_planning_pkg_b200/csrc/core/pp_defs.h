@@ -27,11 +27,13 @@
 
 // query status bits
 #define PP_OK 0
+#ifndef PP_STATUS_OPEN_OVERFLOW       /* same values in include/pp_b200.h */
 #define PP_STATUS_OPEN_OVERFLOW 1     /* 3D open-list node pool exhausted */
 #define PP_STATUS_CLOSED_OVERFLOW 2   /* expansion cap (closed log) reached */
 #define PP_STATUS_OPEN2D_OVERFLOW 4   /* 2D open-list node pool exhausted */
 #define PP_STATUS_PATH_OVERFLOW 8     /* path / dubins sample buffer too small */
 #define PP_STATUS_NULL_TERMINAL 16    /* reference would dereference a null _prev */
+#endif
 
 // Constants derived on the host exactly as the reference constructors derive them
 // (Grid2D.cpp:7-20, VehicleModel.cpp:7-47, HybridAStar.cpp:7-24) and uploaded once per context.

@@ -14,7 +14,8 @@
 //
 // Data structures (per query slot, global memory), all driven by the 32 lanes together:
 //   nodes[]   append-only log of generated nodes (parent links are log indices)
-//   table[]   open-addressing hash (key -> best pack, best node, closed bit); candidates race with atomicMin(pack):
+//   table[]   open-addressing hash (key -> best pack, best node, closed bit), all-ones = empty, cleaned by the query that
+//             filled it (cost proportional to the nodes generated, not to the capacity); candidates race with atomicMin(pack):
 //             the winner is the minimum, independent of thread order => deterministic
 //   LSM queue sorted runs in levels of capacity 256 << level (log-structured merge): a batch of new entries is
 //             bitonic-sorted in shared memory and merged down the levels with warp merge-path merges; the k smallest are
@@ -30,12 +31,12 @@
 #define PP_K_MAXCAND (PP_K_MAXPOP * PP_K_MAXSUCC)        // 256
 #define PP_K_LEVELS 16                                   // LSM levels: capacity 256 << level
 #define PP_K_RUN0 256
-#define PP_K_NONE 0x7fffffffu
-#define PP_K_CLOSED 0x80000000u
+#define PP_K_NONE 0xffffffffu                           // node word of a key without a node yet (= the all-ones empty state)
+#define PP_K_OPEN 0x80000000u                           // node word = index | PP_K_OPEN while the key is open, index alone once closed
 #define PP_K_EMPTY 0xffffffffu
 
 struct PPKEntry { float f; unsigned key; unsigned idx; unsigned pad; };               // 16 B queue entry
-struct PPKNode { float x, y, heading, g, v2, f; int curv, bin, cell, parent; unsigned key; int pad; };   // 48 B
+struct PPKNode { float x, y, heading, g, v2, f; int curv, bin, cell, parent; unsigned key; int slot; };   // 48 B; slot = its key's hash slot
 struct PPKSlot { unsigned key; unsigned node; unsigned long long pack; };             // 16 B hash slot
 struct PPKCand { float x, y, heading, g, v2; int curv_bin_ok; int cell; int slot; unsigned long long pack; };   // 40 B
 
@@ -352,7 +353,7 @@ PP_HD bool pp_try_shot(const W& w, const PPConsts& C, const float* map, const PP
                        PPPathPt* path, int path_cap, float* accb, int acc_cap, int* scratch, float (*shot)[5], float& len_out, int& n_dubins,
                        int& overflow)
 {
-    int type = PP_RSR; float p[4]; PPDubinsCenters cen; PPDubinsPlan pl;
+    int type = PP_RSR; float p[4] = {0.0f, 0.0f, 0.0f, 0.0f}; PPDubinsCenters cen; PPDubinsPlan pl;
     // the four candidates on four lanes, then the sequential fold of Dubins.cpp:36-68 on every lane
     pp_dubins_centers(C.r_min, x, y, h, F.goal_x, F.goal_y, F.goal_h, cen);
     for (int t = w.lane(); t < 4; t += W::LANES)
@@ -438,11 +439,7 @@ PP_HD_NOINLINE void pp_search_kpop(const W& w, const PPConsts& C, const float* o
     const int n_succ = 2 * C.A + 1;
     const unsigned goal_cell = (unsigned)(F.goal_ci * N + F.goal_cj);
 
-    // ---- init ----
-    for (int t = lane; t < wk.table_cap; t += W::LANES)
-    {
-        PPKSlot e; e.key = PP_K_EMPTY; e.node = PP_K_NONE; e.pack = ~0ull; wk.table[t] = e;
-    }
+    // ---- init ----  (the hash table arrives all-ones = empty: the host clears it once, every query cleans up after itself)
     for (int t = lane; t < PP_K_LEVELS; t += W::LANES) { sm.head[t] = 0; sm.size[t] = 0; sm.taken[t] = 0; }
     w.sync();
     PPDubinsGoal gc;
@@ -458,11 +455,12 @@ PP_HD_NOINLINE void pp_search_kpop(const W& w, const PPConsts& C, const float* o
         PPKNode n0;
         n0.x = start.x; n0.y = start.y; n0.heading = start.heading; n0.g = 0.0f; n0.v2 = start.vmin_sqr; n0.f = start.f;
         n0.curv = start.curv; n0.bin = start.bin; n0.cell = start.ci * N + start.cj; n0.parent = -1;
-        n0.key = (unsigned)n0.cell * kb + (unsigned)start.bin; n0.pad = 0;
-        wk.nodes[0] = n0;
+        n0.key = (unsigned)n0.cell * kb + (unsigned)start.bin;
         unsigned nw0;
         int slot = pp_ktable_find_or_insert(wk, n0.key, nw0);
-        wk.table[slot].node = 0u;
+        n0.slot = slot;
+        wk.nodes[0] = n0;
+        wk.table[slot].node = 0u | PP_K_OPEN;
         wk.table[slot].pack = ((unsigned long long)pp_fbits(0.0f) << 32);
         PPKEntry e; e.f = n0.f; e.key = n0.key; e.idx = 0u; e.pad = 0;
         pp_klevel(wk, 0)[0] = e;
@@ -499,14 +497,14 @@ PP_HD_NOINLINE void pp_search_kpop(const W& w, const PPConsts& C, const float* o
                     me = sm.popped[b];
                     unsigned nw = 0u;
                     slot = pp_ktable_find(wk, me.key, nw);
-                    valid = (slot >= 0) && (nw == me.idx);                       // closed or superseded => mismatch
+                    valid = (slot >= 0) && (nw == (me.idx | PP_K_OPEN));         // closed or superseded => mismatch
                 }
                 const unsigned vm = w.ballot(valid);
                 int rank = n_valid;
                 { unsigned below = vm & w.lanemask_lt(); while (below) { rank++; below &= below - 1; } }
                 if (valid)
                 {
-                    wk.table[slot].node = me.idx | PP_K_CLOSED;
+                    wk.table[slot].node = me.idx;                                // closed: open bit cleared
                     const PPKNode nd = wk.nodes[me.idx];
                     sm.parents[rank] = nd;
                     sm.pop_idx[rank] = (int)me.idx;
@@ -614,7 +612,7 @@ PP_HD_NOINLINE void pp_search_kpop(const W& w, const PPConsts& C, const float* o
                 const unsigned key = (unsigned)cell * kb + (unsigned)o.bin;
                 unsigned nw = 0u;
                 const int sl2 = pp_ktable_find_or_insert(wk, key, nw);
-                if (!(nw & PP_K_CLOSED))
+                if (nw & PP_K_OPEN)                                          // not closed (includes: no node yet)
                 {
                     cd.x = o.x; cd.y = o.y; cd.heading = o.heading; cd.g = g; cd.v2 = o.vmin_sqr;
                     cd.curv_bin_ok = (o.curv & 0xff) | ((o.bin & 0xff) << 8) | (1 << 16);
@@ -666,9 +664,9 @@ PP_HD_NOINLINE void pp_search_kpop(const W& w, const PPConsts& C, const float* o
                 nd.f = cd.g + ((h1 < h2) ? h2 : h1);
                 nd.curv = cd.curv_bin_ok & 0xff; nd.bin = (cd.curv_bin_ok >> 8) & 0xff; nd.cell = cd.cell;
                 nd.parent = sm.pop_idx[r];
-                nd.key = (unsigned)cd.cell * kb + (unsigned)nd.bin; nd.pad = 0;
+                nd.key = (unsigned)cd.cell * kb + (unsigned)nd.bin; nd.slot = cd.slot;
                 wk.nodes[idx] = nd;
-                wk.table[cd.slot].node = (unsigned)idx;
+                wk.table[cd.slot].node = (unsigned)idx | PP_K_OPEN;
                 e.f = nd.f; e.key = nd.key; e.idx = (unsigned)idx; e.pad = 0;
             }
             w.sync();
@@ -709,6 +707,14 @@ PP_HD_NOINLINE void pp_search_kpop(const W& w, const PPConsts& C, const float* o
         res.max_open = 0;
         res.n_closed = n_nodes; res.pad = 0;
     }
+    // ---- leave the hash table empty for the slot's next query: every inserted key belongs to at least one logged node ----
+    w.sync();
+    for (int t = lane; t < n_nodes; t += W::LANES)
+    {
+        PPKSlot e; e.key = PP_K_EMPTY; e.node = PP_K_NONE; e.pack = ~0ull;
+        wk.table[wk.nodes[t].slot] = e;
+    }
+    w.sync();
 }
 
 #endif

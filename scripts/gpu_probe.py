@@ -32,6 +32,7 @@ def main():
     ap.add_argument("--max-open", type=int, default=1 << 16)
     ap.add_argument("--mode", type=int, default=0)
     ap.add_argument("--k", type=int, default=32)
+    ap.add_argument("--dump", default="", help="write per-query statistics to this .npz")
     a = ap.parse_args()
     P = pp.make_params(grid_size=512, resolution=0.2)
     ctx = pp.Context(P, num_groups=a.groups)
@@ -62,6 +63,15 @@ def main():
             it.mean(), it.max(), np_.sum() / it.sum(), tk.sum() / it.sum(), res["n_closed"].max()))
         order = np.argsort(-np_)[:5]
         print("longest queries: pops", np_[order], "iterations", res["n_lazy_searches"][order], "success", res["success"][order])
+    if a.dump:
+        h1 = np.zeros(len(q), np.float32)
+        st = ctx.set_start(q)
+        for g in range(a.groups):
+            f, _, _ = ctx.field2d(group=g)
+            m = qgroups == g
+            h1[m] = f[st["ci"][m], st["cj"][m]]
+        np.savez_compressed(a.dump, queries=queries, qgroups=qgroups, n_pops=res["n_pops"], iters=res["n_lazy_searches"], success=res["success"],
+                            cost=res["cost"], h1=h1, n_nodes=res["n_closed"])
     if prof and a.mode == 1:
         t0 = res["max_open"].astype(np.int64); t1 = res["n_pops_bin_oob"].astype(np.int64)
         base = t0.min(); t0 -= base; t1 -= base

@@ -381,7 +381,8 @@ void emu_find_path_kpop(void* h, float vel, const float* s, int k, const float* 
     std::vector<PPKNode> nodes(max_nodes);
     int tc = 1; while (tc < 2 * max_nodes) tc <<= 1;
     std::vector<PPKSlot> table(tc);
-    int levels = 1; while ((PP_K_RUN0 * ((1 << levels) - 1)) < max_nodes + PP_K_RUN0 && levels < PP_K_LEVELS) levels++;
+    std::memset(table.data(), 0xFF, sizeof(PPKSlot) * table.size());     // all-ones = empty, as the C ABI hands it to the kernel
+    int levels = 1; while (((size_t)PP_K_RUN0 << (levels - 1)) < (size_t)max_nodes + PP_K_RUN0 && levels < PP_K_LEVELS) levels++;
     std::vector<PPKEntry> arena((size_t)PP_K_RUN0 * ((1 << levels) - 1)), ta(max_nodes + 2 * PP_K_RUN0), tb(max_nodes + 2 * PP_K_RUN0);
     std::vector<PPPathPt> path(4096);
     wk.nodes = nodes.data(); wk.nodes_cap = max_nodes; wk.table = table.data(); wk.table_cap = tc;
@@ -396,6 +397,12 @@ void emu_find_path_kpop(void* h, float vel, const float* s, int k, const float* 
     pp_search_kpop(w, C, e->m.off_xy.data(), G, st, k, wk, *sm, r);
     res->success = r.success; res->cost = r.cost; res->n_pops = r.n_pops; res->n_pops_bin_oob = r.n_pops_bin_oob;
     if (r.status) std::fprintf(stderr, "emu_find_path_kpop: status %d\n", r.status);
+    {   // the query must leave its hash table empty (all-ones) for the slot's next query
+        const unsigned char* b = reinterpret_cast<const unsigned char*>(table.data());
+        size_t dirty = 0;
+        for (size_t t = 0; t < sizeof(PPKSlot) * table.size(); t++) dirty += (b[t] != 0xFF);
+        if (dirty) { std::fprintf(stderr, "emu_find_path_kpop: %zu table bytes left dirty\n", dirty); res->success = -1; }
+    }
     if (std::getenv("PP_EMU_VERBOSE")) std::fprintf(stderr, "kpop k=%d: pops %d iterations %d entries taken %d nodes %d\n", k, r.n_pops, r.n_lazy_searches, r.n_lazy_pops, r.n_closed);
     int n = 0;
     if (r.success)

@@ -248,6 +248,62 @@ def test_search_c1_exact(seed):
     assert a["cost"] == b["cost"] and np.array_equal(_bits(a["path"]), _bits(b["path"]))
 
 
+def test_search_c1_100_seeds_report():
+    """seeds 0-99 (N=200, 0.2 m, 5 boxes, 4 rounds).  Every query must be identical to the pinned-libm
+    reference (expansion count, cost, path bits); the stock-glibc match rate, the pop counts and the single-query
+    latencies (reference on one host core vs one warp on the GPU, through the C ABI) are reported."""
+    import json
+    import os
+    import time
+    seeds = list(range(100))
+    scs = [S.c1_scenario(s) for s in seeds]
+    P = orc.make_params(grid_size=scs[0]["grid_size"], resolution=scs[0]["resolution"])
+    ctx = _ctx(P, groups=len(seeds))
+    crm, ref = orc.crm(P), orc.ref(P)
+    queries = []
+    for gi, sc in enumerate(scs):
+        ctx.update_goal(sc["goal"], sc["frame_start"], group=gi)
+        for _ in range(sc["rounds"]):
+            ctx.update_boxes(sc["boxes"], sc["conf"], S.APF_ADDED_RADIUS, group=gi)
+            ctx.decay(group=gi)
+        queries.append(sc["queries"][0])
+    q = ctx.make_queries(np.array(queries), list(range(len(seeds))))
+    opts = ctx.make_opts(path_cap=2048)
+    res, paths, curv, _ = ctx.find_path_batch(q, opts)
+    lat_gpu, lat_cpu, same_stock, undefined, pops = [], [], 0, 0, []
+    for gi, sc in enumerate(scs):
+        qq = sc["queries"][0]
+        for o in (crm, ref):
+            o.set_map(np.zeros((sc["grid_size"], sc["grid_size"]), np.float32))
+            S.build_map(o, sc)
+        assert np.array_equal(_bits(ctx.get_map(gi)), _bits(ref.get_map())), gi
+        crm.scrub(); ref.scrub()                       # SURVEY F12: reset() alone leaves stale heuristic state
+        b = crm.find_path(float(qq[3]), qq[:3])
+        t0 = time.perf_counter(); r0 = ref.find_path(float(qq[3]), qq[:3]); lat_cpu.append((time.perf_counter() - t0) * 1e3)
+        t0 = time.perf_counter(); ctx.find_path_batch(q[gi:gi + 1], ctx.make_opts(path_cap=2048, max_slots=1)); lat_gpu.append((time.perf_counter() - t0) * 1e3)
+        r = res[gi]
+        assert r["status"] == 0
+        if b["n_pops_bin_oob"] > 0 or r["n_pops_bin_oob"] > 0:
+            undefined += 1
+            continue
+        assert bool(r["success"]) == b["success"] and r["n_pops"] == b["n_pops"], (gi, r["n_pops"], b["n_pops"])
+        assert np.float32(r["cost"]) == b["cost"]
+        assert np.array_equal(_bits(paths[gi, :r["n_path"]]), _bits(b["path"]))
+        assert np.array_equal(_bits(curv[gi, :r["n_path"]]), _bits(b["curvature"]))
+        same_stock += int(r0["n_pops"] == r["n_pops"] and np.float32(r0["cost"]) == np.float32(r["cost"]))
+        pops.append(int(r["n_pops"]))
+    rep = {"config": "C1: N=200, res 0.2, 5 boxes, 4 rounds, seeds 0-99, EXACT mode",
+           "identical_to_pinned_libm_reference": len(pops), "undefined_in_reference_bin72": undefined,
+           "identical_to_stock_glibc_reference": same_stock, "pops_p50": float(np.median(pops)), "pops_p95": float(np.percentile(pops, 95)),
+           "gpu_single_query_ms": {"p50": float(np.median(lat_gpu)), "p95": float(np.percentile(lat_gpu, 95))},
+           "cpu_reference_single_query_ms_1core": {"p50": float(np.median(lat_cpu)), "p95": float(np.percentile(lat_cpu, 95))}}
+    print("C1 report:", json.dumps(rep))
+    out = os.path.join(orc.ROOT, "gpurun_out")
+    if os.path.isdir(out):
+        json.dump(rep, open(os.path.join(out, "r1_c1_report.json"), "w"))
+    assert len(pops) + undefined == 100 and len(pops) >= 90
+
+
 def test_search_c4_batch_exact():
     """C4 shape (512^2 x 72, 96 boxes): a batch over 2 groups x 6 starts, each compared with a scrubbed reference."""
     groups = [S.c4_group(s, n_starts=6) for s in (0, 1)]
