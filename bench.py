@@ -143,7 +143,11 @@ def run_c5(args, rank, local_rank, world):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     total_groups = args.c5_groups
-    mine = list(range(rank, total_groups, world))
+    # --c5-shard group: rank r owns groups r, r+world, ... (fields only for its own groups, but the ranks' work
+    #                   differs by the difficulty of their groups)
+    # --c5-shard query (default): every rank holds every map (replicated, as after the broadcast) and takes every world-th
+    #                   query of every group: equal work per rank
+    mine = list(range(rank, total_groups, world)) if args.c5_shard == "group" else list(range(total_groups))
     P = pp.make_params(grid_size=N_GRID, resolution=RES)
     ctx = pp.Context(P, num_groups=len(mine), device=local_rank)
     groups = [S.c4_group(g, n_starts=args.starts, grid_size=N_GRID, resolution=RES) for g in mine]
@@ -160,10 +164,12 @@ def run_c5(args, rank, local_rank, world):
             dist.broadcast(scratch, src=0)
         e1.record(); torch.cuda.synchronize()
         map_bcast_ms = e0.elapsed_time(e1) / 8
+    if args.c5_shard == "query":
+        queries, qgroups = queries[rank::world], qgroups[rank::world]
     q = ctx.make_queries(queries, qgroups)
     nq = len(q)
     pc = 1024
-    opts = ctx.make_opts(max_expansions=1 << 17, path_cap=pc, max_slots=args.max_slots, mode=1, kpop=32)
+    opts = ctx.make_opts(max_expansions=1 << 18, path_cap=pc, max_slots=args.max_slots, mode=1, kpop=32)
 
     def barrier():
         torch.cuda.synchronize()
@@ -181,6 +187,7 @@ def run_c5(args, rank, local_rank, world):
     barrier()
     clocks = sampler.finish()
     launches = ctx.kernel_launches() - l0
+    retried = ctx.batch_retried()
     res, _, _ = ctx.batch_fetch()
     pops = int(res["n_pops"].sum())
     # end to end: host buffers in, results + paths out
@@ -199,21 +206,22 @@ def run_c5(args, rank, local_rank, world):
     barrier()
     e2e_s = time.perf_counter() - t0
     t = torch.tensor([float(np.sum(ms)), e2e_s], dtype=torch.float64, device="cuda")
-    cnt = torch.tensor([float(pops), float(nq), float(res["success"].sum()), float((res["status"] != 0).sum())], dtype=torch.float64, device="cuda")
+    cnt = torch.tensor([float(pops), float(nq), float(res["success"].sum()), float((res["status"] != 0).sum()), float(retried)],
+                       dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
     if rank == 0:
         max_ms, e2e_max = float(t[0].item()), float(t[1].item())
-        all_pops, all_q, all_succ, all_flags = [float(v) for v in cnt.tolist()]
+        all_pops, all_q, all_succ, all_flags, all_retried = [float(v) for v in cnt.tolist()]
         peak, peak_src = peaks()
         achieved = all_pops / world * ALGO_BYTES_PER_EXPANSION / (max_ms / args.steps * 1e-3) / 1e9
         line = {"metric": "hybrid_astar_node_expansions_per_s", "value": all_pops * args.steps / (max_ms * 1e-3), "unit": "expansions/s",
                 "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": max_ms / args.steps, "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "queries_per_s": all_q * args.steps / (max_ms * 1e-3), "expansions_per_step": int(all_pops), "queries_per_step": int(all_q),
-                "success_rate": all_succ / all_q, "capacity_flags": int(all_flags),
-                "config": {"workload": f"C5: {total_groups} groups x {args.starts} starts = {int(all_q)} Hybrid A* queries in total, sharded by group over "
+                "success_rate": all_succ / all_q, "capacity_flags": int(all_flags), "retried_queries": int(all_retried),
+                "config": {"workload": f"C5: {total_groups} groups x {args.starts} starts = {int(all_q)} Hybrid A* queries in total, sharded by {args.c5_shard} over "
                                        f"{world} GPU(s), {N_GRID}x{N_GRID}x72, 96 boxes/group, K-POP(32) mode (own semantics, DESIGN.md section 9)",
                            "l2": "per-query pools are tens of GB per step, far larger than the 126 MB L2",
                            "map_build_s": map_build_s, "map_broadcast_ms": map_bcast_ms},
@@ -249,6 +257,7 @@ def main():
     ap.add_argument("--large-starts", type=int, default=1024, help="starts per group of the C5-sized K-POP batch")
     ap.add_argument("--workload", default="c4", choices=["c4", "c5"], help="c4: EXACT-mode headline (default); c5: 65 536 queries, K-POP(32), strong scaling")
     ap.add_argument("--c5-groups", type=int, default=1024)
+    ap.add_argument("--c5-shard", default="query", choices=["query", "group"])
     args = ap.parse_args()
     rank, local_rank, world = dist_env()
     if args.workload == "c5" and args.impl == "b200":
@@ -398,7 +407,7 @@ def main():
     # reference's; reported beside the headline, never instead of it) ----
     kpop_info = None
     if not args.no_kpop:
-        kopts = ctx.make_opts(max_expansions=1 << 17, path_cap=2048, max_slots=args.max_slots, mode=1, kpop=32)
+        kopts = ctx.make_opts(max_expansions=1 << 18, path_cap=2048, max_slots=args.max_slots, mode=1, kpop=32)
         ctx.batch_upload(q, kopts)
         ksteps = max(args.steps, 5)
         for _ in range(args.warmup):
@@ -440,7 +449,7 @@ def main():
         klat = []
         for k in range(min(16, nq)):
             t1 = time.perf_counter()
-            ctx.find_path_batch(q[k:k + 1], ctx.make_opts(max_expansions=1 << 17, path_cap=pc, max_slots=1, mode=1, kpop=32))
+            ctx.find_path_batch(q[k:k + 1], ctx.make_opts(max_expansions=1 << 18, path_cap=pc, max_slots=1, mode=1, kpop=32))
             klat.append((time.perf_counter() - t1) * 1e3)
         kpop_info["p50_single_query_ms"] = float(np.median(klat))
         # the same mode on a C5-sized batch (BASELINE configs[4]: 65536 queries, k-pop = 32): 1024 starts on each of the
@@ -455,7 +464,7 @@ def main():
                 sel = cand[free][:args.large_starts]
                 big_q.append(sel); big_g += [gi] * len(sel)
             bq = ctx.make_queries(np.concatenate(big_q), np.array(big_g, np.int32))
-            bopts = ctx.make_opts(max_expansions=1 << 17, path_cap=1024, max_slots=args.max_slots, mode=1, kpop=32)
+            bopts = ctx.make_opts(max_expansions=1 << 18, path_cap=1024, max_slots=args.max_slots, mode=1, kpop=32)
             ctx.batch_upload(bq, bopts)
             for _ in range(args.warmup):
                 ctx.batch_run()

@@ -229,6 +229,8 @@ int  pp_batch_run(pp_context* ctx, float* kernel_ms);
 int  pp_batch_fetch(pp_context* ctx, pp_result* results, float* paths_xyh, float* curvature, pp_pop* trace);
 /* number of CUDA kernels this context has launched so far (bench.py's gpu_launches) */
 unsigned long long pp_kernel_launches(pp_context* ctx);
+/* queries of the last pp_batch_run / pp_find_path_batch that exhausted a pool and were re-run with larger pools */
+int  pp_batch_retried(pp_context* ctx);
 /* CUDA-event bracket on the context's stream (for measuring the asynchronous map / field calls in between) */
 int  pp_timer_begin(pp_context* ctx);
 int  pp_timer_end(pp_context* ctx, float* ms);

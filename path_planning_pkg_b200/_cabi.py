@@ -208,6 +208,9 @@ class Context:
     def kernel_launches(self):
         return int(self.lib.pp_kernel_launches(self.h))
 
+    def batch_retried(self):
+        return int(self.lib.pp_batch_retried(self.h))
+
     # ---- stateless batches ----
     def set_start(self, queries):
         q = np.ascontiguousarray(queries, QUERY_DT)

@@ -106,6 +106,11 @@ struct pp_context
     // heuristic fields (throughput modes / C3)
     DevBuf<float> d_field2d;              // num_groups x N*N, filled per group on demand
     std::vector<char> field2d_valid;
+    // K-POP scheduling hint: mean iterations per query the group needed in its last batch (0 = unknown; reset by any map /
+    // goal change).  Only the order in which resident slots fetch the work items depends on it, never a result.
+    std::vector<float> kpop_group_cost;
+    DevBuf<float> d_group_cost;
+    bool group_cost_dirty = true;
     DevBuf<unsigned> d_f2d_work; DevBuf<unsigned char> d_f2d_flags; DevBuf<float> d_dubins_field;
     DevBuf<int> d_qmap, d_order;
     int retried = 0;       // queries re-run in the last pp_batch_run
@@ -125,6 +130,7 @@ static int sync_groups(pp_context* c)
 static void map_changed(pp_context* c, int g)
 {
     if (g >= 0 && g < (int)c->field2d_valid.size()) c->field2d_valid[g] = 0;
+    if (g >= 0 && g < (int)c->kpop_group_cost.size() && c->kpop_group_cost[g] != 0.0f) { c->kpop_group_cost[g] = 0.0f; c->group_cost_dirty = true; }
 }
 
 static int check_group(pp_context* c, int g)
@@ -213,7 +219,7 @@ void pp_destroy(pp_context* c)
     cudaFree(c->d_groups); cudaFree(c->d_counter);
     c->s0.release(); c->s1.release(); c->s2.release(); c->s3.release(); c->s4.release();
     c->d_queries.release(); c->d_results.release(); c->d_paths.release(); c->d_trace.release();
-    c->wp.release(); c->wp_retry.release(); c->wp_lazy.release(); c->d_qmap.release(); c->d_order.release();
+    c->wp.release(); c->wp_retry.release(); c->wp_lazy.release(); c->d_qmap.release(); c->d_order.release(); c->d_group_cost.release();
     cudaFree(c->d_lazy_sid);
     c->kp.release(); c->kp_retry.release();
     c->d_field2d.release(); c->d_f2d_work.release(); c->d_f2d_flags.release(); c->d_dubins_field.release();
@@ -757,7 +763,19 @@ static int launch_kpop(pp_context* c, const pp_context::KPools& k, int n_slots, 
     if (n_work > n_slots && n_work <= (1 << 16))
     {
         PP_CUDA(c->d_order.ensure((size_t)n_work));
-        pp_kpop_order_kernel<<<(n_work + 255) / 256, 256, 0, c->stream>>>(a.queries, qmap, n_work, a.field2d, a.C.N, c->d_order.p);
+        if ((int)c->kpop_group_cost.size() != c->num_groups) { c->kpop_group_cost.assign(c->num_groups, 0.0f); c->group_cost_dirty = true; }
+        float known = 0.0f; int n_known = 0;
+        for (float v : c->kpop_group_cost) if (v > 0.0f) { known += v; n_known++; }
+        const float unknown_cost = n_known ? known / n_known : 1.0f;
+        if (c->group_cost_dirty)
+        {
+            PP_CUDA(c->d_group_cost.ensure((size_t)c->num_groups));
+            PP_CUDA(cudaMemcpyAsync(c->d_group_cost.p, c->kpop_group_cost.data(), sizeof(float) * c->num_groups, cudaMemcpyHostToDevice, c->stream));
+            PP_CUDA(cudaStreamSynchronize(c->stream));
+            c->group_cost_dirty = false;
+        }
+        pp_kpop_order_kernel<<<(n_work + 255) / 256, 256, 0, c->stream>>>(a.queries, qmap, n_work, a.field2d, a.C.N, c->d_group_cost.p,
+                                                                            unknown_cost, c->d_order.p);
         c->launches += 1;
         a.order = c->d_order.p;
     }
@@ -857,6 +875,20 @@ int pp_batch_run(pp_context* c, float* kernel_ms)
     {
         PP_CUDA(cudaMemcpyAsync(r.data(), c->d_results.p, sizeof(PPResult) * n, cudaMemcpyDeviceToHost, c->stream));
         PP_CUDA(cudaStreamSynchronize(c->stream));
+        if (kmode && level == 0)
+        {
+            // remember how hard every group was (mean iterations per query) for the next batch's launch order
+            if ((int)c->kpop_group_cost.size() != c->num_groups) c->kpop_group_cost.assign(c->num_groups, 0.0f);
+            std::vector<double> sum(c->num_groups, 0.0); std::vector<int> cnt(c->num_groups, 0);
+            for (int k = 0; k < n; k++) { int g = c->h_queries[k].group; sum[g] += (double)r[k].n_lazy_searches; cnt[g]++; }
+            for (int g = 0; g < c->num_groups; g++)
+                if (cnt[g] > 0)
+                {
+                    float now = (float)(sum[g] / cnt[g]) + 1.0f, old = c->kpop_group_cost[g];
+                    float upd = old > 0.0f ? 0.5f * old + 0.5f * now : now;
+                    if (upd != old) { c->kpop_group_cost[g] = upd; c->group_cost_dirty = true; }
+                }
+        }
         std::vector<int> redo;
         for (int k = 0; k < n; k++) if (r[k].status & overflow) redo.push_back(k);
         if (redo.empty()) break;
@@ -1057,6 +1089,7 @@ int pp_heuristic_field_3d(pp_context* c, int g, int use_h2d, float* out_nnb, flo
 }
 
 unsigned long long pp_kernel_launches(pp_context* c) { return c ? c->launches : 0ull; }
+int pp_batch_retried(pp_context* c) { return c ? c->retried : 0; }
 
 // CUDA-event bracket on the context's stream (the stream every kernel of this context is launched on)
 int pp_timer_begin(pp_context* c)

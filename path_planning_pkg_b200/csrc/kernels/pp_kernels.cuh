@@ -250,29 +250,40 @@ __global__ void __launch_bounds__(32 * NW, PP_KPOP_MIN_BLOCKS) pp_kpop_kernel(co
     }
 }
 
-// Longest-expected-first launch order of a K-POP batch: rank the work items by the exact 2D distance of their start
-// cell (descending; ties by index).  Only the order in which the resident slots fetch queries changes -- every query
-// is independent, results are unaffected -- but the batch no longer ends on a long query that was fetched last.
-__global__ void __launch_bounds__(256) pp_kpop_order_kernel(const PPQuery* queries, const int* qmap, int n, const float* field2d,
-                                                            int N, int* order)
+// Longest-expected-first launch order of a K-POP batch: rank the work items by (exact 2D distance of the start cell) x
+// (how many iterations per query the item's group needed in the previous batch, when known), descending, ties by index.
+// Only the order in which the resident slots fetch queries changes -- every query is independent, results are
+// unaffected -- but the batch no longer ends on a long query that was fetched last.
+__device__ __forceinline__ float pp_kpop_order_key(const PPQuery& Q, const float* field2d, int N, const float* group_cost, float unknown_cost)
 {
+    const bool in = Q.start.ci >= 0 && Q.start.ci < N && Q.start.cj >= 0 && Q.start.cj < N;
+    float k = in ? field2d[(size_t)N * N * Q.group + (size_t)Q.start.ci * N + Q.start.cj] : 0.0f;
+    if (!(k < 3.0e38f)) return 0.0f;                                  // unreachable: ends at once
+    const float gc = group_cost[Q.group];
+    return k * (gc > 0.0f ? gc : unknown_cost);
+}
+
+__global__ void __launch_bounds__(256) pp_kpop_order_kernel(const PPQuery* queries, const int* qmap, int n, const float* field2d,
+                                                            int N, const float* group_cost, float unknown_cost, int* order)
+{
+    __shared__ float s_key[256];
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const size_t nn = (size_t)N * N;
-    const PPQuery Qi = queries[qmap ? qmap[i] : i];
-    const bool in_i = Qi.start.ci >= 0 && Qi.start.ci < N && Qi.start.cj >= 0 && Qi.start.cj < N;
-    float ki = in_i ? field2d[nn * Qi.group + (size_t)Qi.start.ci * N + Qi.start.cj] : 0.0f;
-    if (!(ki < 3.0e38f)) ki = 0.0f;                                   // unreachable: ends at once
+    const float ki = (i < n) ? pp_kpop_order_key(queries[qmap ? qmap[i] : i], field2d, N, group_cost, unknown_cost) : 0.0f;
     int rank = 0;
-    for (int j = 0; j < n; j++)
+    for (int base = 0; base < n; base += 256)                          // tiles of 256 keys staged in shared memory
     {
-        const PPQuery Qj = queries[qmap ? qmap[j] : j];
-        const bool in_j = Qj.start.ci >= 0 && Qj.start.ci < N && Qj.start.cj >= 0 && Qj.start.cj < N;
-        float kj = in_j ? field2d[nn * Qj.group + (size_t)Qj.start.ci * N + Qj.start.cj] : 0.0f;
-        if (!(kj < 3.0e38f)) kj = 0.0f;
-        rank += (kj > ki || (kj == ki && j < i)) ? 1 : 0;
+        const int j = base + threadIdx.x;
+        __syncthreads();
+        s_key[threadIdx.x] = (j < n) ? pp_kpop_order_key(queries[qmap ? qmap[j] : j], field2d, N, group_cost, unknown_cost) : -1.0f;
+        __syncthreads();
+        const int m = min(256, n - base);
+        for (int t = 0; t < m; t++)
+        {
+            const float kj = s_key[t];
+            rank += (kj > ki || (kj == ki && base + t < i)) ? 1 : 0;
+        }
     }
-    order[rank] = i;
+    if (i < n) order[rank] = i;
 }
 
 // ---------------------------------------------------------------------------------------------------
