@@ -165,38 +165,98 @@ int pp_launch_field2d(cudaStream_t stream, const float* map, int N, float log_th
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// FP32 transcendentals of the field sweep: CUDA's single-precision functions (<= 2 ulp), not the FP64 "pinned libm"
+// Dubins field sweep, FP32 SIMT (north_star (d)).  Everything is single precision and branch-light: the lengths carry a
+// 1e-5 relative tolerance (tests/test_gpu_fields.py), not bit-exactness, so this translation unit may use FFMA, the
+// approximate divide, and the closed form of the tangent segment.
+//   atan2 : one divide (the octant picks the quotient directly) + a degree-4 odd polynomial in t^2
+//   acos  : sqrt reduction + degree-5 polynomial (|x| > 0.5), NaN outside [-1, 1] (circles closer than 2r: the RSL / LSR
+//           candidate never wins the fold, Dubins.cpp:42-66)
+//   RSL / LSR straight segment: sqrt(D^2 - 4 r^2) instead of the distance between the two tangent points the reference
+//           builds with four sin / cos calls (Dubins.cpp:232-236, :281-285) -- the same number to ~1e-7 relative
+#define FLD_PI    3.14159274101257324219f
+#define FLD_PI_2  1.57079637050628662109f
+#define FLD_PI_4  0.78539818525314331055f
+#define FLD_2PI   6.28318548202514648438f
+
+__device__ __forceinline__ float fld_atan2(float y, float x)
+{
+    const float ax = fabsf(x), ay = fabsf(y);
+    float y0, num, den;
+    if (ay > 2.414213562373095f * ax) { y0 = FLD_PI_2; num = -ax; den = ay; }
+    else if (ay > 0.4142135623730950f * ax) { y0 = FLD_PI_4; num = ay - ax; den = ay + ax; }
+    else { y0 = 0.0f; num = ay; den = ax; }
+    const float t = (den == 0.0f) ? 0.0f : __fdividef(num, den);
+    const float z = t * t;
+    float a = y0 + ((((8.05374449538e-2f * z - 1.38776856032e-1f) * z + 1.99777106478e-1f) * z - 3.33329491539e-1f) * z * t + t);
+    if (x < 0.0f) a = FLD_PI - a;
+    return (y < 0.0f) ? -a : a;
+}
+
+__device__ __forceinline__ float fld_asin_core(float a)
+{
+    const float z = a * a;
+    return ((((4.2163199048e-2f * z + 2.4181311049e-2f) * z + 4.5470025998e-2f) * z + 7.4953002686e-2f) * z + 1.6666752422e-1f) * z * a + a;
+}
+
+__device__ __forceinline__ float fld_acos(float x)       // NaN for |x| > 1 through the sqrt of a negative number
+{
+    if (x > 0.5f) return 2.0f * fld_asin_core(sqrtf(0.5f * (1.0f - x)));
+    if (x < -0.5f) return FLD_PI - 2.0f * fld_asin_core(sqrtf(0.5f * (1.0f + x)));
+    return FLD_PI_2 - fld_asin_core(x);
+}
+
+// shortest of RSR, RSL, LSR, LSL in the reference's fold order; (ssn, scs) = sin / cos of the start heading
 __device__ __forceinline__ float fld_dubins(float r, float sx, float sy, float sh, float ssn, float scs, float gh,
                                             float grx, float gry, float glx, float gly)
 {
     const float srx = sx + r * ssn, sry = sy - r * scs, slx = sx - r * ssn, sly = sy + r * scs;
-    float best = 0.0f;
-#pragma unroll
-    for (int type = 0; type < 4; type++)
+    const float four_r2 = 4.0f * r * r, two_r = 2.0f * r;
+    // RSR (Dubins.cpp:180-206): both arcs clockwise
+    float dx = grx - srx, dy = gry - sry;
+    float d2 = dx * dx + dy * dy, th = fld_atan2(dy, dx);
+    float p1 = th - sh; if (p1 > 0.0f) p1 -= FLD_2PI;
+    float p3 = gh - th; if (p3 > 0.0f) p3 -= FLD_2PI;
+    float best = sqrtf(d2) - r * (p1 + p3);
+    // RSL (Dubins.cpp:209-255)
+    dx = glx - srx; dy = gly - sry;
+    d2 = dx * dx + dy * dy; th = fld_atan2(dy, dx);
     {
-        const bool s_right = (type == PP_RSR) || (type == PP_RSL), g_right = (type == PP_RSR) || (type == PP_LSR);
-        const float csx = s_right ? srx : slx, csy = s_right ? sry : sly;
-        const float cgx = g_right ? grx : glx, cgy = g_right ? gry : gly;
-        const float theta = atan2f(cgy - csy, cgx - csx);
-        float ac = 0.0f, c1 = 0.0f, s1 = 0.0f, c2 = 0.0f, s2 = 0.0f, p[4];
-        if (type == PP_RSL || type == PP_LSR)
-        {
-            ac = acosf(pp_dubins_acos_arg(r, csx, csy, cgx, cgy));
-            const float t1 = pp_dubins_theta_t1(type, ac, theta);
-            const float p2 = pp_dubins_p2(type, t1);
-            sincosf(t1, &s1, &c1);
-            sincosf(p2, &s2, &c2);
-        }
-        const float len = pp_dubins_finish(type, r, sh, gh, csx, csy, cgx, cgy, theta, ac, c1, s1, c2, s2, p);
-        if (type == 0 || len < best) best = len;      // NaN never wins (Dubins.cpp:42-66)
+        const float ac = fld_acos(two_r / sqrtf(d2));          // IEEE divide + sqrt: acos amplifies argument error near 1
+        const float t1 = ac + th, p2 = t1 - FLD_PI;
+        p1 = t1 - (FLD_PI_2 + sh); if (p1 > 0.0f) p1 -= FLD_2PI;
+        p3 = (gh - FLD_PI_2) - p2; if (p3 < 0.0f) p3 += FLD_2PI;
+        const float len = sqrtf(d2 - four_r2) + r * (p3 - p1);
+        if (len < best) best = len;                       // NaN (circles overlap) never wins
+    }
+    // LSR (Dubins.cpp:258-304)
+    dx = grx - slx; dy = gry - sly;
+    d2 = dx * dx + dy * dy; th = fld_atan2(dy, dx);
+    {
+        const float ac = fld_acos(two_r / sqrtf(d2));          // IEEE divide + sqrt: acos amplifies argument error near 1
+        const float t1 = th - ac, p2 = t1 + FLD_PI;
+        p1 = t1 - (sh - FLD_PI_2); if (p1 < 0.0f) p1 += FLD_2PI;
+        p3 = (gh + FLD_PI_2) - p2; if (p3 > 0.0f) p3 -= FLD_2PI;
+        const float len = sqrtf(d2 - four_r2) + r * (p1 - p3);
+        if (len < best) best = len;
+    }
+    // LSL (Dubins.cpp:307-323): both arcs counter-clockwise
+    dx = glx - slx; dy = gly - sly;
+    d2 = dx * dx + dy * dy; th = fld_atan2(dy, dx);
+    p1 = th - sh; if (p1 < 0.0f) p1 += FLD_2PI;
+    p3 = gh - th; if (p3 < 0.0f) p3 += FLD_2PI;
+    {
+        const float len = sqrtf(d2) + r * (p1 + p3);
+        if (len < best) best = len;
     }
     return best;
 }
 
-// out[(i*N + j)*bins + b] = max(h2d[i*N + j], dubins((i*res, j*res, -pi + b*precision) -> goal))
-__global__ void __launch_bounds__(256)
-pp_dubins_field_kernel(const float* __restrict__ h2d, float* __restrict__ out, int N, int bins, float res, float precision, float r_min,
-                       float goal_x, float goal_y, float goal_h)
+// out[(i*N + j)*bins + b] = max(h2d[i*N + j], dubins((i*res, j*res, -pi + b*precision) -> goal)).
+// One thread per (cell-in-group, bin); a CTA covers cpb = blockDim.x / bins consecutive cells per step, so consecutive
+// threads write consecutive floats; (i, j) advance incrementally (no division in the loop).
+__global__ void __launch_bounds__(320)
+pp_dubins_field_kernel(const float* __restrict__ h2d, float* __restrict__ out, int N, int bins, int cpb, float res, float precision,
+                       float r_min, float goal_x, float goal_y, float goal_h)
 {
     __shared__ float s_sin[PP_MAX_BINS], s_cos[PP_MAX_BINS], s_head[PP_MAX_BINS];
     for (int b = threadIdx.x; b < bins; b += blockDim.x)
@@ -209,22 +269,33 @@ pp_dubins_field_kernel(const float* __restrict__ h2d, float* __restrict__ out, i
     sincosf(goal_h, &gs, &gcs);
     const float grx = goal_x + r_min * gs, gry = goal_y - r_min * gcs, glx = goal_x - r_min * gs, gly = goal_y + r_min * gcs;
     __syncthreads();
-    const size_t total = (size_t)N * N * bins, stride = (size_t)gridDim.x * blockDim.x;
-    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride)
+    const int c = threadIdx.x / bins, b = threadIdx.x - c * bins;
+    if (c >= cpb) return;
+    const float sh = s_head[b], ssn = s_sin[b], scs = s_cos[b];
+    const long long n_cells = (long long)N * N, stride = (long long)gridDim.x * cpb;
+    const int stride_i = (int)(stride / N), stride_j = (int)(stride % N);
+    long long cell = (long long)blockIdx.x * cpb + c;
+    int i = (int)(cell / N), j = (int)(cell % N);
+    for (; cell < n_cells; cell += stride)
     {
-        const size_t cell = t / bins;
-        const int b = (int)(t - cell * bins);
-        const int i = (int)(cell / N), j = (int)(cell - (size_t)i * N);
-        const float len = fld_dubins(r_min, i * res, j * res, s_head[b], s_sin[b], s_cos[b], goal_h, grx, gry, glx, gly);
+        const float len = fld_dubins(r_min, i * res, j * res, sh, ssn, scs, goal_h, grx, gry, glx, gly);
         const float h1 = h2d ? h2d[cell] : 0.0f;
-        out[t] = (h1 < len) ? len : h1;
+        out[cell * bins + b] = (h1 < len) ? len : h1;
+        i += stride_i; j += stride_j;
+        if (j >= N) { j -= N; i++; }
     }
 }
 
 int pp_launch_dubins_field(cudaStream_t stream, const float* h2d, float* out, int N, int bins, float res, float precision, float r_min,
                            float goal_x, float goal_y, float goal_h, int sm_count, unsigned long long* launches)
 {
-    pp_dubins_field_kernel<<<sm_count * 8, 256, 0, stream>>>(h2d, out, N, bins, res, precision, r_min, goal_x, goal_y, goal_h);
+    int cpb = 288 / bins; if (cpb < 1) cpb = 1;                       // 72 bins: 4 cells = 288 threads = 9 warps per step
+    int threads = ((cpb * bins + 31) / 32) * 32;
+    if (threads > 320) { cpb = 320 / bins; if (cpb < 1) cpb = 1; threads = ((cpb * bins + 31) / 32) * 32; }
+    long long groups = ((long long)N * N + cpb - 1) / cpb;
+    long long blocks = (long long)sm_count * 6;
+    if (blocks > groups) blocks = groups;
+    pp_dubins_field_kernel<<<(int)blocks, threads, 0, stream>>>(h2d, out, N, bins, cpb, res, precision, r_min, goal_x, goal_y, goal_h);
     *launches += 1;
     return (int)cudaGetLastError();
 }
