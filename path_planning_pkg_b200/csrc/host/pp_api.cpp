@@ -190,6 +190,14 @@ std::pair<T, bool> HybridAStar<T>::find_path(const T vel_init, const Vector3D<T>
     pp_search_opts o;
     std::memset(&o, 0, sizeof(o));
     o.path_cap = 8192; o.max_slots = 1;
+    // The class API returns what the reference returns (EXACT mode).  A deployment that prefers latency over
+    // reference-identical plans can opt into the K-POP mode without touching the caller: PP_B200_SEARCH_MODE=kpop
+    // (own semantics, ~20x lower single-query latency).
+    static const int env_mode = [] {
+        const char* e = std::getenv("PP_B200_SEARCH_MODE");
+        return (e && (std::strcmp(e, "kpop") == 0 || std::strcmp(e, "KPOP") == 0)) ? PP_MODE_KPOP : PP_MODE_EXACT;
+    }();
+    o.mode = env_mode; o.kpop = 32;
     pp_result r;
     std::vector<float> xyh((size_t)o.path_cap * 3), curv(o.path_cap);
     check(pp_find_path_batch(_impl->b->ctx, &q, 1, &o, &r, xyh.data(), curv.data(), nullptr), "find_path");
