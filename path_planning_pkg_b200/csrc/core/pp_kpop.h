@@ -1,25 +1,30 @@
-// K-POP search mode: up to k <= 32 nodes popped and expanded per iteration by one warp, on a warp-parallel
-// priority queue, with the exact 2D distance field as the holonomic heuristic.
+// K-POP search mode: up to k <= 32 nodes popped and expanded per iteration by one CTA (W::LANES cooperating lanes: 4 warps
+// on the device, 1 lane in the host emulation of tests/cpp), on a CTA-parallel priority queue, with the exact 2D
+// distance field as the holonomic heuristic.
 //
 // This is NEW semantics (north_star: "optionally k pops per iteration within one query"; SURVEY.md §7 mode
 // definitions): the reference's equal-f drops (F5) and its order-dependent lazy 2D A* (F4) are replaced by clean rules
-// that parallelise, so results differ from the reference (typically a few % lower cost with 4-7x fewer expansions).
+// that parallelise, so results differ from the reference (typically a few % lower cost with fewer expansions).
 // The rules are stated in oracle/port/kpop.inc (CPU restatement); this file must reproduce that restatement bit
 // for bit -- pop sequence, cost, path.  Summary:
 //   open list = total order (f, key, idx), lazy deletion, best-g-wins per key; an iteration takes the min(k, |open|)
 //   smallest entries, the valid ones are the pops (rank order), all closed at once; goal / Dubins shot decided in rank
 //   order; every pop expands every steering primitive of its window -> candidates c = rank*(2A+1) + a; per key the
 //   smallest pack(g, order = iteration*1024 + c) wins, also against the key's recorded best; winners get node indices in
-//   c order and f = g + max(h1[cell], Dubins).
+//   c order and f = g + max(h1[cell], Dubins).  The heuristic Dubins length and the APF term are evaluated with the
+//   fixed-order FP32 functions of pp_fmath.h; the Dubins shot keeps the double-evaluated "pinned libm" of pp_math.h.
 //
-// Data structures (per query slot, global memory), all driven by the 32 lanes together:
-//   nodes[]   append-only log of generated nodes (parent links are log indices)
+// Data structures (per query slot, global memory), all driven by the CTA's lanes together:
+//   nodes[]   append-only log of generated nodes (parent links are log indices; every node remembers its key's hash slot)
 //   table[]   open-addressing hash (key -> best pack, best node, closed bit), all-ones = empty, cleaned by the query that
 //             filled it (cost proportional to the nodes generated, not to the capacity); candidates race with atomicMin(pack):
 //             the winner is the minimum, independent of thread order => deterministic
 //   LSM queue sorted runs in levels of capacity 256 << level (log-structured merge): a batch of new entries is
-//             bitonic-sorted in shared memory and merged down the levels with warp merge-path merges; the k smallest are
-//             found by ranking the first k entries of every run against each other (binary searches in shared memory)
+//             rank-sorted in shared memory and merged down the levels with merge-path merges (the carry settles in the
+//             first level that can hold it together with that level's run); the k smallest are found by ranking the first
+//             k entries of every non-empty run against each other (binary searches in shared memory)
+// Decisions that need a ballot over the <= 32 popped entries (validity, ranks, shot counter) are taken by ballot group 0
+// and broadcast through shared memory; prefix counts over all lanes go through W::scan_count.
 #ifndef PP_KPOP_H
 #define PP_KPOP_H
 
