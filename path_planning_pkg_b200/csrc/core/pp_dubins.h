@@ -18,12 +18,13 @@ struct PPDubinsCenters
     float grx, gry, glx, gly;   // goal right / left circle centres
 };
 
-// Dubins.cpp:23-34
+// Dubins.cpp:23-34.  M = math policy (PPMathPinned: reference parity; PPMathFp32: K-POP mode)
+template <class M = PPMathPinned>
 PP_HD void pp_dubins_centers(float r, float sx, float sy, float sh, float gx, float gy, float gh,
                              PPDubinsCenters& c)
 {
-    float ss = pp_sinf(sh), cs = pp_cosf(sh);
-    float sg = pp_sinf(gh), cg = pp_cosf(gh);
+    float ss = M::sin(sh), cs = M::cos(sh);
+    float sg = M::sin(gh), cg = M::cos(gh);
     c.srx = sx + r * ss; c.sry = sy - r * cs;
     c.slx = sx - r * ss; c.sly = sy + r * cs;
     c.grx = gx + r * sg; c.gry = gy - r * cg;
@@ -120,33 +121,35 @@ PP_HD float pp_dubins_acos_arg(float r, float csx, float csy, float cgx, float c
 
 // One candidate, all of it on the calling thread (stateless kernels, the Dubins shot).  Returns the path length
 // (NaN for RSL/LSR when the centres are closer than 2r).
+template <class M = PPMathPinned>
 PP_HD_NOINLINE_FN float pp_dubins_candidate(int type, float r, float sh, float gh,
                                          float csx, float csy, float cgx, float cgy, float p[4])
 {
-    float theta = pp_atan2f(cgy - csy, cgx - csx);
+    float theta = M::atan2(cgy - csy, cgx - csx);
     float ac = 0.0f, c1 = 0.0f, s1 = 0.0f, c2 = 0.0f, s2 = 0.0f;
     if (type == PP_RSL || type == PP_LSR)
     {
-        ac = pp_acosf(pp_dubins_acos_arg(r, csx, csy, cgx, cgy));
+        ac = M::acos(pp_dubins_acos_arg(r, csx, csy, cgx, cgy));
         float t1 = pp_dubins_theta_t1(type, ac, theta);
         float p2 = pp_dubins_p2(type, t1);
-        c1 = pp_cosf(t1); s1 = pp_sinf(t1); c2 = pp_cosf(p2); s2 = pp_sinf(p2);
+        c1 = M::cos(t1); s1 = M::sin(t1); c2 = M::cos(p2); s2 = M::sin(p2);
     }
     return pp_dubins_finish(type, r, sh, gh, csx, csy, cgx, cgy, theta, ac, c1, s1, c2, s2, p);
 }
 
 // Sequential fold of the four candidates, Dubins.cpp:36-68.
+template <class M = PPMathPinned>
 PP_HD_NOINLINE_FN float pp_dubins_shortest(float r, float sx, float sy, float sh, float gx, float gy, float gh,
                                int& best_type, float best_p[4], PPDubinsCenters& c)
 {
-    pp_dubins_centers(r, sx, sy, sh, gx, gy, gh, c);
+    pp_dubins_centers<M>(r, sx, sy, sh, gx, gy, gh, c);
     float best = 0.0f;
     best_type = PP_RSR;
     for (int type = 0; type < 4; type++)
     {
         float csx, csy, cgx, cgy, p[4];
         pp_dubins_pick(c, type, csx, csy, cgx, cgy);
-        float len = pp_dubins_candidate(type, r, sh, gh, csx, csy, cgx, cgy, p);
+        float len = pp_dubins_candidate<M>(type, r, sh, gh, csx, csy, cgx, cgy, p);
         if (type == 0 || len < best)
         {
             best = len; best_type = type;
@@ -169,6 +172,7 @@ struct PPDubinsPlan
     float curvature;            // 1 / r_min
 };
 
+template <class M = PPMathPinned>
 PP_HD_NOINLINE_FN void pp_dubins_plan(float r, float step, float ang_step, int type, const float p[4],
                           const PPDubinsCenters& c, PPDubinsPlan& pl)
 {
@@ -177,10 +181,10 @@ PP_HD_NOINLINE_FN void pp_dubins_plan(float r, float step, float ang_step, int t
     pp_dubins_pick(c, type, pl.csx, pl.csy, pl.cgx, pl.cgy);
     pl.s1 = ((type == PP_RSR) || (type == PP_RSL)) ? -1.0f : 1.0f;
     pl.s2 = ((type == PP_RSR) || (type == PP_LSR)) ? -1.0f : 1.0f;
-    pl.ssx = pl.csx + r * pp_cosf(p[0] + p[1]);
-    pl.ssy = pl.csy + r * pp_sinf(p[0] + p[1]);
-    float esx = pl.cgx + r * pp_cosf(p[2]);
-    float esy = pl.cgy + r * pp_sinf(p[2]);
+    pl.ssx = pl.csx + r * M::cos(p[0] + p[1]);
+    pl.ssy = pl.csy + r * M::sin(p[0] + p[1]);
+    float esx = pl.cgx + r * M::cos(p[2]);
+    float esy = pl.cgy + r * M::sin(p[2]);
     float dx = esx - pl.ssx, dy = esy - pl.ssy;
     float length_st = sqrtf(dx * dx + dy * dy);
     // floor(-p1/as) for a right first arc, floor(p1/as) for a left one (Dubins.cpp:342, :407, :467, :527)
@@ -189,21 +193,22 @@ PP_HD_NOINLINE_FN void pp_dubins_plan(float r, float step, float ang_step, int t
     pl.size_1 = (int)floorf(a1 / ang_step);
     pl.size_2 = pl.size_1 + (int)floorf(length_st / step);
     pl.size_3 = pl.size_2 + (int)floorf(a3 / ang_step);
-    pl.st_theta = pp_atan2f(dy, dx);
-    pl.st_cos = pp_cosf(pl.st_theta);
-    pl.st_sin = pp_sinf(pl.st_theta);
+    pl.st_theta = M::atan2(dy, dx);
+    pl.st_cos = M::cos(pl.st_theta);
+    pl.st_sin = M::sin(pl.st_theta);
     pl.curvature = 1 / r;
 }
 
 // Sample k of the plan.  `acc` is the float accumulator of the segment the sample lies on:
 // theta (arcs; p0 -/+ k*ang_step accumulated one step at a time) or dist (straight; k*step likewise).
+template <class M = PPMathPinned>
 PP_HD_NOINLINE_FN void pp_dubins_sample(const PPDubinsPlan& pl, float r, int k, float acc,
                             float& x, float& y, float& heading, float& curvature)
 {
     if (k < pl.size_1)
     {
-        x = pl.csx + r * pp_cosf(acc);
-        y = pl.csy + r * pp_sinf(acc);
+        x = pl.csx + r * M::cos(acc);
+        y = pl.csy + r * M::sin(acc);
         heading = (float)pp_wrap_pi_d((double)acc + (double)pl.s1 * PP_PI_2);
         curvature = pl.curvature;
     }
@@ -216,16 +221,16 @@ PP_HD_NOINLINE_FN void pp_dubins_sample(const PPDubinsPlan& pl, float r, int k, 
     }
     else if (k < pl.size_3)
     {
-        x = pl.cgx + r * pp_cosf(acc);
-        y = pl.cgy + r * pp_sinf(acc);
+        x = pl.cgx + r * M::cos(acc);
+        y = pl.cgy + r * M::sin(acc);
         heading = (float)pp_wrap_pi_d((double)acc + (double)pl.s2 * PP_PI_2);
         curvature = pl.curvature;
     }
     else
     {
         float a = pl.p[2] + pl.p[3];
-        x = pl.cgx + r * pp_cosf(a);
-        y = pl.cgy + r * pp_sinf(a);
+        x = pl.cgx + r * M::cos(a);
+        y = pl.cgy + r * M::sin(a);
         heading = (float)pp_wrap_pi_d((double)a + (double)pl.s2 * PP_PI_2);
         curvature = 0.0f;
     }

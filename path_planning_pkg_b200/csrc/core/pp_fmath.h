@@ -73,4 +73,13 @@ PP_HD float pp_fm_acos(float x)
     return PP_FM_PI_2 - pp_fm_asin_core(x);
 }
 
+// math policy of the Dubins code (pp_dubins.h): the K-POP flavour
+struct PPMathFp32
+{
+    PP_HD static float sin(float x) { float s, c; pp_fm_sincos(x, s, c); return s; }
+    PP_HD static float cos(float x) { float s, c; pp_fm_sincos(x, s, c); return c; }
+    PP_HD static float atan2(float y, float x) { return pp_fm_atan2(y, x); }
+    PP_HD static float acos(float x) { return pp_fm_acos(x); }
+};
+
 #endif

@@ -12,7 +12,7 @@
 //   order; every pop expands every steering primitive of its window -> candidates c = rank*(2A+1) + a; per key the
 //   smallest pack(g, order = iteration*1024 + c) wins, also against the key's recorded best; winners get node indices in
 //   c order and f = g + max(h1[cell], Dubins).  The heuristic Dubins length and the APF term are evaluated with the
-//   fixed-order FP32 functions of pp_fmath.h; the Dubins shot keeps the double-evaluated "pinned libm" of pp_math.h.
+//   fixed-order FP32 functions of pp_fmath.h, and so is the Dubins shot (centres, candidates, plan, samples).
 //
 // Data structures (per query slot, global memory), all driven by the CTA's lanes together:
 //   nodes[]   append-only log of generated nodes (parent links are log indices; every node remembers its key's hash slot)
@@ -360,12 +360,12 @@ PP_HD bool pp_try_shot(const W& w, const PPConsts& C, const float* map, const PP
 {
     int type = PP_RSR; float p[4] = {0.0f, 0.0f, 0.0f, 0.0f}; PPDubinsCenters cen; PPDubinsPlan pl;
     // the four candidates on four lanes, then the sequential fold of Dubins.cpp:36-68 on every lane
-    pp_dubins_centers(C.r_min, x, y, h, F.goal_x, F.goal_y, F.goal_h, cen);
+    pp_dubins_centers<PPMathFp32>(C.r_min, x, y, h, F.goal_x, F.goal_y, F.goal_h, cen);
     for (int t = w.lane(); t < 4; t += W::LANES)
     {
         float csx, csy, cgx, cgy, pc[4];
         pp_dubins_pick(cen, t, csx, csy, cgx, cgy);
-        shot[t][0] = pp_dubins_candidate(t, C.r_min, h, F.goal_h, csx, csy, cgx, cgy, pc);
+        shot[t][0] = pp_dubins_candidate<PPMathFp32>(t, C.r_min, h, F.goal_h, csx, csy, cgx, cgy, pc);
         shot[t][1] = pc[0]; shot[t][2] = pc[1]; shot[t][3] = pc[2]; shot[t][4] = pc[3];
     }
     w.sync();
@@ -374,7 +374,7 @@ PP_HD bool pp_try_shot(const W& w, const PPConsts& C, const float* map, const PP
         if (t == 0 || shot[t][0] < len) { len = shot[t][0]; type = t; p[0] = shot[t][1]; p[1] = shot[t][2]; p[2] = shot[t][3]; p[3] = shot[t][4]; }
     w.sync();
     if (fabsf(p[1]) > (float)PP_PI_2) return false;                       // Dubins.cpp:152
-    pp_dubins_plan(C.r_min, C.step, C.ang_step, type, p, cen, pl);
+    pp_dubins_plan<PPMathFp32>(C.r_min, C.step, C.ang_step, type, p, cen, pl);
     const int total = pl.size_3 + 1;
     bool blocked = false, over = false;
     if (total <= acc_cap)
@@ -392,13 +392,16 @@ PP_HD bool pp_try_shot(const W& w, const PPConsts& C, const float* map, const PP
         }
         w.sync();
         // a blocked sample anywhere rejects the shot: stop after the first round of samples that saw one
-        for (int base = 0; base < total; base += W::LANES)
+        // lane l takes samples l*R, l*R + 1, ...: every round looks at points spread over the whole path, so a blocked path
+        // is usually rejected in the first round
+        const int R = (total + W::LANES - 1) / W::LANES;
+        for (int rr = 0; rr < R; rr++)
         {
-            const int k = base + w.lane();
+            const int k = w.lane() * R + rr;
             if (k < total)
             {
                 float sx, sy, sh, kappa;
-                pp_dubins_sample(pl, C.r_min, k, accb[k], sx, sy, sh, kappa);
+                pp_dubins_sample<PPMathFp32>(pl, C.r_min, k, accb[k], sx, sy, sh, kappa);
                 if (pp_path_point_blocked(C, map, sx, sy)) blocked = true;
                 if (k < path_cap) { PPPathPt& q = path[k]; q.x = sx; q.y = sy; q.heading = sh; q.curvature = kappa; }
                 else over = true;
@@ -416,7 +419,7 @@ PP_HD bool pp_try_shot(const W& w, const PPConsts& C, const float* map, const PP
             if ((k % W::LANES) == w.lane())
             {
                 float sx, sy, sh, kappa;
-                pp_dubins_sample(pl, C.r_min, k, acc, sx, sy, sh, kappa);
+                pp_dubins_sample<PPMathFp32>(pl, C.r_min, k, acc, sx, sy, sh, kappa);
                 if (pp_path_point_blocked(C, map, sx, sy)) blocked = true;
                 if (k < path_cap) { PPPathPt& q = path[k]; q.x = sx; q.y = sy; q.heading = sh; q.curvature = kappa; }
                 else over = true;

@@ -20,6 +20,15 @@ PP_HD_NOINLINE_FN float pp_cosf(float x) { return (float)cos((double)x); }
 PP_HD_NOINLINE_FN float pp_atan2f(float y, float x) { return (float)atan2((double)y, (double)x); }
 PP_HD_NOINLINE_FN float pp_acosf(float x) { return (float)acos((double)x); }
 
+// math policy of the Dubins code (pp_dubins.h): the reference-parity flavour
+struct PPMathPinned
+{
+    PP_HD static float sin(float x) { return pp_sinf(x); }
+    PP_HD static float cos(float x) { return pp_cosf(x); }
+    PP_HD static float atan2(float y, float x) { return pp_atan2f(y, x); }
+    PP_HD static float acos(float x) { return pp_acosf(x); }
+};
+
 // glibc hypotf == (float)sqrt((double)x*x + (double)y*y) (checked on 2e8 random pairs)
 PP_HD float pp_hypotf(float x, float y)
 {
