@@ -50,6 +50,7 @@ struct PPKWork
     PPKNode*  nodes;   int nodes_cap;
     PPKSlot*  table;   int table_cap;          // power of two
     PPKEntry* arena;                           // level l at offset PP_K_RUN0 * ((1 << l) - 1), PP_K_LEVELS levels used up to lsm_levels
+    PPKEntry* l0;                              // level 0 of the queue: PPKSmem::l0 (set by pp_search_kpop)
     PPKEntry* tmp_a;   PPKEntry* tmp_b;        // merge scratch, each nodes_cap + PP_K_RUN0 entries
     int       lsm_levels;
     const float* h1;                           // N*N exact 2D distance field of the query's group
@@ -65,6 +66,7 @@ struct PPKSmem
         PPKEntry sel[PP_K_LEVELS * PP_K_MAXPOP];           // pop selection: first k entries of every run
         struct { PPKEntry batch[PP_K_MAXCAND]; PPKEntry sorted[PP_K_MAXCAND]; } q;   // new queue entries of this iteration
     } u;
+    PPKEntry l0[PP_K_RUN0];                                // level 0 of the LSM queue
     PPKEntry popped[PP_K_MAXPOP];
     PPKNode  parents[PP_K_MAXPOP];                         // copies of this iteration's pops, by rank
     int      pop_idx[PP_K_MAXPOP];                         // their node indices
@@ -204,7 +206,8 @@ PP_HD void pp_kcopy(const W& w, const PPKEntry* src, PPKEntry* dst, int n)
     w.sync();
 }
 
-PP_HD PPKEntry* pp_klevel(const PPKWork& wk, int l) { return wk.arena + (size_t)PP_K_RUN0 * (((size_t)1 << l) - 1); }
+// run of level l: level 0 (<= 256 entries, touched by almost every iteration) lives in shared memory, the rest in the arena
+PP_HD PPKEntry* pp_klevel(const PPKWork& wk, int l) { return l == 0 ? wk.l0 : wk.arena + (size_t)PP_K_RUN0 * (((size_t)1 << l) - 1); }
 
 // insert a sorted batch (shared memory, m <= PP_K_MAXCAND entries); false = queue capacity exhausted.
 // The carry walks down the levels: it settles in the first level that can hold it together with that level's live run
@@ -228,11 +231,13 @@ PP_HD bool pp_klsm_insert(const W& w, PPKWork& wk, PPKSmem& sm, const PPKEntry* 
             w.sync();
             return true;
         }
-        pp_kmerge(w, L + sm.head[l], cnt, carry, carry_n, t0);
+        // level 0 settles without leaving shared memory: the merge target is the (now free) unsorted-batch area
+        PPKEntry* dst = (l == 0 && cnt + carry_n <= cap && carry != sm.u.q.batch) ? sm.u.q.batch : t0;
+        pp_kmerge(w, L + sm.head[l], cnt, carry, carry_n, dst);
         carry_n += cnt;
         if (carry_n <= cap)
         {
-            pp_kcopy(w, t0, L, carry_n);
+            pp_kcopy(w, dst, L, carry_n);
             if (w.lane() == 0) { sm.head[l] = 0; sm.size[l] = carry_n; }
             w.sync();
             return true;
@@ -447,6 +452,7 @@ PP_HD_NOINLINE void pp_search_kpop(const W& w, const PPConsts& C, const float* o
     const int n_succ = 2 * C.A + 1;
     const unsigned goal_cell = (unsigned)(F.goal_ci * N + F.goal_cj);
 
+    wk.l0 = sm.l0;
     // ---- init ----  (the hash table arrives all-ones = empty: the host clears it once, every query cleans up after itself)
     for (int t = lane; t < PP_K_LEVELS; t += W::LANES) { sm.head[t] = 0; sm.size[t] = 0; sm.taken[t] = 0; }
     w.sync();
