@@ -422,4 +422,55 @@ void emu_find_path_kpop(void* h, float vel, const float* s, int k, const float* 
     res->n_path = n;
 }
 
+// pp_fmath.h on n inputs: kind 0 sin, 1 cos, 2 atan2(y = a, x = b), 3 acos
+void emu_fmath_batch(int kind, const float* a, const float* b, float* out, int n)
+{
+    for (int k = 0; k < n; k++)
+    {
+        float s, c;
+        switch (kind)
+        {
+            case 0: pp_fm_sincos(a[k], s, c); out[k] = s; break;
+            case 1: pp_fm_sincos(a[k], s, c); out[k] = c; break;
+            case 2: out[k] = pp_fm_atan2(a[k], b[k]); break;
+            default: out[k] = pp_fm_acos(a[k]); break;
+        }
+    }
+}
+
+// K-POP APF sum of n poses (x, y, heading): through the spatial index (as the kernel does) and by scanning every obstacle
+void emu_kapf_batch(void* h, const float* xyh, int n, float* via_bins, float* via_scan)
+{
+    Emu* e = static_cast<Emu*>(h);
+    const PPConsts& C = e->m.C;
+    PPGroup G = group_of(e);
+    for (int k = 0; k < n; k++)
+    {
+        const float x = xyh[3 * k], y = xyh[3 * k + 1], hd = xyh[3 * k + 2];
+        float a = 0.0f, b = 0.0f;
+        for (int q = 0; q < G.K; q++)
+        {
+            float t = pp_kapf_term(C, G.apf[3 * q], G.apf[3 * q + 1], G.apf[3 * q + 2], x, y, hd);
+            if (t != 0.0f) b = b + t;
+        }
+        int ci, cj;
+        if (pp_collision_free(C, G.map, x, y, ci, cj) || (ci > -1 && ci < C.N && cj > -1 && cj < C.N))
+        {
+            if (G.bin_off)
+            {
+                const int bb = (ci >> G.bin_shift) * G.bin_n + (cj >> G.bin_shift);
+                for (int qq = G.bin_off[bb]; qq < G.bin_off[bb + 1]; qq++)
+                {
+                    const int q = G.bin_idx[qq];
+                    float t = pp_kapf_term(C, G.apf[3 * q], G.apf[3 * q + 1], G.apf[3 * q + 2], x, y, hd);
+                    if (t != 0.0f) a = a + t;
+                }
+            }
+            else a = b;
+        }
+        else a = b;                                        // outside the grid: the search never evaluates the APF there
+        via_bins[k] = a; via_scan[k] = b;
+    }
+}
+
 } // extern "C"

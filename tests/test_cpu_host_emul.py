@@ -218,3 +218,54 @@ def test_kpop_core_c4_and_backward_start(emu_lib):
             assert a["success"] == b["success"] and a["n_pops"] == b["n_pops"] and a["oob"] == b["oob"]
             assert np.array_equal(a["pops"], b["pops"]) and a["cost"] == b["cost"]
             assert np.array_equal(_bits(a["path"]), _bits(b["path"]))
+
+
+def test_fp32_math_product_equals_restatement_and_libm(emu_lib):
+    """csrc/core/pp_fmath.h (product, compiled for the host) vs oracle/port/fmath.inc (restatement): the same bits on
+    2e5 random arguments per function; both within 3e-7 absolute of the double-precision libm value."""
+    import ctypes as C
+    o = orc.port(orc.ref_test_params())
+    rs = np.random.RandomState(9)
+    n = 200000
+    cases = [(0, rs.uniform(-20, 20, n), None, np.sin), (1, rs.uniform(-20, 20, n), None, np.cos),
+             (2, rs.uniform(-50, 50, n), rs.uniform(-50, 50, n), np.arctan2), (3, rs.uniform(-1, 1, n), None, np.arccos)]
+    for kind, a, b, fn in cases:
+        a = a.astype(np.float32); b = (b if b is not None else np.zeros(n)).astype(np.float32)
+        if kind == 2:
+            a[:4] = [0.0, 0.0, 1.0, -1.0]; b[:4] = [0.0, -2.0, 0.0, 0.0]           # axes and the origin
+        if kind == 3:
+            a[:4] = [1.0, -1.0, 0.5, -0.5]
+        x = np.empty(n, np.float32); y = np.empty(n, np.float32)
+        emu_lib.emu_fmath_batch(C.c_int(kind), orc._fp(a), orc._fp(b), orc._fp(x), C.c_int(n))
+        o.lib.port_fmath_batch(C.c_int(kind), orc._fp(a), orc._fp(b), orc._fp(y), C.c_int(n))
+        assert np.array_equal(_bits(x), _bits(y)), kind
+        ref = fn(a.astype(np.float64), b.astype(np.float64)) if kind == 2 else fn(a.astype(np.float64))
+        assert np.abs(x.astype(np.float64) - ref).max() < 3e-7 * max(1.0, np.abs(ref).max()), (kind, np.abs(x - ref).max())
+    out = np.empty(2, np.float32)
+    emu_lib.emu_fmath_batch(C.c_int(3), orc._fp(np.array([1.5, -1.0000001], np.float32)), orc._fp(np.zeros(2, np.float32)), orc._fp(out), C.c_int(2))
+    assert np.isnan(out).all()                                   # acos outside [-1, 1]: NaN (the candidate never wins)
+
+
+def test_apf_spatial_index_is_conservative(emu_lib):
+    """pp_host_apf_bins: summing only the obstacles listed for a pose's bin equals the scan over all obstacles, bit for
+    bit, on a cluttered C4 map (96 obstacles) and on the reference's scenario."""
+    import ctypes as C
+    for name in ("c4", "ref"):
+        if name == "c4":
+            sc = S.c4_group(7, n_starts=1)
+            P = orc.make_params(grid_size=512, resolution=0.2)
+            e = _emu(emu_lib, P)
+            S.build_map(e, sc)
+            L = 512 * 0.2
+        else:
+            P = orc.ref_test_params()
+            e = _emu(emu_lib, P)
+            orc.setup_ref_test_scenario(e)
+            L = P.grid_size * P.resolution
+        rs = np.random.RandomState(4)
+        n = 100000
+        xyh = np.stack([rs.uniform(-1, L + 1, n), rs.uniform(-1, L + 1, n), rs.uniform(-3.14, 3.14, n)], 1).astype(np.float32)
+        a = np.empty(n, np.float32); b = np.empty(n, np.float32)
+        emu_lib.emu_kapf_batch(e.h, orc._fp(xyh), C.c_int(n), orc._fp(a), orc._fp(b))
+        assert np.array_equal(_bits(a), _bits(b)), name
+        assert (b != 0).sum() > n // 50, name                    # the test does exercise non-zero fields
