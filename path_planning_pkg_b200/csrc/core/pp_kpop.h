@@ -93,11 +93,15 @@ PP_HD PPKEntry pp_kinf()
     PPKEntry e; e.f = INFINITY; e.key = 0xffffffffu; e.idx = 0xffffffffu; e.pad = 0; return e;
 }
 
-// ---- atomics (device) / plain (single host lane) ----------------------------------------------------------------
+// ---- atomics: device / plain (single host lane) / GCC builtins (PP_HOST_ATOMICS: the multi-threaded host emulation of
+// tests/cpp/kpop_mt.cpp, which runs this file under ThreadSanitizer) ----------------------------------------------------
 PP_HD unsigned pp_atomic_cas_u32(unsigned* p, unsigned expect, unsigned val)
 {
 #ifdef __CUDA_ARCH__
     return atomicCAS(p, expect, val);
+#elif defined(PP_HOST_ATOMICS)
+    __atomic_compare_exchange_n(p, &expect, val, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED);
+    return expect;                                   // the old value in either case
 #else
     unsigned old = *p; if (old == expect) *p = val; return old;
 #endif
@@ -106,8 +110,21 @@ PP_HD void pp_atomic_min_u64(unsigned long long* p, unsigned long long val)
 {
 #ifdef __CUDA_ARCH__
     atomicMin(p, val);
+#elif defined(PP_HOST_ATOMICS)
+    unsigned long long cur = __atomic_load_n(p, __ATOMIC_RELAXED);
+    while (val < cur && !__atomic_compare_exchange_n(p, &cur, val, true, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
 #else
     if (val < *p) *p = val;
+#endif
+}
+PP_HD void pp_atomic_inc_i32(int* p)
+{
+#ifdef __CUDA_ARCH__
+    atomicAdd(p, 1);
+#elif defined(PP_HOST_ATOMICS)
+    __atomic_fetch_add(p, 1, __ATOMIC_RELAXED);
+#else
+    (*p)++;
 #endif
 }
 PP_HD void pp_fence()
@@ -124,8 +141,20 @@ PP_HD void pp_kslot_load(const PPKSlot* s, unsigned& key, unsigned& node)
 #ifdef __CUDA_ARCH__
     const uint2 v = *reinterpret_cast<const uint2*>(s);
     key = v.x; node = v.y;
+#elif defined(PP_HOST_ATOMICS)
+    key = __atomic_load_n(&s->key, __ATOMIC_RELAXED); node = s->node;   // the key may be CAS-ed by another lane right now
 #else
     key = s->key; node = s->node;
+#endif
+}
+PP_HD void pp_kslot_clear(PPKSlot* s)
+{
+#if !defined(__CUDA_ARCH__) && defined(PP_HOST_ATOMICS)
+    __atomic_store_n(&s->key, PP_K_EMPTY, __ATOMIC_RELAXED); __atomic_store_n(&s->node, PP_K_NONE, __ATOMIC_RELAXED);
+    __atomic_store_n(&s->pack, ~0ull, __ATOMIC_RELAXED);
+#else
+    PPKSlot e; e.key = PP_K_EMPTY; e.node = PP_K_NONE; e.pack = ~0ull;
+    *s = e;
 #endif
 }
 PP_HD int pp_ktable_find(const PPKWork& wk, unsigned key, unsigned& node)
@@ -290,11 +319,7 @@ PP_HD int pp_klsm_pop(const W& w, PPKWork& wk, PPKSmem& sm, int k)
         if (rank < k)
         {
             sm.popped[rank] = e;
-#ifdef __CUDA_ARCH__
-            atomicAdd(&sm.taken[lv[c]], 1);
-#else
-            sm.taken[lv[c]]++;
-#endif
+            pp_atomic_inc_i32(&sm.taken[lv[c]]);
         }
     }
     w.sync();
@@ -723,11 +748,8 @@ PP_HD_NOINLINE void pp_search_kpop(const W& w, const PPConsts& C, const float* o
     }
     // ---- leave the hash table empty for the slot's next query: every inserted key belongs to at least one logged node ----
     w.sync();
-    for (int t = lane; t < n_nodes; t += W::LANES)
-    {
-        PPKSlot e; e.key = PP_K_EMPTY; e.node = PP_K_NONE; e.pack = ~0ull;
-        wk.table[wk.nodes[t].slot] = e;
-    }
+    // (superseded nodes of one key share a slot: several lanes may store the same all-ones record to it -- harmless)
+    for (int t = lane; t < n_nodes; t += W::LANES) pp_kslot_clear(wk.table + wk.nodes[t].slot);
     w.sync();
 }
 
