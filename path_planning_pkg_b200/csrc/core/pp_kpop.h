@@ -94,7 +94,7 @@ PP_HD PPKEntry pp_kinf()
 }
 
 // ---- atomics: device / plain (single host lane) / GCC builtins (PP_HOST_ATOMICS: the multi-threaded host emulation of
-// tests/cpp/kpop_mt.cpp, which runs this file under ThreadSanitizer) ----------------------------------------------------
+// tests/cpp/search_mt.cpp, which runs this file under ThreadSanitizer) ----------------------------------------------------
 PP_HD unsigned pp_atomic_cas_u32(unsigned* p, unsigned expect, unsigned val)
 {
 #ifdef __CUDA_ARCH__

@@ -1,13 +1,13 @@
 // TEST INFRASTRUCTURE ONLY -- not part of the product.
 //
-// Race check of the multi-warp K-POP core on the CPU.  The product's pp_search_kpop (csrc/core/pp_kpop.h) is written
-// against a lane policy W (lane ids, barriers, ballots); the CUDA kernel instantiates it with a CTA of 4 warps.  Here the
+// Race check of the search cores on the CPU (K-POP: multi-warp CTA; EXACT: one warp).  The product's pp_search_kpop
+// (csrc/core/pp_kpop.h) and pp_search_exact (csrc/core/pp_search.h) are written against a lane policy W (lane ids, barriers, ballots); the CUDA kernel instantiates it with a CTA of 4 warps.  Here the
 // same code runs on NL host threads, one per lane, in ballot groups ("warps") of BW lanes, with every barrier a
 // pthread barrier and every device atomic a GCC builtin (PP_HOST_ATOMICS).  Built with -fsanitize=thread, any pair of
 // conflicting shared-memory / pool accesses that is not ordered by a barrier is reported by ThreadSanitizer, and the
 // result must be bit-identical to the single-lane run of the same code.
 //
-//   kpop_mt <scenario.bin>     (written by tests/test_cpu_kpop_mt.py; layout in read_scenario below)
+//   search_mt <scenario.bin>     (written by tests/test_cpu_search_mt.py; layout above main below)
 #define PP_HOST_ATOMICS 1
 #include <pthread.h>
 #include <thread>
@@ -72,6 +72,94 @@ struct PPBlockHost
     }
 };
 
+// one warp of NL lanes for the EXACT mode (pp_search_exact): sync = the warp barrier, ballots / shuffles over all NL lanes
+template <int NL>
+struct MTWarpShared
+{
+    pthread_barrier_t bar;
+    unsigned bal[NL];
+    unsigned char xch[NL][16];
+    MTWarpShared() { pthread_barrier_init(&bar, nullptr, NL); }
+};
+
+template <int NL>
+struct PPWarpHostMT
+{
+    enum { LANES = NL };
+    int id;
+    MTWarpShared<NL>* sh;
+    int lane() const { return id; }
+    void sync() const { pthread_barrier_wait(&sh->bar); }
+    unsigned ballot(bool p) const
+    {
+        sh->bal[id] = p ? 1u : 0u;
+        sync();
+        unsigned m = 0;
+        for (int t = 0; t < NL; t++) m |= sh->bal[t] << t;
+        sync();
+        return m;
+    }
+    unsigned lanemask_lt() const { return (1u << id) - 1u; }
+    template <class T> T shfl(T v, int src) const
+    {
+        static_assert(sizeof(T) <= 16, "shuffle payload");
+        std::memcpy(sh->xch[id], &v, sizeof(T));
+        sync();
+        T r; std::memcpy(&r, sh->xch[src], sizeof(T));
+        sync();
+        return r;
+    }
+};
+
+struct ExactPools
+{
+    std::vector<PPNode3> open3; std::vector<PPClosed3> closed; std::vector<PPHashSlot> chash; std::vector<unsigned> cell_state;
+    std::vector<float> nm_g, nm_f, cl_g; std::vector<int> cl_prev; std::vector<PPNode2> open2; std::vector<PPPathPt> path;
+    std::vector<PPPop> trace;
+    PPWork wk;
+    explicit ExactPools(int N)
+    {
+        const int closed_cap = 1 << 16, open_cap = 1 << 15, open2_cap = 1 << 14;
+        open3.resize(open_cap); closed.resize(closed_cap);
+        int hc = 1; while (hc < 2 * closed_cap) hc <<= 1;
+        chash.resize(hc);
+        cell_state.resize((size_t)N * N); nm_g.resize((size_t)N * N); nm_f.resize((size_t)N * N); cl_g.resize((size_t)N * N);
+        cl_prev.resize((size_t)N * N); open2.resize(open2_cap); path.resize(4096); trace.resize(1 << 16);
+        wk.open3 = open3.data(); wk.open3_cap = open_cap; wk.closed = closed.data(); wk.closed_cap = closed_cap;
+        wk.chash = chash.data(); wk.chash_cap = hc; wk.cell_state = cell_state.data(); wk.nm_g = nm_g.data(); wk.nm_f = nm_f.data();
+        wk.cl_g = cl_g.data(); wk.cl_prev = cl_prev.data(); wk.open2 = open2.data(); wk.open2_cap = open2_cap;
+        wk.path = path.data(); wk.path_cap = (int)path.size(); wk.trace = trace.data(); wk.trace_cap = (int)trace.size();
+    }
+};
+
+template <int NL>
+PPResult run_exact_mt(Emu* e, const PPState& st, ExactPools& P)
+{
+    MTWarpShared<NL> sh;
+    std::unique_ptr<PPSmem> sm(new PPSmem());
+    PPResult res[NL];
+    PPGroup G = group_of(e);
+    std::vector<std::thread> th;
+    for (int t = 0; t < NL; t++)
+        th.emplace_back([&, t] {
+            PPWarpHostMT<NL> w; w.id = t; w.sh = &sh;
+            PPWork wk = P.wk;
+            pp_search_exact(w, e->m.C, e->m.off_xy.data(), G, st, wk, *sm, res[t]);
+        });
+    for (auto& t : th) t.join();
+    return res[0];
+}
+
+bool same_exact(const PPResult& a, const ExactPools& A, const PPResult& b, const ExactPools& B)
+{
+    if (a.success != b.success || a.status != b.status || a.n_pops != b.n_pops || a.n_chain != b.n_chain || a.n_dubins != b.n_dubins ||
+        a.n_closed != b.n_closed || a.n_lazy_pops != b.n_lazy_pops || std::memcmp(&a.cost, &b.cost, 4) != 0) return false;
+    int np = std::min(a.n_pops, (int)A.trace.size());
+    if (std::memcmp(A.trace.data(), B.trace.data(), sizeof(PPPop) * np) != 0) return false;
+    int n = std::min(a.n_chain + a.n_dubins, (int)A.path.size());
+    return std::memcmp(A.path.data(), B.path.data(), sizeof(PPPathPt) * n) == 0;
+}
+
 struct Pools
 {
     std::vector<PPKNode> nodes; std::vector<PPKSlot> table; std::vector<PPKEntry> arena, ta, tb; std::vector<PPPathPt> path;
@@ -131,7 +219,7 @@ bool same(const PPResult& a, const Pools& A, const PPResult& b, const Pools& B)
 //               h1[N*N] | int n_queries | queries[n][4] (x, y, heading, vel) | int k
 int main(int argc, char** argv)
 {
-    if (argc < 2) { std::fprintf(stderr, "usage: kpop_mt scenario.bin\n"); return 2; }
+    if (argc < 2) { std::fprintf(stderr, "usage: search_mt scenario.bin\n"); return 2; }
     FILE* f = std::fopen(argv[1], "rb");
     if (!f) { std::perror("scenario"); return 2; }
     auto rd = [&](void* p, size_t n) { if (std::fread(p, 1, n, f) != n) { std::fprintf(stderr, "short scenario file\n"); std::exit(2); } };
@@ -166,6 +254,17 @@ int main(int argc, char** argv)
         std::printf("query %d: success %d pops %d cost %.6f nodes %d | 4 lanes (2 x 2) and 8 lanes (2 x 4): %s\n", i, r1.success, r1.n_pops,
                     r1.cost, r1.n_closed, ok ? "identical" : "MISMATCH");
         if (!ok) bad++;
+        // EXACT mode: one lane vs a warp of 8 and of 32 lanes
+        ExactPools E1(N), E8(N), E32(N);
+        std::unique_ptr<PPSmem> xsm(new PPSmem());
+        PPResult x1;
+        { PPGroup G = group_of(e); PPWork wk = E1.wk; pp_search_exact(w1, e->m.C, e->m.off_xy.data(), G, st, wk, *xsm, x1); }
+        PPResult x8 = run_exact_mt<8>(e, st, E8);
+        PPResult x32 = run_exact_mt<32>(e, st, E32);
+        bool xok = same_exact(x1, E1, x8, E8) && same_exact(x1, E1, x32, E32) && x1.status == 0;
+        std::printf("query %d EXACT: success %d pops %d cost %.6f lazy pops %d | 8 and 32 lanes: %s\n", i, x1.success, x1.n_pops, x1.cost,
+                    x1.n_lazy_pops, xok ? "identical" : "MISMATCH");
+        if (!xok) bad++;
     }
     emu_destroy(e);
     return bad ? 1 : 0;

@@ -1,6 +1,6 @@
-"""CPU race check of the multi-warp K-POP core: tests/cpp/kpop_mt.cpp runs the product's pp_search_kpop on 4 and 8 host
-threads (one per lane, pthread barriers for the CTA barriers, GCC atomics for the device atomics) under ThreadSanitizer and
-compares the result with the single-lane run of the same code, bit for bit.  (compute-sanitizer's racecheck is not
+"""CPU race check of the search cores: tests/cpp/search_mt.cpp runs the product's pp_search_kpop on 4 and 8 host threads and
+pp_search_exact on 8 and 32 (one thread per lane, pthread barriers for the CTA / warp barriers, GCC atomics for the device
+atomics) under ThreadSanitizer and compares every result with the single-lane run of the same code, bit for bit.  (compute-sanitizer's racecheck is not
 available on the GPU pool, so this is where unordered shared-memory accesses would show up.)"""
 import ctypes as C
 import os
@@ -13,13 +13,13 @@ import orc
 import scenarios as S
 
 BIN = os.path.join(orc.ROOT, "tests", "cpp", "bin")
-SRC = os.path.join(orc.ROOT, "tests", "cpp", "kpop_mt.cpp")
+SRC = os.path.join(orc.ROOT, "tests", "cpp", "search_mt.cpp")
 
 
 @pytest.fixture(scope="module")
 def exe():
     os.makedirs(BIN, exist_ok=True)
-    out = os.path.join(BIN, "kpop_mt")
+    out = os.path.join(BIN, "search_mt")
     cmd = ["g++", "-std=c++14", "-O1", "-g", "-fsanitize=thread", "-ffp-contract=off", "-Wno-unknown-pragmas", "-o", out, SRC, "-lpthread"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0 and "sanitize" in r.stderr:
@@ -46,7 +46,7 @@ def _field(port):
 
 
 @pytest.mark.parametrize("k", [32, 5])
-def test_kpop_multilane_race_free_and_identical(exe, tmp_path, k):
+def test_multilane_race_free_and_identical(exe, tmp_path, k):
     runs = []
     # the reference's own test scenario (lane lines + boxes)
     P = orc.ref_test_params()
