@@ -165,7 +165,9 @@ def run_c5(args, rank, local_rank, world):
         e1.record(); torch.cuda.synchronize()
         map_bcast_ms = e0.elapsed_time(e1) / 8
     if args.c5_shard == "query":
-        queries, qgroups = queries[rank::world], qgroups[rank::world]
+        from path_planning_pkg_b200.shard import shard_queries
+        mine_q = shard_queries(len(queries), rank, world)
+        queries, qgroups = queries[mine_q], qgroups[mine_q]
     q = ctx.make_queries(queries, qgroups)
     nq = len(q)
     pc = 1024

@@ -13,6 +13,12 @@ def shard_groups(n_groups_total, rank, world):
     return list(range(rank, n_groups_total, world))
 
 
+def shard_queries(n_queries_total, rank, world):
+    """Interleaved partition of query indices (every world-th query): with every map replicated on every rank this gives
+    all ranks statistically equal work, whatever the difficulty of the individual groups (bench.py --workload c5)."""
+    return np.arange(rank, n_queries_total, world)
+
+
 def owner_of(group, world):
     return group % world
 

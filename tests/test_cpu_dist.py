@@ -71,3 +71,12 @@ def test_shard_groups_partition():
         assert seen == list(range(64))
         sizes = [len(shard.shard_groups(64, r, world)) for r in range(world)]
         assert max(sizes) - min(sizes) <= 1
+
+
+def test_shard_queries_partition():
+    from path_planning_pkg_b200 import shard
+    import numpy as np
+    for world in (1, 2, 3, 8):
+        parts = [shard.shard_queries(65536 + 5, r, world) for r in range(world)]
+        assert np.array_equal(np.sort(np.concatenate(parts)), np.arange(65536 + 5))
+        assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 1
