@@ -40,6 +40,20 @@ PPWalk
 
 struct PPKey { unsigned key; float f; };
 
+// The walk record of a node with ONE 128-bit load.  Left to itself the compiler loads (f, key) first and the child index
+// it needs afterwards -- two dependent loads per tree level on the latency-critical path of every find.
+PP_HD PPWalk pp_walk_load(const PPWalk* p)
+{
+#ifdef __CUDA_ARCH__
+    uint4 v = *reinterpret_cast<const uint4*>(p);
+    asm volatile("" : "+r"(v.x), "+r"(v.y), "+r"(v.z), "+r"(v.w));     // all four words are live here: no narrowing of the load
+    PPWalk r; r.left = (int)v.x; r.right = (int)v.y; r.f = __uint_as_float(v.z); r.key = v.w;
+    return r;
+#else
+    return *p;
+#endif
+}
+
 // the reference's non-strict-weak ordering
 PP_HD bool pp_lt(unsigned ka, float fa, unsigned kb, float fb) { return (ka != kb) && (fa < fb); }
 
@@ -318,7 +332,7 @@ struct PPRbTree
         PPWalk yw; yw.left = 0; yw.right = 0; yw.f = 0.0f; yw.key = 0u;
         while (x != PP_RB_NIL)
         {
-            const PPWalk r = n[x].w;                       // one 128-bit load per level
+            const PPWalk r = pp_walk_load(&n[x].w);        // one 128-bit load per level
             if (!pp_lt(r.key, r.f, k.key, k.f)) { y = x; yw = r; x = r.left; }
             else x = r.right;
         }
@@ -334,7 +348,7 @@ struct PPRbTree
         bool comp = true;
         while (x != PP_RB_NIL)
         {
-            const PPWalk r = n[x].w;
+            const PPWalk r = pp_walk_load(&n[x].w);
             y = x;
             comp = pp_lt(k.key, k.f, r.key, r.f);
             x = comp ? r.left : r.right;
