@@ -40,6 +40,13 @@ PPWalk
 
 struct PPKey { unsigned key; float f; };
 
+// the node pools live in global memory: saying so lets the compiler emit LDG / STG instead of generic loads and stores
+#ifdef __CUDA_ARCH__
+#define PP_ASSUME_GLOBAL(ptr) __builtin_assume(__isGlobal(ptr))
+#else
+#define PP_ASSUME_GLOBAL(ptr)
+#endif
+
 // The walk record of a node with ONE 128-bit load.  Left to itself the compiler loads (f, key) first and the child index
 // it needs afterwards -- two dependent loads per tree level on the latency-critical path of every find.
 PP_HD PPWalk pp_walk_load(const PPWalk* p)
@@ -124,6 +131,7 @@ struct PPRbTree
     // _Rb_tree_decrement
     PP_HD_NOINLINE int decrement(int x) const
     {
+        PP_ASSUME_GLOBAL(n);
         if (x == PP_RB_HEADER) return n[x].w.right;   // end() -> rightmost
         if (n[x].w.left != PP_RB_NIL)
         {
@@ -139,6 +147,7 @@ struct PPRbTree
     // _Rb_tree_insert_and_rebalance
     PP_HD_NOINLINE void insert_and_rebalance(bool insert_left, int x, int p)
     {
+        PP_ASSUME_GLOBAL(n);
         n[x].parent = p; n[x].w.left = PP_RB_NIL; n[x].w.right = PP_RB_NIL; n[x].color = PP_RB_RED;
         if (insert_left)
         {
@@ -195,6 +204,7 @@ struct PPRbTree
     // _Rb_tree_rebalance_for_erase; recycles slot z
     PP_HD_NOINLINE void erase(int z)
     {
+        PP_ASSUME_GLOBAL(n);
         int y = z, x = PP_RB_NIL, x_parent = PP_RB_NIL;
         if (n[y].w.left == PP_RB_NIL) x = n[y].w.right;
         else if (n[y].w.right == PP_RB_NIL) x = n[y].w.left;
@@ -328,6 +338,7 @@ struct PPRbTree
     // std::set::find(k): lower-bound walk, then reject when k < *j.
     PP_HD_NOINLINE int find(const PPKey& k) const
     {
+        PP_ASSUME_GLOBAL(n);
         int x = n[PP_RB_HEADER].parent, y = PP_RB_HEADER;
         PPWalk yw; yw.left = 0; yw.right = 0; yw.f = 0.0f; yw.key = 0u;
         while (x != PP_RB_NIL)
@@ -344,6 +355,7 @@ struct PPRbTree
     // inserted under parent `p` (left child iff `left`); false when an equivalent element exists.
     PP_HD_NOINLINE bool insert_pos(const PPKey& k, int& p, bool& left) const
     {
+        PP_ASSUME_GLOBAL(n);
         int x = n[PP_RB_HEADER].parent, y = PP_RB_HEADER;
         bool comp = true;
         while (x != PP_RB_NIL)
