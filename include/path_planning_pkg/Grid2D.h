@@ -26,19 +26,26 @@ namespace planning
                bool allow_diag_moves);
         virtual ~Grid2D();
 
-        void get_neighbors(const int xd, const int yd, std::vector<std::pair<Node2D<T>*, T>>& neighbors);
+        // ---- map updates: all three run on the device map (pp_update_obstacles_* of include/pp_b200.h) ----
+        // boxes -> pp_map_boxes_kernel (Grid2D.cpp:99-139), lane lines -> pp_map_lines_kernel (Grid2D.cpp:142-194),
+        // no argument -> whole-map decay, pp_map_decay_kernel (Grid2D.cpp:197-208); clear_obstacles zeroes the map.
         void update_obstacles(const std::vector<Obstacle<T>>& obstacles, const std::vector<T>& confidence);
         void update_obstacles(const std::vector<std::pair<Vector2D<T>, Vector2D<T>>>& lines, const std::vector<T>& confidence,
                               const T line_width);
         void update_obstacles();
         void clear_obstacles();
-        void update_costs(const T total_cost, const Node2D<T>& last_node);
-        T get_node_total_cost(const int i, const int j) const;
+
+        // ---- frame ----
+        Node2D<T> update_goal_heading(const Vector2D<T>& goal, const Vector2D<T>& start);   // Grid2D.cpp:260-266
         T get_grid_heading() const;
         T get_grid_resolution() const;
         int get_grid_size() const;
-        const std::vector<std::vector<T>>& get_obstacle_map() const;
-        Node2D<T> update_goal_heading(const Vector2D<T>& goal, const Vector2D<T>& start);
+        const std::vector<std::vector<T>>& get_obstacle_map() const;                       // downloads the host mirror when stale
+
+        // ---- host-side Node2D table, for callers that drive a 2D search by hand (AStar does not need it here) ----
+        void get_neighbors(const int xd, const int yd, std::vector<std::pair<Node2D<T>*, T>>& neighbors);
+        void update_costs(const T total_cost, const Node2D<T>& last_node);
+        T get_node_total_cost(const int i, const int j) const;
         Node2D<T> set_start_node(const Vector2D<T>& start);
         Node2D<T> set_start_node_grid(const int i, const int j);
 
