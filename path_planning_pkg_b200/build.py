@@ -133,6 +133,12 @@ def build_cpp_tests(force=False, verbose=True, reference="/root/reference"):
     if force or _newer(target, _sources(CSRC, os.path.join(ROOT, "include")) + [drv]):
         _run([cxx, "-std=c++14", "-O1", "-DSTORE_GRID_AS_REFERENCE", "-I", inc, drv, "-o", target] + link, verbose)
     built.append(target)
+    # SURVEY 8(f) N3 / N4 parity driver (host classes only, runs without a GPU)
+    drv = os.path.join(ROOT, "tests", "cpp", "velped_driver.cpp")
+    target = os.path.join(out_dir, "velped_b200")
+    if force or _newer(target, _sources(CSRC, os.path.join(ROOT, "include")) + [drv]):
+        _run([cxx, "-std=c++14", "-O1", "-DSTORE_GRID_AS_REFERENCE", "-I", inc, drv, "-o", target] + link, verbose)
+    built.append(target)
     lp = os.path.join(reference, "src", "local_planner.cpp")
     if os.path.exists(lp):
         target = os.path.join(out_dir, "local_planner_linkcheck")
