@@ -156,8 +156,18 @@ int  pp_get_tables(pp_context* ctx, float* offset_xy, float* offset_heading, flo
 /* HybridAStar::update_goal (lib/HybridAStar.cpp:55-59 -> Grid3D::update_goal_heading, Grid3D.cpp:102-124,
  * including relocate_obstacles, Grid3D.cpp:169-203). */
 int  pp_update_goal(pp_context* ctx, int group, const float* goal3, const float* start3);
-/* HybridAStar::reset (lib/HybridAStar.cpp:49-52).  The lazy A* cache is per query here, so this is a no-op kept for API parity. */
+/* HybridAStar::reset (lib/HybridAStar.cpp:49-52 -> AStar::reset, lib/AStar.cpp:56-60).  Without history (below) every query
+ * starts on a fresh 2D heuristic cache and this is a no-op; with history it drops the carried cache's visited flags and, like
+ * the reference, keeps the node costs. */
 int  pp_reset(pp_context* ctx, int group);
+/* Planner-object history.  One reference HybridAStar object keeps the `_visted` flags and `_node_map` costs of
+ * its 2D heuristic (lib/AStar.cpp:100-113, lib/Grid2D.cpp:219-227) from one find_path call to the next: only reset() clears
+ * the flags, nothing clears the costs, map updates invalidate neither.  enable = 1 gives `group` that object semantics: a
+ * pp_find_path_batch of ONE query in PP_MODE_EXACT on this group continues on the cache the group's earlier single queries
+ * left (starting from the freshly constructed state), so a sequence of update / find_path / reset calls returns what the same
+ * sequence returns on one reference object.  Batches of several queries always run every query on a fresh cache.
+ * enable = 0 drops the cache.  The C++ class HybridAStar<T> enables it for its planner. */
+int  pp_set_history(pp_context* ctx, int group, int enable);
 /* HybridAStar::update_obstacles(boxes, confidence, apf_added_radius) (lib/HybridAStar.cpp:29-33 ->
  * Grid3D.cpp:22-44 -> Grid2D.cpp:99-139).  boxes = n x (x, y, dx, dy), world frame. */
 int  pp_update_obstacles_boxes(pp_context* ctx, int group, const float* boxes_xydxdy, const float* confidence,

@@ -156,6 +156,11 @@ class Context:
     def reset(self, group=0):
         self._chk(self.lib.pp_reset(self.h, C.c_int(group)))
 
+    def set_history(self, group=0, enable=True):
+        """Planner-object semantics for `group` (pp_set_history): single EXACT-mode queries continue on the 2D heuristic
+        cache earlier single queries left, like successive find_path calls on one reference HybridAStar object."""
+        self._chk(self.lib.pp_set_history(self.h, C.c_int(group), C.c_int(1 if enable else 0)))
+
     def update_boxes(self, boxes, conf, apf_added_radius, group=0):
         b = np.ascontiguousarray(boxes, np.float32); c = np.ascontiguousarray(conf, np.float32)
         self._chk(self.lib.pp_update_obstacles_boxes(self.h, C.c_int(group), _p(b), _p(c), C.c_int(len(c)),

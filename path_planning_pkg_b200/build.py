@@ -120,8 +120,9 @@ def build_host_emul(force=False, verbose=True):
 
 def build_cpp_tests(force=False, verbose=True, reference="/root/reference"):
     """g++ -> tests/cpp/bin/api_driver (C++ API test driver) and, when the reference tree is present,
-    tests/cpp/bin/local_planner_linkcheck = the reference's UNMODIFIED src/local_planner.cpp compiled against this repo's
-    headers (with ROS stub headers) and linked against libpath_planning_b200.so."""
+    tests/cpp/bin/local_planner_b200 = the reference's UNMODIFIED src/local_planner.cpp compiled against this repo's
+    headers (with the in-process ROS stand-in tests/ros_stubs) and linked against libpath_planning_b200.so: the link check
+    of the drop-in boundary and, driven by a script, the replay harness (tests/test_gpu_replay.py)."""
     out_dir = os.path.join(ROOT, "tests", "cpp", "bin")
     os.makedirs(out_dir, exist_ok=True)
     cxx = os.environ.get("CXX", "g++")
@@ -141,7 +142,7 @@ def build_cpp_tests(force=False, verbose=True, reference="/root/reference"):
     built.append(target)
     lp = os.path.join(reference, "src", "local_planner.cpp")
     if os.path.exists(lp):
-        target = os.path.join(out_dir, "local_planner_linkcheck")
+        target = os.path.join(out_dir, "local_planner_b200")
         if force or _newer(target, _sources(CSRC, os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "ros_stubs")) + [lp]):
             _run([cxx, "-std=c++14", "-O1", "-DSTORE_GRID_AS_REFERENCE", "-I", os.path.join(ROOT, "tests", "ros_stubs"), "-I", inc,
                   "-I", os.path.join(reference, "src"), lp, "-o", target] + link, verbose)

@@ -98,6 +98,13 @@ struct pp_context
     WorkPools wp_lazy;     // persistent cache of the stand-alone lazy 2D A* (AStar<T> handle)
     unsigned* d_lazy_sid = nullptr;
     int lazy_group = -1;
+    // planner-object history (pp_set_history): per group the carried 2D cache (`_visted` + `_node_map` costs) of one
+    // reference planner object, plus the snapshot a capacity retry restores
+    struct HistBuf { bool on = false; DevBuf<unsigned> cell_state, cell_state_bak, sid; DevBuf<float> nm_g, nm_f, nm_g_bak, nm_f_bak;
+                     void release() { cell_state.release(); cell_state_bak.release(); sid.release(); nm_g.release(); nm_f.release();
+                                      nm_g_bak.release(); nm_f_bak.release(); on = false; } };
+    std::vector<HistBuf> hist;
+    int batch_hist_group = -1;    // group whose history the uploaded batch runs on (-1 = fresh cache per query)
     // K-POP mode pools (per slot): node log, hash table, LSM queue arena + merge scratch
     struct KPools { int alloc_slots = 0, nodes_cap = 0, table_cap = 0, levels = 0; size_t arena_cap = 0, tmp_cap = 0;
                     DevBuf<PPKNode> nodes; DevBuf<PPKSlot> table; DevBuf<PPKEntry> arena, tmp_a, tmp_b;
@@ -221,6 +228,7 @@ void pp_destroy(pp_context* c)
     c->d_queries.release(); c->d_results.release(); c->d_paths.release(); c->d_trace.release();
     c->wp.release(); c->wp_retry.release(); c->wp_lazy.release(); c->d_qmap.release(); c->d_order.release(); c->d_group_cost.release();
     cudaFree(c->d_lazy_sid);
+    for (auto& h : c->hist) h.release();
     c->kp.release(); c->kp_retry.release();
     c->d_field2d.release(); c->d_f2d_work.release(); c->d_f2d_flags.release(); c->d_dubins_field.release();
     cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
@@ -299,7 +307,37 @@ int pp_update_goal(pp_context* c, int g, const float* goal3, const float* start3
     return PP_SUCCESS;
 }
 
-int pp_reset(pp_context* c, int g) { return check_group(c, g); }
+int pp_reset(pp_context* c, int g)
+{
+    int rc = check_group(c, g); if (rc) return rc;
+    if ((int)c->hist.size() > g && c->hist[g].on)
+    {
+        // AStar::reset() on the carried cache: the visited flags go, the node costs stay
+        PP_CUDA(cudaSetDevice(c->device));
+        int nn = (int)nn_of(c);
+        pp_hist_reset_kernel<<<std::min((nn + 255) / 256, 4 * c->sm_count), 256, 0, c->stream>>>(c->hist[g].cell_state.p, nn);
+        c->launches += 1;
+        PP_CUDA(cudaGetLastError());
+    }
+    return PP_SUCCESS;
+}
+
+int pp_set_history(pp_context* c, int g, int enable)
+{
+    int rc = check_group(c, g); if (rc) return rc;
+    PP_CUDA(cudaSetDevice(c->device));
+    if ((int)c->hist.size() != c->num_groups) c->hist.resize(c->num_groups);
+    pp_context::HistBuf& h = c->hist[g];
+    if (!enable) { PP_CUDA(cudaStreamSynchronize(c->stream)); h.release(); return PP_SUCCESS; }
+    size_t nn = nn_of(c);
+    PP_CUDA(h.cell_state.ensure(nn)); PP_CUDA(h.cell_state_bak.ensure(nn + 1)); PP_CUDA(h.sid.ensure(1));
+    PP_CUDA(h.nm_g.ensure(nn)); PP_CUDA(h.nm_f.ensure(nn)); PP_CUDA(h.nm_g_bak.ensure(nn)); PP_CUDA(h.nm_f_bak.ensure(nn));
+    // the freshly constructed planner: nothing visited, no node touched (g = 0, f = Euclidean h), search id 0
+    PP_CUDA(cudaMemsetAsync(h.cell_state.p, 0, nn * sizeof(unsigned), c->stream));
+    PP_CUDA(cudaMemsetAsync(h.sid.p, 0, sizeof(unsigned), c->stream));
+    h.on = true;
+    return PP_SUCCESS;
+}
 
 int pp_update_obstacles_decay(pp_context* c, int g)
 {
@@ -631,6 +669,26 @@ static void fill_args(pp_context* c, const WorkPools& w, int n_slots, const int*
     a.open3 = w.open3.p; a.open3_cap = w.open3_cap; a.closed = w.closed.p; a.closed_cap = w.closed_cap;
     a.chash = w.chash.p; a.chash_cap = w.chash_cap; a.cell_state = w.cell_state.p; a.nm_g = w.nm_g.p; a.nm_f = w.nm_f.p;
     a.cl_g = w.cl_g.p; a.cl_prev = w.cl_prev.p; a.open2 = w.open2.p; a.open2_cap = w.open2_cap;
+    a.hist_cell_state = nullptr; a.hist_nm_g = nullptr; a.hist_nm_f = nullptr; a.hist_sid = nullptr;
+    if (c->batch_hist_group >= 0 && n_slots == 1 && n_work == 1)
+    {
+        pp_context::HistBuf& h = c->hist[c->batch_hist_group];
+        a.hist_cell_state = h.cell_state.p; a.hist_nm_g = h.nm_g.p; a.hist_nm_f = h.nm_f.p; a.hist_sid = h.sid.p;
+    }
+}
+
+// snapshot / restore of a carried cache around one query, so that a capacity retry re-runs it from the same history
+static int hist_copy(pp_context* c, int g, bool restore)
+{
+    pp_context::HistBuf& h = c->hist[g];
+    size_t nn = nn_of(c);
+    unsigned *cs_a = restore ? h.cell_state.p : h.cell_state_bak.p, *cs_b = restore ? h.cell_state_bak.p : h.cell_state.p;
+    PP_CUDA(cudaMemcpyAsync(cs_a, cs_b, nn * sizeof(unsigned), cudaMemcpyDeviceToDevice, c->stream));
+    PP_CUDA(cudaMemcpyAsync(restore ? h.nm_g.p : h.nm_g_bak.p, restore ? h.nm_g_bak.p : h.nm_g.p, nn * sizeof(float), cudaMemcpyDeviceToDevice, c->stream));
+    PP_CUDA(cudaMemcpyAsync(restore ? h.nm_f.p : h.nm_f_bak.p, restore ? h.nm_f_bak.p : h.nm_f.p, nn * sizeof(float), cudaMemcpyDeviceToDevice, c->stream));
+    PP_CUDA(cudaMemcpyAsync(restore ? h.sid.p : h.cell_state_bak.p + nn, restore ? h.cell_state_bak.p + nn : h.sid.p, sizeof(unsigned),
+                            cudaMemcpyDeviceToDevice, c->stream));
+    return PP_SUCCESS;
 }
 
 // (re)allocate `w` for `want_slots` slots of the given capacities, limited to `mem_frac` of the free memory
@@ -807,6 +865,8 @@ int pp_batch_upload(pp_context* c, const pp_query* q, int n, const pp_search_opt
         c->h_queries[k].pad = 0;
     }
     c->n_queries = n;
+    // one EXACT-mode query on a group with history enabled continues on that planner's carried 2D cache
+    c->batch_hist_group = (n == 1 && o.mode == PP_MODE_EXACT && (int)c->hist.size() > q[0].group && c->hist[q[0].group].on) ? q[0].group : -1;
     int hw_slots = 0;
     int rc = hw_slots_of(c, &hw_slots); if (rc) return rc;
     int want = std::min(n, hw_slots);
@@ -862,7 +922,10 @@ int pp_batch_run(pp_context* c, float* kernel_ms)
     const int n = c->n_queries;
     PP_CUDA(cudaEventRecord(c->ev0, c->stream));
     const bool kmode = (c->opts.mode == PP_MODE_KPOP);
-    int rc = kmode ? launch_kpop(c, c->kp, c->n_slots, nullptr, n) : launch_search(c, c->wp, c->n_slots, nullptr, n);
+    const int hist_g = kmode ? -1 : c->batch_hist_group;
+    int rc = 0;
+    if (hist_g >= 0) { rc = hist_copy(c, hist_g, false); if (rc) return rc; }
+    rc = kmode ? launch_kpop(c, c->kp, c->n_slots, nullptr, n) : launch_search(c, c->wp, c->n_slots, nullptr, n);
     if (rc) return rc;
     // The reference's containers are unbounded.  Queries that exhausted a pool are re-run from scratch with
     // 8x larger pools (fewer resident slots), up to 3 escalations; what still overflows stays flagged.
@@ -911,6 +974,7 @@ int pp_batch_run(pp_context* c, float* kernel_ms)
         else
         {
             rc = ensure_work(c, c->wp_retry, want, max_exp, max_open, max_open2d, 0.85); if (rc) return rc;
+            if (hist_g >= 0) { rc = hist_copy(c, hist_g, true); if (rc) return rc; }     // the aborted attempt never happened
             int slots = std::max(std::min(c->wp_retry.alloc_slots, want), 1);
             rc = launch_search(c, c->wp_retry, slots, c->d_qmap.p, (int)redo.size()); if (rc) return rc;
         }

@@ -108,6 +108,11 @@ struct PPWork
     PPNode2*   open2;      int open2_cap;
     PPPathPt*  path;       int path_cap;      // [dubins samples (forward) | parent chain (terminal -> start)]
     PPPop*     trace;      int trace_cap;     // optional
+    // Planner-object history: nullptr = every query starts on the freshly constructed 2D cache
+    // (cell_state cleared here).  Otherwise cell_state / nm_g / nm_f are the carried `_visted` + `_node_map` of ONE
+    // reference planner object and *lazy_sid its running lazy-search id: nothing is cleared, the query continues on
+    // whatever the object's earlier find_path calls left behind (AStar::reset() only drops the visited flags).
+    unsigned*  lazy_sid = nullptr;
 };
 
 struct PPSmem   // per-warp staging area (shared memory on the device)
@@ -631,7 +636,27 @@ PP_HD_NOINLINE_FN void pp_search_exact(const W& w, const PPConsts& C, const floa
 
     PP_PROF_DECL
     // ---- scratch init (all lanes) ----
-    for (int c = lane; c < N * N; c += W::LANES) wk.cell_state[c] = 0u;
+    const bool carry = (wk.lazy_sid != nullptr);
+    unsigned sid0 = 0u;
+    if (!carry) { for (int c = lane; c < N * N; c += W::LANES) wk.cell_state[c] = 0u; }
+    else
+    {
+        sid0 = *wk.lazy_sid;
+        if (sid0 > (PP_CS_STAMP >> 1))      // the 30-bit search id is half used up: drop all closed stamps, restart at 0
+        {
+            for (int c = lane; c < N * N; c += W::LANES) wk.cell_state[c] &= ~PP_CS_STAMP;
+            sid0 = 0u;
+        }
+        w.sync();
+        if (lane == 0)
+        {
+            // Grid3D::set_start_node (Grid3D.cpp:146, :154): soft_reset of the start cell's map node -> g = 0, f = h;
+            // its visited flag is NOT touched
+            int c0 = start.ci * N + start.cj;
+            wk.nm_g[c0] = 0.0f; wk.nm_f[c0] = pp_h2d(C, start.ci, start.cj);
+            wk.cell_state[c0] |= PP_CS_TOUCHED;
+        }
+    }
     for (int c = lane; c < wk.chash_cap; c += W::LANES) { PPHashSlot e; e.key = 0xffffffffu; e.idx = -1; wk.chash[c] = e; }
     w.sync();
     PP_PROF_MARK(0)
@@ -647,7 +672,7 @@ PP_HD_NOINLINE_FN void pp_search_exact(const W& w, const PPConsts& C, const floa
     {
         S.open.init(wk.open3, wk.open3_cap);
         S.lazy.open.init(wk.open2, wk.open2_cap);
-        S.lazy.search_id = 0; S.lazy.status = 0; S.lazy.n_searches = 0; S.lazy.n_pops = 0;
+        S.lazy.search_id = sid0; S.lazy.status = 0; S.lazy.n_searches = 0; S.lazy.n_pops = 0;
         S.n_closed = 0; S.status = 0; S.max_open = 0;
         // _open_set.insert(start_node), HybridAStar.cpp:103
         PPSucc s0;
@@ -862,6 +887,7 @@ PP_HD_NOINLINE_FN void pp_search_exact(const W& w, const PPConsts& C, const floa
 
     if (lane == 0)
     {
+        if (carry) *wk.lazy_sid = S.lazy.search_id;
         res.success = success;
         res.status = S.status;
         res.cost = cost;

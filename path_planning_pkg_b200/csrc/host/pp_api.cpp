@@ -131,6 +131,11 @@ HybridAStar<T>::HybridAStar(int dubins_shot_interval, int dubins_shot_interval_d
         max_lat_acc, max_long_dec, wheelbase, rear_to_cg, apf_rep_constant, apf_active_angle, num_angle_bins, num_actions, steering,
         curvature_weights));
     _impl->map_mirror.assign(grid_size, std::vector<T>(grid_size, T(0)));
+    // One reference planner object carries its 2D heuristic cache from one find_path to the next; this
+    // object does the same, so a whole session of update / find_path / reset calls returns what the reference returns.
+    // PP_B200_HISTORY=0 gives every find_path a fresh cache instead.
+    const char* e = std::getenv("PP_B200_HISTORY");
+    if (!(e && std::strcmp(e, "0") == 0)) check(pp_set_history(_impl->b->ctx, 0, 1), "pp_set_history");
 }
 
 template <typename T> HybridAStar<T>::~HybridAStar() {}

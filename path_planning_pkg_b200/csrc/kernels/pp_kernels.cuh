@@ -131,6 +131,11 @@ struct PPBatchArgs
     float*          cl_g;
     int*            cl_prev;
     PPNode2*        open2;      int open2_cap;
+    // planner-object history (pp_set_history): the carried 2D cache of ONE planner; only valid with one slot and one query
+    unsigned*       hist_cell_state;
+    float*          hist_nm_g;
+    float*          hist_nm_f;
+    unsigned*       hist_sid;   // nullptr = fresh cache per query
 };
 
 __device__ __forceinline__ void pp_slot_work(const PPBatchArgs& a, int slot, PPWork& wk)
@@ -146,6 +151,17 @@ __device__ __forceinline__ void pp_slot_work(const PPBatchArgs& a, int slot, PPW
     wk.cl_prev = a.cl_prev + slot * nn;
     wk.open2 = a.open2 + (size_t)slot * a.open2_cap;   wk.open2_cap = a.open2_cap;
     wk.path = nullptr; wk.path_cap = 0; wk.trace = nullptr; wk.trace_cap = 0;
+    wk.lazy_sid = nullptr;
+    if (a.hist_sid)
+    {
+        wk.cell_state = a.hist_cell_state; wk.nm_g = a.hist_nm_g; wk.nm_f = a.hist_nm_f; wk.lazy_sid = a.hist_sid;
+    }
+}
+
+// AStar::reset() (AStar.cpp:56-60) on a carried cache: only the visited flags go, node costs stay
+__global__ void __launch_bounds__(256) pp_hist_reset_kernel(unsigned* __restrict__ cell_state, int n)
+{
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < n; c += gridDim.x * blockDim.x) cell_state[c] &= ~PP_CS_VISITED;
 }
 
 __global__ void __launch_bounds__(PP_SEARCH_WARPS * 32, PP_SEARCH_MIN_BLOCKS)

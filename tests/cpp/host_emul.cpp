@@ -38,6 +38,8 @@ namespace
         std::vector<int> bin_off, bin_idx; int bin_n = 0;
         PPLazy lazy;               // persistent lazy-A* state for emu_astar_lazy_batch
         bool lazy_init = false;
+        bool hist_on = false;      // planner-object history (pp_set_history): cell_state / nm_g / nm_f carried between queries
+        unsigned hist_sid = 0;
     };
 
     PPGroup group_of(Emu* e)
@@ -107,7 +109,22 @@ void emu_update_goal(void* h, const float* goal3, const float* start3)
     pp_host_update_goal(e->m.C, goal3, start3, e->fr);
 }
 
-void emu_reset(void*) {}
+// AStar::reset() on the carried cache = pp_reset with history enabled (pp_hist_reset_kernel)
+void emu_reset(void* h)
+{
+    Emu* e = static_cast<Emu*>(h);
+    if (e->hist_on) for (auto& st : e->cell_state) st &= ~PP_CS_VISITED;
+}
+// = pp_set_history: the freshly constructed cache, carried from now on
+void emu_set_history(void* h, int enable)
+{
+    Emu* e = static_cast<Emu*>(h);
+    size_t nn = (size_t)e->m.C.N * e->m.C.N;
+    e->hist_on = enable != 0; e->hist_sid = 0;
+    e->cell_state.assign(nn, 0u); e->nm_g.assign(nn, 0.0f); e->nm_f.assign(nn, 0.0f);
+}
+// test hook: force the running lazy-search id (exercises the stamp wrap-around of pp_search_exact)
+void emu_set_history_sid(void* h, unsigned sid) { static_cast<Emu*>(h)->hist_sid = sid; }
 void emu_scrub(void* h) { static_cast<Emu*>(h)->lazy_init = false; }
 
 void emu_update_boxes_2d(void* h, const float* boxes, const float* conf, int n)
@@ -348,6 +365,7 @@ void emu_find_path(void* h, float vel, const float* s, orc_result* res, float* p
     PPSmem sm;
     PPResult r;
     PPWarpSerial w;
+    wk.lazy_sid = e->hist_on ? &e->hist_sid : nullptr;
     pp_search_exact(w, C, e->m.off_xy.data(), G, st, wk, sm, r);
     e->lazy_init = false;
     res->success = r.success; res->cost = r.cost; res->n_pops = r.n_pops; res->n_pops_bin_oob = r.n_pops_bin_oob;

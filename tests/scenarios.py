@@ -89,3 +89,55 @@ def c2_scenario(seed=42, n_boxes=256, grid_size=2048, resolution=0.2):
     conf = (0.55 + 0.44 * _u(rs, n_boxes)).astype(np.float32)
     return dict(grid_size=grid_size, resolution=resolution, goal=goal, frame_start=np.zeros(3, np.float32),
                 boxes=boxes, conf=conf, rounds=3)
+
+
+def session_ops(seed, goal_changes=True, n_ticks=6):
+    """A planner SESSION on one object, as src/local_planner.cpp drives it: waypoint -> update_goal + reset,
+    then per tick new detections (boxes + decay) and one find_path from the advancing vehicle pose, with NO reset in between;
+    later a bare reset, and (optionally) a second waypoint whose update_goal relocates the non-empty map.  C1 shape
+    (N = 200, 0.2 m).  Returns a list of ops: ("goal", goal3, start3) | ("reset",) | ("boxes", boxes, conf) | ("decay",) |
+    ("query", vel, start3)."""
+    rs = np.random.RandomState(7000 + seed)
+    sc = c1_scenario(seed)
+    ops = [("goal", sc["goal"], sc["frame_start"]), ("reset",)]
+    for _ in range(sc["rounds"]):
+        ops += [("boxes", sc["boxes"], sc["conf"]), ("decay",)]
+    pose = np.array([0.0, 0.0, 0.0], np.float32)
+
+    def tick(pose, k):
+        extra = np.array([[8.0 + 10.0 * _u(rs, 1)[0], -4.0 + 10.0 * _u(rs, 1)[0], 1.0 + _u(rs, 1)[0], 1.0 + _u(rs, 1)[0]]], np.float32)
+        boxes = np.concatenate([sc["boxes"], extra]).astype(np.float32)
+        return [("boxes", boxes, np.full(len(boxes), 0.85, np.float32)), ("decay",),
+                ("query", np.float32(2.0 + 0.2 * k), pose.copy())]
+
+    for k in range(n_ticks):
+        ops += tick(pose, k)
+        pose = (pose + np.array([0.9, 0.12 * (k % 3 - 1), 0.03 * (k % 2)], np.float32)).astype(np.float32)
+    ops += [("reset",)] + tick(pose, n_ticks) + tick(pose, n_ticks + 1)
+    if goal_changes:
+        goal2 = np.array([30.0, -6.0, -0.2], np.float32)
+        ops += [("goal", goal2, pose.copy()), ("reset",)]
+        for k in range(3):
+            ops += tick(pose, k)
+            pose = (pose + np.array([0.8, -0.2, -0.02], np.float32)).astype(np.float32)
+    return sc, ops
+
+
+def run_session(planner, ops, fresh_each_query=None):
+    """Apply `ops` to any object with the oracle-style interface; returns the find_path results in order.
+    `fresh_each_query(planner)` is called before every query when given (the fresh-cache comparison)."""
+    out = []
+    for op in ops:
+        if op[0] == "goal":
+            planner.update_goal(op[1], op[2])
+        elif op[0] == "reset":
+            planner.reset()
+        elif op[0] == "boxes":
+            planner.update_boxes(op[1], op[2], APF_ADDED_RADIUS)
+        elif op[0] == "decay":
+            planner.decay()
+        elif op[0] == "query":
+            if fresh_each_query:
+                fresh_each_query(planner)
+            out.append(planner.find_path(float(op[1]), op[2]))
+    return out

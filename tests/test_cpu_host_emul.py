@@ -269,3 +269,54 @@ def test_apf_spatial_index_is_conservative(emu_lib):
         emu_lib.emu_kapf_batch(e.h, orc._fp(xyh), C.c_int(n), orc._fp(a), orc._fp(b))
         assert np.array_equal(_bits(a), _bits(b)), name
         assert (b != 0).sum() > n // 50, name                    # the test does exercise non-zero fields
+
+
+def _same_result(a, b):
+    return (a["success"] == b["success"] and a["n_pops"] == b["n_pops"] and np.array_equal(a["pops"], b["pops"]) and
+            a["cost"] == b["cost"] and np.array_equal(_bits(a["path"]), _bits(b["path"])) and
+            np.array_equal(_bits(a["curvature"]), _bits(b["curvature"])))
+
+
+@pytest.mark.skipif(not orc.have_ref(), reason="needs the pinned-libm compiled reference")
+@pytest.mark.parametrize("seed", [0, 3])
+def test_planner_object_history_bitexact(emu_lib, seed):
+    """successive find_path calls on ONE reference object share the 2D heuristic cache (`_visted` flags until
+    reset(), `_node_map` costs for ever, stale against map updates).  The product core with history enabled (pp_set_history;
+    here the host-lane build of the same source) must return what the unmodified reference object returns for every query
+    of a session, bit for bit -- and the session must be one where the history matters."""
+    sc, ops = S.session_ops(seed, goal_changes=False)      # the host emulation has no map relocation (GPU test covers it)
+    P = orc.make_params(grid_size=sc["grid_size"], resolution=sc["resolution"])
+    e, o, fresh = _emu(emu_lib, P), _pinned(P), _pinned(P)
+    emu_lib.emu_set_history(e.h, C.c_int(1))
+    ra, rb = S.run_session(e, ops), S.run_session(o, ops)
+    rf = S.run_session(fresh, ops, fresh_each_query=lambda p: p.scrub())
+    assert len(ra) == len(rb) == 8
+    usable = [k for k in range(len(rb)) if rb[k]["n_pops_bin_oob"] == 0]      # F7: undefined in the reference
+    assert len(usable) >= 6
+    for k in usable:
+        assert _same_result(ra[k], rb[k]), (k, ra[k]["n_pops"], rb[k]["n_pops"], ra[k]["cost"], rb[k]["cost"])
+    # not vacuous: with a fresh cache per query the reference itself expands differently somewhere after the first query
+    assert _same_result(rb[0], rf[0])
+    assert any(rb[k]["n_pops"] != rf[k]["n_pops"] or rb[k]["cost"] != rf[k]["cost"] for k in range(1, len(rb)))
+
+
+@pytest.mark.skipif(not orc.have_ref(), reason="needs the pinned-libm compiled reference")
+def test_planner_object_history_stamp_wrap(emu_lib):
+    """The carried cache stamps closed cells with a running 30-bit lazy-search id; when half the range is used the stamps
+    are dropped and the id restarts -- invisible in the results."""
+    sc, ops = S.session_ops(1, goal_changes=False, n_ticks=3)
+    P = orc.make_params(grid_size=sc["grid_size"], resolution=sc["resolution"])
+    e, o = _emu(emu_lib, P), _pinned(P)
+    emu_lib.emu_set_history(e.h, C.c_int(1))
+    rb = S.run_session(o, ops)
+    ra, nq = [], 0
+    for op in ops:
+        if op[0] == "query":
+            if nq == 2:
+                emu_lib.emu_set_history_sid(e.h, C.c_uint(0x3ffffff0 >> 1))       # just below the wrap threshold
+            ra += S.run_session(e, [op]); nq += 1
+        else:
+            S.run_session(e, [op])
+    for k in range(len(rb)):
+        if rb[k]["n_pops_bin_oob"] == 0:
+            assert _same_result(ra[k], rb[k]), k

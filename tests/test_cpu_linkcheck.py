@@ -28,7 +28,7 @@ def test_api_driver_builds(bins):
 
 @pytest.mark.skipif(not os.path.exists(REF_LP), reason="reference tree not present")
 def test_unmodified_local_planner_links(bins):
-    exe = [b for b in bins if b.endswith("local_planner_linkcheck")]
+    exe = [b for b in bins if b.endswith("local_planner_b200")]
     assert exe and os.path.exists(exe[0])
     und = subprocess.run(["nm", "-C", "-u", exe[0]], capture_output=True, text=True).stdout
     need = [l.split(" U ")[1] for l in und.split("\n") if " U planning::" in l]
