@@ -196,6 +196,19 @@ int  pp_rollout_batch(pp_context* ctx, const pp_state* in, int n, pp_state* out,
 int  pp_expand_batch(pp_context* ctx, int group, const pp_state* in, int n, pp_state* out, int* n_out, int* flags);
 /* successor collision lookup alone (lib/Grid3D.cpp:56-59): free[k] = 1 when in bounds and below threshold; cells out */
 int  pp_collision_batch(pp_context* ctx, int group, const float* xy, int n, int* free_out, int* cells_ij);
+/* ---- generic vehicle-footprint collision check (north_star (c)) ----
+ * The reference's check is the one-cell footprint: a pose is free iff map[int(x/res)][int(y/res)] is inside the grid and below
+ * the threshold (lib/Grid3D.cpp:53-59); the vehicle's size is folded into the obstacles by the caller
+ * (src/local_planner.cpp:230-231, :287).  pp_set_footprint builds, per heading bin, the cell offsets an oriented rectangle
+ * [-rear_overhang, length - rear_overhang] x [-width/2, +width/2] (vehicle frame, x forward, origin = the pose) covers, sampled
+ * every half cell like the reference's box rasteriser (lib/Grid2D.cpp:110-133); length = width = 0 gives {(0, 0)}, i.e. exactly
+ * the reference's check.  pp_footprint_batch tests n grid-frame poses (x, y, heading): free_out[k] = 1 iff every footprint cell
+ * around the pose's cell is inside the grid and below the threshold; cells_ij (optional) = the pose's cell as the reference
+ * indexes it; hits_out (optional) = number of blocked footprint cells; kernel_ms (optional) = device time of the kernel alone. */
+int  pp_set_footprint(pp_context* ctx, float length, float width, float rear_overhang);
+int  pp_get_footprint(pp_context* ctx, int bin, int* count, short* offs_ij, int cap);
+int  pp_footprint_batch(pp_context* ctx, int group, const float* xyh, int n, int* free_out, int* cells_ij, int* hits_out,
+                        float* kernel_ms);
 /* Grid3D::get_field_intensity (lib/Grid3D.cpp:206-227) for n poses (x, y, heading) */
 int  pp_apf_batch(pp_context* ctx, int group, const float* xyh, int n, float* out);
 /* Grid3D::check_path (lib/Grid3D.cpp:78-93): blocked[k] per point, returns collision-free flag in *free_out */

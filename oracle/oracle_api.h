@@ -119,6 +119,11 @@ typedef struct orc_result
 ORC_DECL(ref)
 ORC_DECL(port)
 
+/* New semantics, stated by the port only (oracle/port/footprint.inc): generic vehicle-footprint collision check. */
+int  port_footprint_table(void* h, int bin, float length, float width, float rear, short* offs_ij, int cap);
+void port_footprint_check(void* h, const float* xyh, int n, float length, float width, float rear, int* free_out,
+                          int* cells_ij, int* hits_out);
+
 #ifdef __cplusplus
 }
 #endif

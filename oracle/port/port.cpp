@@ -860,6 +860,8 @@ void port_find_path(void* hv, float vel, const float* s, orc_result* res, float*
     }
     res->n_path = n;
 }
+
+#include "footprint.inc"
 }   // extern "C"
 
 #include "kpop.inc"

@@ -247,6 +247,22 @@ class Context:
         self._chk(self.lib.pp_collision_batch(self.h, C.c_int(group), _p(xy), C.c_int(n), _p(fr), _p(cells)))
         return fr.astype(bool), cells
 
+    def set_footprint(self, length, width, rear_overhang):
+        """Per-heading-bin cell offsets of the vehicle rectangle (pp_set_footprint); (0, 0, 0) = the reference's one-cell check."""
+        self._chk(self.lib.pp_set_footprint(self.h, C.c_float(length), C.c_float(width), C.c_float(rear_overhang)))
+
+    def footprint_table(self, bin_, cap=4096):
+        n = C.c_int(); offs = np.zeros((cap, 2), np.int16)
+        self._chk(self.lib.pp_get_footprint(self.h, C.c_int(bin_), C.byref(n), _p(offs), C.c_int(cap)))
+        return offs[:n.value].copy()
+
+    def footprint(self, xyh, group=0, want_ms=False):
+        """pp_footprint_batch: free flags, base cells, blocked-cell counts for n grid-frame poses (x, y, heading)."""
+        p = np.ascontiguousarray(xyh, np.float32); n = len(p)
+        free = np.zeros(n, np.int32); cells = np.zeros((n, 2), np.int32); hits = np.zeros(n, np.int32); ms = C.c_float()
+        self._chk(self.lib.pp_footprint_batch(self.h, C.c_int(group), _p(p), C.c_int(n), _p(free), _p(cells), _p(hits), C.byref(ms)))
+        return (free, cells, hits, ms.value) if want_ms else (free, cells, hits)
+
     def check_path(self, xyh, group=0):
         xyh = np.ascontiguousarray(xyh, np.float32)
         fr = C.c_int()

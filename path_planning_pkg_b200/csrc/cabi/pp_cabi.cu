@@ -11,6 +11,7 @@
 
 #include "../kernels/pp_kernels.cuh"
 #include "../host/pp_host.h"
+#include "../host/pp_footprint_host.h"
 #include "../kernels/pp_fields.h"
 #include "../../../include/pp_b200.h"
 
@@ -105,6 +106,10 @@ struct pp_context
                                       nm_g_bak.release(); nm_f_bak.release(); on = false; } };
     std::vector<HistBuf> hist;
     int batch_hist_group = -1;    // group whose history the uploaded batch runs on (-1 = fresh cache per query)
+    // generic footprint collision check (pp_set_footprint): per-bin offset table on the host and the device
+    std::vector<PPFootBin> foot_bins; std::vector<PPCellOff> foot_offs; int foot_win = 0;
+    DevBuf<PPFootBin> d_foot_bins; DevBuf<PPCellOff> d_foot_offs;
+    DevBuf<float> d_foot_xyh; DevBuf<int> d_foot_out;
     // K-POP mode pools (per slot): node log, hash table, LSM queue arena + merge scratch
     struct KPools { int alloc_slots = 0, nodes_cap = 0, table_cap = 0, levels = 0; size_t arena_cap = 0, tmp_cap = 0;
                     DevBuf<PPKNode> nodes; DevBuf<PPKSlot> table; DevBuf<PPKEntry> arena, tmp_a, tmp_b;
@@ -229,6 +234,7 @@ void pp_destroy(pp_context* c)
     c->wp.release(); c->wp_retry.release(); c->wp_lazy.release(); c->d_qmap.release(); c->d_order.release(); c->d_group_cost.release();
     cudaFree(c->d_lazy_sid);
     for (auto& h : c->hist) h.release();
+    c->d_foot_bins.release(); c->d_foot_offs.release(); c->d_foot_xyh.release(); c->d_foot_out.release();
     c->kp.release(); c->kp_retry.release();
     c->d_field2d.release(); c->d_f2d_work.release(); c->d_f2d_flags.release(); c->d_dubins_field.release();
     cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
@@ -550,6 +556,65 @@ int pp_collision_batch(pp_context* c, int g, const float* xy, int n, int* free_o
     PP_CUDA(cudaMemcpyAsync(free_out, c->s1.p, sizeof(int) * n, cudaMemcpyDeviceToHost, c->stream));
     if (cells_ij) PP_CUDA(cudaMemcpyAsync(cells_ij, c->s2.p, sizeof(int) * 2 * n, cudaMemcpyDeviceToHost, c->stream));
     PP_CUDA(cudaStreamSynchronize(c->stream));
+    return PP_SUCCESS;
+}
+
+// ---- generic vehicle-footprint collision check (north_star (c); core/pp_footprint.h) ----
+int pp_set_footprint(pp_context* c, float length, float width, float rear_overhang)
+{
+    if (!c || !(length >= 0.0f) || !(width >= 0.0f) || !(rear_overhang >= 0.0f) || rear_overhang > length)
+        return pp_fail(PP_ERR_INVALID, "pp_set_footprint: need 0 <= rear_overhang <= length, width >= 0");
+    PP_CUDA(cudaSetDevice(c->device));
+    int win = pp_footprint_build(c->model.C, length, width, rear_overhang, c->foot_bins, c->foot_offs);
+    if (win > PP_FOOT_MAX_WIN) { c->foot_bins.clear(); return pp_fail(PP_ERR_CAPACITY, "pp_set_footprint: footprint spans more than 96 cells"); }
+    c->foot_win = win;
+    PP_CUDA(c->d_foot_bins.ensure(c->foot_bins.size()));
+    PP_CUDA(c->d_foot_offs.ensure(c->foot_offs.size()));
+    PP_CUDA(cudaMemcpyAsync(c->d_foot_bins.p, c->foot_bins.data(), sizeof(PPFootBin) * c->foot_bins.size(), cudaMemcpyHostToDevice, c->stream));
+    PP_CUDA(cudaMemcpyAsync(c->d_foot_offs.p, c->foot_offs.data(), sizeof(PPCellOff) * c->foot_offs.size(), cudaMemcpyHostToDevice, c->stream));
+    PP_CUDA(cudaStreamSynchronize(c->stream));
+    return PP_SUCCESS;
+}
+
+int pp_get_footprint(pp_context* c, int bin, int* count, short* offs_ij, int cap)
+{
+    if (!c || c->foot_bins.empty()) return pp_fail(PP_ERR_INVALID, "pp_get_footprint: call pp_set_footprint first");
+    if (bin < 0 || bin >= (int)c->foot_bins.size()) return pp_fail(PP_ERR_INVALID, "pp_get_footprint: bin out of range");
+    const PPFootBin& b = c->foot_bins[bin];
+    if (count) *count = b.count;
+    for (int k = 0; offs_ij && k < b.count && k < cap; k++) { offs_ij[2 * k] = c->foot_offs[b.first + k].di; offs_ij[2 * k + 1] = c->foot_offs[b.first + k].dj; }
+    return PP_SUCCESS;
+}
+
+int pp_footprint_batch(pp_context* c, int g, const float* xyh, int n, int* free_out, int* cells_ij, int* hits_out, float* kernel_ms)
+{
+    int rc = check_group(c, g); if (rc) return rc;
+    if (c->foot_bins.empty()) return pp_fail(PP_ERR_INVALID, "pp_footprint_batch: call pp_set_footprint first");
+    if (n <= 0) return PP_SUCCESS;
+    if (!xyh || !free_out) return pp_fail(PP_ERR_INVALID, "pp_footprint_batch: null buffer");
+    PP_CUDA(cudaSetDevice(c->device));
+    PP_CUDA(c->d_foot_xyh.ensure((size_t)3 * n));
+    PP_CUDA(c->d_foot_out.ensure((size_t)4 * n));
+    PP_CUDA(cudaMemcpyAsync(c->d_foot_xyh.p, xyh, sizeof(float) * 3 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    PPFootArgs a;
+    a.C = c->model.C; a.map = c->d_maps + (size_t)g * nn_of(c); a.xyh = c->d_foot_xyh.p; a.n = n;
+    a.bins = c->d_foot_bins.p; a.offs = c->d_foot_offs.p; a.win = c->foot_win;
+    a.free_out = c->d_foot_out.p; a.cells = cells_ij ? c->d_foot_out.p + n : nullptr; a.hits = hits_out ? c->d_foot_out.p + 3 * (size_t)n : nullptr;
+    size_t smem = (size_t)PP_FOOT_WARPS * a.win * a.win * sizeof(float);
+    PP_CUDA(cudaFuncSetAttribute(pp_footprint_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 48 * 1024)));
+    int occ = 0;
+    PP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pp_footprint_kernel, PP_FOOT_WARPS * 32, smem));
+    int blocks = std::min((n + PP_FOOT_WARPS - 1) / PP_FOOT_WARPS, std::max(1, occ) * c->sm_count);     // a whole number of waves
+    PP_CUDA(cudaEventRecord(c->ev0, c->stream));
+    pp_footprint_kernel<<<blocks, PP_FOOT_WARPS * 32, smem, c->stream>>>(a);
+    c->launches += 1;
+    PP_CUDA(cudaGetLastError());
+    PP_CUDA(cudaEventRecord(c->ev1, c->stream));
+    PP_CUDA(cudaMemcpyAsync(free_out, c->d_foot_out.p, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+    if (cells_ij) PP_CUDA(cudaMemcpyAsync(cells_ij, c->d_foot_out.p + n, sizeof(int) * 2 * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+    if (hits_out) PP_CUDA(cudaMemcpyAsync(hits_out, c->d_foot_out.p + 3 * (size_t)n, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+    PP_CUDA(cudaStreamSynchronize(c->stream));
+    if (kernel_ms) PP_CUDA(cudaEventElapsedTime(kernel_ms, c->ev0, c->ev1));
     return PP_SUCCESS;
 }
 

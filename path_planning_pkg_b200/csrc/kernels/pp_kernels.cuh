@@ -6,6 +6,7 @@
 //                           collision lookup, APF lanes = obstacles           (north_star (b), (c))
 //   pp_apf_kernel           one warp per pose, order-preserving warp sum
 //   pp_collision_kernel     one thread per point (the reference's check is a single-cell lookup, F3)
+//   pp_footprint_kernel     one warp per pose: footprint window staged in shared memory, lanes = footprint cells, ballot
 //   pp_dubins_length_kernel 4 lanes per state (one per CSC candidate), FP64-evaluated/rounded ("pinned libm")
 //   pp_dubins_path_kernel   one warp: plan + parallel sampling
 //   pp_lazy_astar_kernel    one control lane: the lazy cached 2D A* on a fresh cache (parity tests)
@@ -23,6 +24,7 @@ __device__ unsigned long long pp_prof_acc[8];
 #include "../core/pp_search.h"
 #include "../core/pp_kpop.h"
 #include "../core/pp_map.h"
+#include "../core/pp_footprint.h"
 
 #define PP_SEARCH_WARPS 4
 #ifndef PP_SEARCH_MIN_BLOCKS
@@ -388,6 +390,72 @@ __global__ void pp_collision_kernel(const __grid_constant__ PPConsts C, const fl
         if (cells) { cells[2 * k] = ci; cells[2 * k + 1] = cj; }
     }
     else free_out[k] = pp_path_point_blocked(C, map, x, y) ? 0 : 1;
+}
+
+// Generic vehicle-footprint collision check (core/pp_footprint.h; north_star (c)).  One warp per pose, warps stride over the
+// batch.  Per pose: base cell by truncation like the reference's successor check (Grid3D.cpp:53-54), heading bin -> offset
+// list; the bounding window of the list is staged into the warp's shared-memory tile with row-contiguous loads (a row of the
+// window is consecutive j = consecutive addresses; cells outside the grid are staged as +inf, i.e. blocked); every lane tests
+// its share of the footprint cells against the tile; blocked counts are summed over the warp and the verdict is
+// `no lane saw a blocked cell` (ballot).  free_out[k] = 1 / 0, cells[2k..] = base cell, hits[k] = blocked footprint cells.
+#define PP_FOOT_WARPS 4
+struct PPFootArgs
+{
+    PPConsts         C;
+    const float*     map;
+    const float*     xyh;      // n x (x, y, heading), grid frame
+    int              n;
+    const PPFootBin* bins;     // C.bins + 1
+    const PPCellOff* offs;
+    int              win;      // tile side (>= every bin's bounding box)
+    int*             free_out;
+    int*             cells;    // optional
+    int*             hits;     // optional
+};
+
+__global__ void __launch_bounds__(PP_FOOT_WARPS * 32) pp_footprint_kernel(const __grid_constant__ PPFootArgs a)
+{
+    extern __shared__ float pp_foot_tiles[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float* tile = pp_foot_tiles + (size_t)warp * a.win * a.win;
+    const int N = a.C.N;
+    const float inf = __int_as_float(0x7f800000);
+    for (int k = blockIdx.x * PP_FOOT_WARPS + warp; k < a.n; k += gridDim.x * PP_FOOT_WARPS)
+    {
+        const float x = a.xyh[3 * (size_t)k], y = a.xyh[3 * (size_t)k + 1], h = a.xyh[3 * (size_t)k + 2];
+        const int ci = (int)(x / a.C.res), cj = (int)(y / a.C.res);
+        const PPFootBin B = a.bins[pp_foot_bin(h, a.C.precision, a.C.bins)];
+        const int rows = B.imax - B.imin + 1, cols = B.jmax - B.jmin + 1;
+        const int i0 = ci + B.imin, j0 = cj + B.jmin;
+        for (int t = lane; t < rows * cols; t += 32)
+        {
+            int r = t / cols, c = t - r * cols;
+            int gi = i0 + r, gj = j0 + c;
+            bool inside = (gi > -1) && (gi < N) && (gj > -1) && (gj < N);
+            tile[r * a.win + c] = inside ? a.map[(size_t)gi * N + gj] : inf;
+        }
+        __syncwarp();
+        int blocked = 0;
+        for (int t = lane; t < B.count; t += 32)
+        {
+            const PPCellOff o = a.offs[B.first + t];
+            float v = tile[(o.di - B.imin) * a.win + (o.dj - B.jmin)];
+            if (!(v < a.C.log_thr)) blocked++;
+        }
+        const unsigned any = __ballot_sync(0xffffffffu, blocked != 0);
+        if (a.hits)
+        {
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) blocked += __shfl_xor_sync(0xffffffffu, blocked, d);
+        }
+        if (lane == 0)
+        {
+            a.free_out[k] = any ? 0 : 1;
+            if (a.cells) { a.cells[2 * (size_t)k] = ci; a.cells[2 * (size_t)k + 1] = cj; }
+            if (a.hits) a.hits[k] = blocked;
+        }
+        __syncwarp();       // the tile is restaged for the warp's next pose
+    }
 }
 
 // 4 lanes per state: one CSC candidate each, folded in candidate order (Dubins.cpp:36-68)

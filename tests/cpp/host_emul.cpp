@@ -15,6 +15,7 @@
 #include "../../path_planning_pkg_b200/csrc/core/pp_kpop.h"
 #include "../../path_planning_pkg_b200/csrc/core/pp_map.h"
 #include "../../path_planning_pkg_b200/csrc/host/pp_host.h"
+#include "../../path_planning_pkg_b200/csrc/host/pp_footprint_host.h"
 #include "../../oracle/oracle_api.h"
 
 namespace
@@ -318,6 +319,36 @@ int emu_dubins_path(void* h, const float* s, const float* g, float* xyh, float* 
         else if (k < pl.size_3) acc = (pl.s2 < 0) ? acc - C.ang_step : acc + C.ang_step;
     }
     return total;
+}
+
+// generic footprint check: the product's table builder (host/pp_footprint_host.h) and the predicates the kernel executes
+int emu_footprint_table(void* h, int bin, float length, float width, float rear, short* offs_ij, int cap)
+{
+    Emu* e = static_cast<Emu*>(h);
+    std::vector<PPFootBin> bins; std::vector<PPCellOff> offs;
+    pp_footprint_build(e->m.C, length, width, rear, bins, offs);
+    const PPFootBin& b = bins[bin];
+    for (int k = 0; k < b.count && k < cap; k++) { offs_ij[2 * k] = offs[b.first + k].di; offs_ij[2 * k + 1] = offs[b.first + k].dj; }
+    return b.count;
+}
+
+void emu_footprint_check(void* h, const float* xyh, int n, float length, float width, float rear, int* free_out, int* cells_ij,
+                         int* hits_out)
+{
+    Emu* e = static_cast<Emu*>(h);
+    const PPConsts& C = e->m.C;
+    std::vector<PPFootBin> bins; std::vector<PPCellOff> offs;
+    pp_footprint_build(C, length, width, rear, bins, offs);
+    for (int k = 0; k < n; k++)
+    {
+        float x = xyh[3 * k], y = xyh[3 * k + 1];
+        int ci = (int)(x / C.res), cj = (int)(y / C.res);
+        const PPFootBin& B = bins[pp_foot_bin(xyh[3 * k + 2], C.precision, C.bins)];
+        int hits = 0;
+        for (int t = 0; t < B.count; t++)
+            if (pp_foot_cell_blocked(C, e->map.data(), ci + offs[B.first + t].di, cj + offs[B.first + t].dj)) hits++;
+        free_out[k] = hits == 0; if (cells_ij) { cells_ij[2 * k] = ci; cells_ij[2 * k + 1] = cj; } if (hits_out) hits_out[k] = hits;
+    }
 }
 
 void emu_astar_lazy_batch(void* h, const int* ij, int n, float* out)

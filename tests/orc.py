@@ -216,6 +216,20 @@ class Oracle:
         self._fn("astar_dump")(self.h, _fp(v), _fp(g), _fp(f))
         return v, g, f
 
+    # -- generic footprint collision check (port / emu only: new semantics, oracle/port/footprint.inc) --
+    def footprint_table(self, bin_, length, width, rear, cap=4096):
+        offs = np.zeros((cap, 2), np.int16)
+        fn = self._fn("footprint_table"); fn.restype = C.c_int
+        n = fn(self.h, C.c_int(bin_), C.c_float(length), C.c_float(width), C.c_float(rear), _fp(offs), C.c_int(cap))
+        return offs[:n].copy()
+
+    def footprint_check(self, xyh, length, width, rear):
+        p = np.ascontiguousarray(xyh, np.float32); n = len(p)
+        free = np.zeros(n, np.int32); cells = np.zeros((n, 2), np.int32); hits = np.zeros(n, np.int32)
+        self._fn("footprint_check")(self.h, _fp(p), C.c_int(n), C.c_float(length), C.c_float(width), C.c_float(rear),
+                                    _fp(free), _fp(cells), _fp(hits))
+        return free, cells, hits
+
     # -- the search --------------------------------------------------------------------------
     def find_path(self, vel, start, pop_cap=1 << 20, path_cap=1 << 14):
         s = np.asarray(start, np.float32)
