@@ -600,13 +600,20 @@ int pp_footprint_batch(pp_context* c, int g, const float* xyh, int n, int* free_
     a.C = c->model.C; a.map = c->d_maps + (size_t)g * nn_of(c); a.xyh = c->d_foot_xyh.p; a.n = n;
     a.bins = c->d_foot_bins.p; a.offs = c->d_foot_offs.p; a.win = c->foot_win;
     a.free_out = c->d_foot_out.p; a.cells = cells_ij ? c->d_foot_out.p + n : nullptr; a.hits = hits_out ? c->d_foot_out.p + 3 * (size_t)n : nullptr;
-    size_t smem = (size_t)PP_FOOT_WARPS * a.win * a.win * sizeof(float);
-    PP_CUDA(cudaFuncSetAttribute(pp_footprint_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 48 * 1024)));
+    // default: direct gather (L1 is the staging buffer); PP_B200_FOOT_STAGED=1 selects the shared-memory-staged variant
+    static const bool staged = [] { const char* e = std::getenv("PP_B200_FOOT_STAGED"); return e && e[0] == '1'; }();
+    const size_t smem = staged ? (size_t)PP_FOOT_WARPS * a.win * a.win * sizeof(float) : 0;
     int occ = 0;
-    PP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pp_footprint_kernel, PP_FOOT_WARPS * 32, smem));
-    int blocks = std::min((n + PP_FOOT_WARPS - 1) / PP_FOOT_WARPS, std::max(1, occ) * c->sm_count);     // a whole number of waves
+    if (staged)
+    {
+        PP_CUDA(cudaFuncSetAttribute(pp_footprint_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 48 * 1024)));
+        PP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pp_footprint_kernel<true>, PP_FOOT_WARPS * 32, smem));
+    }
+    else PP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pp_footprint_kernel<false>, PP_FOOT_WARPS * 32, 0));
+    int blocks = std::min((n + 32 * PP_FOOT_WARPS - 1) / (32 * PP_FOOT_WARPS), std::max(1, occ) * c->sm_count);     // 32 poses per warp step, at most one full wave
     PP_CUDA(cudaEventRecord(c->ev0, c->stream));
-    pp_footprint_kernel<<<blocks, PP_FOOT_WARPS * 32, smem, c->stream>>>(a);
+    if (staged) pp_footprint_kernel<true><<<blocks, PP_FOOT_WARPS * 32, smem, c->stream>>>(a);
+    else pp_footprint_kernel<false><<<blocks, PP_FOOT_WARPS * 32, 0, c->stream>>>(a);
     c->launches += 1;
     PP_CUDA(cudaGetLastError());
     PP_CUDA(cudaEventRecord(c->ev1, c->stream));

@@ -24,9 +24,9 @@
 
 #define PP_FOOT_MAX_WIN 96      // largest supported window side (cells): 96*96*4 B = 36 KB of shared memory per warp
 
-struct PPCellOff { short di, dj; };
+struct alignas(4) PPCellOff { short di, dj; };      // one 32-bit load
 
-struct PPFootBin
+struct alignas(16) PPFootBin      // one 128-bit load
 {
     short imin, imax, jmin, jmax;    // bounding box of the bin's offsets
     int   first, count;              // slice of the offset list

@@ -394,10 +394,15 @@ __global__ void pp_collision_kernel(const __grid_constant__ PPConsts C, const fl
 
 // Generic vehicle-footprint collision check (core/pp_footprint.h; north_star (c)).  One warp per pose, warps stride over the
 // batch.  Per pose: base cell by truncation like the reference's successor check (Grid3D.cpp:53-54), heading bin -> offset
-// list; the bounding window of the list is staged into the warp's shared-memory tile with row-contiguous loads (a row of the
-// window is consecutive j = consecutive addresses; cells outside the grid are staged as +inf, i.e. blocked); every lane tests
-// its share of the footprint cells against the tile; blocked counts are summed over the warp and the verdict is
-// `no lane saw a blocked cell` (ballot).  free_out[k] = 1 / 0, cells[2k..] = base cell, hits[k] = blocked footprint cells.
+// list, lanes = footprint cells, verdict = `no lane saw a blocked cell` (ballot; the blocked count by a warp reduce on request).
+// free_out[k] = 1 / 0, cells[2k..] = base cell, hits[k] = blocked footprint cells.
+//   STAGED = false (default): every lane gathers its cells straight from the map.  The offset list is sorted (di, dj), so
+//     32 consecutive entries cover 2-3 rows of the rectangle = a handful of 32-byte sectors per warp load, and L1 plays the
+//     staging buffer.  No map cell is read twice for one pose, so there is nothing for shared memory to reuse.
+//   STAGED = true (PP_B200_FOOT_STAGED=1, kept for the A/B record in profiles/): the bounding window of the list is first
+//     staged into the warp's shared-memory tile with row-contiguous loads (cells outside the grid staged as +inf), then tested
+//     from the tile.  Measured 4x more instructions per pose (index arithmetic of the staging loop; the window holds ~1.7x the
+//     cells the footprint needs) and issue-bound -- see DESIGN.md section 12.
 #define PP_FOOT_WARPS 4
 struct PPFootArgs
 {
@@ -407,54 +412,82 @@ struct PPFootArgs
     int              n;
     const PPFootBin* bins;     // C.bins + 1
     const PPCellOff* offs;
-    int              win;      // tile side (>= every bin's bounding box)
+    int              win;      // tile side (>= every bin's bounding box), STAGED only
     int*             free_out;
     int*             cells;    // optional
     int*             hits;     // optional
 };
 
+template <bool STAGED>
 __global__ void __launch_bounds__(PP_FOOT_WARPS * 32) pp_footprint_kernel(const __grid_constant__ PPFootArgs a)
 {
     extern __shared__ float pp_foot_tiles[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float* tile = pp_foot_tiles + (size_t)warp * a.win * a.win;
     const int N = a.C.N;
     const float inf = __int_as_float(0x7f800000);
-    for (int k = blockIdx.x * PP_FOOT_WARPS + warp; k < a.n; k += gridDim.x * PP_FOOT_WARPS)
+    const float thr = a.C.log_thr;
+    // a warp takes 32 poses at a time: lane l does the exact index arithmetic of pose base + l once (IEEE division,
+    // double-precision heading index -- the expensive, bit-exact part), then the warp walks the 32 footprints together
+    for (int base = (blockIdx.x * PP_FOOT_WARPS + warp) * 32; base < a.n; base += gridDim.x * PP_FOOT_WARPS * 32)
     {
-        const float x = a.xyh[3 * (size_t)k], y = a.xyh[3 * (size_t)k + 1], h = a.xyh[3 * (size_t)k + 2];
-        const int ci = (int)(x / a.C.res), cj = (int)(y / a.C.res);
-        const PPFootBin B = a.bins[pp_foot_bin(h, a.C.precision, a.C.bins)];
-        const int rows = B.imax - B.imin + 1, cols = B.jmax - B.jmin + 1;
-        const int i0 = ci + B.imin, j0 = cj + B.jmin;
-        for (int t = lane; t < rows * cols; t += 32)
+        const int k = base + lane;
+        int ci = 0, cj = 0, bin = 0;
+        if (k < a.n)
         {
-            int r = t / cols, c = t - r * cols;
-            int gi = i0 + r, gj = j0 + c;
-            bool inside = (gi > -1) && (gi < N) && (gj > -1) && (gj < N);
-            tile[r * a.win + c] = inside ? a.map[(size_t)gi * N + gj] : inf;
+            const float x = a.xyh[3 * (size_t)k], y = a.xyh[3 * (size_t)k + 1], h = a.xyh[3 * (size_t)k + 2];
+            ci = (int)(x / a.C.res); cj = (int)(y / a.C.res);
+            bin = pp_foot_bin(h, a.C.precision, a.C.bins);
         }
-        __syncwarp();
-        int blocked = 0;
-        for (int t = lane; t < B.count; t += 32)
+        const int cnt = min(32, a.n - base);
+        int my_hits = 0;
+        for (int p = 0; p < cnt; p++)
         {
-            const PPCellOff o = a.offs[B.first + t];
-            float v = tile[(o.di - B.imin) * a.win + (o.dj - B.jmin)];
-            if (!(v < a.C.log_thr)) blocked++;
+            const int pci = __shfl_sync(0xffffffffu, ci, p), pcj = __shfl_sync(0xffffffffu, cj, p);
+            const PPFootBin B = a.bins[__shfl_sync(0xffffffffu, bin, p)];
+            int blocked = 0;
+            if (STAGED)
+            {
+                float* tile = pp_foot_tiles + (size_t)warp * a.win * a.win;
+                const int rows = B.imax - B.imin + 1, cols = B.jmax - B.jmin + 1;
+                const int i0 = pci + B.imin, j0 = pcj + B.jmin;
+                for (int t = lane; t < rows * cols; t += 32)
+                {
+                    int r = t / cols, c = t - r * cols;
+                    int gi = i0 + r, gj = j0 + c;
+                    bool inside = (gi > -1) && (gi < N) && (gj > -1) && (gj < N);
+                    tile[r * a.win + c] = inside ? a.map[(size_t)gi * N + gj] : inf;
+                }
+                __syncwarp();
+                for (int t = lane; t < B.count; t += 32)
+                {
+                    const PPCellOff o = a.offs[B.first + t];
+                    float v = tile[(o.di - B.imin) * a.win + (o.dj - B.jmin)];
+                    if (!(v < thr)) blocked++;
+                }
+                __syncwarp();       // the tile is restaged for the next pose
+            }
+            else
+            {
+                const PPCellOff* __restrict__ offs = a.offs + B.first;
+                for (int t = lane; t < B.count; t += 32)
+                {
+                    const PPCellOff o = offs[t];
+                    const int gi = pci + o.di, gj = pcj + o.dj;
+                    const bool inside = ((unsigned)gi < (unsigned)N) && ((unsigned)gj < (unsigned)N);
+                    const float v = inside ? __ldg(a.map + (size_t)gi * N + gj) : inf;
+                    if (!(v < thr)) blocked++;
+                }
+            }
+            // verdict by ballot; the count only when the caller asked for it (one REDUX)
+            int total = a.hits ? __reduce_add_sync(0xffffffffu, blocked) : (__ballot_sync(0xffffffffu, blocked != 0) ? 1 : 0);
+            if (lane == p) my_hits = total;
         }
-        const unsigned any = __ballot_sync(0xffffffffu, blocked != 0);
-        if (a.hits)
+        if (k < a.n)
         {
-#pragma unroll
-            for (int d = 16; d > 0; d >>= 1) blocked += __shfl_xor_sync(0xffffffffu, blocked, d);
-        }
-        if (lane == 0)
-        {
-            a.free_out[k] = any ? 0 : 1;
+            a.free_out[k] = my_hits ? 0 : 1;
             if (a.cells) { a.cells[2 * (size_t)k] = ci; a.cells[2 * (size_t)k + 1] = cj; }
-            if (a.hits) a.hits[k] = blocked;
+            if (a.hits) a.hits[k] = my_hits;
         }
-        __syncwarp();       // the tile is restaged for the warp's next pose
     }
 }
 

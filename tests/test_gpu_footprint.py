@@ -72,10 +72,11 @@ def test_kernel_rate(pair):
     ctx.footprint(p)
     best = min(ctx.footprint(p, want_ms=True)[3] for _ in range(5))
     cells = float(np.mean([len(ctx.footprint_table(b)) for b in range(P.num_angle_bins)]))
-    out = {"kernel": "pp_footprint_kernel", "poses": len(p), "vehicle_m": [4.0, 2.0, 1.0], "grid": [P.grid_size, P.resolution],
+    variant = "staged" if os.environ.get("PP_B200_FOOT_STAGED") == "1" else "direct"
+    out = {"kernel": f"pp_footprint_kernel<{variant}>", "poses": len(p), "vehicle_m": [4.0, 2.0, 1.0], "grid": [P.grid_size, P.resolution],
            "mean_footprint_cells": cells, "kernel_ms": best, "poses_per_s": len(p) / (best * 1e-3),
            "algorithmic_GBps": len(p) * (cells * 4 + 12 + 12) / (best * 1e-3) / 1e9}
     d = os.path.join(orc.ROOT, "gpurun_out")
     if os.path.isdir(d):
-        json.dump(out, open(os.path.join(d, "footprint_kernel.json"), "w"))
+        json.dump(out, open(os.path.join(d, f"footprint_kernel_{variant}.json"), "w"))
     assert best > 0
