@@ -108,7 +108,7 @@ struct pp_context
     int batch_hist_group = -1;    // group whose history the uploaded batch runs on (-1 = fresh cache per query)
     // generic footprint collision check (pp_set_footprint): per-bin offset table on the host and the device
     std::vector<PPFootBin> foot_bins; std::vector<PPCellOff> foot_offs; int foot_win = 0;
-    DevBuf<PPFootBin> d_foot_bins; DevBuf<PPCellOff> d_foot_offs;
+    DevBuf<PPFootBin> d_foot_bins; DevBuf<PPCellOff> d_foot_offs; DevBuf<int> d_foot_lin;
     DevBuf<float> d_foot_xyh; DevBuf<int> d_foot_out;
     // K-POP mode pools (per slot): node log, hash table, LSM queue arena + merge scratch
     struct KPools { int alloc_slots = 0, nodes_cap = 0, table_cap = 0, levels = 0; size_t arena_cap = 0, tmp_cap = 0;
@@ -234,7 +234,7 @@ void pp_destroy(pp_context* c)
     c->wp.release(); c->wp_retry.release(); c->wp_lazy.release(); c->d_qmap.release(); c->d_order.release(); c->d_group_cost.release();
     cudaFree(c->d_lazy_sid);
     for (auto& h : c->hist) h.release();
-    c->d_foot_bins.release(); c->d_foot_offs.release(); c->d_foot_xyh.release(); c->d_foot_out.release();
+    c->d_foot_bins.release(); c->d_foot_offs.release(); c->d_foot_lin.release(); c->d_foot_xyh.release(); c->d_foot_out.release();
     c->kp.release(); c->kp_retry.release();
     c->d_field2d.release(); c->d_f2d_work.release(); c->d_f2d_flags.release(); c->d_dubins_field.release();
     cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
@@ -572,6 +572,10 @@ int pp_set_footprint(pp_context* c, float length, float width, float rear_overha
     PP_CUDA(c->d_foot_offs.ensure(c->foot_offs.size()));
     PP_CUDA(cudaMemcpyAsync(c->d_foot_bins.p, c->foot_bins.data(), sizeof(PPFootBin) * c->foot_bins.size(), cudaMemcpyHostToDevice, c->stream));
     PP_CUDA(cudaMemcpyAsync(c->d_foot_offs.p, c->foot_offs.data(), sizeof(PPCellOff) * c->foot_offs.size(), cudaMemcpyHostToDevice, c->stream));
+    std::vector<int> lin(c->foot_offs.size());
+    for (size_t k = 0; k < lin.size(); k++) lin[k] = (int)c->foot_offs[k].di * c->model.C.N + (int)c->foot_offs[k].dj;
+    PP_CUDA(c->d_foot_lin.ensure(lin.size()));
+    PP_CUDA(cudaMemcpyAsync(c->d_foot_lin.p, lin.data(), sizeof(int) * lin.size(), cudaMemcpyHostToDevice, c->stream));
     PP_CUDA(cudaStreamSynchronize(c->stream));
     return PP_SUCCESS;
 }
@@ -598,7 +602,7 @@ int pp_footprint_batch(pp_context* c, int g, const float* xyh, int n, int* free_
     PP_CUDA(cudaMemcpyAsync(c->d_foot_xyh.p, xyh, sizeof(float) * 3 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
     PPFootArgs a;
     a.C = c->model.C; a.map = c->d_maps + (size_t)g * nn_of(c); a.xyh = c->d_foot_xyh.p; a.n = n;
-    a.bins = c->d_foot_bins.p; a.offs = c->d_foot_offs.p; a.win = c->foot_win;
+    a.bins = c->d_foot_bins.p; a.offs = c->d_foot_offs.p; a.lin = c->d_foot_lin.p; a.win = c->foot_win;
     a.free_out = c->d_foot_out.p; a.cells = cells_ij ? c->d_foot_out.p + n : nullptr; a.hits = hits_out ? c->d_foot_out.p + 3 * (size_t)n : nullptr;
     // default: direct gather (L1 is the staging buffer); PP_B200_FOOT_STAGED=1 selects the shared-memory-staged variant
     static const bool staged = [] { const char* e = std::getenv("PP_B200_FOOT_STAGED"); return e && e[0] == '1'; }();

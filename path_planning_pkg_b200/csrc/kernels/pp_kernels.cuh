@@ -412,6 +412,7 @@ struct PPFootArgs
     int              n;
     const PPFootBin* bins;     // C.bins + 1
     const PPCellOff* offs;
+    const int*       lin;      // per offset: di * N + dj (the interior fast path adds it to the pose's cell address)
     int              win;      // tile side (>= every bin's bounding box), STAGED only
     int*             free_out;
     int*             cells;    // optional
@@ -468,14 +469,33 @@ __global__ void __launch_bounds__(PP_FOOT_WARPS * 32) pp_footprint_kernel(const 
             }
             else
             {
-                const PPCellOff* __restrict__ offs = a.offs + B.first;
-                for (int t = lane; t < B.count; t += 32)
+                // the rectangle's bounding box lies inside the grid for all but border poses: no per-cell bounds test then,
+                // one precomputed linear offset per cell
+                const bool interior = (pci + B.imin > -1) && (pci + B.imax < N) && (pcj + B.jmin > -1) && (pcj + B.jmax < N);
+                if (interior)
                 {
-                    const PPCellOff o = offs[t];
-                    const int gi = pci + o.di, gj = pcj + o.dj;
-                    const bool inside = ((unsigned)gi < (unsigned)N) && ((unsigned)gj < (unsigned)N);
-                    const float v = inside ? __ldg(a.map + (size_t)gi * N + gj) : inf;
-                    if (!(v < thr)) blocked++;
+                    // 32-bit cell indices (N * N < 2^31): one IMAD.WIDE per address instead of 64-bit pointer arithmetic
+                    const int cell0 = pci * N + pcj;
+                    const float* __restrict__ map = a.map;
+                    const int* __restrict__ lin = a.lin;
+                    // warp-uniform trip count (a per-lane bound makes the unrolled loop and its remainders diverge)
+                    for (int t0 = B.first; t0 < B.first + B.count; t0 += 32)
+                    {
+                        const int t = t0 + lane;
+                        if (t < B.first + B.count && !(__ldg(map + (cell0 + lin[t])) < thr)) blocked++;
+                    }
+                }
+                else
+                {
+                    const PPCellOff* __restrict__ offs = a.offs + B.first;
+                    for (int t = lane; t < B.count; t += 32)
+                    {
+                        const PPCellOff o = offs[t];
+                        const int gi = pci + o.di, gj = pcj + o.dj;
+                        const bool inside = ((unsigned)gi < (unsigned)N) && ((unsigned)gj < (unsigned)N);
+                        const float v = inside ? __ldg(a.map + (size_t)gi * N + gj) : inf;
+                        if (!(v < thr)) blocked++;
+                    }
                 }
             }
             // verdict by ballot; the count only when the caller asked for it (one REDUX)
