@@ -116,6 +116,7 @@ struct ExactPools
     std::vector<PPNode3> open3; std::vector<PPClosed3> closed; std::vector<PPHashSlot> chash; std::vector<unsigned> cell_state;
     std::vector<float> nm_g, nm_f, cl_g; std::vector<int> cl_prev; std::vector<PPNode2> open2; std::vector<PPPathPt> path;
     std::vector<PPPop> trace;
+    unsigned hist_sid = 0;      // planner-object history (PPWork::lazy_sid), used by the carried-cache pass only
     PPWork wk;
     explicit ExactPools(int N)
     {
@@ -265,6 +266,35 @@ int main(int argc, char** argv)
         std::printf("query %d EXACT: success %d pops %d cost %.6f lazy pops %d | 8 and 32 lanes: %s\n", i, x1.success, x1.n_pops, x1.cost,
                     x1.n_lazy_pops, xok ? "identical" : "MISMATCH");
         if (!xok) bad++;
+    }
+    // EXACT mode with planner-object history (pp_set_history): all queries in sequence on ONE carried 2D cache, one lane vs a
+    // warp of 32, the second half of the sequence started just below the stamp wrap-around so that the all-lane stamp drop
+    // of pp_search_exact runs under the race detector too.  Results and the carried cache must stay identical.
+    {
+        ExactPools H1(N), H32(N);
+        H1.wk.lazy_sid = &H1.hist_sid; H32.wk.lazy_sid = &H32.hist_sid;
+        std::unique_ptr<PPSmem> xsm(new PPSmem());
+        PPWarpSerial w1;
+        for (int rep = 0; rep < 2; rep++)
+            for (int i = 0; i < nq; i++)
+            {
+                if (rep == 1 && i == 0) { H1.hist_sid = (PP_CS_STAMP >> 1) - 3; H32.hist_sid = (PP_CS_STAMP >> 1) - 3; }
+                PPState st = pp_host_set_start(e->m.C, e->fr, q[4 * i], q[4 * i + 1], q[4 * i + 2], q[4 * i + 3]);
+                PPResult x1;
+                { PPGroup G = group_of(e); PPWork wk = H1.wk; pp_search_exact(w1, e->m.C, e->m.off_xy.data(), G, st, wk, *xsm, x1); }
+                PPResult x32 = run_exact_mt<32>(e, st, H32);
+                bool cache_ok = H1.hist_sid == H32.hist_sid;
+                for (size_t c = 0; c < H1.cell_state.size() && cache_ok; c++)
+                {
+                    cache_ok = H1.cell_state[c] == H32.cell_state[c];
+                    if (cache_ok && (H1.cell_state[c] & PP_CS_TOUCHED))
+                        cache_ok = std::memcmp(&H1.nm_g[c], &H32.nm_g[c], 4) == 0 && std::memcmp(&H1.nm_f[c], &H32.nm_f[c], 4) == 0;
+                }
+                bool hok = same_exact(x1, H1, x32, H32) && cache_ok && x1.status == 0;
+                std::printf("query %d.%d EXACT on the carried cache: pops %d cost %.6f lazy searches %d sid %u | 32 lanes: %s\n", rep, i,
+                            x1.n_pops, x1.cost, x1.n_lazy_searches, H1.hist_sid, hok ? "identical" : "MISMATCH");
+                if (!hok) bad++;
+            }
     }
     emu_destroy(e);
     return bad ? 1 : 0;

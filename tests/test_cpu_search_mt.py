@@ -70,3 +70,4 @@ def test_multilane_race_free_and_identical(exe, tmp_path, k):
         assert "ThreadSanitizer" not in r.stderr, r.stderr[:3000]
         assert r.returncode == 0, (r.returncode, r.stdout[-500:], r.stderr[-1500:])
         assert "MISMATCH" not in r.stdout and "identical" in r.stdout
+        assert "EXACT on the carried cache" in r.stdout          # the planner-object-history pass (incl. the stamp wrap) ran
