@@ -521,6 +521,22 @@ def main():
         "clocks": clocks,
         "kpop": kpop_info,
     }
+    # north_star (c): the generic vehicle-footprint collision kernel on this batch's first map (4.0 x 2.0 m rectangle, 2^20 poses);
+    # a side measurement, never allowed to break the headline line
+    try:
+        rs = np.random.RandomState(3)
+        L = N_GRID * RES
+        fp = np.concatenate([rs.uniform(0.0, L, (1 << 20, 2)), rs.uniform(-np.pi, np.pi, (1 << 20, 1))], 1).astype(np.float32)
+        ctx.set_footprint(4.0, 2.0, 1.0)
+        ctx.footprint(fp)
+        fms = min(ctx.footprint(fp, want_ms=True)[3] for _ in range(5))
+        fcells = float(np.mean([len(ctx.footprint_table(b)) for b in range(72)]))
+        line["footprint_kernel"] = {"poses": len(fp), "vehicle_m": [4.0, 2.0, 1.0], "mean_cells_per_pose": fcells, "kernel_ms": fms,
+                                    "poses_per_s": len(fp) / (fms * 1e-3),
+                                    "algorithmic_GBps": len(fp) * (fcells * 4 + 24) / (fms * 1e-3) / 1e9,
+                                    "note": "map is L1/L2-resident (1 MiB): issue/L1-bound, see DESIGN.md section 12"}
+    except Exception as e:
+        line["footprint_kernel"] = {"error": str(e)}
     if not args.no_cpu_baseline:
         try:
             rs = np.random.RandomState(1)
