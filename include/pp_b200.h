@@ -250,6 +250,26 @@ int  pp_find_path_batch(pp_context* ctx, const pp_query* queries, int n, const p
 int  pp_batch_upload(pp_context* ctx, const pp_query* queries, int n, const pp_search_opts* opts);
 int  pp_batch_run(pp_context* ctx, float* kernel_ms);
 int  pp_batch_fetch(pp_context* ctx, pp_result* results, float* paths_xyh, float* curvature, pp_pop* trace);
+/* ---- the step after the path: velocity profile and trajectory message ---- */
+/* The five constructor arguments of VelocityGenerator<T> (lib/VelocityGenerator.cpp:6-14). */
+typedef struct pp_velocity_limits
+{
+    float max_velocity, coast_velocity, max_lat_acc, max_long_acc, max_long_dec;
+} pp_velocity_limits;
+/* VelocityGenerator::generate_velocity_profile (lib/VelocityGenerator.cpp:19-85) for n independent paths: paths_xy [n][cap][2] and
+ * curvature [n][cap] in the reference's order (goal -> start), counts[k] points each (>= 1); vel_init[k]; max_velocity_curr may be
+ * NULL (no cap); flags[k] bit 0 = coast_to_goal, bit 1 = stop_at_goal (NULL = 0).  velocity [n][cap] (index 0 = the path's start)
+ * and the feasibility flag out.  Bit-identical to the reference except for the sign / payload of NaN results. */
+int  pp_velocity_profile_batch(pp_context* ctx, const pp_velocity_limits* limits, const float* paths_xy, const float* curvature,
+                               const int* counts, int n, int cap, const float* vel_init, const float* max_velocity_curr,
+                               const int* flags, float* velocity, int* feasible);
+/* For every query of the last pp_batch_run / pp_find_path_batch, on the device and straight from the device-resident path records:
+ * HybridAStar::reconstruct_path (lib/HybridAStar.cpp:208-262) + generate_velocity_profile (vel_init = the query's, coast_to_goal =
+ * false) + the layout LocalPlanner::publish_trajectory gives /local_planner/trajectory (src/local_planner.cpp:346-372):
+ * traj[k] = x[0..m), y[0..m), heading[0..m) from start to goal, then velocity[0..m), m = n_samples[k] (0 for a failed query),
+ * one row of 4 * path_cap floats per query.  max_velocity_curr / stop_at_goal per query may be NULL. */
+int  pp_trajectory_batch(pp_context* ctx, const pp_velocity_limits* limits, const float* max_velocity_curr, const int* stop_at_goal,
+                         float* traj, int* n_samples, int* feasible, float* kernel_ms);
 /* number of CUDA kernels this context has launched so far (bench.py's gpu_launches) */
 unsigned long long pp_kernel_launches(pp_context* ctx);
 /* queries of the last pp_batch_run / pp_find_path_batch that exhausted a pool and were re-run with larger pools */

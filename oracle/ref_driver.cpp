@@ -35,6 +35,7 @@
 #define private public
 #define protected public
 #include "HybridAStar.h"
+#include "VelocityGenerator.h"
 #undef private
 #undef protected
 
@@ -382,6 +383,20 @@ void ref_find_path(void* hv, float vel, const float* s, orc_result* res, float* 
         path_xyh[3 * k] = path[k]._x; path_xyh[3 * k + 1] = path[k]._y; path_xyh[3 * k + 2] = path[k]._heading;
         curv[k] = c[k];
     }
+}
+
+// VelocityGenerator<float>::generate_velocity_profile (lib/VelocityGenerator.cpp:19-85) on a caller-supplied path
+// (goal -> start order, as find_path returns it).  lim5 = the five constructor arguments.  Returns the feasibility flag.
+int ref_velocity_profile(const float* lim5, float vel_init, float max_velocity_curr, const float* path_xyh, const float* curv, int n,
+                         int coast, int stop, float* vel_out)
+{
+    VelocityGenerator<float> vg(lim5[0], lim5[1], lim5[2], lim5[3], lim5[4]);
+    std::vector<Vector3D<float>> path;
+    for (int k = 0; k < n; k++) path.emplace_back(path_xyh[3 * k], path_xyh[3 * k + 1], path_xyh[3 * k + 2]);
+    std::vector<float> c(curv, curv + n), v;
+    bool ok = vg.generate_velocity_profile(vel_init, max_velocity_curr, path, c, v, coast != 0, stop != 0);
+    for (int k = 0; k < n; k++) vel_out[k] = v[k];
+    return ok ? 1 : 0;
 }
 
 // ---- CPU baseline: many queries on one map, fresh-state planner per thread, scrub per query ------

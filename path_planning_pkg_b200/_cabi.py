@@ -326,6 +326,7 @@ class Context:
         paths = np.zeros((n, pc, 3), np.float32) if want_paths else None
         curv = np.zeros((n, pc), np.float32) if want_paths else None
         trace = np.zeros((n, opts.trace_cap), POP_DT) if opts.trace_cap > 0 else None
+        self._opts, self._n = opts, n
         self._chk(self.lib.pp_find_path_batch(self.h, _p(q), C.c_int(n), C.byref(opts), _p(res),
                                               _p(paths) if want_paths else None, _p(curv) if want_paths else None,
                                               _p(trace) if trace is not None else None))
@@ -363,6 +364,35 @@ class Context:
         return dict(success=bool(r["success"]), cost=np.float32(r["cost"]), path=paths[0, :n].copy(),
                     curvature=curv[0, :n].copy(), pops=trace[0, :min(int(r["n_pops"]), pop_cap)].copy(),
                     n_pops=int(r["n_pops"]), n_pops_bin_oob=int(r["n_pops_bin_oob"]), status=int(r["status"]), raw=r)
+
+    # ---- velocity profile / trajectory ----
+    @staticmethod
+    def _limits(lim5):
+        return (C.c_float * 5)(*[float(v) for v in lim5])
+
+    def velocity_profile_batch(self, lim5, paths_xy, curvature, counts, vel_init, vcap=None, flags=None):
+        """pp_velocity_profile_batch: paths_xy [n][cap][2], curvature [n][cap] (goal -> start) -> velocity [n][cap], feasible [n]."""
+        xy = np.ascontiguousarray(paths_xy, np.float32); cv = np.ascontiguousarray(curvature, np.float32)
+        n, cap = cv.shape
+        cnt = np.ascontiguousarray(counts, np.int32); vi = np.ascontiguousarray(vel_init, np.float32)
+        vc = None if vcap is None else np.ascontiguousarray(vcap, np.float32)
+        fl = None if flags is None else np.ascontiguousarray(flags, np.int32)
+        vel = np.zeros((n, cap), np.float32); ok = np.zeros(n, np.int32)
+        self._chk(self.lib.pp_velocity_profile_batch(self.h, self._limits(lim5), _p(xy), _p(cv), _p(cnt), C.c_int(n), C.c_int(cap), _p(vi),
+                                                     _p(vc) if vc is not None else None, _p(fl) if fl is not None else None, _p(vel), _p(ok)))
+        return vel, ok
+
+    def trajectory_batch(self, lim5, vcap=None, stop=None, want_ms=False):
+        """pp_trajectory_batch on the last batch: list of per-query (4, m) arrays [x, y, heading, velocity] start -> goal, feasible flags."""
+        n, opts = self._n, self._opts
+        pc = opts.path_cap if opts.path_cap > 0 else 2048
+        traj = np.zeros((n, 4 * pc), np.float32); m = np.zeros(n, np.int32); ok = np.zeros(n, np.int32); ms = C.c_float()
+        vc = None if vcap is None else np.ascontiguousarray(vcap, np.float32)
+        st = None if stop is None else np.ascontiguousarray(stop, np.int32)
+        self._chk(self.lib.pp_trajectory_batch(self.h, self._limits(lim5), _p(vc) if vc is not None else None,
+                                               _p(st) if st is not None else None, _p(traj), _p(m), _p(ok), C.byref(ms)))
+        out = [traj[k, :4 * m[k]].reshape(4, m[k]).copy() for k in range(n)]
+        return (out, ok, ms.value) if want_ms else (out, ok)
 
     # ---- heuristic fields ----
     def field2d(self, group=0, download=True):

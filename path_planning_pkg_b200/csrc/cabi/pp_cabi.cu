@@ -110,6 +110,9 @@ struct pp_context
     std::vector<PPFootBin> foot_bins; std::vector<PPCellOff> foot_offs; int foot_win = 0;
     DevBuf<PPFootBin> d_foot_bins; DevBuf<PPCellOff> d_foot_offs; DevBuf<int> d_foot_lin;
     DevBuf<float> d_foot_xyh; DevBuf<int> d_foot_out;
+    // velocity profile / trajectory (pp_velocity_profile_batch, pp_trajectory_batch)
+    std::vector<float> h_vel;             // vel_init of the uploaded queries
+    DevBuf<float> d_traj, d_traj_tmp, d_vel_in; DevBuf<int> d_traj_int; DevBuf<PPWorldFrame> d_wframes;
     // K-POP mode pools (per slot): node log, hash table, LSM queue arena + merge scratch
     struct KPools { int alloc_slots = 0, nodes_cap = 0, table_cap = 0, levels = 0; size_t arena_cap = 0, tmp_cap = 0;
                     DevBuf<PPKNode> nodes; DevBuf<PPKSlot> table; DevBuf<PPKEntry> arena, tmp_a, tmp_b;
@@ -235,6 +238,7 @@ void pp_destroy(pp_context* c)
     cudaFree(c->d_lazy_sid);
     for (auto& h : c->hist) h.release();
     c->d_foot_bins.release(); c->d_foot_offs.release(); c->d_foot_lin.release(); c->d_foot_xyh.release(); c->d_foot_out.release();
+    c->d_traj.release(); c->d_traj_tmp.release(); c->d_vel_in.release(); c->d_traj_int.release(); c->d_wframes.release();
     c->kp.release(); c->kp_retry.release();
     c->d_field2d.release(); c->d_f2d_work.release(); c->d_f2d_flags.release(); c->d_dubins_field.release();
     cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
@@ -932,9 +936,10 @@ int pp_batch_upload(pp_context* c, const pp_query* q, int n, const pp_search_opt
     PP_CUDA(cudaSetDevice(c->device));
     pp_search_opts o = default_opts(opts);
     c->opts = o;
-    c->h_queries.resize(n);
+    c->h_queries.resize(n); c->h_vel.resize(n);
     for (int k = 0; k < n; k++)
     {
+        c->h_vel[k] = q[k].vel;
         if (q[k].group < 0 || q[k].group >= c->num_groups) return pp_fail(PP_ERR_INVALID, "query group out of range");
         c->h_queries[k].start = pp_host_set_start(c->model.C, c->frames[q[k].group], q[k].x, q[k].y, q[k].heading, q[k].vel);
         c->h_queries[k].group = q[k].group;
@@ -1113,6 +1118,90 @@ int pp_find_path_batch(pp_context* c, const pp_query* q, int n, const pp_search_
     int rc = pp_batch_upload(c, q, n, opts); if (rc) return rc;
     rc = pp_batch_run(c, nullptr); if (rc) return rc;
     return pp_batch_fetch(c, results, paths_xyh, curvature, trace);
+}
+
+// ---- velocity profile / trajectory ----
+static PPVelLimits limits_of(const pp_velocity_limits* l)
+{
+    PPVelLimits L; L.max_velocity = l->max_velocity; L.coast_velocity = l->coast_velocity; L.max_lat_acc = l->max_lat_acc;
+    L.max_long_acc = l->max_long_acc; L.max_long_dec = l->max_long_dec;
+    return L;
+}
+
+int pp_velocity_profile_batch(pp_context* c, const pp_velocity_limits* lim, const float* paths_xy, const float* curvature, const int* counts,
+                              int n, int cap, const float* vel_init, const float* max_velocity_curr, const int* flags, float* velocity,
+                              int* feasible)
+{
+    if (!c || !lim || !paths_xy || !curvature || !counts || !vel_init || !velocity || !feasible || cap < 1)
+        return pp_fail(PP_ERR_INVALID, "pp_velocity_profile_batch: bad arguments");
+    if (n <= 0) return PP_SUCCESS;
+    PP_CUDA(cudaSetDevice(c->device));
+    const size_t nc = (size_t)n * cap;
+    // one float arena: xy | curvature | velocity | v2 | vel_init | vcap ; one int arena: counts | flags | feasible
+    PP_CUDA(c->d_traj.ensure(nc * 5 + 2 * (size_t)n));
+    PP_CUDA(c->d_traj_int.ensure(3 * (size_t)n));
+    float* d_xy = c->d_traj.p; float* d_curv = d_xy + 2 * nc; float* d_vel = d_curv + nc; float* d_v2 = d_vel + nc;
+    float* d_vi = d_v2 + nc; float* d_vc = d_vi + n;
+    int* d_cnt = c->d_traj_int.p; int* d_fl = d_cnt + n; int* d_ok = d_fl + n;
+    PP_CUDA(cudaMemcpyAsync(d_xy, paths_xy, sizeof(float) * 2 * nc, cudaMemcpyHostToDevice, c->stream));
+    PP_CUDA(cudaMemcpyAsync(d_curv, curvature, sizeof(float) * nc, cudaMemcpyHostToDevice, c->stream));
+    PP_CUDA(cudaMemcpyAsync(d_cnt, counts, sizeof(int) * n, cudaMemcpyHostToDevice, c->stream));
+    PP_CUDA(cudaMemcpyAsync(d_vi, vel_init, sizeof(float) * n, cudaMemcpyHostToDevice, c->stream));
+    if (max_velocity_curr) PP_CUDA(cudaMemcpyAsync(d_vc, max_velocity_curr, sizeof(float) * n, cudaMemcpyHostToDevice, c->stream));
+    if (flags) PP_CUDA(cudaMemcpyAsync(d_fl, flags, sizeof(int) * n, cudaMemcpyHostToDevice, c->stream));
+    PP_CUDA(cudaMemsetAsync(d_vel, 0, sizeof(float) * nc, c->stream));
+    pp_velocity_profile_kernel<<<(n + 127) / 128, 128, 0, c->stream>>>(limits_of(lim), d_xy, d_curv, d_cnt, n, cap, d_vi,
+                                                                       max_velocity_curr ? d_vc : nullptr, flags ? d_fl : nullptr, d_vel, d_v2, d_ok);
+    c->launches += 1;
+    PP_CUDA(cudaGetLastError());
+    PP_CUDA(cudaMemcpyAsync(velocity, d_vel, sizeof(float) * nc, cudaMemcpyDeviceToHost, c->stream));
+    PP_CUDA(cudaMemcpyAsync(feasible, d_ok, sizeof(int) * n, cudaMemcpyDeviceToHost, c->stream));
+    PP_CUDA(cudaStreamSynchronize(c->stream));
+    return PP_SUCCESS;
+}
+
+int pp_trajectory_batch(pp_context* c, const pp_velocity_limits* lim, const float* max_velocity_curr, const int* stop_at_goal, float* traj,
+                        int* n_samples, int* feasible, float* kernel_ms)
+{
+    if (!c || !lim || !traj || !n_samples || !feasible) return pp_fail(PP_ERR_INVALID, "pp_trajectory_batch: bad arguments");
+    if (c->n_queries <= 0 || (int)c->h_vel.size() != c->n_queries) return pp_fail(PP_ERR_INVALID, "pp_trajectory_batch: run a batch first");
+    PP_CUDA(cudaSetDevice(c->device));
+    const int n = c->n_queries, pc = c->opts.path_cap;
+    // world frames of the groups: cos / sin of -grid_heading with the host libm, once per frame (pp_host_to_world does it per point)
+    std::vector<PPWorldFrame> wf(c->num_groups);
+    for (int g = 0; g < c->num_groups; g++)
+    {
+        const PPHostFrame& fr = c->frames[g];
+        PPWorldFrame& F = wf[g];
+        F.goal_gx = fr.F.goal_x; F.goal_gy = fr.F.goal_y; F.goal_wx = fr.goal_world[0]; F.goal_wy = fr.goal_world[1];
+        F.angle = -fr.grid_heading; F.c = std::cos(F.angle); F.s = std::sin(F.angle);
+    }
+    PP_CUDA(c->d_wframes.ensure(wf.size()));
+    PP_CUDA(cudaMemcpyAsync(c->d_wframes.p, wf.data(), sizeof(PPWorldFrame) * wf.size(), cudaMemcpyHostToDevice, c->stream));
+    PP_CUDA(c->d_traj.ensure((size_t)n * 4 * pc));
+    PP_CUDA(c->d_traj_tmp.ensure((size_t)n * 2 * pc));
+    PP_CUDA(c->d_vel_in.ensure(2 * (size_t)n));
+    PP_CUDA(c->d_traj_int.ensure(3 * (size_t)n));
+    PP_CUDA(cudaMemcpyAsync(c->d_vel_in.p, c->h_vel.data(), sizeof(float) * n, cudaMemcpyHostToDevice, c->stream));
+    if (max_velocity_curr) PP_CUDA(cudaMemcpyAsync(c->d_vel_in.p + n, max_velocity_curr, sizeof(float) * n, cudaMemcpyHostToDevice, c->stream));
+    if (stop_at_goal) PP_CUDA(cudaMemcpyAsync(c->d_traj_int.p, stop_at_goal, sizeof(int) * n, cudaMemcpyHostToDevice, c->stream));
+    PPTrajArgs a;
+    a.L = limits_of(lim); a.results = c->d_results.p; a.paths = c->d_paths.p; a.path_cap = pc; a.queries = c->d_queries.p;
+    a.frames = c->d_wframes.p; a.vel_init = c->d_vel_in.p; a.vcap = max_velocity_curr ? c->d_vel_in.p + n : nullptr;
+    a.stop = stop_at_goal ? c->d_traj_int.p : nullptr; a.n = n; a.traj = c->d_traj.p; a.tmp = c->d_traj_tmp.p;
+    a.n_samples = c->d_traj_int.p + n; a.feasible = c->d_traj_int.p + 2 * (size_t)n;
+    int blocks = std::min((n + 3) / 4, 16 * c->sm_count);
+    PP_CUDA(cudaEventRecord(c->ev0, c->stream));
+    pp_trajectory_kernel<<<blocks, 128, 0, c->stream>>>(a);
+    c->launches += 1;
+    PP_CUDA(cudaGetLastError());
+    PP_CUDA(cudaEventRecord(c->ev1, c->stream));
+    PP_CUDA(cudaMemcpyAsync(traj, c->d_traj.p, sizeof(float) * (size_t)n * 4 * pc, cudaMemcpyDeviceToHost, c->stream));
+    PP_CUDA(cudaMemcpyAsync(n_samples, a.n_samples, sizeof(int) * n, cudaMemcpyDeviceToHost, c->stream));
+    PP_CUDA(cudaMemcpyAsync(feasible, a.feasible, sizeof(int) * n, cudaMemcpyDeviceToHost, c->stream));
+    PP_CUDA(cudaStreamSynchronize(c->stream));
+    if (kernel_ms) PP_CUDA(cudaEventElapsedTime(kernel_ms, c->ev0, c->ev1));
+    return PP_SUCCESS;
 }
 
 static int lazy_run(pp_context* c, int g, const int* ij, int n, float* out, int restart)

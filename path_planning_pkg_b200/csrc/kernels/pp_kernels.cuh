@@ -7,6 +7,8 @@
 //   pp_apf_kernel           one warp per pose, order-preserving warp sum
 //   pp_collision_kernel     one thread per point (the reference's check is a single-cell lookup, F3)
 //   pp_footprint_kernel     one warp per pose: footprint window staged in shared memory, lanes = footprint cells, ballot
+//   pp_velocity_profile_kernel  one thread per path: the three sequential v^2 passes of VelocityGenerator
+//   pp_trajectory_kernel    one warp per query of the last batch: world transform (lanes = points) + profile + message layout
 //   pp_dubins_length_kernel 4 lanes per state (one per CSC candidate), FP64-evaluated/rounded ("pinned libm")
 //   pp_dubins_path_kernel   one warp: plan + parallel sampling
 //   pp_lazy_astar_kernel    one control lane: the lazy cached 2D A* on a fresh cache (parity tests)
@@ -25,6 +27,7 @@ __device__ unsigned long long pp_prof_acc[8];
 #include "../core/pp_kpop.h"
 #include "../core/pp_map.h"
 #include "../core/pp_footprint.h"
+#include "../core/pp_velocity.h"
 
 #define PP_SEARCH_WARPS 4
 #ifndef PP_SEARCH_MIN_BLOCKS
@@ -508,6 +511,65 @@ __global__ void __launch_bounds__(PP_FOOT_WARPS * 32) pp_footprint_kernel(const 
             if (a.cells) { a.cells[2 * (size_t)k] = ci; a.cells[2 * (size_t)k + 1] = cj; }
             if (a.hits) a.hits[k] = my_hits;
         }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// velocity profile / trajectory (core/pp_velocity.h)
+static_assert(sizeof(PPTrajPt) == sizeof(PPPathPt), "PPTrajPt mirrors PPPathPt");
+
+// VelocityGenerator::generate_velocity_profile for n independent paths, one thread each (the passes are sequential scans).
+// paths_xy [n][cap][2] and curvature [n][cap] in the reference's order (goal -> start); flags bit 0 = coast_to_goal, bit 1 =
+// stop_at_goal; velocity [n][cap] out, v2 [n][cap] scratch.
+__global__ void __launch_bounds__(128) pp_velocity_profile_kernel(PPVelLimits L, const float* paths_xy, const float* curvature,
+                                                                   const int* counts, int n, int cap, const float* vel_init,
+                                                                   const float* vcap, const int* flags, float* velocity, float* v2,
+                                                                   int* feasible)
+{
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    int m = counts[k];
+    if (m < 1) { feasible[k] = 0; return; }
+    if (m > cap) m = cap;
+    const float* xy = paths_xy + (size_t)k * cap * 2;
+    int fl = flags ? flags[k] : 0;
+    bool ok = pp_velocity_profile(L, vel_init[k], vcap ? vcap[k] : FLT_MAX, xy, xy + 1, 2, curvature + (size_t)k * cap, 1, m,
+                                  v2 + (size_t)k * cap, velocity + (size_t)k * cap, (fl & 1) != 0, (fl & 2) != 0);
+    feasible[k] = ok ? 1 : 0;
+}
+
+struct PPTrajArgs
+{
+    PPVelLimits         L;
+    const PPResult*     results;
+    const PPPathPt*     paths;      int path_cap;
+    const PPQuery*      queries;
+    const PPWorldFrame* frames;     // per group
+    const float*        vel_init;   // per query
+    const float*        vcap;       // per query or nullptr (no cap)
+    const int*          stop;       // per query or nullptr
+    int                 n;
+    float*              traj;       // [n][4 * path_cap]
+    float*              tmp;        // [n][2 * path_cap]
+    int*                n_samples;
+    int*                feasible;
+};
+
+__global__ void __launch_bounds__(128) pp_trajectory_kernel(const __grid_constant__ PPTrajArgs a)
+{
+    PPWarpDev w;
+    const int warps = blockDim.x >> 5;
+    for (int q = blockIdx.x * warps + (threadIdx.x >> 5); q < a.n; q += gridDim.x * warps)
+    {
+        const PPResult r = a.results[q];
+        int n = 0;
+        if (r.success)
+            n = pp_trajectory_assemble(w, a.frames[a.queries[q].group], a.L, reinterpret_cast<const PPTrajPt*>(a.paths + (size_t)q * a.path_cap),
+                                       r.n_dubins, r.n_chain, a.path_cap, a.vel_init[q], a.vcap ? a.vcap[q] : FLT_MAX,
+                                       a.stop ? a.stop[q] != 0 : false, a.traj + (size_t)q * 4 * a.path_cap,
+                                       a.tmp + (size_t)q * 2 * a.path_cap, a.tmp + (size_t)q * 2 * a.path_cap + a.path_cap, a.feasible + q);
+        else if (w.lane() == 0) a.feasible[q] = 0;
+        if (w.lane() == 0) a.n_samples[q] = n;
     }
 }
 

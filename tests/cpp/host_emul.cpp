@@ -14,6 +14,7 @@
 #include "../../path_planning_pkg_b200/csrc/core/pp_search.h"
 #include "../../path_planning_pkg_b200/csrc/core/pp_kpop.h"
 #include "../../path_planning_pkg_b200/csrc/core/pp_map.h"
+#include "../../path_planning_pkg_b200/csrc/core/pp_velocity.h"
 #include "../../path_planning_pkg_b200/csrc/host/pp_host.h"
 #include "../../path_planning_pkg_b200/csrc/host/pp_footprint_host.h"
 #include "../../oracle/oracle_api.h"
@@ -39,6 +40,7 @@ namespace
         std::vector<int> bin_off, bin_idx; int bin_n = 0;
         PPLazy lazy;               // persistent lazy-A* state for emu_astar_lazy_batch
         bool lazy_init = false;
+        PPResult last; float last_vel = 0.0f; bool have_last = false;   // the last emu_find_path, for emu_trajectory
         bool hist_on = false;      // planner-object history (pp_set_history): cell_state / nm_g / nm_f carried between queries
         unsigned hist_sid = 0;
     };
@@ -321,6 +323,40 @@ int emu_dubins_path(void* h, const float* s, const float* g, float* xyh, float* 
     return total;
 }
 
+// velocity profile / trajectory: the PP_HD code the kernels run, on one host lane
+void emu_velocity_profile_batch(const float* lim5, const float* paths_xy, const float* curv, const int* counts, int n, int cap,
+                                const float* vel_init, const float* vcap, const int* flags, float* velocity, int* feasible)
+{
+    PPVelLimits L; L.max_velocity = lim5[0]; L.coast_velocity = lim5[1]; L.max_lat_acc = lim5[2]; L.max_long_acc = lim5[3]; L.max_long_dec = lim5[4];
+    std::vector<float> v2(cap);
+    for (int k = 0; k < n; k++)
+    {
+        int m = std::min(counts[k], cap);
+        if (m < 1) { feasible[k] = 0; continue; }
+        const float* xy = paths_xy + (size_t)k * cap * 2;
+        int fl = flags ? flags[k] : 0;
+        feasible[k] = pp_velocity_profile(L, vel_init[k], vcap ? vcap[k] : FLT_MAX, xy, xy + 1, 2, curv + (size_t)k * cap, 1, m, v2.data(),
+                                          velocity + (size_t)k * cap, (fl & 1) != 0, (fl & 2) != 0) ? 1 : 0;
+    }
+}
+
+// trajectory of the last emu_find_path (= pp_trajectory_batch for that query); traj has room for 4 * 4096 floats
+int emu_trajectory(void* h, const float* lim5, float vcap, int stop, float* traj, int* feasible)
+{
+    Emu* e = static_cast<Emu*>(h);
+    if (!e->have_last || !e->last.success) { *feasible = 0; return 0; }
+    PPVelLimits L; L.max_velocity = lim5[0]; L.coast_velocity = lim5[1]; L.max_lat_acc = lim5[2]; L.max_long_acc = lim5[3]; L.max_long_dec = lim5[4];
+    PPWorldFrame F;
+    F.goal_gx = e->fr.F.goal_x; F.goal_gy = e->fr.F.goal_y; F.goal_wx = e->fr.goal_world[0]; F.goal_wy = e->fr.goal_world[1];
+    F.angle = -e->fr.grid_heading; F.c = std::cos(F.angle); F.s = std::sin(F.angle);
+    const int cap = (int)e->path.size();
+    std::vector<float> tmp(2 * (size_t)cap);
+    PPWarpSerial w;
+    static_assert(sizeof(PPTrajPt) == sizeof(PPPathPt), "PPTrajPt mirrors PPPathPt");
+    return pp_trajectory_assemble(w, F, L, reinterpret_cast<const PPTrajPt*>(e->path.data()), e->last.n_dubins, e->last.n_chain, cap,
+                                  e->last_vel, vcap, stop != 0, traj, tmp.data(), tmp.data() + cap, feasible);
+}
+
 // generic footprint check: the product's table builder (host/pp_footprint_host.h) and the predicates the kernel executes
 int emu_footprint_table(void* h, int bin, float length, float width, float rear, short* offs_ij, int cap)
 {
@@ -399,6 +435,7 @@ void emu_find_path(void* h, float vel, const float* s, orc_result* res, float* p
     wk.lazy_sid = e->hist_on ? &e->hist_sid : nullptr;
     pp_search_exact(w, C, e->m.off_xy.data(), G, st, wk, sm, r);
     e->lazy_init = false;
+    e->last = r; e->last_vel = vel; e->have_last = true;
     res->success = r.success; res->cost = r.cost; res->n_pops = r.n_pops; res->n_pops_bin_oob = r.n_pops_bin_oob;
     if (r.status) std::fprintf(stderr, "emu_find_path: status %d\n", r.status);
     // assemble in the reference's order (HybridAStar.cpp:208-262): reversed Dubins samples, then the chain

@@ -230,6 +230,22 @@ class Oracle:
                                     _fp(free), _fp(cells), _fp(hits))
         return free, cells, hits
 
+    # -- velocity profile / trajectory --------------------------------------------
+    def velocity_profile(self, lim5, vel_init, vcap, path_xyh, curvature, coast=False, stop=False):
+        """ref only: VelocityGenerator<float>::generate_velocity_profile on a path in find_path's order (goal -> start)."""
+        p = np.ascontiguousarray(path_xyh, np.float32); cv = np.ascontiguousarray(curvature, np.float32)
+        vel = np.zeros(len(cv), np.float32); lim = np.asarray(lim5, np.float32)
+        fn = self._fn("velocity_profile"); fn.restype = C.c_int
+        ok = fn(_fp(lim), C.c_float(vel_init), C.c_float(vcap), _fp(p), _fp(cv), C.c_int(len(cv)), C.c_int(int(coast)), C.c_int(int(stop)), _fp(vel))
+        return vel, bool(ok)
+
+    def trajectory(self, lim5, vcap, stop):
+        """emu only: the trajectory of the last find_path (= pp_trajectory_batch for that query): (4, m) array, feasible."""
+        traj = np.zeros(4 * 4096, np.float32); ok = C.c_int(); lim = np.asarray(lim5, np.float32)
+        fn = self._fn("trajectory"); fn.restype = C.c_int
+        m = fn(self.h, _fp(lim), C.c_float(vcap), C.c_int(int(stop)), _fp(traj), C.byref(ok))
+        return traj[:4 * m].reshape(4, m).copy(), bool(ok.value)
+
     # -- the search --------------------------------------------------------------------------
     def find_path(self, vel, start, pop_cap=1 << 20, path_cap=1 << 14):
         s = np.asarray(start, np.float32)
