@@ -320,3 +320,16 @@ def test_planner_object_history_stamp_wrap(emu_lib):
     for k in range(len(rb)):
         if rb[k]["n_pops_bin_oob"] == 0:
             assert _same_result(ra[k], rb[k]), k
+
+
+def test_rbtree_equals_libstdcxx_set_node_for_node(built):
+    """tests/cpp/rbtree_fuzz.cpp: 288 000 random insert / find / erase / pop-min operations under the reference's non-strict
+    comparator; std::set and the product's PPRbTree agree on every outcome and, after every operation, on shape, colours, keys
+    and costs of every node (the search's results depend on exactly that)."""
+    import subprocess
+    exe = os.path.join(orc.ROOT, "tests", "cpp", "bin", "rbtree_fuzz")
+    src = os.path.join(orc.ROOT, "tests", "cpp", "rbtree_fuzz.cpp")
+    r = subprocess.run(["g++", "-std=c++14", "-O1", "-ffp-contract=off", "-Wno-unknown-pragmas", "-o", exe, src], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    r = subprocess.run([exe, "48"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "trees identical after every operation" in r.stdout, r.stdout[-500:]
