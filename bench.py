@@ -547,6 +547,15 @@ def main():
                                     "sample": f"{len(idx)} of the {nq} queries, one reference planner per thread, scrubbed per query ({secs:.1f} s)",
                                     "queries_per_s": len(idx) / secs,
                                     "same_expansion_count_as_gpu": f"{same}/{len(idx)} (stock glibc libm vs pinned libm, see DESIGN.md)"}
+            # also the single-threaded reference as it ships (one planner, one core), on the 8 shortest queries
+            # of the same sample so that the side measurement stays bounded
+            try:
+                short = idx[np.argsort(cpops)[:8]]
+                s1, p1, _, _ = cpu_reference_run(groups, queries, qgroups, maps, short, 1)
+                line["cpu_baseline"]["one_core"] = {"value": float(p1.sum() / s1), "unit": "expansions/s", "queries_per_s": len(short) / s1,
+                                                    "sample": f"the {len(short)} shortest queries of the sample above ({s1:.1f} s)"}
+            except Exception as e:
+                line["cpu_baseline"]["one_core"] = {"error": str(e)}
         except Exception as e:  # the reference .so is test infrastructure; report rather than die
             line["cpu_baseline"] = {"error": str(e)}
     print(json.dumps(line), flush=True)
