@@ -112,6 +112,7 @@ struct pp_context
     DevBuf<float> d_foot_xyh; DevBuf<int> d_foot_out;
     // velocity profile / trajectory (pp_velocity_profile_batch, pp_trajectory_batch)
     std::vector<float> h_vel;             // vel_init of the uploaded queries
+    bool batch_done = false;              // pp_batch_run finished on the uploaded batch (results / path records valid)
     DevBuf<float> d_traj, d_traj_tmp, d_vel_in; DevBuf<int> d_traj_int; DevBuf<PPWorldFrame> d_wframes;
     // K-POP mode pools (per slot): node log, hash table, LSM queue arena + merge scratch
     struct KPools { int alloc_slots = 0, nodes_cap = 0, table_cap = 0, levels = 0; size_t arena_cap = 0, tmp_cap = 0;
@@ -945,7 +946,7 @@ int pp_batch_upload(pp_context* c, const pp_query* q, int n, const pp_search_opt
         c->h_queries[k].group = q[k].group;
         c->h_queries[k].pad = 0;
     }
-    c->n_queries = n;
+    c->n_queries = n; c->batch_done = false;
     // one EXACT-mode query on a group with history enabled continues on that planner's carried 2D cache
     c->batch_hist_group = (n == 1 && o.mode == PP_MODE_EXACT && (int)c->hist.size() > q[0].group && c->hist[q[0].group].on) ? q[0].group : -1;
     int hw_slots = 0;
@@ -1064,6 +1065,7 @@ int pp_batch_run(pp_context* c, float* kernel_ms)
     PP_CUDA(cudaEventRecord(c->ev1, c->stream));
     PP_CUDA(cudaStreamSynchronize(c->stream));
     if (kernel_ms) PP_CUDA(cudaEventElapsedTime(kernel_ms, c->ev0, c->ev1));
+    c->batch_done = true;
     return PP_SUCCESS;
 }
 
@@ -1164,7 +1166,8 @@ int pp_trajectory_batch(pp_context* c, const pp_velocity_limits* lim, const floa
                         int* n_samples, int* feasible, float* kernel_ms)
 {
     if (!c || !lim || !traj || !n_samples || !feasible) return pp_fail(PP_ERR_INVALID, "pp_trajectory_batch: bad arguments");
-    if (c->n_queries <= 0 || (int)c->h_vel.size() != c->n_queries) return pp_fail(PP_ERR_INVALID, "pp_trajectory_batch: run a batch first");
+    if (c->n_queries <= 0 || (int)c->h_vel.size() != c->n_queries || !c->batch_done)
+        return pp_fail(PP_ERR_INVALID, "pp_trajectory_batch: run a batch first (pp_find_path_batch or pp_batch_upload + pp_batch_run)");
     PP_CUDA(cudaSetDevice(c->device));
     const int n = c->n_queries, pc = c->opts.path_cap;
     // world frames of the groups: cos / sin of -grid_heading with the host libm, once per frame (pp_host_to_world does it per point)
