@@ -216,3 +216,21 @@ def test_fp32_dubins_restatement_close_to_reference():
     assert jumps <= n // 2000, jumps
     assert rel[rel <= 1e-5].max() < 1e-5
     print(f"fp32 restatement vs reference: max rel {rel[rel <= 1e-5].max():.3g}, flips {jumps}/{n}")
+
+
+@pytest.mark.skipif(not orc.have_ref(), reason="compiled reference not present")
+@pytest.mark.parametrize("seed", [0, 3])
+def test_port_session_on_one_object_equals_reference(seed):
+    """the restatement carries the 2D heuristic cache from query to query like one reference object does (11-query
+    session incl. a bare reset and a second waypoint whose update_goal relocates the non-empty map)."""
+    import scenarios as S
+    sc, ops = S.session_ops(seed, goal_changes=True)
+    P = orc.make_params(grid_size=sc["grid_size"], resolution=sc["resolution"])
+    a, b = orc.port(P), orc.ref(P)
+    ra, rb = S.run_session(a, ops), S.run_session(b, ops)
+    assert len(ra) == len(rb) == 11
+    for k, (x, y) in enumerate(zip(ra, rb)):
+        if y["n_pops_bin_oob"]:
+            continue
+        assert x["n_pops"] == y["n_pops"] and np.array_equal(x["pops"], y["pops"]), k
+        assert x["cost"] == y["cost"] and np.array_equal(x["path"].view(np.uint32), y["path"].view(np.uint32)), k
