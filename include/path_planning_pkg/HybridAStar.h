@@ -40,11 +40,16 @@ namespace planning
                               const T line_width);
         // whole-map decay towards "free" (reference lib/HybridAStar.cpp:43-46)
         void update_obstacles();
+        // drops the visited flags of the planner's 2D heuristic cache and, like the reference, keeps the node costs (reference
+        // lib/HybridAStar.cpp:49-52 -> lib/AStar.cpp:56-60; C ABI pp_reset on the carried cache, pp_set_history)
         void reset();
+        // new goal / grid heading, obstacles relocated into the new frame (reference lib/HybridAStar.cpp:55-59; pp_update_goal)
         void update_goal(const Vector3D<T>& goal, const Vector3D<T>& start);
         const std::vector<std::vector<T>>& get_obstacles() const;
         // {cost, success}; on success appends the path (goal -> start order, world frame) and its curvature; on failure
-        // returns {numeric_limits<T>::max(), false} and leaves the vectors untouched (reference lib/HybridAStar.cpp:68-88)
+        // returns {numeric_limits<T>::max(), false} and leaves the vectors untouched (reference lib/HybridAStar.cpp:68-88).
+        // Successive calls share the 2D heuristic cache exactly like successive calls on one reference object:
+        // whole sessions return the reference's results, not only the first query (PP_B200_HISTORY=0 turns that off).
         std::pair<T, bool> find_path(const T vel_init, const Vector3D<T>& start, std::vector<Vector3D<T>>& path,
                                      std::vector<T>& curvature);
 
