@@ -41,3 +41,23 @@ def test_reference_node_reproduces_golden(seed, built):
     assert ticks == GOLD[str(seed)]["ref_crm"]["ticks"]
     assert digest(pubs) == GOLD[str(seed)]["ref_crm"]["pubs"], "golden is stale: rerun tests/golden/make_replay_golden.py"
     assert "Velocity Generator: Failed" not in log
+
+
+def test_product_node_fails_loudly_without_a_gpu(tmp_path):
+    """The same node on libpath_planning_b200.so has no CPU path: on a machine without a CUDA device the planner's
+    constructor aborts with the C ABI's error text instead of computing anything on the host."""
+    import subprocess
+    try:
+        import torch
+        if torch.cuda.is_available():
+            pytest.skip("a GPU is present")
+    except ImportError:
+        pass
+    node = os.path.join(orc.ROOT, "tests", "cpp", "bin", "local_planner_b200")
+    if not os.path.exists(node):
+        pytest.skip("local_planner_b200 is built from /root/reference/src/local_planner.cpp, absent here")
+    script = tmp_path / "script.txt"
+    script.write_text(R.make_script(0))
+    r = subprocess.run([node], capture_output=True, text=True, env=dict(os.environ, PP_REPLAY_SCRIPT=str(script), PP_REPLAY_OUT=str(tmp_path / "out.txt")))
+    assert r.returncode != 0 and "no CUDA device" in r.stderr and "no CPU path" in r.stderr
+    assert not (tmp_path / "out.txt").exists() or "pub" not in (tmp_path / "out.txt").read_text()
