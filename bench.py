@@ -250,8 +250,13 @@ def main():
     ap.add_argument("--starts", type=int, default=64)
     ap.add_argument("--cpu-sample", type=int, default=64, help="queries in the cpu_baseline sample")
     ap.add_argument("--max-slots", type=int, default=0)
-    ap.add_argument("--max-expansions", type=int, default=1 << 17)
-    ap.add_argument("--max-open", type=int, default=1 << 16)
+    # EXACT-mode pools sized so that no query of the C4 batch is re-run: with the library defaults (131 072 expansions, 8x
+    # escalation) the batch's longest query (1.32 M expansions) is executed three times -- aborted at 131 k and at 1.05 M, then
+    # completed -- and those passes are sequential.  157 MB per slot, 512 slots = 80 GB.
+    ap.add_argument("--max-expansions", type=int, default=1 << 21)
+    ap.add_argument("--max-open", type=int, default=1 << 19)
+    ap.add_argument("--max-open2d", type=int, default=1 << 16)
+    ap.add_argument("--exact-slots", type=int, default=512, help="resident EXACT-mode query slots (0 = auto); --max-slots overrides")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=1, help="timed end-to-end steps (each is a full batch)")
     ap.add_argument("--no-kpop", action="store_true", help="skip the additional K-POP(32) throughput measurement")
@@ -343,7 +348,17 @@ def main():
 
     q = ctx.make_queries(queries, qgroups)
     nq = len(q)
-    opts = ctx.make_opts(max_expansions=args.max_expansions, max_open=args.max_open, path_cap=2048, max_slots=args.max_slots)
+    exact_slots = args.max_slots if args.max_slots > 0 else args.exact_slots
+    opts = ctx.make_opts(max_expansions=args.max_expansions, max_open=args.max_open, max_open2d=args.max_open2d, path_cap=2048,
+                         max_slots=exact_slots)
+    pool_note = "sized for the batch's longest query: no query is re-run"
+    try:
+        ctx.batch_upload(q, opts)
+    except pp.PPError as e:      # e.g. not enough free memory on this device: the library defaults (small pools, automatic 8x retries)
+        pool_note = f"library defaults after the sized pools could not be set up ({e})"
+        args.max_expansions, args.max_open, args.max_open2d = 1 << 17, 1 << 16, 1 << 14
+        opts = ctx.make_opts(max_expansions=args.max_expansions, max_open=args.max_open, max_open2d=args.max_open2d, path_cap=2048,
+                             max_slots=args.max_slots)
     launches0 = ctx.kernel_launches()
 
     def barrier():
@@ -365,6 +380,7 @@ def main():
     barrier()
     clocks = sampler.finish()
     timed_launches = ctx.kernel_launches() - launches1
+    retried_exact = ctx.batch_retried()
     res, _, _ = ctx.batch_fetch()
     pops = int(res["n_pops"].sum())
     total_ms = float(np.sum(kernel_ms))
@@ -488,7 +504,8 @@ def main():
     lat = []
     for k in range(min(16, nq)):
         t1 = time.perf_counter()
-        ctx.find_path_batch(q[k:k + 1], ctx.make_opts(max_expansions=args.max_expansions, max_open=args.max_open, path_cap=pc, max_slots=1))
+        ctx.find_path_batch(q[k:k + 1], ctx.make_opts(max_expansions=args.max_expansions, max_open=args.max_open,
+                                                      max_open2d=args.max_open2d, path_cap=pc, max_slots=1))
         lat.append((time.perf_counter() - t1) * 1e3)
 
     if rank != 0:
@@ -509,6 +526,8 @@ def main():
         "success_rate": float(res["success"].mean()), "capacity_flags": int((res["status"] != 0).sum()),
         "expansions_bin_oob": int(res["n_pops_bin_oob"].sum()),
         "config": {"workload": workload, "slots": int(opts.max_slots) or "auto",
+                   "pools": {"max_expansions": int(opts.max_expansions), "max_open": int(opts.max_open), "max_open2d": int(opts.max_open2d),
+                             "note": pool_note, "retried_queries": int(retried_exact)},
                    "per_rank_batch": "identical on every rank (same seeds): the step is bound by the batch's single longest query",
                    "l2": "per-query scratch (open/closed sets, lazy-A* cache) is tens of GB per step, far larger than the 126 MB L2",
                    "map_build_s": map_build_s, "map_broadcast_ms": map_bcast_ms},
