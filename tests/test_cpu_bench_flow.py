@@ -1,0 +1,118 @@
+"""Dry run of bench.py's whole default flow on the CPU against a stub device context: every branch of main() -- EXACT timing,
+end-to-end pass, K-POP blocks, single-query latencies, footprint side block, reference baseline (the real compiled reference on a
+tiny sample) and the JSON line with every key the bench contract names -- executes without a GPU, so that an edit of bench.py
+cannot break the round-end measurement with a NameError / TypeError.  The numbers the stub returns are meaningless; only the
+control flow and the shape of the JSON line are checked here."""
+import ctypes as C
+import json
+import sys
+import types
+
+import numpy as np
+import pytest
+
+import orc
+
+pytestmark = pytest.mark.skipif(not orc.have_ref(), reason="needs the compiled reference for the cpu_baseline leg")
+
+
+def _fake_pp(real):
+    RESULT_DT = real._cabi.RESULT_DT
+
+    class FakeLib:
+        def __init__(self, ctx):
+            self.ctx = ctx
+
+        def pp_find_path_batch(self, h, q, n, opts, res, paths, curv, trace):
+            r = self.ctx._results(n.value)
+            C.memmove(res.value, r.ctypes.data, r.nbytes)
+            return 0
+
+        def pp_last_error(self):
+            return b""
+
+    class FakeContext:
+        make_queries = staticmethod(real.Context.make_queries)
+        make_opts = staticmethod(real.Context.make_opts)
+
+        def __init__(self, params, num_groups=1, device=0):
+            self.N, self.h, self.lib, self._n, self.launches = params.grid_size, C.c_void_p(1), FakeLib(self), 0, 0
+
+        def _results(self, n):
+            r = np.zeros(n, RESULT_DT)
+            r["success"] = 1; r["cost"] = 10.0; r["n_pops"] = 100 + np.arange(n) % 7; r["n_path"] = 4
+            return r
+
+        def consts(self):
+            return types.SimpleNamespace(log_threshold=0.85)
+
+        def update_goal(self, *a, **k): pass
+        def update_boxes(self, *a, **k): pass
+        def decay(self, *a, **k): pass
+        def sync(self): pass
+        def set_footprint(self, *a): pass
+        def map_device_ptr(self, g=0): return 0
+        def kernel_launches(self): self.launches += 1; return self.launches
+        def batch_retried(self): return 0
+        def get_map(self, g=0): return np.zeros((self.N, self.N), np.float32)
+
+        def set_start(self, q):
+            return {"ci": np.full(len(q), 10, np.int32), "cj": np.full(len(q), 10, np.int32)}
+
+        def batch_upload(self, q, opts=None): self._n = len(q)
+        def batch_run(self): return 1.5
+
+        def batch_fetch(self, want_paths=False):
+            return self._results(self._n), None, None
+
+        def find_path_batch(self, q, opts=None, want_paths=True):
+            return self._results(len(q)), None, None, None
+
+        def footprint(self, xyh, group=0, want_ms=False):
+            n = len(xyh)
+            out = (np.ones(n, np.int32), np.zeros((n, 2), np.int32), np.zeros(n, np.int32))
+            return out + (0.3,) if want_ms else out
+
+        def footprint_table(self, b):
+            return np.zeros((200, 2), np.int16)
+
+    fake = types.ModuleType("path_planning_pkg_b200")
+    fake.Context, fake.PPError, fake.make_params, fake._cabi = FakeContext, real.PPError, real.make_params, real._cabi
+    return fake
+
+
+def test_default_bench_flow_prints_a_complete_line(monkeypatch, capsys):
+    import torch
+    import path_planning_pkg_b200 as real
+    import bench
+
+    class Ev:
+        def __init__(self, enable_timing=True): pass
+        def record(self): pass
+        def elapsed_time(self, other): return 1.0
+
+    real_tensor = torch.tensor
+    monkeypatch.setattr(torch.cuda, "set_device", lambda d: None)
+    monkeypatch.setattr(torch.cuda, "synchronize", lambda *a: None)
+    monkeypatch.setattr(torch.cuda, "Event", Ev)
+    monkeypatch.setattr(torch, "tensor", lambda data, dtype=None, device=None: real_tensor(data, dtype=dtype))
+    monkeypatch.setattr(torch.Tensor, "pin_memory", lambda self: self)
+    monkeypatch.setitem(sys.modules, "path_planning_pkg_b200", _fake_pp(real))
+    monkeypatch.setattr(sys, "argv", ["bench.py", "--groups", "2", "--starts", "4", "--steps", "1", "--warmup", "0", "--cpu-sample", "4",
+                                      "--large-starts", "8"])
+    for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE"):
+        monkeypatch.delenv(k, raising=False)
+    bench.main()
+    out = [l for l in capsys.readouterr().out.split("\n") if l.startswith("{")]
+    assert len(out) == 1
+    line = json.loads(out[0])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+                "dtype", "data", "config", "e2e", "gpu_launches", "roofline", "cpu_baseline", "clocks", "kpop", "footprint_kernel",
+                "p50_single_query_ms"):
+        assert key in line, key
+    assert line["config"]["pools"]["max_expansions"] == 1 << 21 and line["config"]["pools"]["retried_queries"] == 0
+    assert set(line["roofline"]) >= {"bound", "achieved", "peak", "unit", "frac", "traffic"}
+    assert set(line["e2e"]) >= {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"}
+    assert "error" not in line["footprint_kernel"] and "error" not in line["cpu_baseline"], line["cpu_baseline"]
+    assert line["cpu_baseline"]["kind"] == "reference" and "one_core" in line["cpu_baseline"] and "error" not in line["cpu_baseline"]["one_core"]
+    assert "c5_batch" in line["kpop"]
