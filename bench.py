@@ -250,13 +250,15 @@ def main():
     ap.add_argument("--starts", type=int, default=64)
     ap.add_argument("--cpu-sample", type=int, default=64, help="queries in the cpu_baseline sample")
     ap.add_argument("--max-slots", type=int, default=0)
-    # EXACT-mode pools sized so that no query of the C4 batch is re-run: with the library defaults (131 072 expansions, 8x
-    # escalation) the batch's longest query (1.32 M expansions) is executed three times -- aborted at 131 k and at 1.05 M, then
-    # completed -- and those passes are sequential.  157 MB per slot, 512 slots = 80 GB.
-    ap.add_argument("--max-expansions", type=int, default=1 << 21)
-    ap.add_argument("--max-open", type=int, default=1 << 19)
-    ap.add_argument("--max-open2d", type=int, default=1 << 16)
-    ap.add_argument("--exact-slots", type=int, default=512, help="resident EXACT-mode query slots (0 = auto); --max-slots overrides")
+    # EXACT-mode pools: the library defaults (131 072 closed states per query, automatic re-run of the queries that need more in 8x
+    # larger pools).  Measured structure of a step (profiles/r1_bench_search_launches.csv): the main launch on 2 368 slots = 11.4 s,
+    # then the retry launch of the 116 long queries = 28.1 s, bounded by the batch's longest query.  Larger first-pass pools
+    # (--max-expansions 1048576 --max-open 524288 --max-open2d 65536 --exact-slots N) avoid the re-run but leave room for fewer
+    # resident queries; which side wins has to be measured (DESIGN.md sections 7 and 13).
+    ap.add_argument("--max-expansions", type=int, default=1 << 17)
+    ap.add_argument("--max-open", type=int, default=1 << 16)
+    ap.add_argument("--max-open2d", type=int, default=1 << 14)
+    ap.add_argument("--exact-slots", type=int, default=0, help="resident EXACT-mode query slots (0 = auto); --max-slots overrides")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=1, help="timed end-to-end steps (each is a full batch)")
     ap.add_argument("--no-kpop", action="store_true", help="skip the additional K-POP(32) throughput measurement")
@@ -351,7 +353,7 @@ def main():
     exact_slots = args.max_slots if args.max_slots > 0 else args.exact_slots
     opts = ctx.make_opts(max_expansions=args.max_expansions, max_open=args.max_open, max_open2d=args.max_open2d, path_cap=2048,
                          max_slots=exact_slots)
-    pool_note = "sized for the batch's longest query: no query is re-run"
+    pool_note = "library defaults" if args.max_expansions == 1 << 17 else "caller-sized pools"
     try:
         ctx.batch_upload(q, opts)
     except pp.PPError as e:      # e.g. not enough free memory on this device: the library defaults (small pools, automatic 8x retries)

@@ -110,7 +110,7 @@ def test_default_bench_flow_prints_a_complete_line(monkeypatch, capsys):
                 "dtype", "data", "config", "e2e", "gpu_launches", "roofline", "cpu_baseline", "clocks", "kpop", "footprint_kernel",
                 "p50_single_query_ms"):
         assert key in line, key
-    assert line["config"]["pools"]["max_expansions"] == 1 << 21 and line["config"]["pools"]["retried_queries"] == 0
+    assert line["config"]["pools"]["max_expansions"] == 1 << 17 and line["config"]["pools"]["retried_queries"] == 0
     assert set(line["roofline"]) >= {"bound", "achieved", "peak", "unit", "frac", "traffic"}
     assert set(line["e2e"]) >= {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"}
     assert "error" not in line["footprint_kernel"] and "error" not in line["cpu_baseline"], line["cpu_baseline"]
