@@ -94,6 +94,35 @@ def main():
     ms = timed(ctx, lambda: ctx.dubins_length_fp32(starts, goal), 3)
     out.append(dict(kernel="pp_dubins_length_fp32_kernel (+H2D 12 B, D2H 4 B per state, pageable host memory)", config=f"{m} states",
                     ms=ms, states_per_s=m / (ms * 1e-3)))
+    # north_star (c): generic footprint collision kernel on this map (4.0 x 2.0 m rectangle), kernel time alone
+    try:
+        mfp = 1 << 20
+        L = a.n * sc["resolution"]
+        rs = np.random.RandomState(3)
+        fp = np.concatenate([rs.uniform(0.0, L, (mfp, 2)), rs.uniform(-np.pi, np.pi, (mfp, 1))], 1).astype(np.float32)
+        ctx.set_footprint(4.0, 2.0, 1.0)
+        ctx.footprint(fp)
+        fms = min(ctx.footprint(fp, want_ms=True)[3] for _ in range(5))
+        cells = float(np.mean([len(ctx.footprint_table(b)) for b in range(72)]))
+        out.append(dict(kernel="pp_footprint_kernel", config=f"{mfp} poses, 4x2 m rectangle on {a.n}^2", ms=fms, poses_per_s=mfp / (fms * 1e-3),
+                        mean_cells_per_pose=cells, algorithmic_gbs=mfp * (cells * 4 + 24) / (fms * 1e-3) / 1e9, peak_gbs=peak,
+                        note="map reads are served by L1/L2 (DESIGN.md section 12)"))
+    except Exception as e:     # a side measurement of this script
+        out.append(dict(kernel="pp_footprint_kernel", error=str(e)))
+    # stateless velocity-profile kernel (one thread per path, 64-point paths), host buffers included
+    try:
+        npth, cap = 1 << 16, 64
+        rs = np.random.RandomState(4)
+        xy = np.cumsum(rs.uniform(0.1, 0.4, (npth, cap, 2)), 1).astype(np.float32)[:, ::-1].copy()
+        cv = np.abs(rs.uniform(-0.2, 0.2, (npth, cap))).astype(np.float32)
+        cnt = np.full(npth, cap, np.int32); vi = rs.uniform(0, 2, npth).astype(np.float32)
+        lim = [5.0, 1.0, 2.0, 1.0, 2.5]
+        ctx.velocity_profile_batch(lim, xy, cv, cnt, vi)
+        t = time.perf_counter(); ctx.velocity_profile_batch(lim, xy, cv, cnt, vi); vms = (time.perf_counter() - t) * 1e3
+        out.append(dict(kernel="pp_velocity_profile_kernel (+H2D / D2H, pageable host memory)", config=f"{npth} paths x {cap} points", ms=vms,
+                        paths_per_s=npth / (vms * 1e-3)))
+    except Exception as e:
+        out.append(dict(kernel="pp_velocity_profile_kernel", error=str(e)))
     if a.cpu:
         import orc
         o = orc.ref(orc.make_params(grid_size=a.n, resolution=sc["resolution"])) if orc.have_ref() else orc.port(orc.make_params(grid_size=a.n, resolution=sc["resolution"]))
