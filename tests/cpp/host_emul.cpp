@@ -107,9 +107,24 @@ void emu_destroy(void* h) { delete static_cast<Emu*>(h); }
 void emu_update_goal(void* h, const float* goal3, const float* start3)
 {
     Emu* e = static_cast<Emu*>(h);
-    // relocation of a non-zero map is exercised on the GPU path (pp_update_goal); the emulation only
-    // supports goal changes on an empty map
-    pp_host_update_goal(e->m.C, goal3, start3, e->fr);
+    const PPConsts& C = e->m.C;
+    PPHostFrame prev = e->fr;
+    pp_host_update_goal(C, goal3, start3, e->fr);
+    // relocate_obstacles exactly as pp_update_goal does it (pp_map_reloc_{fill,scatter,gather}_kernel): forward scatter of the
+    // source index, the largest source index (= last writer in raster order) wins, then gather
+    PPRelocDesc d;
+    pp_host_reloc_desc(C, e->fr.grid_heading, prev.grid_heading, e->fr.goal_world, prev.goal_world, d);
+    const int N = C.N;
+    std::vector<int> idx((size_t)N * N, -1);
+    for (int s = 0; s < N * N; s++)
+    {
+        int in, jn;
+        pp_reloc_target(d, s / N, s % N, in, jn);
+        if (in > -1 && in < N && jn > -1 && jn < N && idx[(size_t)in * N + jn] < s) idx[(size_t)in * N + jn] = s;
+    }
+    std::vector<float> moved((size_t)N * N);
+    for (int t = 0; t < N * N; t++) moved[t] = idx[t] >= 0 ? e->map[idx[t]] : 0.0f;
+    e->map.swap(moved);
 }
 
 // AStar::reset() on the carried cache = pp_reset with history enabled (pp_hist_reset_kernel)

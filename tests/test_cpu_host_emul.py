@@ -284,15 +284,16 @@ def test_planner_object_history_bitexact(emu_lib, seed):
     reset(), `_node_map` costs for ever, stale against map updates).  The product core with history enabled (pp_set_history;
     here the host-lane build of the same source) must return what the unmodified reference object returns for every query
     of a session, bit for bit -- and the session must be one where the history matters."""
-    sc, ops = S.session_ops(seed, goal_changes=False)      # the host emulation has no map relocation (GPU test covers it)
+    sc, ops = S.session_ops(seed, goal_changes=True)       # incl. a second waypoint: update_goal relocates the non-empty map
     P = orc.make_params(grid_size=sc["grid_size"], resolution=sc["resolution"])
     e, o, fresh = _emu(emu_lib, P), _pinned(P), _pinned(P)
     emu_lib.emu_set_history(e.h, C.c_int(1))
     ra, rb = S.run_session(e, ops), S.run_session(o, ops)
     rf = S.run_session(fresh, ops, fresh_each_query=lambda p: p.scrub())
-    assert len(ra) == len(rb) == 8
+    assert np.array_equal(_bits(e.get_map()), _bits(o.get_map()))            # relocation + all updates, bit for bit
+    assert len(ra) == len(rb) == 11
     usable = [k for k in range(len(rb)) if rb[k]["n_pops_bin_oob"] == 0]      # F7: undefined in the reference
-    assert len(usable) >= 6
+    assert len(usable) >= 8
     for k in usable:
         assert _same_result(ra[k], rb[k]), (k, ra[k]["n_pops"], rb[k]["n_pops"], ra[k]["cost"], rb[k]["cost"])
     # not vacuous: with a fresh cache per query the reference itself expands differently somewhere after the first query
