@@ -403,10 +403,27 @@ int ref_velocity_profile(const float* lim5, float vel_init, float max_velocity_c
 // queries: n x (x, y, heading, vel); group maps are applied by the caller through `maps` (n_groups x N*N),
 // goal/start frames through `frames` (n_groups x 6: goal3, start3) and APF lists rebuilt from `boxes`.
 // Returns wall seconds; fills per-query cost/success/pops.
-double ref_bench_queries(const orc_params* p, const float* frames6, const float* maps, const float* boxes,
-                         const float* conf, int n_boxes, float apf_added_radius, int n_groups,
-                         const float* queries4, const int* group_of, int n_queries, int n_threads,
-                         float* cost, int* success, int* pops)
+// Polynomial hash (mod 2^64) over the IEEE words of the returned path (x, y, heading per point) followed by its curvature:
+// h = sum_k (w_k + 1) * P^(k+1).  The per-query path identity the parity checks compare; tests/orc.py::path_hash computes the
+// same, vectorised, over the device's output.
+static unsigned long long path_hash(const std::vector<Vector3D<float>>& path, const std::vector<float>& c)
+{
+    const unsigned long long P = 1099511628211ull;
+    unsigned long long h = 0, pw = 1;
+    auto mix = [&](float v) { unsigned u; std::memcpy(&u, &v, 4); pw *= P; h += ((unsigned long long)u + 1ull) * pw; };
+    for (size_t k = 0; k < path.size(); k++) { mix(path[k]._x); mix(path[k]._y); mix(path[k]._heading); }
+    for (size_t k = 0; k < c.size(); k++) mix(c[k]);
+    return h;
+}
+
+// n_queries independent find_path calls on n_threads reference planners (one per thread, scrubbed per query).
+// Optional per-query outputs: cost, success, pops, pops in heading bin == num_angle_bins, path points,
+// path hash, seconds spent inside find_path.  Returns the wall-clock seconds of the whole batch.
+double ref_bench_queries_ex(const orc_params* p, const float* frames6, const float* maps, const float* boxes,
+                            const float* conf, int n_boxes, float apf_added_radius, int n_groups,
+                            const float* queries4, const int* group_of, int n_queries, int n_threads,
+                            float* cost, int* success, int* pops, int* pops_oob, int* n_path, unsigned long long* hash,
+                            double* busy_s)
 {
     std::atomic<int> next(0);
     auto worker = [&]()
@@ -441,11 +458,17 @@ double ref_bench_queries(const orc_params* p, const float* frames6, const float*
             g_trace.buf = nullptr; g_trace.cap = 0; g_trace.n = 0; g_trace.n_oob = 0;
             g_trace.bins = p->num_angle_bins; g_trace.active = true;
             const float* qq = queries4 + 4 * (size_t)q;
+            auto q0 = std::chrono::steady_clock::now();
             auto r = pl->find_path(qq[3], Vector3D<float>(qq[0], qq[1], qq[2]), path, c);
+            auto q1 = std::chrono::steady_clock::now();
             g_trace.active = false;
             if (cost) cost[q] = r.first;
             if (success) success[q] = r.second ? 1 : 0;
             if (pops) pops[q] = (int)g_trace.n;
+            if (pops_oob) pops_oob[q] = (int)g_trace.n_oob;
+            if (n_path) n_path[q] = (int)path.size();
+            if (hash) hash[q] = path_hash(path, c);
+            if (busy_s) busy_s[q] = std::chrono::duration<double>(q1 - q0).count();
         }
     };
     auto t0 = std::chrono::steady_clock::now();
@@ -454,6 +477,15 @@ double ref_bench_queries(const orc_params* p, const float* frames6, const float*
     for (auto& t : th) t.join();
     auto t1 = std::chrono::steady_clock::now();
     return std::chrono::duration<double>(t1 - t0).count();
+}
+
+double ref_bench_queries(const orc_params* p, const float* frames6, const float* maps, const float* boxes,
+                         const float* conf, int n_boxes, float apf_added_radius, int n_groups,
+                         const float* queries4, const int* group_of, int n_queries, int n_threads,
+                         float* cost, int* success, int* pops)
+{
+    return ref_bench_queries_ex(p, frames6, maps, boxes, conf, n_boxes, apf_added_radius, n_groups, queries4, group_of, n_queries,
+                                n_threads, cost, success, pops, nullptr, nullptr, nullptr, nullptr);
 }
 
 } // extern "C"

@@ -118,6 +118,19 @@ def build_host_emul(force=False, verbose=True):
     return target
 
 
+def build_gmath_check(force=False, verbose=True):
+    """g++ -> tests/cpp/bin/gmath_check (TEST ONLY): exhaustive check of csrc/core/pp_gmath.h against the installed libm.
+    -mfma so that fma() is the hardware instruction glibc's own __sinf_fma / __cosf_fma use; -fno-builtin keeps the libm calls calls."""
+    out_dir = os.path.join(ROOT, "tests", "cpp", "bin")
+    os.makedirs(out_dir, exist_ok=True)
+    cxx = os.environ.get("CXX", "g++")
+    drv = os.path.join(ROOT, "tests", "cpp", "gmath_check.cpp")
+    target = os.path.join(out_dir, "gmath_check")
+    if force or _newer(target, [drv, os.path.join(CSRC, "core", "pp_gmath.h"), os.path.join(CSRC, "core", "pp_defs.h")]):
+        _run([cxx, "-std=c++14", "-O2", "-ffp-contract=off", "-mfma", "-fno-builtin", drv, "-o", target, "-lpthread", "-lm"], verbose)
+    return target
+
+
 def build_cpp_tests(force=False, verbose=True, reference="/root/reference"):
     """g++ -> tests/cpp/bin/api_driver (C++ API test driver) and, when the reference tree is present,
     tests/cpp/bin/local_planner_b200 = the reference's UNMODIFIED src/local_planner.cpp compiled against this repo's
@@ -140,6 +153,7 @@ def build_cpp_tests(force=False, verbose=True, reference="/root/reference"):
     if force or _newer(target, _sources(CSRC, os.path.join(ROOT, "include")) + [drv]):
         _run([cxx, "-std=c++14", "-O1", "-DSTORE_GRID_AS_REFERENCE", "-I", inc, drv, "-o", target] + link, verbose)
     built.append(target)
+    built.append(build_gmath_check(force, verbose))
     lp = os.path.join(reference, "src", "local_planner.cpp")
     if os.path.exists(lp):
         target = os.path.join(out_dir, "local_planner_b200")
@@ -158,8 +172,20 @@ def build_oracle(verbose=True):
     subprocess.check_call(cmd, stdout=None if verbose else subprocess.DEVNULL)
 
 
+def build_cuda_pinned(force=False, verbose=True):
+    """lib/libpp_b200_pinned.so: the same library with the round-1 math policy (-DPP_MATH_PINNED: float transcendentals evaluated
+    in double and rounded once; equals oracle/_ref/libref_oracle_crm.so).  Loaded only through PP_B200_LIB (tests/test_gpu_pinned_variant.py)."""
+    target = os.path.join(LIB, "libpp_b200_pinned.so")
+    srcs = _sources(CSRC, os.path.join(ROOT, "include"))
+    if force or _newer(target, srcs):
+        nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+        _nvcc_link(nvcc, ["-DPP_MATH_PINNED"], target, verbose)
+    return target
+
+
 def build_all(force=False, verbose=True):
     build_cuda(force, verbose)
+    build_cuda_pinned(force, verbose)
     build_host(force, verbose)
     build_host_emul(force, verbose)
     build_cpp_tests(force, verbose)

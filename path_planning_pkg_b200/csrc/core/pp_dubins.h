@@ -18,8 +18,8 @@ struct PPDubinsCenters
     float grx, gry, glx, gly;   // goal right / left circle centres
 };
 
-// Dubins.cpp:23-34.  M = math policy (PPMathPinned: reference parity; PPMathFp32: K-POP mode)
-template <class M = PPMathPinned>
+// Dubins.cpp:23-34.  M = math policy (PPMathExact: reference parity, pp_math.h; PPMathFp32: K-POP mode)
+template <class M = PPMathExact>
 PP_HD void pp_dubins_centers(float r, float sx, float sy, float sh, float gx, float gy, float gh,
                              PPDubinsCenters& c)
 {
@@ -121,7 +121,7 @@ PP_HD float pp_dubins_acos_arg(float r, float csx, float csy, float cgx, float c
 
 // One candidate, all of it on the calling thread (stateless kernels, the Dubins shot).  Returns the path length
 // (NaN for RSL/LSR when the centres are closer than 2r).
-template <class M = PPMathPinned>
+template <class M = PPMathExact>
 PP_HD_NOINLINE_FN float pp_dubins_candidate(int type, float r, float sh, float gh,
                                          float csx, float csy, float cgx, float cgy, float p[4])
 {
@@ -138,7 +138,7 @@ PP_HD_NOINLINE_FN float pp_dubins_candidate(int type, float r, float sh, float g
 }
 
 // Sequential fold of the four candidates, Dubins.cpp:36-68.
-template <class M = PPMathPinned>
+template <class M = PPMathExact>
 PP_HD_NOINLINE_FN float pp_dubins_shortest(float r, float sx, float sy, float sh, float gx, float gy, float gh,
                                int& best_type, float best_p[4], PPDubinsCenters& c)
 {
@@ -172,7 +172,7 @@ struct PPDubinsPlan
     float curvature;            // 1 / r_min
 };
 
-template <class M = PPMathPinned>
+template <class M = PPMathExact>
 PP_HD_NOINLINE_FN void pp_dubins_plan(float r, float step, float ang_step, int type, const float p[4],
                           const PPDubinsCenters& c, PPDubinsPlan& pl)
 {
@@ -201,7 +201,7 @@ PP_HD_NOINLINE_FN void pp_dubins_plan(float r, float step, float ang_step, int t
 
 // Sample k of the plan.  `acc` is the float accumulator of the segment the sample lies on:
 // theta (arcs; p0 -/+ k*ang_step accumulated one step at a time) or dist (straight; k*step likewise).
-template <class M = PPMathPinned>
+template <class M = PPMathExact>
 PP_HD_NOINLINE_FN void pp_dubins_sample(const PPDubinsPlan& pl, float r, int k, float acc,
                             float& x, float& y, float& heading, float& curvature)
 {

@@ -3,31 +3,45 @@
 // (nvcc -fmad=false, g++ -ffp-contract=off): the reference is built for baseline x86-64, which has
 // no FMA, so every a*b+c below must round twice.
 //
-// Float transcendentals: the reference calls glibc's sinf/cosf/atan2f/acosf, which are not
-// correctly rounded and are libm-version dependent.  The device evaluates them in double and rounds
-// once to float ("pinned libm"); oracle/_ref/libref_oracle_crm.so is the reference
-// built against the same definition.
+// Float transcendentals: the reference calls glibc's sinf/cosf/atan2f/acosf, which are not correctly
+// rounded and are libm-version dependent.  Two policies:
+//   PPMathGlibc  (default)  pp_gmath.h: the algorithms of glibc 2.39 / x86-64 restated operation by operation;
+//                           bit-identical to the stock reference build on this image (oracle/_ref/libref_oracle.so)
+//   PPMathPinned (-DPP_MATH_PINNED builds lib/libpp_b200_pinned.so)  evaluate in double, round once to float:
+//                           libm-version independent; oracle/_ref/libref_oracle_crm.so is the reference built
+//                           against the same definition
 #ifndef PP_MATH_H
 #define PP_MATH_H
 
 #include "pp_defs.h"
+#include "pp_gmath.h"
 
 #define PP_PI    3.14159265358979323846   /* M_PI   */
 #define PP_PI_2  1.57079632679489661923   /* M_PI_2 */
 
-PP_HD_NOINLINE_FN float pp_sinf(float x) { return (float)sin((double)x); }
-PP_HD_NOINLINE_FN float pp_cosf(float x) { return (float)cos((double)x); }
-PP_HD_NOINLINE_FN float pp_atan2f(float y, float x) { return (float)atan2((double)y, (double)x); }
-PP_HD_NOINLINE_FN float pp_acosf(float x) { return (float)acos((double)x); }
+PP_HD_NOINLINE_FN float pp_pin_sinf(float x) { return (float)sin((double)x); }
+PP_HD_NOINLINE_FN float pp_pin_cosf(float x) { return (float)cos((double)x); }
+PP_HD_NOINLINE_FN float pp_pin_atan2f(float y, float x) { return (float)atan2((double)y, (double)x); }
+PP_HD_NOINLINE_FN float pp_pin_acosf(float x) { return (float)acos((double)x); }
 
-// math policy of the Dubins code (pp_dubins.h): the reference-parity flavour
 struct PPMathPinned
 {
-    PP_HD static float sin(float x) { return pp_sinf(x); }
-    PP_HD static float cos(float x) { return pp_cosf(x); }
-    PP_HD static float atan2(float y, float x) { return pp_atan2f(y, x); }
-    PP_HD static float acos(float x) { return pp_acosf(x); }
+    PP_HD static float sin(float x) { return pp_pin_sinf(x); }
+    PP_HD static float cos(float x) { return pp_pin_cosf(x); }
+    PP_HD static float atan2(float y, float x) { return pp_pin_atan2f(y, x); }
+    PP_HD static float acos(float x) { return pp_pin_acosf(x); }
 };
+
+// the policy of the reference-parity (EXACT) code paths
+#ifdef PP_MATH_PINNED
+typedef PPMathPinned PPMathExact;
+#else
+typedef PPMathGlibc PPMathExact;
+#endif
+PP_HD float pp_sinf(float x) { return PPMathExact::sin(x); }
+PP_HD float pp_cosf(float x) { return PPMathExact::cos(x); }
+PP_HD float pp_atan2f(float y, float x) { return PPMathExact::atan2(y, x); }
+PP_HD float pp_acosf(float x) { return PPMathExact::acos(x); }
 
 // glibc hypotf == (float)sqrt((double)x*x + (double)y*y) (checked on 2e8 random pairs)
 PP_HD float pp_hypotf(float x, float y)

@@ -18,5 +18,6 @@ def built():
     """Build (if stale) the native pieces the CPU tests need: host emulation + oracles."""
     from path_planning_pkg_b200 import build
     build.build_host_emul(verbose=False)
+    build.build_gmath_check(verbose=False)
     build.build_oracle(verbose=False)
     return True

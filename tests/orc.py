@@ -294,6 +294,53 @@ def port(params):
     return Oracle(_load(PORT_SO), "port", params)
 
 
+_HASH_P = np.uint64(1099511628211)
+
+
+def path_hash(path_xyh, curvature):
+    """Same polynomial hash as oracle/ref_driver.cpp::path_hash over one query's path (n x 3 float32) + curvature (n)."""
+    w = np.concatenate([np.ascontiguousarray(path_xyh, np.float32).reshape(-1).view(np.uint32),
+                        np.ascontiguousarray(curvature, np.float32).reshape(-1).view(np.uint32)]).astype(np.uint64)
+    if len(w) == 0:
+        return 0
+    with np.errstate(over="ignore"):
+        pw = np.cumprod(np.full(len(w), _HASH_P, np.uint64))
+        return int(np.sum((w + np.uint64(1)) * pw, dtype=np.uint64))
+
+
+def ref_batch(P, groups, queries, qgroups, maps, idx=None, n_threads=None, so=None):
+    """The unmodified reference on n_threads host threads (one HybridAStar<float> per thread, scrubbed per query) over
+    queries[idx]: `groups` = scenario dicts (goal, frame_start, boxes, conf), `maps` = their final maps.  Returns a dict of
+    per-query arrays (cost, success, pops, pops_oob, n_path, hash, busy_s) and the wall-clock seconds of the batch."""
+    lib = _load(so or REF_SO)
+    lib.ref_bench_queries_ex.restype = C.c_double
+    G = len(groups)
+    N = int(P.grid_size)
+    frames = np.zeros((G, 6), np.float32)
+    nb = len(groups[0]["boxes"])
+    boxes = np.zeros((G, nb, 4), np.float32); conf = np.zeros((G, nb), np.float32)
+    for g, sc in enumerate(groups):
+        frames[g, :3] = sc["goal"]; frames[g, 3:] = sc["frame_start"]
+        boxes[g] = sc["boxes"]; conf[g] = sc["conf"]
+    mp = np.ascontiguousarray(np.stack(maps), np.float32)
+    assert mp.shape == (G, N, N)
+    if idx is None:
+        idx = np.arange(len(queries))
+    q4 = np.ascontiguousarray(np.asarray(queries)[idx], np.float32)
+    go = np.ascontiguousarray(np.asarray(qgroups)[idx], np.int32)
+    n = len(q4)
+    out = dict(cost=np.zeros(n, np.float32), success=np.zeros(n, np.int32), pops=np.zeros(n, np.int32),
+               pops_oob=np.zeros(n, np.int32), n_path=np.zeros(n, np.int32), hash=np.zeros(n, np.uint64),
+               busy_s=np.zeros(n, np.float64))
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    secs = lib.ref_bench_queries_ex(C.byref(P), vp(frames), vp(mp), vp(boxes), vp(conf), C.c_int(nb), C.c_float(1.5), C.c_int(G),
+                                    vp(q4), vp(go), C.c_int(n), C.c_int(n_threads or (os.cpu_count() or 1)),
+                                    vp(out["cost"]), vp(out["success"]), vp(out["pops"]), vp(out["pops_oob"]), vp(out["n_path"]),
+                                    vp(out["hash"]), vp(out["busy_s"]))
+    out["secs"] = float(secs)
+    return out
+
+
 # ---- the reference's own scenario (utils/hybrid_astar/test_hybrid_astar.cpp:13-91) ---------------
 def ref_test_params():
     st = [float(np.float32(a) * np.float32(np.pi) / np.float32(180.0)) for a in (-30, -15, 0, 15, 30)]

@@ -29,8 +29,8 @@ def _emu(lib, P):
 
 
 def _pinned(P):
-    """Oracle with the device's float-transcendental definition: compiled reference (crm flavour) when present."""
-    return orc.crm(P) if orc.have_ref() else None
+    """Oracle with the device's float-transcendental definition: compiled reference (stock libm: the device restates glibc, pp_gmath.h) when present."""
+    return orc.ref(P) if orc.have_ref() else None
 
 
 def test_constants_tables_map(emu_lib):

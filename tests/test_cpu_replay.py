@@ -17,7 +17,7 @@ sys.path.insert(0, os.path.join(orc.ROOT, "tests", "golden"))
 from make_replay_golden import SEEDS, digest, run_node  # noqa: E402
 
 GOLD = json.load(open(os.path.join(orc.ROOT, "tests", "golden", "replay_ref.json")))
-REF_NODE = os.path.join(orc.ROOT, "oracle", "_ref", "local_planner_ref_crm")
+REF_NODE = os.path.join(orc.ROOT, "oracle", "_ref", "local_planner_ref")
 
 
 def test_scripts_are_reproducible():
@@ -28,7 +28,7 @@ def test_scripts_are_reproducible():
 def test_golden_covers_the_callers_paths():
     """Every tick after the first waypoint publishes one trajectory of (x, y, heading, velocity) rows."""
     for seed in SEEDS:
-        g = GOLD[str(seed)]["ref_crm"]
+        g = GOLD[str(seed)]["ref"]
         assert g["ticks"] == 18 and len(g["pubs"]) == 17
         assert [p["tick"] for p in g["pubs"]] == list(range(1, 18))
         assert all(p["topic"] == "/local_planner/trajectory" and p["n"] % 4 == 0 and p["n"] >= 8 for p in g["pubs"])
@@ -38,8 +38,8 @@ def test_golden_covers_the_callers_paths():
 @pytest.mark.parametrize("seed", SEEDS)
 def test_reference_node_reproduces_golden(seed, built):
     pubs, ticks, times, log = run_node(REF_NODE, R.make_script(seed))
-    assert ticks == GOLD[str(seed)]["ref_crm"]["ticks"]
-    assert digest(pubs) == GOLD[str(seed)]["ref_crm"]["pubs"], "golden is stale: rerun tests/golden/make_replay_golden.py"
+    assert ticks == GOLD[str(seed)]["ref"]["ticks"]
+    assert digest(pubs) == GOLD[str(seed)]["ref"]["pubs"], "golden is stale: rerun tests/golden/make_replay_golden.py"
     assert "Velocity Generator: Failed" not in log
 
 

@@ -77,7 +77,7 @@ def test_trajectory_equals_reference_pipeline(emu_lib, seed):
     """find_path -> velocity profile -> /local_planner/trajectory layout, device code vs the reference's classes."""
     sc = S.c1_scenario(seed)
     P = orc.make_params(grid_size=sc["grid_size"], resolution=sc["resolution"])
-    e, o = orc.Oracle(emu_lib, "emu", P), orc.crm(P)
+    e, o = orc.Oracle(emu_lib, "emu", P), orc.ref(P)
     for x in (e, o):
         S.build_map(x, sc)
     for vel, vcap, stop in [(3.0, FLT_MAX, False), (1.0, 2.5, True), (0.0, 4.0, True)]:

@@ -34,7 +34,7 @@ def test_hybrid_astar_float_matches_golden(output):
     gold = np.load(orc.ROOT + "/tests/golden/hybrid_astar_path.npy")
     assert pts.shape == gold.shape and np.allclose(pts, gold, rtol=2e-5, atol=2e-5)
     if orc.have_ref():
-        o = orc.crm(orc.ref_test_params())
+        o = orc.ref(orc.ref_test_params())
         orc.setup_ref_test_scenario(o)
         b = o.find_path(2.0, orc.REF_TEST_START)
         assert np.allclose(pts, b["path"][::-1], rtol=0, atol=5e-6)     # printed with 6 decimals

@@ -25,7 +25,7 @@ def test_empty_inputs_and_free_map():
     """n = 0 boxes / lines are no-ops (Grid2D.cpp:99-139, :142-194 loop zero times); a query on the empty map is the
     reference's, expansion by expansion."""
     P = orc.ref_test_params()
-    ctx, crm = _ctx(P), orc.crm(P)
+    ctx, crm = _ctx(P), orc.ref(P)
     for o in (ctx, crm):
         orc.setup_ref_test_scenario(o)
     empty4 = np.zeros((0, 4), np.float32); empty1 = np.zeros(0, np.float32)
@@ -53,7 +53,7 @@ def test_start_outside_grid_and_in_occupied_cell():
     cell is not rejected by the reference either.  Whatever the reference returns, the device returns."""
     sc = S.c1_scenario(3)
     P = orc.make_params(grid_size=sc["grid_size"], resolution=sc["resolution"])
-    ctx, crm = _ctx(P), orc.crm(P)
+    ctx, crm = _ctx(P), orc.ref(P)
     for o in (ctx, crm):
         S.build_map(o, sc)
     box = sc["boxes"][0]

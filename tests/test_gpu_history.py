@@ -27,7 +27,7 @@ def test_session_on_one_planner_object_bitexact(seed):
     """11 queries: 6 ticks without reset, a bare reset, a second waypoint (update_goal relocates the non-empty map, reset)."""
     sc, ops = S.session_ops(seed, goal_changes=True)
     P = orc.make_params(grid_size=sc["grid_size"], resolution=sc["resolution"])
-    ctx, crm, fresh = _ctx(P), orc.crm(P), orc.crm(P)
+    ctx, crm, fresh = _ctx(P), orc.ref(P), orc.ref(P)
     ctx.set_history(0, True)
     ra, rb = S.run_session(ctx, ops), S.run_session(crm, ops)
     rf = S.run_session(fresh, ops, fresh_each_query=lambda p: p.scrub())
@@ -45,7 +45,7 @@ def test_history_off_and_batches_use_a_fresh_cache():
     """Without pp_set_history, and for every batch of more than one query, each query sees the freshly constructed cache."""
     sc, ops = S.session_ops(0, goal_changes=False, n_ticks=3)
     P = orc.make_params(grid_size=sc["grid_size"], resolution=sc["resolution"])
-    ctx, fresh = _ctx(P), orc.crm(P)
+    ctx, fresh = _ctx(P), orc.ref(P)
     ra = S.run_session(ctx, ops)
     rf = S.run_session(fresh, ops, fresh_each_query=lambda p: p.scrub())
     for a, b in zip(ra, rf):
@@ -66,7 +66,7 @@ def test_capacity_retry_restarts_from_the_same_history():
     leave a trace in the carried cache."""
     sc, ops = S.session_ops(0, goal_changes=False, n_ticks=5)
     P = orc.make_params(grid_size=sc["grid_size"], resolution=sc["resolution"])
-    ctx, crm = _ctx(P), orc.crm(P)
+    ctx, crm = _ctx(P), orc.ref(P)
     ctx.set_history(0, True)
     rb = S.run_session(crm, ops)
     ra, retried = [], 0

@@ -1,12 +1,12 @@
 """GPU parity tests (run with `pytest -m gpu` on a B200): every call goes through the C ABI of
 libpp_b200.so and is compared with the compiled, unmodified reference (oracle/_ref).
 
-Oracle flavours (tests/orc.py):
-  ref = stock glibc float libm; crm = same objects with the float transcendentals of the device-executed
-  functions (Dubins.cpp, atan2f of Grid3D::get_field_intensity) pinned to correctly-rounded values.
-Bit-exact targets (map, indices, collision booleans, roll-out) are checked against BOTH flavours;
-APF / Dubins values bit-exactly against crm and within 1e-5 relative against ref; the expansion
-sequence and path bit-exactly against crm, with the match rate against ref reported.
+The oracle is `orc.ref`: the reference's own objects linked against the stock glibc of this image.  The device
+restates glibc's binary32 sinf / cosf / atan2f / acosf (csrc/core/pp_gmath.h, pinned exhaustively by
+tests/test_cpu_gmath.py), so EVERYTHING here is bit-exact against the stock build: map, indices, collision booleans,
+roll-out, APF and Dubins values, the expansion sequence, cost, path and curvature.  (`crm` below is an alias of the
+same stock oracle, kept so that the test bodies read as before; the pinned-libm flavour of round 1 is a build variant,
+tests/test_gpu_pinned_variant.py.)
 """
 import numpy as np
 import pytest
@@ -40,8 +40,9 @@ def _states_equal(a, b):
 @pytest.fixture(scope="module")
 def golden():
     P = orc.ref_test_params()
-    ctx, ref, crm = _ctx(P), orc.ref(P), orc.crm(P)
-    for o in (ctx, ref, crm):
+    ctx, ref = _ctx(P), orc.ref(P)
+    crm = ref
+    for o in (ctx, ref):
         orc.setup_ref_test_scenario(o)
     return P, ctx, ref, crm
 
@@ -142,11 +143,7 @@ def test_apf_values(golden):
     a = ctx.apf(xyh); b = crm.apf(xyh); r = ref.apf(xyh)
     assert (b > 0).sum() > 1000
     assert np.array_equal(_bits(a), _bits(b))
-    # vs stock glibc: atan2f there is off by up to 1 ulp and the (alpha - |angle|)/alpha weight amplifies it near
-    # the edge of the active cone, so the bound is absolute on the weight scale, not 1e-5 relative
-    err = np.abs(a - r)
-    assert (err <= 1e-4 * np.maximum(np.abs(r), 1.0)).all(), err.max()
-    print(f"apf vs glibc: {(a != r).mean() * 100:.2f}% of values differ, max abs err {err.max():.3g}")
+    assert np.array_equal(_bits(a), _bits(r))
 
 
 def test_dubins_length(golden):
@@ -159,12 +156,8 @@ def test_dubins_length(golden):
     b, bt, bp = crm.dubins_length(starts, goal)
     r, rt, rp = ref.dubins_length(starts, goal)
     assert np.array_equal(_bits(a), _bits(b)) and np.array_equal(at, bt) and np.array_equal(_bits(ap), _bits(bp))
-    # vs stock glibc: 1e-5 relative, except where an ulp flips one of the +-2pi corrections (a discontinuity of
-    # the reference formula itself, Dubins.cpp:196-204): those are counted, not hidden
-    rel = np.abs(a - r) / np.maximum(np.abs(r), 1e-6)
-    jumps = int((rel > 1e-5).sum())
-    print(f"dubins vs glibc: max rel (non-jump) {rel[rel <= 1e-5].max():.3g}, branch flips {jumps}/{n}")
-    assert jumps <= n // 2000
+    # north_star asks for 1e-5 relative; the glibc restatement gives the stock build's bits (NaN candidates included)
+    assert np.array_equal(_bits(a), _bits(r)) and np.array_equal(at, rt) and np.array_equal(_bits(ap), _bits(rp))
 
 
 def test_dubins_length_fp32(golden):
@@ -218,7 +211,7 @@ def test_lazy_astar_sequence(golden):
 def test_search_golden_sequence_and_path(golden):
     """utils/hybrid_astar/plot.py:47-51: cost 33.0305, 43 points; full expansion sequence vs the reference."""
     P, ctx, ref, crm = golden
-    crm.scrub(); ref.scrub()
+    ref.scrub()
     a = ctx.find_path(2.0, orc.REF_TEST_START)
     b = crm.find_path(2.0, orc.REF_TEST_START)
     assert a["success"] and a["status"] == 0
@@ -236,8 +229,9 @@ def test_search_golden_sequence_and_path(golden):
 def test_search_c1_exact(seed):
     sc = S.c1_scenario(seed)
     P = orc.make_params(grid_size=sc["grid_size"], resolution=sc["resolution"])
-    ctx, crm, ref = _ctx(P), orc.crm(P), orc.ref(P)
-    for o in (ctx, crm, ref):
+    ctx, ref = _ctx(P), orc.ref(P)
+    crm = ref
+    for o in (ctx, ref):
         S.build_map(o, sc)
     assert np.array_equal(_bits(ctx.get_map()), _bits(ref.get_map()))
     q = sc["queries"][0]
@@ -248,10 +242,10 @@ def test_search_c1_exact(seed):
     assert a["cost"] == b["cost"] and np.array_equal(_bits(a["path"]), _bits(b["path"]))
 
 
-def test_search_c1_100_seeds_report():
-    """seeds 0-99 (N=200, 0.2 m, 5 boxes, 4 rounds).  Every query must be identical to the pinned-libm
-    reference (expansion count, cost, path bits); the stock-glibc match rate, the pop counts and the single-query
-    latencies (reference on one host core vs one warp on the GPU, through the C ABI) are reported."""
+def test_search_c1_100_seeds_identical_to_stock_reference():
+    """seeds 0-99 (N=200, 0.2 m, 5 boxes, 4 rounds).  Every query whose reference run is defined (no pop in
+    heading bin 72) must be identical to the STOCK reference build: expansion count, cost bits, path and
+    curvature bits.  Single-query latencies (reference on one host core vs the GPU through the C ABI) are reported."""
     import json
     import os
     import time
@@ -259,7 +253,7 @@ def test_search_c1_100_seeds_report():
     scs = [S.c1_scenario(s) for s in seeds]
     P = orc.make_params(grid_size=scs[0]["grid_size"], resolution=scs[0]["resolution"])
     ctx = _ctx(P, groups=len(seeds))
-    crm, ref = orc.crm(P), orc.ref(P)
+    ref = orc.ref(P)
     queries = []
     for gi, sc in enumerate(scs):
         ctx.update_goal(sc["goal"], sc["frame_start"], group=gi)
@@ -270,16 +264,14 @@ def test_search_c1_100_seeds_report():
     q = ctx.make_queries(np.array(queries), list(range(len(seeds))))
     opts = ctx.make_opts(path_cap=2048)
     res, paths, curv, _ = ctx.find_path_batch(q, opts)
-    lat_gpu, lat_cpu, same_stock, undefined, pops = [], [], 0, 0, []
+    lat_gpu, lat_cpu, undefined, pops = [], [], 0, []
     for gi, sc in enumerate(scs):
         qq = sc["queries"][0]
-        for o in (crm, ref):
-            o.set_map(np.zeros((sc["grid_size"], sc["grid_size"]), np.float32))
-            S.build_map(o, sc)
+        ref.set_map(np.zeros((sc["grid_size"], sc["grid_size"]), np.float32))
+        S.build_map(ref, sc)
         assert np.array_equal(_bits(ctx.get_map(gi)), _bits(ref.get_map())), gi
-        crm.scrub(); ref.scrub()                       # reset() alone leaves stale heuristic state
-        b = crm.find_path(float(qq[3]), qq[:3])
-        t0 = time.perf_counter(); r0 = ref.find_path(float(qq[3]), qq[:3]); lat_cpu.append((time.perf_counter() - t0) * 1e3)
+        ref.scrub()                       # reset() alone leaves stale heuristic state
+        t0 = time.perf_counter(); b = ref.find_path(float(qq[3]), qq[:3]); lat_cpu.append((time.perf_counter() - t0) * 1e3)
         t0 = time.perf_counter(); ctx.find_path_batch(q[gi:gi + 1], ctx.make_opts(path_cap=2048, max_slots=1)); lat_gpu.append((time.perf_counter() - t0) * 1e3)
         r = res[gi]
         assert r["status"] == 0
@@ -290,47 +282,57 @@ def test_search_c1_100_seeds_report():
         assert np.float32(r["cost"]) == b["cost"]
         assert np.array_equal(_bits(paths[gi, :r["n_path"]]), _bits(b["path"]))
         assert np.array_equal(_bits(curv[gi, :r["n_path"]]), _bits(b["curvature"]))
-        same_stock += int(r0["n_pops"] == r["n_pops"] and np.float32(r0["cost"]) == np.float32(r["cost"]))
         pops.append(int(r["n_pops"]))
     rep = {"config": "C1: N=200, res 0.2, 5 boxes, 4 rounds, seeds 0-99, EXACT mode",
-           "identical_to_pinned_libm_reference": len(pops), "undefined_in_reference_bin72": undefined,
-           "identical_to_stock_glibc_reference": same_stock, "pops_p50": float(np.median(pops)), "pops_p95": float(np.percentile(pops, 95)),
+           "identical_to_stock_glibc_reference": len(pops), "undefined_in_reference_bin72": undefined,
+           "pops_p50": float(np.median(pops)), "pops_p95": float(np.percentile(pops, 95)),
            "gpu_single_query_ms": {"p50": float(np.median(lat_gpu)), "p95": float(np.percentile(lat_gpu, 95))},
            "cpu_reference_single_query_ms_1core": {"p50": float(np.median(lat_cpu)), "p95": float(np.percentile(lat_cpu, 95))}}
     print("C1 report:", json.dumps(rep))
     out = os.path.join(orc.ROOT, "gpurun_out")
     if os.path.isdir(out):
-        json.dump(rep, open(os.path.join(out, "r1_c1_report.json"), "w"))
-    assert len(pops) + undefined == 100 and len(pops) >= 90
+        json.dump(rep, open(os.path.join(out, "r2_c1_report.json"), "w"))
+    assert len(pops) + undefined == 100 and undefined <= 5
 
 
-def test_search_c4_batch_exact():
-    """C4 shape (512^2 x 72, 96 boxes): a batch over 2 groups x 6 starts, each compared with a scrubbed reference."""
-    groups = [S.c4_group(s, n_starts=6) for s in (0, 1)]
+def _c4_setup(seeds, n_starts):
+    """C4 groups on the device and in the reference: returns ctx, params, scenario dicts, queries, their groups, the maps."""
+    groups = [S.c4_group(s, n_starts=n_starts) for s in seeds]
     P = orc.make_params(grid_size=512, resolution=0.2)
     ctx = _ctx(P, groups=len(groups))
-    oracles = []
-    queries, qgroups = [], []
+    ref = orc.ref(P)
+    queries, qgroups, maps = [], [], []
     for gi, sc in enumerate(groups):
-        crm = orc.crm(P)
-        S.build_map(crm, sc)
+        ref.set_map(np.zeros((512, 512), np.float32))
+        S.build_map(ref, sc)
         ctx.update_goal(sc["goal"], sc["frame_start"], group=gi)
         for _ in range(sc["rounds"]):
             ctx.update_boxes(sc["boxes"], sc["conf"], S.APF_ADDED_RADIUS, group=gi)
             ctx.decay(group=gi)
-        m = crm.get_map()
+        m = ref.get_map()
         assert np.array_equal(_bits(ctx.get_map(gi)), _bits(m))
-        qs = S.select_starts(sc, m, crm.consts().log_threshold, crm.set_start)
-        queries += list(qs); qgroups += [gi] * len(qs)
-        oracles.append(crm)
-    q = ctx.make_queries(np.array(queries), qgroups)
+        qs = S.select_starts(sc, m, ref.consts().log_threshold, ref.set_start)
+        queries += list(qs); qgroups += [gi] * len(qs); maps.append(m)
+    return ctx, P, groups, np.array(queries, np.float32), np.array(qgroups, np.int32), maps
+
+
+def test_search_c4_batch_exact_sequences():
+    """C4 shape (512^2 x 72, 96 boxes): a batch over 2 groups x 6 starts; the full expansion SEQUENCE (every popped state with
+    its g and f), cost, path and curvature of every query against the stock reference, scrubbed per query."""
+    ctx, P, groups, queries, qgroups, maps = _c4_setup((0, 1), 6)
+    q = ctx.make_queries(queries, qgroups)
     opts = ctx.make_opts(trace_cap=1 << 17, path_cap=2048)
     res, paths, curv, trace = ctx.find_path_batch(q, opts)
+    ref = orc.ref(P)
     n_match = n_undefined = 0
+    cur = -1
     for k in range(len(q)):
-        o = oracles[qgroups[k]]
-        o.scrub()
-        b = o.find_path(float(q["vel"][k]), np.array([q["x"][k], q["y"][k], q["heading"][k]], np.float32))
+        if qgroups[k] != cur:
+            cur = int(qgroups[k])
+            ref.set_map(np.zeros((512, 512), np.float32))
+            S.build_map(ref, groups[cur])
+        ref.scrub()
+        b = ref.find_path(float(queries[k][3]), queries[k][:3])
         r = res[k]
         assert r["status"] == 0
         if b["n_pops_bin_oob"] > 0 or r["n_pops_bin_oob"] > 0:
@@ -346,6 +348,36 @@ def test_search_c4_batch_exact():
         assert np.array_equal(_bits(paths[k, :r["n_path"]]), _bits(b["path"]))
         assert np.array_equal(_bits(curv[k, :r["n_path"]]), _bits(b["curvature"]))
         n_match += 1
-    print(f"C4 batch: {n_match}/{len(q)} queries identical, {n_undefined} undefined in the reference (bin-72 UB), "
-          f"{int(res['n_pops'].sum())} expansions")
-    assert n_match >= len(q) // 2
+    print(f"C4 batch: {n_match}/{len(q)} queries identical to the stock reference, {n_undefined} undefined in the reference "
+          f"(bin-72 UB), {int(res['n_pops'].sum())} expansions")
+    assert n_match + n_undefined == len(q) and n_undefined <= 2
+
+
+def test_search_c4_first_256_queries_identical():
+    """full-set parity on the first 256 C4 queries (groups 0-3 x 64 starts).  Expansion count, cost bits,
+    path length and the hash of the path + curvature bits of every query against the stock reference (all host threads, one
+    planner per thread, scrubbed per query).  Queries in which the reference pops a state in heading bin 72 (undefined
+    behaviour) are excluded: their number is printed and bounded."""
+    ctx, P, groups, queries, qgroups, maps = _c4_setup((0, 1, 2, 3), 64)
+    assert len(queries) == 256
+    q = ctx.make_queries(queries, qgroups)
+    res, paths, curv, _ = ctx.find_path_batch(q, ctx.make_opts(path_cap=2048))
+    assert (res["status"] == 0).all()
+    b = orc.ref_batch(P, groups, queries, qgroups, maps)
+    excluded = (b["pops_oob"] > 0) | (res["n_pops_bin_oob"] > 0)
+    bad = []
+    for k in range(256):
+        if excluded[k]:
+            continue
+        r = res[k]
+        h = orc.path_hash(paths[k, :r["n_path"]], curv[k, :r["n_path"]]) if r["success"] else 0
+        same = (int(r["success"]) == int(b["success"][k]) and int(r["n_pops"]) == int(b["pops"][k])
+                and np.float32(r["cost"]).view(np.uint32) == b["cost"][k].view(np.uint32)
+                and int(r["n_path"]) == int(b["n_path"][k]) and h == int(b["hash"][k]))
+        if not same:
+            bad.append((k, int(r["n_pops"]), int(b["pops"][k]), float(r["cost"]), float(b["cost"][k])))
+    print(f"C4 first 256: {256 - int(excluded.sum()) - len(bad)} identical (count, cost bits, path hash), {int(excluded.sum())} excluded "
+          f"(bin-72 UB in the reference), {len(bad)} different; {int(res['n_pops'].sum())} expansions; reference "
+          f"{b['secs']:.1f} s on {__import__('os').cpu_count()} threads")
+    assert not bad, bad[:5]
+    assert excluded.sum() <= 16

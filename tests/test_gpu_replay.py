@@ -3,7 +3,7 @@ headers and libpath_planning_b200.so (tests/cpp/bin/local_planner_b200, built by
 reference tree exists) replays scripted sessions behind the in-process ROS stand-in (tests/ros_stubs).  Every trajectory it
 publishes -- path from HybridAStar<float>::find_path on the device (EXACT mode, planner-object history), velocity profile
 from VelocityGenerator, pedestrian cap from PedestrianHandler -- must equal, word for word, what the same node publishes on
-the unmodified reference library with pinned libm (golden: tests/golden/replay_ref.json; live when oracle/_ref has it)."""
+the unmodified reference library with the stock glibc (golden: tests/golden/replay_ref.json; live when oracle/_ref has it)."""
 import json
 import os
 import sys
@@ -18,7 +18,7 @@ from make_replay_golden import SEEDS, digest, run_node  # noqa: E402
 
 pytestmark = pytest.mark.gpu
 NODE = os.path.join(orc.ROOT, "tests", "cpp", "bin", "local_planner_b200")
-REF_NODE = os.path.join(orc.ROOT, "oracle", "_ref", "local_planner_ref_crm")
+REF_NODE = os.path.join(orc.ROOT, "oracle", "_ref", "local_planner_ref")
 GOLD = json.load(open(os.path.join(orc.ROOT, "tests", "golden", "replay_ref.json")))
 
 
@@ -27,7 +27,7 @@ GOLD = json.load(open(os.path.join(orc.ROOT, "tests", "golden", "replay_ref.json
 def test_unmodified_node_publishes_the_reference_trajectories(seed):
     script = R.make_script(seed)
     pubs, ticks, times, log = run_node(NODE, script)
-    gold = GOLD[str(seed)]["ref_crm"]
+    gold = GOLD[str(seed)]["ref"]
     assert ticks == gold["ticks"] and len(pubs) == len(gold["pubs"])
     mine = digest(pubs)
     bad = [a["tick"] for a, b in zip(mine, gold["pubs"]) if a != b]
