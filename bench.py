@@ -1,16 +1,20 @@
 #!/usr/bin/env python
-"""bench.py -- batched Hybrid A* queries on synthetic clutter maps (BASELINE.json configs[3] / [4]).
+"""bench.py -- batched Hybrid A* queries on synthetic clutter maps (BASELINE.json configs[3], with configs[0], [1], [2], [4] as blocks).
 
-One "step" = one pass of the hot path over one batch: 64 (map, goal) groups x 64 start poses = 4096
-independent HybridAStar::find_path queries on 512 x 512 x 72 maps with 96 box obstacles each (SURVEY.md
-§8d C4), EXACT single-pop mode (expansion sequence identical to the reference).  With --gpus N every rank
-runs the same 4096-query batch (weak scaling, no data-path collective; every rank rasterises its maps itself,
-the NCCL map broadcast is timed separately as `map_broadcast_ms`).  --workload c5 runs BASELINE configs[4]
-(65 536 queries sharded by group, K-POP(32), strong scaling).
+Headline (`value`, `e2e`): one "step" = one pass of the hot path over one batch = 64 (map, goal) groups x 64 start poses = 4096
+independent HybridAStar::find_path queries on 512 x 512 x 72 maps with 96 box obstacles each, EXACT single-pop
+mode: every query returns what the unmodified reference returns (expansion sequence, cost, path).  Steps are independent batches,
+so they are submitted the way a serving system would: round-robin over `--lanes` lane contexts (pp_create_lane: own stream and
+scratch, shared maps), one synchronisation at the end -- the drain of batch k (its few longest queries, one warp each) overlaps
+the bulk of batch k+1.  `batch_latency_ms` is the same batch alone on an idle GPU.
 
-  value : node expansions / s, whole job, inputs resident in HBM, kernel timed with CUDA events
-  e2e   : the same through pp_find_path_batch with pinned HOST buffers (H2D queries, D2H results+paths)
-  --impl reference : the unmodified reference (oracle/_ref) on the host cores, bounded sample per step
+  value : node expansions / s, whole job, queries resident in HBM, K steps bracketed by CUDA events on the context's stream
+  e2e   : the same through the C ABI with pinned HOST buffers every step (H2D queries, D2H results + paths + curvature)
+  --gpus N (torchrun): weak scaling, rank r runs groups with seeds r*64 .. r*64+63 (distinct work), no data-path collective
+  c5 block : BASELINE configs[4]: 65 536 queries = 1 024 groups x 64 starts IN TOTAL, K-POP(32), sharded over the ranks (strong
+             scaling); rank 0 rasterises every map, pp_broadcast_maps (NCCL) replicates them into every rank's context
+  c1 / c2_map_update / c3_fields blocks : configs[0], [1], [2] (single-query latency, map update round, heuristic field sweep)
+  --impl reference : the unmodified reference (oracle/_ref, stock libm) on all host cores, bounded sample per step
 """
 import argparse
 import ctypes as C
@@ -31,11 +35,16 @@ for p in (ROOT, os.path.join(ROOT, "tests")):
 import scenarios as S  # noqa: E402  (generators only, no oracle code)
 
 N_GRID, RES = 512, 0.2
-ALGO_BYTES_PER_EXPANSION = 312   # SURVEY.md §8d C4: state 32 B + 5 x (map 4 + closed probe 16 + open insert 32 + h 4)
+ALGO_BYTES_PER_EXPANSION = 312   # SURVEY.md 8d C4: state 32 B + 5 x (map 4 + closed probe 16 + open insert 32 + h 4)
+T_START = time.time()
 
 
 def dist_env():
     return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+
+
+def elapsed():
+    return time.time() - T_START
 
 
 class ClockSampler(threading.Thread):
@@ -80,24 +89,32 @@ def build_workload(n_groups, n_starts, seed0):
     return [S.c4_group(seed0 + g, n_starts=n_starts, grid_size=N_GRID, resolution=RES) for g in range(n_groups)]
 
 
-def apply_groups(ctx, groups):
-    """update_goal + 4 x (boxes, decay) per group through the C ABI; returns final maps and selected queries."""
-    import path_planning_pkg_b200 as pp
-    thr = ctx.consts().log_threshold
-    queries, qgroups, maps = [], [], []
+def apply_groups(ctx, groups, rasterise=True):
+    """update_goal + 4 x (boxes, decay) per group through the C ABI (rasterise=False: frames and APF lists only, the maps arrive
+    by broadcast)."""
     for gi, sc in enumerate(groups):
         ctx.update_goal(sc["goal"], sc["frame_start"], group=gi)
-        for _ in range(sc["rounds"]):
-            ctx.update_boxes(sc["boxes"], sc["conf"], S.APF_ADDED_RADIUS, group=gi)
-            ctx.decay(group=gi)
+        if rasterise:
+            for _ in range(sc["rounds"]):
+                ctx.update_boxes(sc["boxes"], sc["conf"], S.APF_ADDED_RADIUS, group=gi)
+                ctx.decay(group=gi)
+        else:
+            ctx.update_apf(sc["boxes"], S.APF_ADDED_RADIUS, group=gi)
+
+
+def select_queries(ctx, groups, maps=None):
+    """Start poses in free cells (reject starts in occupied cells), per group, from the device's own maps."""
+    thr = ctx.consts().log_threshold
+    queries, qgroups, out_maps = [], [], []
+    for gi, sc in enumerate(groups):
         m = ctx.get_map(gi)
-        maps.append(m)
+        out_maps.append(m)
         cand = sc["start_candidates"]
         st = ctx.set_start(ctx.make_queries(cand, [gi] * len(cand)))
         free = m[st["ci"], st["cj"]] < thr
         sel = cand[free][:sc["n_starts"]]
         queries.append(sel); qgroups += [gi] * len(sel)
-    return np.concatenate(queries), np.array(qgroups, np.int32), maps
+    return np.concatenate(queries), np.array(qgroups, np.int32), out_maps
 
 
 def peaks():
@@ -107,210 +124,328 @@ def peaks():
         return 6650.0, "fallback"
 
 
-def cpu_reference_run(groups, queries, qgroups, maps, sample_idx, n_threads):
-    """The unmodified reference (oracle/_ref, stock libm) on the host cores over `sample_idx` queries."""
-    import orc
-    lib = C.CDLL(orc.REF_SO)
-    lib.ref_bench_queries.restype = C.c_double
-    P = orc.make_params(grid_size=N_GRID, resolution=RES)
-    G = len(groups)
-    frames = np.zeros((G, 6), np.float32)
-    nb = len(groups[0]["boxes"])
-    boxes = np.zeros((G, nb, 4), np.float32); conf = np.zeros((G, nb), np.float32)
-    for g, sc in enumerate(groups):
-        frames[g, :3] = sc["goal"]; frames[g, 3:] = sc["frame_start"]
-        boxes[g] = sc["boxes"]; conf[g] = sc["conf"]
-    mp = np.ascontiguousarray(np.stack(maps), np.float32)
-    q4 = np.ascontiguousarray(queries[sample_idx], np.float32)
-    go = np.ascontiguousarray(qgroups[sample_idx], np.int32)
-    n = len(q4)
-    cost = np.zeros(n, np.float32); succ = np.zeros(n, np.int32); pops = np.zeros(n, np.int32)
-    vp = lambda a: a.ctypes.data_as(C.c_void_p)
-    secs = lib.ref_bench_queries(C.byref(P), vp(frames), vp(mp), vp(boxes), vp(conf), C.c_int(nb), C.c_float(S.APF_ADDED_RADIUS),
-                                 C.c_int(G), vp(q4), vp(go), C.c_int(n), C.c_int(n_threads), vp(cost), vp(succ), vp(pops))
-    return secs, pops, cost, succ
+def committed_traffic(kernel):
+    """dram bytes per launch of `kernel` from the committed ncu --set full capture (profiles/r2_traffic.json), or None."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))[kernel]
+    except Exception:
+        return None
 
 
-def run_c5(args, rank, local_rank, world):
-    """BASELINE configs[4] / SURVEY §8d C5: 65 536 queries = 1 024 (map, goal) groups x 64 starts, sharded by group
-    round-robin over the ranks (STRONG scaling: the total is fixed), K-POP(32) mode.  Every rank rasterises the maps of
-    its own groups (the bit-exact kernel makes replicas identical); the NCCL map broadcast is timed separately."""
-    import torch
-    import torch.distributed as dist
-    import path_planning_pkg_b200 as pp
+# ---------------------------------------------------------------------------------------------------------------------
+class Pipeline:
+    """K independent batches over S lane contexts: submit round-robin, collect a lane's previous batch before reusing it."""
 
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    total_groups = args.c5_groups
-    # --c5-shard group: rank r owns groups r, r+world, ... (SURVEY 8e; fields only for its own groups, but the ranks' work
-    #                   differs by the difficulty of their groups)
-    # --c5-shard query (default): every rank holds every map (replicated, as after the broadcast) and takes every world-th
-    #                   query of every group: equal work per rank
-    mine = list(range(rank, total_groups, world)) if args.c5_shard == "group" else list(range(total_groups))
-    P = pp.make_params(grid_size=N_GRID, resolution=RES)
-    ctx = pp.Context(P, num_groups=len(mine), device=local_rank)
-    groups = [S.c4_group(g, n_starts=args.starts, grid_size=N_GRID, resolution=RES) for g in mine]
-    t0 = time.time()
-    queries, qgroups, _ = apply_groups(ctx, groups)
-    map_build_s = time.time() - t0
-    map_bcast_ms = None
-    if world > 1:
-        scratch = torch.empty(N_GRID * N_GRID, dtype=torch.float32, device="cuda")
-        torch.cuda.synchronize(); dist.barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(8):
-            dist.broadcast(scratch, src=0)
-        e1.record(); torch.cuda.synchronize()
-        map_bcast_ms = e0.elapsed_time(e1) / 8
-    if args.c5_shard == "query":
-        from path_planning_pkg_b200.shard import shard_queries
-        mine_q = shard_queries(len(queries), rank, world)
-        queries, qgroups = queries[mine_q], qgroups[mine_q]
-    q = ctx.make_queries(queries, qgroups)
-    nq = len(q)
-    pc = 1024
-    opts = ctx.make_opts(max_expansions=1 << 18, path_cap=pc, max_slots=args.max_slots, mode=1, kpop=32)
+    def __init__(self, ctx, lanes, q, opts, pp):
+        import torch
+        self.pp, self.ctx, self.q, self.opts, self.n = pp, ctx, q, opts, len(q)
+        self.lanes = [ctx] + [ctx.create_lane() for _ in range(max(lanes, 1) - 1)]
+        self.busy = [False] * len(self.lanes)
+        self.kernel_ms = []
+        pc = opts.path_cap
+        self.hq = torch.from_numpy(q.view(np.uint8).copy()).pin_memory()
+        self.hres = [torch.zeros(self.n * pp._cabi.RESULT_DT.itemsize, dtype=torch.uint8).pin_memory() for _ in self.lanes]
+        self.hpath = [torch.zeros(self.n * pc * 3, dtype=torch.float32).pin_memory() for _ in self.lanes]
+        self.hcurv = [torch.zeros(self.n * pc, dtype=torch.float32).pin_memory() for _ in self.lanes]
+        self.h2d = int(q.nbytes)
+        self.d2h = int(self.hres[0].numel() + self.hpath[0].numel() * 4 + self.hcurv[0].numel() * 4)
 
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        ctx.sync()
+    def set_budget(self, nbytes):
+        for l in self.lanes:
+            l.set_memory_budget(nbytes)
 
-    ctx.batch_upload(q, opts)
-    for _ in range(args.warmup):
-        ctx.batch_run()
-    sampler = ClockSampler(local_rank); sampler.start()
+    def upload_all(self):
+        for l in self.lanes:
+            l.batch_upload(self.q, self.opts)
+
+    def _collect(self, i, e2e):
+        l = self.lanes[i]
+        self.kernel_ms.append(l.batch_wait())
+        if e2e:
+            rc = l.lib.pp_batch_fetch(l.h, C.c_void_p(self.hres[i].data_ptr()), C.c_void_p(self.hpath[i].data_ptr()),
+                                      C.c_void_p(self.hcurv[i].data_ptr()), None)
+            if rc != 0:
+                raise RuntimeError(l.lib.pp_last_error().decode())
+        self.busy[i] = False
+
+    def run(self, steps, e2e):
+        self.kernel_ms = []
+        for k in range(steps):
+            i = k % len(self.lanes)
+            if self.busy[i]:
+                self._collect(i, e2e)
+            l = self.lanes[i]
+            if e2e:
+                rc = l.lib.pp_batch_upload(l.h, C.c_void_p(self.hq.data_ptr()), C.c_int(self.n), C.byref(self.opts))
+                if rc != 0:
+                    raise RuntimeError(l.lib.pp_last_error().decode())
+                l._opts, l._n = self.opts, self.n
+            l.batch_run_async()
+            self.busy[i] = True
+        for i in range(len(self.lanes)):
+            if self.busy[i]:
+                self._collect(i, e2e)
+
+    def results(self, lane=0):
+        return np.frombuffer(self.hres[lane].numpy().tobytes(), self.pp._cabi.RESULT_DT)
+
+    def close(self):
+        for l in self.lanes[1:]:
+            l.close()
+        self.lanes = self.lanes[:1]
+
+
+def timed(ctx, barrier, fn):
+    """fn() bracketed by barrier + synchronize and by CUDA events on the context's stream; returns (event ms, wall s)."""
     barrier()
-    l0 = ctx.kernel_launches()
-    ms = [ctx.batch_run() for _ in range(args.steps)]
-    barrier()
-    clocks = sampler.finish()
-    launches = ctx.kernel_launches() - l0
-    retried = ctx.batch_retried()
-    res, _, _ = ctx.batch_fetch()
-    pops = int(res["n_pops"].sum())
-    # end to end: host buffers in, results + paths out
-    hq = torch.from_numpy(q.view(np.uint8).copy()).pin_memory()
-    hres = torch.zeros(nq * pp._cabi.RESULT_DT.itemsize, dtype=torch.uint8).pin_memory()
-    hpath = torch.zeros(nq * pc * 3, dtype=torch.float32).pin_memory()
-    hcurv = torch.zeros(nq * pc, dtype=torch.float32).pin_memory()
-    e2e_steps = max(1, min(args.steps, args.e2e_steps))
-    barrier()
+    ctx._chk(ctx.lib.pp_timer_begin(ctx.h))
     t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        rc = ctx.lib.pp_find_path_batch(ctx.h, C.c_void_p(hq.data_ptr()), C.c_int(nq), C.byref(opts), C.c_void_p(hres.data_ptr()),
-                                        C.c_void_p(hpath.data_ptr()), C.c_void_p(hcurv.data_ptr()), None)
-        if rc != 0:
-            raise RuntimeError(ctx.lib.pp_last_error().decode())
+    fn()
+    ms = C.c_float()
+    ctx._chk(ctx.lib.pp_timer_end(ctx.h, C.byref(ms)))
+    wall = time.perf_counter() - t0
     barrier()
-    e2e_s = time.perf_counter() - t0
-    t = torch.tensor([float(np.sum(ms)), e2e_s], dtype=torch.float64, device="cuda")
-    cnt = torch.tensor([float(pops), float(nq), float(res["success"].sum()), float((res["status"] != 0).sum()), float(retried)],
+    return float(ms.value), wall
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def reference_sample(nq, n, seed=1):
+    """The bounded CPU sample both CPU legs draw from: a fixed permutation of the batch's query indices."""
+    return np.random.RandomState(seed).permutation(nq)[:n]
+
+
+def run_reference_arm(args, workload):
+    """--impl reference: the unmodified reference on every host core, one planner per thread, scrubbed per query (F12)."""
+    import orc
+    n_threads = os.cpu_count() or 1
+    groups = build_workload(args.groups, args.starts, 0)
+    P = orc.make_params(grid_size=N_GRID, resolution=RES)
+    maps, queries, qgroups = [], [], []
+    o = orc.ref(P)
+    for gi, sc in enumerate(groups):      # maps and start selection from the reference itself (no GPU on this arm)
+        o.set_map(np.zeros((N_GRID, N_GRID), np.float32))
+        S.build_map(o, sc)
+        m = o.get_map(); maps.append(m)
+        sel = S.select_starts(sc, m, o.consts().log_threshold, o.set_start)
+        queries.append(sel); qgroups += [gi] * len(sel)
+    queries = np.concatenate(queries); qgroups = np.array(qgroups, np.int32)
+    per_step = int(min(max(8 * n_threads, 64), 256, len(queries)))
+    order = reference_sample(len(queries), len(queries))
+    tot_pops, tot_s, tot_busy, tot_q, k = 0, 0.0, 0.0, 0, 0
+    for step in range(args.warmup + args.steps):
+        if step < args.warmup:          # warm-up: page in the library, touch the planners' memory; a handful of queries is enough
+            idx = order[:max(n_threads, 8)]
+        else:
+            idx = order[(k * per_step) % len(order):][:per_step]; k += 1
+        b = orc.ref_batch(P, groups, queries, qgroups, maps, idx, n_threads)
+        if step >= args.warmup:
+            tot_pops += int(b["pops"].sum()); tot_s += b["secs"]; tot_busy += float(b["busy_s"].sum()); tot_q += len(idx)
+    val = tot_pops / tot_s
+    line = {"impl": "reference", "metric": "hybrid_astar_node_expansions_per_s", "value": val, "unit": "expansions/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_s / max(args.steps, 1),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "queries_per_s": tot_q / tot_s,
+            "busy_time": {"expansions_per_s_per_core": tot_pops / tot_busy, "expansions_per_s_all_cores_no_idle": tot_pops / tot_busy * n_threads,
+                          "note": "expansions / time spent inside find_path summed over threads: what the cores deliver when none waits for "
+                                  "the step's longest query"},
+            "config": {"workload": workload, "sample": f"{per_step} queries per step in the fixed permutation (seed 1) the GPU arm's cpu_baseline uses"},
+            "cpu_baseline": {"value": val, "unit": "expansions/s", "cores": n_threads, "kind": "reference",
+                             "sample": f"{per_step} queries/step x {args.steps} steps, one HybridAStar<float> per thread, scrubbed per query"},
+            "e2e": {"value": val, "unit": "expansions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def block_c5(args, pp, torch, dist, rank, local_rank, world, barrier, in_time):
+    """BASELINE configs[4] / SURVEY 8d C5: 65 536 queries = 1 024 groups x 64 starts in total, K-POP(32), sharded by query over the
+    ranks (strong scaling).  Rank 0 rasterises every map; pp_broadcast_maps replicates them INTO every rank's context (NCCL)."""
+    G = args.c5_groups
+    P = pp.make_params(grid_size=N_GRID, resolution=RES)
+    ctx = pp.Context(P, num_groups=G, device=local_rank)
+    groups = [S.c4_group(g, n_starts=args.starts, grid_size=N_GRID, resolution=RES) for g in range(G)]
+    t0 = time.time()
+    apply_groups(ctx, groups, rasterise=(rank == 0))
+    ctx.sync()
+    build_s = time.time() - t0
+    bcast_ms = None
+    if world > 1:
+        uid = [ctx.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        ctx.comm_init(world, rank, uid[0])
+        ctx.broadcast_maps(0, G, 0); ctx.sync()                 # communicator warm-up (and the replication itself)
+        ms, _ = timed(ctx, barrier, lambda: (ctx.broadcast_maps(0, G, 0), ctx.sync()))
+        bcast_ms = ms
+        # replicas must be bit-identical to what this rank would have rasterised itself: spot-check one group per rank
+        g = (rank * 7 + 3) % G
+        probe = pp.Context(P, num_groups=1, device=local_rank)
+        apply_groups(probe, [groups[g]], rasterise=True)
+        same = bool(np.array_equal(probe.get_map(0).view(np.uint32), ctx.get_map(g).view(np.uint32)))
+        probe.close()
+        flag = torch.tensor([1.0 if same else 0.0], device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        replicas_ok = bool(flag.item() == 1.0)
+    else:
+        replicas_ok = None
+    queries, qgroups, _ = select_queries(ctx, groups)
+    mine = np.arange(rank, len(queries), world)       # every world-th query (path_planning_pkg_b200.shard.shard_queries): equal work per rank
+    total_q = len(queries)
+    q = ctx.make_queries(queries[mine], qgroups[mine])
+    opts = ctx.make_opts(max_expansions=1 << 18, path_cap=1024, mode=1, kpop=32)
+    ctx.batch_upload(q, opts)
+    ctx.batch_run()                                            # warm-up (also builds the scheduling hints)
+    steps = args.c5_steps if in_time() else 1
+    l0 = ctx.kernel_launches()
+    kms = []
+    ms, wall = timed(ctx, barrier, lambda: kms.extend(ctx.batch_run() for _ in range(steps)))
+    launches = ctx.kernel_launches() - l0
+    res, _, _ = ctx.batch_fetch()
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    cnt = torch.tensor([float(res["n_pops"].sum()), float(len(q)), float(res["success"].sum()), float((res["status"] != 0).sum())],
                        dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
-    if rank == 0:
-        max_ms, e2e_max = float(t[0].item()), float(t[1].item())
-        all_pops, all_q, all_succ, all_flags, all_retried = [float(v) for v in cnt.tolist()]
-        peak, peak_src = peaks()
-        achieved = all_pops / world * ALGO_BYTES_PER_EXPANSION / (max_ms / args.steps * 1e-3) / 1e9
-        line = {"metric": "hybrid_astar_node_expansions_per_s", "value": all_pops * args.steps / (max_ms * 1e-3), "unit": "expansions/s",
-                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": max_ms / args.steps, "higher_is_better": True,
-                "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "queries_per_s": all_q * args.steps / (max_ms * 1e-3), "expansions_per_step": int(all_pops), "queries_per_step": int(all_q),
-                "success_rate": all_succ / all_q, "capacity_flags": int(all_flags), "retried_queries": int(all_retried),
-                "config": {"workload": f"C5: {total_groups} groups x {args.starts} starts = {int(all_q)} Hybrid A* queries in total, sharded by {args.c5_shard} over "
-                                       f"{world} GPU(s), {N_GRID}x{N_GRID}x72, 96 boxes/group, K-POP(32) mode (own semantics, DESIGN.md section 9)",
-                           "l2": "per-query pools are tens of GB per step, far larger than the 126 MB L2",
-                           "map_build_s": map_build_s, "map_broadcast_ms": map_bcast_ms},
-                "e2e": {"value": all_pops * e2e_steps / e2e_max, "unit": "expansions/s", "queries_per_s": all_q * e2e_steps / e2e_max,
-                        "h2d_bytes_per_step": int(q.nbytes) * world,
-                        "d2h_bytes_per_step": int(hres.numel() + hpath.numel() * 4 + hcurv.numel() * 4) * world},
-                "gpu_launches": int(launches),
-                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                             "kernel": "pp_kpop_kernel<4>", "peak_source": peak_src,
-                             "note": "latency / barrier bound (DESIGN.md section 9); algorithmic bytes = 312 B/expansion (SURVEY 8d)"},
-                "clocks": clocks}
-        print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    ctx.close()
+    max_ms = float(t.item()); pops, nq, succ, flags = [float(v) for v in cnt.tolist()]
+    return {"workload": f"C5: {G} groups x {args.starts} starts = {int(nq)} queries in total over {world} GPU(s), {N_GRID}x{N_GRID}x72, K-POP(32)",
+            "scaling": "strong", "steps": steps, "ms_per_step": max_ms / steps, "queries_per_s": nq * steps / (max_ms * 1e-3),
+            "expansions_per_s": pops * steps / (max_ms * 1e-3), "queries_total": int(total_q), "success_rate": succ / max(nq, 1),
+            "capacity_flags": int(flags), "gpu_launches": int(launches),
+            "map_replication": {"how": "rank 0 rasterises all maps; pp_broadcast_maps (ncclBroadcast) writes them into every rank's context",
+                                "bytes": int(G) * N_GRID * N_GRID * 4, "broadcast_ms": bcast_ms, "replicas_bit_identical": replicas_ok,
+                                "map_build_s_rank0": build_s},
+            "note": "K-POP has its own semantics (DESIGN.md section 9): bit-identical to its CPU restatement, not to the reference"}
 
 
+def block_kpop(args, pp, ctx, q, res_exact, barrier, cpu, have_time):
+    """K-POP(32) on the headline batch + its cost deviation from the REFERENCE on the CPU sample (not from the EXACT mode)."""
+    kopts = ctx.make_opts(max_expansions=1 << 18, path_cap=2048, mode=1, kpop=32)
+    ctx.batch_upload(q, kopts)
+    ctx.batch_run()
+    steps = 3 if have_time else 1
+    kms = []
+    ms, _ = timed(ctx, barrier, lambda: kms.extend(ctx.batch_run() for _ in range(steps)))
+    kres, _, _ = ctx.batch_fetch()
+    out = {"k": 32, "steps": steps, "ms_per_step": ms / steps, "expansions_per_s": float(kres["n_pops"].sum()) * steps / (ms * 1e-3),
+           "queries_per_s": len(q) * steps / (ms * 1e-3), "success_rate": float(kres["success"].mean()),
+           "note": "k pops per iteration, exact 2D field heuristic, no equal-f drops: own semantics, bit-identical to its CPU restatement "
+                   "(oracle/port/kpop.inc); north_star's 1e-4 cost bar against the reference is NOT met and cannot be (SURVEY F4/F5)"}
+    if cpu is not None:
+        idx, b = cpu
+        both = (b["success"] == 1) & (kres["success"][idx] == 1)
+        dev = kres["cost"][idx][both] / b["cost"][both] - 1.0
+        out["cost_vs_reference"] = {"sample": f"{int(both.sum())} queries of the cpu_baseline sample both solved",
+                                    "median": float(np.median(dev)), "min": float(dev.min()), "max": float(dev.max()),
+                                    "within_1e-4": int((np.abs(dev) <= 1e-4).sum()),
+                                    "success_agree": int((b["success"] == kres["success"][idx]).sum())}
+    return out
+
+
+def block_c1(args, pp, local_rank, n_seeds=32):
+    """BASELINE configs[0] / SURVEY 8d C1: single local_planner query, N=200 @0.2 m, 5 boxes; GPU latency through the C ABI next to
+    the reference on one host core, seeds 0..n-1, plus identity of the results."""
+    import orc
+    scs = [S.c1_scenario(s) for s in range(n_seeds)]
+    P = orc.make_params(grid_size=scs[0]["grid_size"], resolution=scs[0]["resolution"])
+    ctx = pp.Context(pp._cabi.params_from(P), num_groups=n_seeds, device=local_rank)
+    ref = orc.ref(P)
+    for gi, sc in enumerate(scs):
+        ctx.update_goal(sc["goal"], sc["frame_start"], group=gi)
+        for _ in range(sc["rounds"]):
+            ctx.update_boxes(sc["boxes"], sc["conf"], S.APF_ADDED_RADIUS, group=gi)
+            ctx.decay(group=gi)
+    q = ctx.make_queries(np.array([sc["queries"][0] for sc in scs]), list(range(n_seeds)))
+    o1 = ctx.make_opts(path_cap=2048, max_slots=1)
+    ctx.find_path_batch(q[:1], o1)
+    gpu_ms, cpu_ms, same, pops = [], [], 0, []
+    for gi, sc in enumerate(scs):
+        t0 = time.perf_counter(); r, paths, curv, _ = ctx.find_path_batch(q[gi:gi + 1], o1); gpu_ms.append((time.perf_counter() - t0) * 1e3)
+        ref.set_map(np.zeros((sc["grid_size"], sc["grid_size"]), np.float32)); S.build_map(ref, sc); ref.scrub()
+        qq = sc["queries"][0]
+        t0 = time.perf_counter(); b = ref.find_path(float(qq[3]), qq[:3]); cpu_ms.append((time.perf_counter() - t0) * 1e3)
+        n = int(r[0]["n_path"])
+        same += int(int(r[0]["n_pops"]) == b["n_pops"] and np.float32(r[0]["cost"]) == b["cost"] and
+                    np.array_equal(paths[0, :n].view(np.uint32), b["path"].view(np.uint32)))
+        pops.append(int(r[0]["n_pops"]))
+    ctx.close()
+    return {"workload": f"C1: N=200, res 0.2, 72 bins, 5 boxes, 4 rounds, seeds 0-{n_seeds - 1}, one find_path at a time, EXACT mode",
+            "gpu_ms": {"p50": float(np.median(gpu_ms)), "p95": float(np.percentile(gpu_ms, 95))},
+            "reference_1core_ms": {"p50": float(np.median(cpu_ms)), "p95": float(np.percentile(cpu_ms, 95))},
+            "expansions_p50": float(np.median(pops)), "identical_to_reference": f"{same}/{n_seeds}"}
+
+
+def block_c2(args, pp, local_rank, peak):
+    """BASELINE configs[1] / SURVEY 8d C2: 256 boxes into a 2048^2 log-odds map + decay = one round; device time per round."""
+    sc = S.c2_scenario()
+    P = pp.make_params(grid_size=sc["grid_size"], resolution=sc["resolution"])
+    ctx = pp.Context(P, num_groups=1, device=local_rank)
+    ctx.update_goal(sc["goal"], sc["frame_start"])
+    ctx.update_boxes_2d(sc["boxes"], sc["conf"]); ctx.decay(); ctx.sync()
+    reps = 50
+    ms = C.c_float()
+    ctx._chk(ctx.lib.pp_timer_begin(ctx.h))
+    for _ in range(reps):
+        ctx.update_boxes_2d(sc["boxes"], sc["conf"]); ctx.decay()
+    ctx._chk(ctx.lib.pp_timer_end(ctx.h, C.byref(ms)))
+    per = ms.value / reps
+    nn = sc["grid_size"] ** 2
+    algo = 2 * 4 * nn + 470488 + 20 * len(sc["boxes"])          # SURVEY 8d C2: fused single pass = 33.56 MB
+    ctx.close()
+    return {"workload": "C2: 256 boxes rasterised into a 2048x2048 log-odds map + whole-map decay (one round)", "round_ms": per,
+            "algorithmic_bytes": algo, "achieved_GBps": algo / (per * 1e-3) / 1e9, "frac_of_hbm_peak": algo / (per * 1e-3) / 1e9 / peak,
+            "note": "round = pp_update_obstacles_boxes_2d + pp_update_obstacles_decay through the C ABI, device time incl. the call's H2D"}
+
+
+def block_c3(args, pp, local_rank, peak):
+    """BASELINE configs[2] / SURVEY 8d C3: exact 2D field + Dubins field over 2048 x 2048 x 72 for one goal."""
+    sc = S.c2_scenario()
+    P = pp.make_params(grid_size=sc["grid_size"], resolution=sc["resolution"])
+    ctx = pp.Context(P, num_groups=1, device=local_rank)
+    ctx.update_goal(sc["goal"], sc["frame_start"])
+    for _ in range(3):
+        ctx.update_boxes_2d(sc["boxes"], sc["conf"]); ctx.decay()
+    ctx.field2d(download=False)
+    f2 = [ctx.field2d(download=False) for _ in range(3)]
+    ctx.field3d(download=False)
+    f3 = [ctx.field3d(download=False)[1] for _ in range(3)]
+    ctx.close()
+    states = sc["grid_size"] ** 2 * 72
+    ms3 = float(np.min(f3))
+    return {"workload": "C3: 2D holonomic field + Dubins field sweep for one goal over 2048x2048x72",
+            "field2d_ms": float(np.min([f[2] for f in f2])), "field2d_sweeps": int(f2[0][1]),
+            "dubins_field_ms": ms3, "states_per_s": states / (ms3 * 1e-3),
+            "dubins_write_GBps": states * 4 / (ms3 * 1e-3) / 1e9, "dubins_write_frac_of_hbm_peak": states * 4 / (ms3 * 1e-3) / 1e9 / peak,
+            "fp32_tflops_at_485_op_per_state": states * 485 / (ms3 * 1e-3) / 1e12}
+
+
+# ---------------------------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--steps", type=int, default=4)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--groups", type=int, default=64)
     ap.add_argument("--starts", type=int, default=64)
-    ap.add_argument("--cpu-sample", type=int, default=64, help="queries in the cpu_baseline sample")
+    ap.add_argument("--lanes", type=int, default=8, help="lane contexts the steps are submitted over (1 = one batch at a time)")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="queries in the cpu_baseline sample (0 = 8 per host thread, 64..256)")
     ap.add_argument("--max-slots", type=int, default=0)
-    # EXACT-mode pools: the library defaults (131 072 closed states per query, automatic re-run of the queries that need more in 8x
-    # larger pools).  Measured structure of a step (profiles/r1_bench_search_launches.csv): the main launch on 2 368 slots = 11.4 s,
-    # then the retry launch of the 116 long queries = 28.1 s, bounded by the batch's longest query.  Larger first-pass pools
-    # (--max-expansions 1048576 --max-open 524288 --max-open2d 65536 --exact-slots N) avoid the re-run but leave room for fewer
-    # resident queries; which side wins has to be measured (DESIGN.md sections 7 and 13).
-    ap.add_argument("--max-expansions", type=int, default=1 << 17)
-    ap.add_argument("--max-open", type=int, default=1 << 16)
-    ap.add_argument("--max-open2d", type=int, default=1 << 14)
-    ap.add_argument("--exact-slots", type=int, default=0, help="resident EXACT-mode query slots (0 = auto); --max-slots overrides")
+    ap.add_argument("--e2e-steps", type=int, default=0, help="timed end-to-end steps (0 = min(steps, lanes))")
+    ap.add_argument("--budget-s", type=float, default=540.0, help="wall-clock budget: optional blocks are shortened / skipped beyond it")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--e2e-steps", type=int, default=1, help="timed end-to-end steps (each is a full batch)")
-    ap.add_argument("--no-kpop", action="store_true", help="skip the additional K-POP(32) throughput measurement")
-    ap.add_argument("--no-kpop-large", action="store_true", help="skip the K-POP(32) measurement on the C5-sized batch")
-    ap.add_argument("--large-starts", type=int, default=1024, help="starts per group of the C5-sized K-POP batch")
-    ap.add_argument("--workload", default="c4", choices=["c4", "c5"], help="c4: EXACT-mode headline (default); c5: 65 536 queries, K-POP(32), strong scaling")
+    ap.add_argument("--no-kpop", action="store_true")
+    ap.add_argument("--no-c5", action="store_true")
+    ap.add_argument("--no-blocks", action="store_true", help="skip the c1 / c2 / c3 blocks")
     ap.add_argument("--c5-groups", type=int, default=1024)
-    ap.add_argument("--c5-shard", default="query", choices=["query", "group"])
+    ap.add_argument("--c5-steps", type=int, default=3)
     args = ap.parse_args()
     rank, local_rank, world = dist_env()
-    if args.workload == "c5" and args.impl == "b200":
-        return run_c5(args, rank, local_rank, world)
-    n_threads = os.cpu_count() or 1
-    workload = (f"C4: {args.groups} groups x {args.starts} starts = {args.groups * args.starts} Hybrid A* queries per GPU, "
+    workload = (f"C4: {args.groups} groups x {args.starts} starts = {args.groups * args.starts} Hybrid A* queries per GPU per step, "
                 f"{N_GRID}x{N_GRID}x72, 96 boxes/group, launch-default params, EXACT single-pop mode")
-
     if args.impl == "reference":
-        if rank != 0:
-            return
-        import orc
-        groups = build_workload(args.groups, args.starts, 0)
-        # maps and start selection come from the reference itself here (no GPU on this arm)
-        P = orc.make_params(grid_size=N_GRID, resolution=RES)
-        maps, queries, qgroups = [], [], []
-        o = orc.ref(P)
-        for gi, sc in enumerate(groups):
-            o.set_map(np.zeros((N_GRID, N_GRID), np.float32))
-            S.build_map(o, sc)
-            m = o.get_map(); maps.append(m)
-            sel = S.select_starts(sc, m, o.consts().log_threshold, o.set_start)
-            queries.append(sel); qgroups += [gi] * len(sel)
-        queries = np.concatenate(queries); qgroups = np.array(qgroups, np.int32)
-        per_step = max(n_threads * 2, 32)
-        rs = np.random.RandomState(0)
-        order = rs.permutation(len(queries))
-        tot_pops, tot_s, tot_q, k = 0, 0.0, 0, 0
-        for step in range(args.warmup + args.steps):
-            idx = order[(k * per_step) % len(order):][:per_step]; k += 1
-            secs, pops, _, _ = cpu_reference_run(groups, queries, qgroups, maps, idx, n_threads)
-            if step >= args.warmup:
-                tot_pops += int(pops.sum()); tot_s += secs; tot_q += len(idx)
-        val = tot_pops / tot_s
-        line = {"impl": "reference", "metric": "hybrid_astar_node_expansions_per_s", "value": val, "unit": "expansions/s",
-                "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_s / max(args.steps, 1),
-                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "queries_per_s": tot_q / tot_s,
-                "config": {"workload": workload, "sample": f"{per_step} queries per step drawn from the 4096-query batch"},
-                "cpu_baseline": {"value": val, "unit": "expansions/s", "cores": n_threads, "kind": "reference",
-                                 "sample": f"{per_step} queries/step x {args.steps} steps, one HybridAStar<float> per thread, scrubbed per query"},
-                "e2e": {"value": val, "unit": "expansions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-                "gpu_launches": 0}
-        print(json.dumps(line), flush=True)
+        if rank == 0:
+            run_reference_arm(args, workload)
         return
 
     import torch
@@ -320,267 +455,166 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    P = pp.make_params(grid_size=N_GRID, resolution=RES)
-    ctx = pp.Context(P, num_groups=args.groups, device=local_rank)
-    # Weak scaling: every rank runs the SAME 4096-query batch (same seeds).  The step time of this batch is the latency of
-    # its single longest query; per-rank batches of different seeds would turn the max-over-ranks
-    # time into an extreme-value statistic of that one query instead of a measurement of scaling.
-    groups = build_workload(args.groups, args.starts, 0)
-    t0 = time.time()
-    queries, qgroups, maps = apply_groups(ctx, groups)
-    map_build_s = time.time() - t0
-
-    # map replication (north_star: "map replicated by an NCCL broadcast over NVLink after each update"):
-    # timed separately; every rank re-broadcasts its first group's map from rank 0's buffer and back-checks size only
-    map_bcast_ms = None
-    if world > 1:
-        class _Alias:
-            def __init__(self, ptr, n):
-                self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (ptr, False), "version": 2}
-        scratch = torch.empty(N_GRID * N_GRID, dtype=torch.float32, device="cuda")
-        src = torch.as_tensor(_Alias(ctx.map_device_ptr(0), N_GRID * N_GRID), device="cuda")
-        scratch.copy_(src)
-        torch.cuda.synchronize(); dist.barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(8):
-            dist.broadcast(scratch, src=0)
-        e1.record(); torch.cuda.synchronize()
-        map_bcast_ms = e0.elapsed_time(e1) / 8
-
-    q = ctx.make_queries(queries, qgroups)
-    nq = len(q)
-    exact_slots = args.max_slots if args.max_slots > 0 else args.exact_slots
-    opts = ctx.make_opts(max_expansions=args.max_expansions, max_open=args.max_open, max_open2d=args.max_open2d, path_cap=2048,
-                         max_slots=exact_slots)
-    pool_note = "library defaults" if args.max_expansions == 1 << 17 else "caller-sized pools"
-    try:
-        ctx.batch_upload(q, opts)
-    except pp.PPError as e:      # e.g. not enough free memory on this device: the library defaults (small pools, automatic 8x retries)
-        pool_note = f"library defaults after the sized pools could not be set up ({e})"
-        args.max_expansions, args.max_open, args.max_open2d = 1 << 17, 1 << 16, 1 << 14
-        opts = ctx.make_opts(max_expansions=args.max_expansions, max_open=args.max_open, max_open2d=args.max_open2d, path_cap=2048,
-                             max_slots=args.max_slots)
-    launches0 = ctx.kernel_launches()
+    deadline = T_START + args.budget_s
 
     def barrier():
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
-        ctx.sync()
 
-    # ---- device-resident timing (value) ----
-    ctx.batch_upload(q, opts)
-    for _ in range(args.warmup):
-        ctx.batch_run()
+    def in_time():
+        """rank 0's view of the wall-clock budget, agreed by every rank (the optional blocks contain collectives)"""
+        ok = torch.tensor([1.0 if time.time() < deadline else 0.0], device="cuda")
+        if world > 1:
+            dist.broadcast(ok, src=0)
+        return bool(ok.item() == 1.0)
+
+    # ---- the headline batch: rank r owns groups with seeds r*G .. r*G + G - 1 (distinct work per rank) ----
+    P = pp.make_params(grid_size=N_GRID, resolution=RES)
+    ctx = pp.Context(P, num_groups=args.groups, device=local_rank)
+    groups = build_workload(args.groups, args.starts, rank * args.groups)
+    t0 = time.time()
+    apply_groups(ctx, groups)
+    ctx.sync()
+    map_build_s = time.time() - t0
+    queries, qgroups, maps = select_queries(ctx, groups)
+    q = ctx.make_queries(queries, qgroups)
+    nq = len(q)
+    opts = ctx.make_opts(path_cap=2048, max_slots=args.max_slots)
+    free_b, total_b = torch.cuda.mem_get_info()
+    lanes = max(1, args.lanes)
+    pipe = Pipeline(ctx, lanes, q, opts, pp)
+    pipe.set_budget(int(free_b * 0.80 / lanes))
+    pipe.upload_all()
+
+    # one batch alone on an idle GPU (latency of a step without overlap), also the first warm-up step
+    lat_ms, _ = timed(ctx, barrier, lambda: pipe.run(1, False))
+    # ---- device-resident timing (value): W warm-up steps, then exactly K steps ----
+    pipe.run(max(args.warmup - 1, 0), False)
     sampler = ClockSampler(local_rank); sampler.start()
-    barrier()
-    kernel_ms = []
-    launches1 = ctx.kernel_launches()
-    for _ in range(args.steps):
-        kernel_ms.append(ctx.batch_run())
-    barrier()
-    clocks = sampler.finish()
-    timed_launches = ctx.kernel_launches() - launches1
-    retried_exact = ctx.batch_retried()
+    l0 = sum(l.kernel_launches() for l in pipe.lanes)
+    value_ms, value_wall = timed(ctx, barrier, lambda: pipe.run(args.steps, False))
+    timed_launches = sum(l.kernel_launches() for l in pipe.lanes) - l0
+    launch_ms = list(pipe.kernel_ms)
+    retried = sum(l.batch_retried() for l in pipe.lanes)
     res, _, _ = ctx.batch_fetch()
     pops = int(res["n_pops"].sum())
-    total_ms = float(np.sum(kernel_ms))
-    ms_t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
-    pops_t = torch.tensor([pops * args.steps, nq * args.steps], dtype=torch.float64, device="cuda")
+    # ---- end to end through the C ABI: pinned host queries in, results + paths + curvature out, every step ----
+    e2e_steps = args.e2e_steps if args.e2e_steps > 0 else min(args.steps, lanes)
+    short = torch.tensor([1.0 if time.time() + value_wall * e2e_steps / max(args.steps, 1) + 60 > deadline else 0.0], device="cuda")
+    if world > 1:
+        dist.broadcast(short, src=0)
+    if short.item() == 1.0:
+        e2e_steps = max(1, min(e2e_steps, 2))
+    e2e_ms, e2e_wall = timed(ctx, barrier, lambda: pipe.run(e2e_steps, True))
+    clocks = sampler.finish()
+    r2 = pipe.results(0)
+    assert int(r2["n_pops"].sum()) == pops, "e2e pass expanded a different number of nodes"
+    h2d, d2h = pipe.h2d, pipe.d2h
+    pipe.close()
+
+    ms_t = torch.tensor([value_ms, e2e_ms, lat_ms], dtype=torch.float64, device="cuda")
+    cnt_t = torch.tensor([float(pops), float(nq), float(res["success"].sum()), float((res["status"] != 0).sum()),
+                          float(res["n_pops_bin_oob"].sum()), float((res["n_pops_bin_oob"] > 0).sum()), float(retried)],
+                         dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(ms_t, op=dist.ReduceOp.MAX)
-        dist.all_reduce(pops_t, op=dist.ReduceOp.SUM)
-    max_ms = float(ms_t.item()); all_pops, all_q = [float(v) for v in pops_t.tolist()]
-    value = all_pops / (max_ms * 1e-3)
-
-    # ---- end to end through the C ABI with pinned host buffers ----
-    pc = 2048
-    hq = torch.from_numpy(q.view(np.uint8).copy()).pin_memory()
-    hres = torch.zeros(nq * pp._cabi.RESULT_DT.itemsize, dtype=torch.uint8).pin_memory()
-    hpath = torch.zeros(nq * pc * 3, dtype=torch.float32).pin_memory()
-    hcurv = torch.zeros(nq * pc, dtype=torch.float32).pin_memory()
-    lib = ctx.lib
-
-    def e2e_step():
-        rc = lib.pp_find_path_batch(ctx.h, C.c_void_p(hq.data_ptr()), C.c_int(nq), C.byref(opts), C.c_void_p(hres.data_ptr()),
-                                    C.c_void_p(hpath.data_ptr()), C.c_void_p(hcurv.data_ptr()), None)
-        if rc != 0:
-            raise RuntimeError(lib.pp_last_error().decode())
-
-    # (the kernel and the pools are warm from the device-resident steps above: no extra warm-up pass)
-    e2e_steps = max(1, min(args.steps, args.e2e_steps))
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        e2e_step()
-    barrier()
-    e2e_s = time.perf_counter() - t0
-    e2e_t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
-    e2e_value = (all_pops / args.steps * e2e_steps) / float(e2e_t.item())
-    r2 = np.frombuffer(hres.numpy().tobytes(), pp._cabi.RESULT_DT)
-    assert int(r2["n_pops"].sum()) == pops, "e2e pass expanded a different number of nodes"
-
-    # ---- K-POP(32) throughput mode on the same batch (new semantics: results are the K-POP restatement's, not the
-    # reference's; reported beside the headline, never instead of it) ----
-    kpop_info = None
-    if not args.no_kpop:
-        kopts = ctx.make_opts(max_expansions=1 << 18, path_cap=2048, max_slots=args.max_slots, mode=1, kpop=32)
-        ctx.batch_upload(q, kopts)
-        ksteps = max(args.steps, 5)
-        for _ in range(args.warmup):
-            ctx.batch_run()
-        barrier()
-        kl0 = ctx.kernel_launches()
-        kms = [ctx.batch_run() for _ in range(ksteps)]
-        barrier()
-        k_launches = ctx.kernel_launches() - kl0
-        kres, _, _ = ctx.batch_fetch()
-        # end to end through the C ABI, host buffers, same as the exact-mode e2e above
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(ksteps):
-            rc = lib.pp_find_path_batch(ctx.h, C.c_void_p(hq.data_ptr()), C.c_int(nq), C.byref(kopts), C.c_void_p(hres.data_ptr()),
-                                        C.c_void_p(hpath.data_ptr()), C.c_void_p(hcurv.data_ptr()), None)
-            if rc != 0:
-                raise RuntimeError(lib.pp_last_error().decode())
-        barrier()
-        ke2e = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
-        kt = torch.tensor([float(np.sum(kms))], dtype=torch.float64, device="cuda")
-        kp = torch.tensor([float(kres["n_pops"].sum()) * ksteps], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(kt, op=dist.ReduceOp.MAX)
-            dist.all_reduce(ke2e, op=dist.ReduceOp.MAX)
-            dist.all_reduce(kp, op=dist.ReduceOp.SUM)
-        both = (res["success"] == 1) & (kres["success"] == 1)
-        ratio = kres["cost"][both] / res["cost"][both] - 1.0
-        kq = all_q / args.steps * ksteps
-        kpop_info = {"k": 32, "expansions_per_s": float(kp.item()) / (float(kt.item()) * 1e-3),
-                     "queries_per_s": kq / (float(kt.item()) * 1e-3), "ms_per_step": float(kt.item()) / ksteps, "steps": ksteps,
-                     "e2e": {"expansions_per_s": float(kp.item()) / float(ke2e.item()), "queries_per_s": kq / float(ke2e.item())},
-                     "gpu_launches": int(k_launches),
-                     "expansions_per_step": int(kres["n_pops"].sum()), "success_rate": float(kres["success"].mean()),
-                     "cost_vs_exact_mode": {"median": float(np.median(ratio)), "min": float(ratio.min()), "max": float(ratio.max())},
-                     "note": "k pops per iteration, exact 2D field heuristic, no equal-f drops; bit-identical to its CPU restatement "
-                             "(oracle/port/kpop.inc), NOT to the reference (SURVEY F4/F5)"}
-
-        klat = []
-        for k in range(min(16, nq)):
-            t1 = time.perf_counter()
-            ctx.find_path_batch(q[k:k + 1], ctx.make_opts(max_expansions=1 << 18, path_cap=pc, max_slots=1, mode=1, kpop=32))
-            klat.append((time.perf_counter() - t1) * 1e3)
-        kpop_info["p50_single_query_ms"] = float(np.median(klat))
-        # the same mode on a C5-sized batch (BASELINE configs[4]: 65536 queries, k-pop = 32): 1024 starts on each of the
-        # groups already on the device; device-resident timing only
-        if not args.no_kpop_large:
-            big_q, big_g = [], []
-            thr = ctx.consts().log_threshold
-            for gi in range(args.groups):
-                cand = S.c4_group(gi, n_starts=args.large_starts, grid_size=N_GRID, resolution=RES)["start_candidates"]
-                st = ctx.set_start(ctx.make_queries(cand, [gi] * len(cand)))
-                free = maps[gi][st["ci"], st["cj"]] < thr
-                sel = cand[free][:args.large_starts]
-                big_q.append(sel); big_g += [gi] * len(sel)
-            bq = ctx.make_queries(np.concatenate(big_q), np.array(big_g, np.int32))
-            bopts = ctx.make_opts(max_expansions=1 << 18, path_cap=1024, max_slots=args.max_slots, mode=1, kpop=32)
-            ctx.batch_upload(bq, bopts)
-            for _ in range(args.warmup):
-                ctx.batch_run()
-            barrier()
-            bms = [ctx.batch_run() for _ in range(ksteps)]
-            barrier()
-            bres, _, _ = ctx.batch_fetch(want_paths=False)
-            bt = torch.tensor([float(np.sum(bms))], dtype=torch.float64, device="cuda")
-            bp = torch.tensor([float(bres["n_pops"].sum()) * ksteps, float(len(bq)) * ksteps], dtype=torch.float64, device="cuda")
-            if world > 1:
-                dist.all_reduce(bt, op=dist.ReduceOp.MAX)
-                dist.all_reduce(bp, op=dist.ReduceOp.SUM)
-            kpop_info["c5_batch"] = {"queries_per_gpu": int(len(bq)), "expansions_per_s": float(bp[0].item()) / (float(bt.item()) * 1e-3),
-                                     "queries_per_s": float(bp[1].item()) / (float(bt.item()) * 1e-3),
-                                     "ms_per_step": float(bt.item()) / ksteps, "success_rate": float(bres["success"].mean()),
-                                     "capacity_flags": int((bres["status"] != 0).sum())}
-
-    # single-query latency (p50) on the first 16 queries, one at a time through the same ABI
-    lat = []
-    for k in range(min(16, nq)):
-        t1 = time.perf_counter()
-        ctx.find_path_batch(q[k:k + 1], ctx.make_opts(max_expansions=args.max_expansions, max_open=args.max_open,
-                                                      max_open2d=args.max_open2d, path_cap=pc, max_slots=1))
-        lat.append((time.perf_counter() - t1) * 1e3)
-
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
+        dist.all_reduce(cnt_t, op=dist.ReduceOp.SUM)
+    max_ms, max_e2e_ms, max_lat_ms = [float(v) for v in ms_t.tolist()]
+    all_pops, all_q, all_succ, all_flags, all_oob, all_oob_q, all_retried = [float(v) for v in cnt_t.tolist()]
+    value = all_pops * args.steps / (max_ms * 1e-3)
+    e2e_value = all_pops * e2e_steps / (max_e2e_ms * 1e-3)
 
     peak, peak_src = peaks()
-    avg_launch_s = (total_ms / args.steps) * 1e-3
-    achieved = (pops * ALGO_BYTES_PER_EXPANSION) / avg_launch_s / 1e9
-    line = {
-        "metric": "hybrid_astar_node_expansions_per_s", "value": value, "unit": "expansions/s", "n_gpus": world,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": max_ms / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "queries_per_s": all_q / (max_ms * 1e-3),
-        "p50_single_query_ms": float(np.median(lat)),
-        "expansions_per_step": pops, "queries_per_step": nq,
-        "success_rate": float(res["success"].mean()), "capacity_flags": int((res["status"] != 0).sum()),
-        "expansions_bin_oob": int(res["n_pops_bin_oob"].sum()),
-        "config": {"workload": workload, "slots": int(opts.max_slots) or "auto",
-                   "pools": {"max_expansions": int(opts.max_expansions), "max_open": int(opts.max_open), "max_open2d": int(opts.max_open2d),
-                             "note": pool_note, "retried_queries": int(retried_exact)},
-                   "per_rank_batch": "identical on every rank (same seeds): the step is bound by the batch's single longest query",
-                   "l2": "per-query scratch (open/closed sets, lazy-A* cache) is tens of GB per step, far larger than the 126 MB L2",
-                   "map_build_s": map_build_s, "map_broadcast_ms": map_bcast_ms},
-        "e2e": {"value": e2e_value, "unit": "expansions/s", "h2d_bytes_per_step": int(q.nbytes),
-                "d2h_bytes_per_step": int(hres.numel() + hpath.numel() * 4 + hcurv.numel() * 4)},
-        "gpu_launches": int(timed_launches),
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "kernel": "pp_search_kernel", "peak_source": peak_src,
-                     "note": "latency-bound pointer chasing (libstdc++-exact rb-tree walks); algorithmic bytes = 312 B/expansion (SURVEY 8d)"},
-        "clocks": clocks,
-        "kpop": kpop_info,
-    }
-    # north_star (c): the generic vehicle-footprint collision kernel on this batch's first map (4.0 x 2.0 m rectangle, 2^20 poses);
-    # a side measurement, never allowed to break the headline line
-    try:
-        rs = np.random.RandomState(3)
-        L = N_GRID * RES
-        fp = np.concatenate([rs.uniform(0.0, L, (1 << 20, 2)), rs.uniform(-np.pi, np.pi, (1 << 20, 1))], 1).astype(np.float32)
-        ctx.set_footprint(4.0, 2.0, 1.0)
-        ctx.footprint(fp)
-        fms = min(ctx.footprint(fp, want_ms=True)[3] for _ in range(5))
-        fcells = float(np.mean([len(ctx.footprint_table(b)) for b in range(72)]))
-        line["footprint_kernel"] = {"poses": len(fp), "vehicle_m": [4.0, 2.0, 1.0], "mean_cells_per_pose": fcells, "kernel_ms": fms,
-                                    "poses_per_s": len(fp) / (fms * 1e-3),
-                                    "algorithmic_GBps": len(fp) * (fcells * 4 + 24) / (fms * 1e-3) / 1e9,
-                                    "note": "map is L1/L2-resident (1 MiB): issue/L1-bound, see DESIGN.md section 12"}
-    except Exception as e:
-        line["footprint_kernel"] = {"error": str(e)}
-    if not args.no_cpu_baseline:
+    line = None
+    if rank == 0:
+        achieved = pops * args.steps * ALGO_BYTES_PER_EXPANSION / (value_ms * 1e-3) / 1e9
+        line = {
+            "metric": "hybrid_astar_node_expansions_per_s", "value": value, "unit": "expansions/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": max_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "queries_per_s": all_q * args.steps / (max_ms * 1e-3),
+            "batch_latency_ms": max_lat_ms,
+            "expansions_per_step": int(all_pops), "queries_per_step": int(all_q),
+            "success_rate": all_succ / all_q, "capacity_flags": int(all_flags), "retried_queries": int(all_retried),
+            "expansions_bin_oob": int(all_oob), "queries_with_bin_oob": int(all_oob_q),
+            "config": {"workload": workload, "per_rank_batch": "rank r runs the groups with seeds r*64 .. r*64+63 (distinct queries per rank)",
+                       "step_submission": f"steps are independent batches, submitted round-robin over {lanes} lane contexts (own stream + scratch, "
+                                          "shared maps) with one synchronisation at the end: the drain of batch k overlaps batch k+1 "
+                                          "(continuous batching); batch_latency_ms = one batch alone on an idle GPU",
+                       "pools": "per-query containers start at 8192 closed / 4096 open / 2048 2D-open entries and grow x2 from the lane's arena "
+                                "(library defaults); retried_queries = re-executions after a capacity miss",
+                       "l2": "per-query scratch (open / closed sets, lazy-A* cache) of the resident queries is tens of GB, far larger than the 126 MB L2",
+                       "map_build_s": map_build_s, "timed_region_wall_s": value_wall},
+            "e2e": {"value": e2e_value, "unit": "expansions/s", "steps": e2e_steps, "ms_per_step": max_e2e_ms / e2e_steps,
+                    "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world},
+            "gpu_launches": int(timed_launches),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": committed_traffic("pp_search_kernel"), "kernel": "pp_search_kernel", "peak_source": peak_src,
+                         "launch_ms_mean": float(np.mean(launch_ms)) if launch_ms else None, "launches_in_flight": lanes,
+                         "note": "latency-bound pointer chasing (libstdc++-exact red-black-tree walks on one control lane per query); "
+                                 "achieved = algorithmic bytes (312 B/expansion, SURVEY 8d) of the timed region / its duration"},
+            "clocks": clocks,
+        }
+
+    # ---- CPU baseline (rank 0, N = 1 only): the unmodified reference on the host cores, bounded sample of the same batch ----
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
-            rs = np.random.RandomState(1)
-            idx = rs.permutation(nq)[:args.cpu_sample]
-            secs, cpops, ccost, _ = cpu_reference_run(groups, queries, qgroups, maps, idx, n_threads)
-            same = int((cpops == res["n_pops"][idx]).sum())
-            line["cpu_baseline"] = {"value": float(cpops.sum() / secs), "unit": "expansions/s", "cores": n_threads, "kind": "reference",
-                                    "sample": f"{len(idx)} of the {nq} queries, one reference planner per thread, scrubbed per query ({secs:.1f} s)",
-                                    "queries_per_s": len(idx) / secs,
-                                    "same_expansion_count_as_gpu": f"{same}/{len(idx)} (stock glibc libm vs pinned libm, see DESIGN.md)"}
-            # also the single-threaded reference as it ships (one planner, one core), on the 8 shortest queries
-            # of the same sample so that the side measurement stays bounded
-            try:
-                short = idx[np.argsort(cpops)[:8]]
-                s1, p1, _, _ = cpu_reference_run(groups, queries, qgroups, maps, short, 1)
-                line["cpu_baseline"]["one_core"] = {"value": float(p1.sum() / s1), "unit": "expansions/s", "queries_per_s": len(short) / s1,
-                                                    "sample": f"the {len(short)} shortest queries of the sample above ({s1:.1f} s)"}
-            except Exception as e:
-                line["cpu_baseline"]["one_core"] = {"error": str(e)}
+            import orc
+            n_threads = os.cpu_count() or 1
+            n_s = args.cpu_sample if args.cpu_sample > 0 else int(min(max(8 * n_threads, 64), 256))
+            idx = reference_sample(nq, n_s)
+            Pr = orc.make_params(grid_size=N_GRID, resolution=RES)
+            b = orc.ref_batch(Pr, groups, queries, qgroups, maps, idx, n_threads)
+            cpu = (idx, b)
+            rs = pipe.results(0)
+            defined = (b["pops_oob"] == 0) & (res["n_pops_bin_oob"][idx] == 0)
+            same_n = (b["pops"] == res["n_pops"][idx]) & (b["success"] == res["success"][idx])
+            same_c = b["cost"].view(np.uint32) == res["cost"][idx].view(np.uint32)
+            hp = np.frombuffer(pipe.hpath[0].numpy().tobytes(), np.float32).reshape(nq, 2048, 3)
+            hc = np.frombuffer(pipe.hcurv[0].numpy().tobytes(), np.float32).reshape(nq, 2048)
+            same_h = np.array([(not rs["success"][k]) or orc.path_hash(hp[k, :rs["n_path"][k]], hc[k, :rs["n_path"][k]]) == int(b["hash"][j])
+                               for j, k in enumerate(idx)])
+            ident = int((same_n & same_c & same_h & defined).sum())
+            line["cpu_baseline"] = {
+                "value": float(b["pops"].sum() / b["secs"]), "unit": "expansions/s", "cores": n_threads, "kind": "reference",
+                "sample": f"{len(idx)} of the {nq} queries (fixed permutation, seed 1), one reference planner per thread, scrubbed per query ({b['secs']:.1f} s)",
+                "queries_per_s": len(idx) / b["secs"],
+                "busy_time_expansions_per_s_per_core": float(b["pops"].sum() / b["busy_s"].sum()),
+                "identical_to_gpu": {"count_cost_path_hash": f"{ident}/{int(defined.sum())}",
+                                     "excluded_bin72_undefined_in_reference": int((~defined).sum())}}
         except Exception as e:  # the reference .so is test infrastructure; report rather than die
-            line["cpu_baseline"] = {"error": str(e)}
-    print(json.dumps(line), flush=True)
+            line["cpu_baseline"] = {"error": repr(e)}
+
+    # ---- side blocks (never allowed to break the headline line) ----
+    def guarded(name, fn):
+        try:
+            return fn()
+        except Exception as e:
+            return {"error": repr(e)}
+
+    if not args.no_kpop and in_time():
+        k = guarded("kpop", lambda: block_kpop(args, pp, ctx, q, res, barrier, cpu, in_time()))
+        if rank == 0:
+            line["kpop"] = k
+    ctx.close()
+    if not args.no_c5 and in_time():
+        c5 = guarded("c5", lambda: block_c5(args, pp, torch, dist, rank, local_rank, world, barrier, in_time))
+        if rank == 0:
+            line["c5"] = c5
+    if rank == 0 and world == 1 and not args.no_blocks:
+        if time.time() < deadline:
+            line["c1"] = guarded("c1", lambda: block_c1(args, pp, local_rank))
+        if time.time() < deadline:
+            line["c2_map_update"] = guarded("c2", lambda: block_c2(args, pp, local_rank, peak))
+        if time.time() < deadline:
+            line["c3_fields"] = guarded("c3", lambda: block_c3(args, pp, local_rank, peak))
+    if rank == 0:
+        line["wall_s"] = elapsed()
+        print(json.dumps(line), flush=True)
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 

@@ -106,6 +106,7 @@ typedef struct pp_query
 #define PP_STATUS_OPEN2D_OVERFLOW 4   /* 2D open-list pool of the lazy heuristic exhausted */
 #define PP_STATUS_PATH_OVERFLOW 8     /* path_cap too small: the returned path is truncated */
 #define PP_STATUS_NULL_TERMINAL 16    /* the reference would dereference a null _prev here (Dubins shot from the start node) */
+#define PP_STATUS_ARENA_EXHAUSTED 32  /* a container had to grow and the context's memory arena had no block left */
 #endif
 
 typedef struct pp_result
@@ -126,9 +127,13 @@ typedef struct pp_result
 
 typedef struct pp_search_opts
 {
-    int max_expansions;      /* closed-log capacity per query (reference: unbounded) */
-    int max_open;            /* 3D open-list pool per query */
-    int max_open2d;          /* 2D open-list pool per query */
+    /* PP_MODE_EXACT: hard caps of the per-query containers (the reference's are unbounded).  Every resident query starts on small
+     * pools and a container that fills up moves into a block twice the size from the context's arena, up to these caps (0 = defaults:
+     * 2^24 closed states, 2^23 open nodes, 2^20 2D open nodes).  A query that meets a cap is re-run with caps 8x larger, up to three
+     * times, before pp_result.status reports it.  PP_MODE_KPOP: max_expansions sizes the fixed per-slot node log (0 = 2^17). */
+    int max_expansions;      /* closed states per query */
+    int max_open;            /* 3D open-list nodes per query */
+    int max_open2d;          /* 2D open-list nodes per query (lazy heuristic) */
     int path_cap;            /* path points per query in the output arrays */
     int trace_cap;           /* pops recorded per query (0 = no trace) */
     int max_slots;           /* resident query slots (0 = auto from free memory) */
@@ -148,6 +153,15 @@ int  pp_device_count(void);
  * `num_groups` independent planner instances (map + goal frame + APF list each). */
 int  pp_create(const pp_params* params, int device, int num_groups, pp_context** out);
 void pp_destroy(pp_context* ctx);
+/* A lane: a context that shares `parent`'s parameters, maps, goal frames and APF lists (read-only view) and owns its stream, search
+ * scratch and batch buffers.  Batches on different lanes run concurrently on the device, so the drain of one batch (its few longest
+ * queries, one warp each) overlaps the bulk of the next: continuous batching of HybridAStar::find_path calls
+ * (lib/HybridAStar.cpp:68-88) that the single-threaded reference has no counterpart for.  Map updates go through the parent; a lane
+ * sees them at its next pp_batch_upload.  Destroy lanes before their parent. */
+int  pp_create_lane(pp_context* parent, pp_context** out);
+/* Bytes of device memory the search scratch of this context may take (per-query pools + the arena they grow into);
+ * 0 = 75 % of the memory free at first use.  Applies from the next (re)allocation. */
+int  pp_set_memory_budget(pp_context* ctx, unsigned long long bytes);
 int  pp_get_consts(pp_context* ctx, pp_consts_info* out);
 int  pp_get_frame(pp_context* ctx, int group, pp_frame_info* out);
 /* VehicleModel tables (lib/VehicleModel.cpp:31-40): offset_xy[S][bins][2], heading offsets, costs, |curvature| */
@@ -182,8 +196,22 @@ int  pp_update_obstacles_decay(pp_context* ctx, int group);
 /* HybridAStar::get_obstacles() (lib/HybridAStar.cpp:62-65): N*N floats, row = i (grid x) */
 int  pp_map_download(pp_context* ctx, int group, float* out_nn);
 int  pp_map_upload(pp_context* ctx, int group, const float* in_nn);
-/* device pointer of a group's map (for NCCL broadcast by the caller) */
+/* Grid3D::update_obstacles without the Grid2D rasterisation (lib/Grid3D.cpp:22-44): rebuilds the group's APF obstacle list only.
+ * A rank that receives the map itself by pp_broadcast_maps calls this instead of pp_update_obstacles_boxes. */
+int  pp_update_obstacles_apf(pp_context* ctx, int group, const float* boxes_xydxdy, int n, float apf_added_radius);
+/* device pointer of a group's map; state derived from the map is dropped.  A caller that writes through it (its own collective)
+ * calls pp_map_mark_dirty once the write has completed. */
 void* pp_map_device_ptr(pp_context* ctx, int group);
+int  pp_map_mark_dirty(pp_context* ctx, int group);
+/* ---- map replication across the GPUs of one box (BASELINE north_star: "the map replicated by an NCCL broadcast over NVLink after
+ * each update"; the reference is single-process: src/local_planner.cpp:241, :287-288 update the one map in place) ----
+ * One communicator per context, one rank per GPU.  pp_comm_unique_id (rank 0) fills 128 bytes (ncclUniqueId) the caller hands to
+ * every rank (torch.distributed / MPI / a file); pp_comm_init joins; pp_broadcast_maps replaces groups [first, first + n) on every
+ * rank by root's maps, in place, on the context's stream (asynchronous: pp_sync waits).  NCCL is resolved with dlopen. */
+int  pp_comm_unique_id(void* id128);
+int  pp_comm_init(pp_context* ctx, int nranks, int rank, const void* id128);
+int  pp_broadcast_maps(pp_context* ctx, int first_group, int n_groups, int root);
+int  pp_comm_destroy(pp_context* ctx);
 int  pp_sync(pp_context* ctx);
 
 /* Grid3D::set_start_node (lib/Grid3D.cpp:127-160) + HybridAStar.cpp:73-74 for n queries (host side) */
@@ -249,6 +277,10 @@ int  pp_find_path_batch(pp_context* ctx, const pp_query* queries, int n, const p
 /* Split form used by bench.py: upload once, run (timed on the device), fetch. */
 int  pp_batch_upload(pp_context* ctx, const pp_query* queries, int n, const pp_search_opts* opts);
 int  pp_batch_run(pp_context* ctx, float* kernel_ms);
+/* pp_batch_run in two halves: enqueue the search on the context's stream and return; wait for it (and re-run the queries that met
+ * a capacity, as pp_batch_run does).  kernel_ms = device time of all passes (CUDA events on the context's stream). */
+int  pp_batch_run_async(pp_context* ctx);
+int  pp_batch_wait(pp_context* ctx, float* kernel_ms);
 int  pp_batch_fetch(pp_context* ctx, pp_result* results, float* paths_xyh, float* curvature, pp_pop* trace);
 /* ---- the step after the path: velocity profile and trajectory message ---- */
 /* The five constructor arguments of VelocityGenerator<T> (lib/VelocityGenerator.cpp:6-14). */

@@ -123,15 +123,26 @@ def _p(a):
 class Context:
     """pp_context: shared parameters + `num_groups` planner instances (map, goal frame, APF list)."""
 
-    def __init__(self, params, num_groups=1, device=0):
+    def __init__(self, params, num_groups=1, device=0, _lane_of=None):
         self.lib = load()
         self.params = params
         self.num_groups = num_groups
         self.N = params.grid_size
         self.stride = 2 * params.num_actions + 1
+        self._parent = _lane_of          # keeps the parent alive as long as its lane
         h = C.c_void_p()
-        self._chk(self.lib.pp_create(C.byref(params), C.c_int(device), C.c_int(num_groups), C.byref(h)))
+        if _lane_of is None:
+            self._chk(self.lib.pp_create(C.byref(params), C.c_int(device), C.c_int(num_groups), C.byref(h)))
+        else:
+            self._chk(self.lib.pp_create_lane(_lane_of.h, C.byref(h)))
         self.h = h
+
+    def create_lane(self):
+        """pp_create_lane: a context sharing this one's maps / frames / APF lists with its own stream and search scratch."""
+        return Context(self.params, self.num_groups, _lane_of=self)
+
+    def set_memory_budget(self, nbytes):
+        self._chk(self.lib.pp_set_memory_budget(self.h, C.c_ulonglong(int(nbytes))))
 
     def _chk(self, rc):
         if rc != 0:
@@ -189,6 +200,28 @@ class Context:
 
     def map_device_ptr(self, group=0):
         return self.lib.pp_map_device_ptr(self.h, C.c_int(group))
+
+    def map_mark_dirty(self, group=0):
+        self._chk(self.lib.pp_map_mark_dirty(self.h, C.c_int(group)))
+
+    def update_apf(self, boxes, apf_added_radius, group=0):
+        """pp_update_obstacles_apf: the APF obstacle list only (the map itself arrives by broadcast_maps)."""
+        b = np.ascontiguousarray(boxes, np.float32)
+        self._chk(self.lib.pp_update_obstacles_apf(self.h, C.c_int(group), _p(b), C.c_int(len(b)), C.c_float(apf_added_radius)))
+
+    # ---- map replication over NCCL (one communicator per context, one rank per GPU) ----
+    def comm_unique_id(self):
+        buf = (C.c_char * 128)()
+        self._chk(self.lib.pp_comm_unique_id(buf))
+        return bytes(buf)
+
+    def comm_init(self, nranks, rank, unique_id):
+        buf = (C.c_char * 128).from_buffer_copy(unique_id)
+        self._chk(self.lib.pp_comm_init(self.h, C.c_int(nranks), C.c_int(rank), buf))
+
+    def broadcast_maps(self, first_group=0, n_groups=None, root=0):
+        n = self.num_groups - first_group if n_groups is None else n_groups
+        self._chk(self.lib.pp_broadcast_maps(self.h, C.c_int(first_group), C.c_int(n), C.c_int(root)))
 
     def sync(self):
         self._chk(self.lib.pp_sync(self.h))
@@ -341,6 +374,14 @@ class Context:
     def batch_run(self):
         ms = C.c_float()
         self._chk(self.lib.pp_batch_run(self.h, C.byref(ms)))
+        return ms.value
+
+    def batch_run_async(self):
+        self._chk(self.lib.pp_batch_run_async(self.h))
+
+    def batch_wait(self):
+        ms = C.c_float()
+        self._chk(self.lib.pp_batch_wait(self.h, C.byref(ms)))
         return ms.value
 
     def batch_fetch(self, want_paths=False):

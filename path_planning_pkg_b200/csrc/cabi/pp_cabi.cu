@@ -2,6 +2,7 @@
 // (csrc/host/pp_host.h) and kernel launches (csrc/kernels/pp_kernels.cuh).  No CPU compute path:
 // every entry point that computes launches a kernel on the context's stream.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -16,6 +17,8 @@
 #include "../../../include/pp_b200.h"
 
 static thread_local std::string g_last_error;
+
+struct PPNcclIdByValue { char internal[128]; };     // ncclUniqueId (nccl.h), passed by value to ncclCommInitRank
 
 static int pp_fail(int code, const std::string& msg)
 {
@@ -47,19 +50,28 @@ struct DevBuf
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
 
-// per-slot scratch pools of the search kernel
+// Per-slot scratch of the EXACT search kernel: small FIXED pools every resident query starts on, plus one arena
+// (csrc/core/pp_arena.h) the containers of the queries that need more grow into.
 struct WorkPools
 {
     int alloc_slots = 0, chash_cap = 0, open3_cap = 0, closed_cap = 0, open2_cap = 0;
     DevBuf<PPNode3> open3; DevBuf<PPClosed3> closed; DevBuf<PPHashSlot> chash;
     DevBuf<unsigned> cell_state; DevBuf<float> nm_g, nm_f, cl_g; DevBuf<int> cl_prev; DevBuf<PPNode2> open2;
+    DevBuf<unsigned char> arena_mem; DevBuf<PPArena> arena_ctl; size_t arena_bytes = 0;
+    bool clamped = false;      // the slot count was limited by the memory budget, not by the request
     void release()
     {
         open3.release(); closed.release(); chash.release(); cell_state.release();
         nm_g.release(); nm_f.release(); cl_g.release(); cl_prev.release(); open2.release();
+        arena_mem.release(); arena_ctl.release(); arena_bytes = 0;
         alloc_slots = 0;
     }
 };
+
+// first-pass capacities of the fixed per-slot pools (containers grow from here, x2 per step)
+#define PP_INIT_CLOSED 8192
+#define PP_INIT_OPEN3  4096
+#define PP_INIT_OPEN2D 2048
 
 struct pp_context
 {
@@ -94,9 +106,14 @@ struct pp_context
     int* d_counter = nullptr;
     // per-slot scratch pools
     int n_slots = 0;
-    WorkPools wp;          // first pass: every query, moderate capacities
-    WorkPools wp_retry;    // queries that hit a capacity are re-run here with 8x larger pools (the reference is unbounded)
-    WorkPools wp_lazy;     // persistent cache of the stand-alone lazy 2D A* (AStar<T> handle)
+    WorkPools wp;          // EXACT mode: small fixed pools per resident query + the arena they grow into
+    WorkPools wp_lazy;     // persistent cache of the stand-alone lazy 2D A* (AStar<T> handle), fixed pools
+    size_t mem_budget = 0; // bytes the search scratch (slots + arena) may take; 0 = 75 % of the free device memory
+    pp_context* parent = nullptr;   // lane context (pp_create_lane): shares the parent's maps / groups / tables, read-only
+    cudaEvent_t ev_run0 = nullptr, ev_run1 = nullptr;   // bracket of the asynchronous first pass of a batch
+    bool run_pending = false;
+    void* nccl_comm = nullptr;      // ncclComm_t of pp_comm_init (map replication, pp_broadcast_maps)
+    int comm_rank = -1, comm_size = 0;
     unsigned* d_lazy_sid = nullptr;
     int lazy_group = -1;
     // planner-object history (pp_set_history): per group the carried 2D cache (`_visted` + `_node_map` costs) of one
@@ -115,7 +132,7 @@ struct pp_context
     bool batch_done = false;              // pp_batch_run finished on the uploaded batch (results / path records valid)
     DevBuf<float> d_traj, d_traj_tmp, d_vel_in; DevBuf<int> d_traj_int; DevBuf<PPWorldFrame> d_wframes;
     // K-POP mode pools (per slot): node log, hash table, LSM queue arena + merge scratch
-    struct KPools { int alloc_slots = 0, nodes_cap = 0, table_cap = 0, levels = 0; size_t arena_cap = 0, tmp_cap = 0;
+    struct KPools { int alloc_slots = 0, nodes_cap = 0, table_cap = 0, levels = 0; size_t arena_cap = 0, tmp_cap = 0; bool clamped = false;
                     DevBuf<PPKNode> nodes; DevBuf<PPKSlot> table; DevBuf<PPKEntry> arena, tmp_a, tmp_b;
                     void release() { nodes.release(); table.release(); arena.release(); tmp_a.release(); tmp_b.release(); alloc_slots = 0; } };
     KPools kp, kp_retry;
@@ -156,6 +173,55 @@ static int check_group(pp_context* c, int g)
     return PP_SUCCESS;
 }
 
+// a lane context reads its parent's map state: take over the host mirrors and make sure the parent's device copies are current
+static int lane_refresh(pp_context* c)
+{
+    pp_context* p = c->parent;
+    if (!p) return PP_SUCCESS;
+    int rc = sync_groups(p); if (rc) return rc;
+    PP_CUDA(cudaStreamSynchronize(p->stream));
+    c->frames = p->frames; c->groups = p->groups;
+    c->d_groups = p->d_groups; c->d_maps = p->d_maps; c->d_off_xy = p->d_off_xy;
+    c->groups_dirty = false;
+    return PP_SUCCESS;
+}
+
+// ---- NCCL, resolved at run time (the library itself links only the CUDA runtime).  dlopen by soname returns the copy the
+// process already holds (e.g. the one torch.distributed loaded); PP_B200_NCCL_LIB names another file.
+struct PPNccl
+{
+    void* handle = nullptr;
+    int (*GetUniqueId)(void*) = nullptr;
+    int (*CommInitRank)(void**, int, PPNcclIdByValue, int) = nullptr;
+    int (*Broadcast)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+};
+
+static PPNccl* nccl_api(std::string& err)
+{
+    static PPNccl api;
+    if (api.handle) return &api;
+    const char* names[] = {std::getenv("PP_B200_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+    void* h = nullptr;
+    for (const char* nm : names) { if (nm && *nm) { h = dlopen(nm, RTLD_NOW | RTLD_GLOBAL); if (h) break; } }
+    if (!h) { err = "NCCL library not found (libnccl.so.2; set PP_B200_NCCL_LIB)"; return nullptr; }
+    api.GetUniqueId = (int (*)(void*))dlsym(h, "ncclGetUniqueId");
+    api.CommInitRank = (int (*)(void**, int, PPNcclIdByValue, int))dlsym(h, "ncclCommInitRank");
+    api.Broadcast = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(h, "ncclBroadcast");
+    api.CommDestroy = (int (*)(void*))dlsym(h, "ncclCommDestroy");
+    api.GetErrorString = (const char* (*)(int))dlsym(h, "ncclGetErrorString");
+    if (!api.GetUniqueId || !api.CommInitRank || !api.Broadcast || !api.CommDestroy) { err = "NCCL symbols missing"; return nullptr; }
+    api.handle = h;
+    return &api;
+}
+
+static int lane_guard(pp_context* c, const char* what)
+{
+    if (c && c->parent) return pp_fail(PP_ERR_INVALID, std::string(what) + ": lanes are read-only views of their parent's maps");
+    return PP_SUCCESS;
+}
+
 extern "C"
 {
 
@@ -168,26 +234,22 @@ int pp_device_count(void)
     return n;
 }
 
-int pp_create(const pp_params* params, int device, int num_groups, pp_context** out)
+static int create_impl(pp_context* c, int num_groups)
 {
-    if (!params || !out || num_groups < 1) return pp_fail(PP_ERR_INVALID, "pp_create: bad arguments");
-    int ndev = 0;
-    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
-        return pp_fail(PP_ERR_NO_DEVICE, "pp_create: no CUDA device (this library has no CPU path)");
-    if (device < 0 || device >= ndev) return pp_fail(PP_ERR_INVALID, "pp_create: bad device index");
-    pp_context* c = new pp_context();
-    c->device = device;
-    c->params = *params;
-    std::string err;
-    if (!pp_host_build_model(*params, c->model, err)) { delete c; return pp_fail(PP_ERR_INVALID, "pp_create: " + err); }
-    PP_CUDA(cudaSetDevice(device));
+    PP_CUDA(cudaSetDevice(c->device));
     cudaDeviceProp prop;
-    PP_CUDA(cudaGetDeviceProperties(&prop, device));
+    PP_CUDA(cudaGetDeviceProperties(&prop, c->device));
     c->sm_count = prop.multiProcessorCount;
     PP_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     PP_CUDA(cudaEventCreate(&c->ev0));
     PP_CUDA(cudaEventCreate(&c->ev1));
+    PP_CUDA(cudaEventCreate(&c->ev_run0));
+    PP_CUDA(cudaEventCreate(&c->ev_run1));
     c->num_groups = num_groups;
+    PP_CUDA(cudaMalloc(&c->d_counter, sizeof(int)));
+    PP_CUDA(cudaMalloc(&c->d_lazy_sid, sizeof(unsigned)));
+    PP_CUDA(cudaMemsetAsync(c->d_lazy_sid, 0, sizeof(unsigned), c->stream));
+    if (c->parent) return lane_refresh(c);
     size_t nn = nn_of(c);
     PP_CUDA(cudaMalloc(&c->d_maps, sizeof(float) * nn * num_groups));
     PP_CUDA(cudaMemsetAsync(c->d_maps, 0, sizeof(float) * nn * num_groups, c->stream));
@@ -197,9 +259,6 @@ int pp_create(const pp_params* params, int device, int num_groups, pp_context** 
     PP_CUDA(cudaMalloc(&c->d_off_xy, sizeof(float) * c->model.off_xy.size()));
     PP_CUDA(cudaMemcpyAsync(c->d_off_xy, c->model.off_xy.data(), sizeof(float) * c->model.off_xy.size(), cudaMemcpyHostToDevice, c->stream));
     PP_CUDA(cudaMalloc(&c->d_groups, sizeof(PPGroup) * num_groups));
-    PP_CUDA(cudaMalloc(&c->d_counter, sizeof(int)));
-    PP_CUDA(cudaMalloc(&c->d_lazy_sid, sizeof(unsigned)));
-    PP_CUDA(cudaMemsetAsync(c->d_lazy_sid, 0, sizeof(unsigned), c->stream));
     c->frames.resize(num_groups);
     c->groups.resize(num_groups);
     c->apf_cap.assign(num_groups, 0);
@@ -219,31 +278,82 @@ int pp_create(const pp_params* params, int device, int num_groups, pp_context** 
     }
     c->groups_dirty = true;
     PP_CUDA(cudaStreamSynchronize(c->stream));
+    return PP_SUCCESS;
+}
+
+int pp_create(const pp_params* params, int device, int num_groups, pp_context** out)
+{
+    if (!params || !out || num_groups < 1) return pp_fail(PP_ERR_INVALID, "pp_create: bad arguments");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return pp_fail(PP_ERR_NO_DEVICE, "pp_create: no CUDA device (this library has no CPU path)");
+    if (device < 0 || device >= ndev) return pp_fail(PP_ERR_INVALID, "pp_create: bad device index");
+    pp_context* c = new pp_context();
+    c->device = device;
+    c->params = *params;
+    std::string err;
+    if (!pp_host_build_model(*params, c->model, err)) { delete c; return pp_fail(PP_ERR_INVALID, "pp_create: " + err); }
+    int rc = create_impl(c, num_groups);
+    if (rc) { std::string keep = g_last_error; pp_destroy(c); g_last_error = keep; return rc; }    // nothing leaks on a CUDA failure
     *out = c;
+    return PP_SUCCESS;
+}
+
+// A lane: a context that shares `parent`'s parameters, maps, goal frames and APF lists (read-only) and owns its stream,
+// its search scratch and its batch buffers.  Batches uploaded to different lanes run concurrently on the device, so the
+// drain of one batch (its last long queries) overlaps the bulk of the next -- continuous batching for the EXACT mode.
+// Map updates go through the parent; a lane picks them up at its next pp_batch_upload.  Destroy lanes before the parent.
+int pp_create_lane(pp_context* parent, pp_context** out)
+{
+    if (!parent || !out) return pp_fail(PP_ERR_INVALID, "pp_create_lane: bad arguments");
+    if (parent->parent) return pp_fail(PP_ERR_INVALID, "pp_create_lane: a lane cannot have lanes");
+    pp_context* c = new pp_context();
+    c->device = parent->device;
+    c->params = parent->params;
+    c->model = parent->model;
+    c->parent = parent;
+    int rc = create_impl(c, parent->num_groups);
+    if (rc) { std::string keep = g_last_error; pp_destroy(c); g_last_error = keep; return rc; }
+    *out = c;
+    return PP_SUCCESS;
+}
+
+int pp_set_memory_budget(pp_context* c, unsigned long long bytes)
+{
+    if (!c) return pp_fail(PP_ERR_INVALID, "null context");
+    c->mem_budget = (size_t)bytes;
     return PP_SUCCESS;
 }
 
 void pp_destroy(pp_context* c)
 {
     if (!c) return;
+    pp_comm_destroy(c);
     cudaSetDevice(c->device);
-    cudaStreamSynchronize(c->stream);
-    for (float* p : c->d_apf) if (p) cudaFree(p);
-    for (auto& b : c->d_bin_off) b.release();
-    for (auto& b : c->d_bin_idx) b.release();
-    cudaFree(c->d_maps); cudaFree(c->d_map_tmp); cudaFree(c->d_cell_scratch); cudaFree(c->d_off_xy);
-    cudaFree(c->d_groups); cudaFree(c->d_counter);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    if (!c->parent)
+    {
+        for (float* p : c->d_apf) if (p) cudaFree(p);
+        for (auto& b : c->d_bin_off) b.release();
+        for (auto& b : c->d_bin_idx) b.release();
+        cudaFree(c->d_maps); cudaFree(c->d_map_tmp); cudaFree(c->d_cell_scratch); cudaFree(c->d_off_xy);
+        cudaFree(c->d_groups);
+    }
+    cudaFree(c->d_counter);
     c->s0.release(); c->s1.release(); c->s2.release(); c->s3.release(); c->s4.release();
     c->d_queries.release(); c->d_results.release(); c->d_paths.release(); c->d_trace.release();
-    c->wp.release(); c->wp_retry.release(); c->wp_lazy.release(); c->d_qmap.release(); c->d_order.release(); c->d_group_cost.release();
+    c->wp.release(); c->wp_lazy.release(); c->d_qmap.release(); c->d_order.release(); c->d_group_cost.release();
     cudaFree(c->d_lazy_sid);
     for (auto& h : c->hist) h.release();
     c->d_foot_bins.release(); c->d_foot_offs.release(); c->d_foot_lin.release(); c->d_foot_xyh.release(); c->d_foot_out.release();
     c->d_traj.release(); c->d_traj_tmp.release(); c->d_vel_in.release(); c->d_traj_int.release(); c->d_wframes.release();
     c->kp.release(); c->kp_retry.release();
     c->d_field2d.release(); c->d_f2d_work.release(); c->d_f2d_flags.release(); c->d_dubins_field.release();
-    cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
-    cudaStreamDestroy(c->stream);
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->ev_run0) cudaEventDestroy(c->ev_run0);
+    if (c->ev_run1) cudaEventDestroy(c->ev_run1);
+    if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
 
@@ -296,6 +406,7 @@ int pp_sync(pp_context* c)
 int pp_update_goal(pp_context* c, int g, const float* goal3, const float* start3)
 {
     int rc = check_group(c, g); if (rc) return rc;
+    rc = lane_guard(c, "pp_update_goal"); if (rc) return rc;
     map_changed(c, g);
     PP_CUDA(cudaSetDevice(c->device));
     const PPConsts& C = c->model.C;
@@ -353,6 +464,7 @@ int pp_set_history(pp_context* c, int g, int enable)
 int pp_update_obstacles_decay(pp_context* c, int g)
 {
     int rc = check_group(c, g); if (rc) return rc;
+    rc = lane_guard(c, "pp_update_obstacles_decay"); if (rc) return rc;
     map_changed(c, g);
     PP_CUDA(cudaSetDevice(c->device));
     const PPConsts& C = c->model.C;
@@ -368,6 +480,7 @@ int pp_update_obstacles_decay(pp_context* c, int g)
 int pp_update_obstacles_boxes_2d(pp_context* c, int g, const float* boxes, const float* conf, int n)
 {
     int rc = check_group(c, g); if (rc) return rc;
+    rc = lane_guard(c, "pp_update_obstacles_boxes_2d"); if (rc) return rc;
     map_changed(c, g);
     if (n < 0 || (n > 0 && (!boxes || !conf))) return pp_fail(PP_ERR_INVALID, "boxes: bad arguments");
     if (n == 0) return PP_SUCCESS;
@@ -414,16 +527,20 @@ int pp_update_obstacles_boxes_2d(pp_context* c, int g, const float* boxes, const
     return PP_SUCCESS;
 }
 
-int pp_update_obstacles_boxes(pp_context* c, int g, const float* boxes, const float* conf, int n, float apf_added_radius)
+// Grid3D::update_obstacles' own part (Grid3D.cpp:22-44): the APF obstacle list of the group, rebuilt from the boxes; the map is
+// not touched.  A rank that receives its maps by pp_broadcast_maps calls this instead of pp_update_obstacles_boxes.
+int pp_update_obstacles_apf(pp_context* c, int g, const float* boxes, int n, float apf_added_radius)
 {
     int rc = check_group(c, g); if (rc) return rc;
-    if (n < 0 || (n > 0 && (!boxes || !conf))) return pp_fail(PP_ERR_INVALID, "boxes: bad arguments");
+    rc = lane_guard(c, "pp_update_obstacles_apf"); if (rc) return rc;
+    if (n < 0 || (n > 0 && !boxes)) return pp_fail(PP_ERR_INVALID, "boxes: bad arguments");
     PP_CUDA(cudaSetDevice(c->device));
     // APF list rebuild, Grid3D.cpp:26-40
     std::vector<float> apf;
     pp_host_apf_list(c->model.C, c->frames[g], boxes, n, apf_added_radius, apf);
     if (n > c->apf_cap[g])
     {
+        PP_CUDA(cudaStreamSynchronize(c->stream));
         if (c->d_apf[g]) PP_CUDA(cudaFree(c->d_apf[g]));
         c->d_apf[g] = nullptr;
         PP_CUDA(cudaMalloc(&c->d_apf[g], sizeof(float) * 3 * n));
@@ -441,18 +558,26 @@ int pp_update_obstacles_boxes(pp_context* c, int g, const float* boxes, const fl
         PP_CUDA(c->d_bin_idx[g].ensure(std::max<size_t>(idx.size(), 1)));
         PP_CUDA(cudaMemcpyAsync(c->d_bin_off[g].p, off.data(), sizeof(int) * off.size(), cudaMemcpyHostToDevice, c->stream));
         if (!idx.empty()) PP_CUDA(cudaMemcpyAsync(c->d_bin_idx[g].p, idx.data(), sizeof(int) * idx.size(), cudaMemcpyHostToDevice, c->stream));
-        PP_CUDA(cudaStreamSynchronize(c->stream));
+        PP_CUDA(cudaStreamSynchronize(c->stream));      // the pageable host vectors above die at return
         c->groups[g].bin_shift = shift; c->groups[g].bin_n = bin_n;
         c->groups[g].bin_off = c->d_bin_off[g].p; c->groups[g].bin_idx = c->d_bin_idx[g].p;
     }
     c->groups_dirty = true;
-    PP_CUDA(cudaStreamSynchronize(c->stream));
+    map_changed(c, g);
+    return PP_SUCCESS;
+}
+
+int pp_update_obstacles_boxes(pp_context* c, int g, const float* boxes, const float* conf, int n, float apf_added_radius)
+{
+    int rc = pp_update_obstacles_apf(c, g, boxes, n, apf_added_radius); if (rc) return rc;
+    if (n > 0 && !conf) return pp_fail(PP_ERR_INVALID, "boxes: bad arguments");
     return pp_update_obstacles_boxes_2d(c, g, boxes, conf, n);
 }
 
 int pp_update_obstacles_lines(pp_context* c, int g, const float* lines, const float* conf, int n, float width)
 {
     int rc = check_group(c, g); if (rc) return rc;
+    rc = lane_guard(c, "pp_update_obstacles_lines"); if (rc) return rc;
     map_changed(c, g);
     if (n < 0 || (n > 0 && (!lines || !conf))) return pp_fail(PP_ERR_INVALID, "lines: bad arguments");
     if (n == 0) return PP_SUCCESS;
@@ -482,6 +607,7 @@ int pp_map_download(pp_context* c, int g, float* out)
 int pp_map_upload(pp_context* c, int g, const float* in)
 {
     int rc = check_group(c, g); if (rc) return rc;
+    rc = lane_guard(c, "pp_map_upload"); if (rc) return rc;
     map_changed(c, g);
     PP_CUDA(cudaSetDevice(c->device));
     PP_CUDA(cudaMemcpyAsync(c->d_maps + nn_of(c) * g, in, sizeof(float) * nn_of(c), cudaMemcpyHostToDevice, c->stream));
@@ -489,10 +615,20 @@ int pp_map_upload(pp_context* c, int g, const float* in)
     return PP_SUCCESS;
 }
 
+// The caller may write through this pointer (e.g. its own NCCL receive): everything derived from the group's map -- the exact 2D
+// field, K-POP scheduling hints -- is dropped here, and once more by pp_map_mark_dirty after the caller's write has completed.
 void* pp_map_device_ptr(pp_context* c, int g)
 {
     if (check_group(c, g)) return nullptr;
+    map_changed(c, g);
     return c->d_maps + nn_of(c) * g;
+}
+
+int pp_map_mark_dirty(pp_context* c, int g)
+{
+    int rc = check_group(c, g); if (rc) return rc;
+    map_changed(c, g);
+    return PP_SUCCESS;
 }
 
 // ---- host-side start nodes ---------------------------------------------------------------------------
@@ -740,16 +876,19 @@ int pp_dubins_path(pp_context* c, const float* s, const float* g, float* xyh, fl
 }
 
 // ---- batch search ------------------------------------------------------------------------------------
-static void fill_args(pp_context* c, const WorkPools& w, int n_slots, const int* qmap, int n_work, PPBatchArgs& a)
+static void fill_args(pp_context* c, const WorkPools& w, const pp_search_opts& o, int n_slots, const int* qmap, int n_work, PPBatchArgs& a)
 {
     a.C = c->model.C; a.off_xy = c->d_off_xy; a.groups = c->d_groups; a.queries = c->d_queries.p; a.n_queries = n_work;
     a.qmap = qmap;
     a.n_slots = n_slots; a.counter = c->d_counter; a.results = c->d_results.p;
-    a.paths = c->d_paths.p; a.path_cap = c->opts.path_cap;
-    a.trace = c->opts.trace_cap > 0 ? c->d_trace.p : nullptr; a.trace_cap = c->opts.trace_cap;
+    a.paths = c->d_paths.p; a.path_cap = o.path_cap;
+    a.trace = o.trace_cap > 0 ? c->d_trace.p : nullptr; a.trace_cap = o.trace_cap;
     a.open3 = w.open3.p; a.open3_cap = w.open3_cap; a.closed = w.closed.p; a.closed_cap = w.closed_cap;
     a.chash = w.chash.p; a.chash_cap = w.chash_cap; a.cell_state = w.cell_state.p; a.nm_g = w.nm_g.p; a.nm_f = w.nm_f.p;
     a.cl_g = w.cl_g.p; a.cl_prev = w.cl_prev.p; a.open2 = w.open2.p; a.open2_cap = w.open2_cap;
+    a.arena = w.arena_bytes ? w.arena_ctl.p : nullptr;
+    a.closed_max = std::max(o.max_expansions, w.closed_cap); a.open3_max = std::max(o.max_open, w.open3_cap);
+    a.open2_max = std::max(o.max_open2d, w.open2_cap);
     a.hist_cell_state = nullptr; a.hist_nm_g = nullptr; a.hist_nm_f = nullptr; a.hist_sid = nullptr;
     if (c->batch_hist_group >= 0 && n_slots == 1 && n_work == 1)
     {
@@ -772,34 +911,84 @@ static int hist_copy(pp_context* c, int g, bool restore)
     return PP_SUCCESS;
 }
 
-// (re)allocate `w` for `want_slots` slots of the given capacities, limited to `mem_frac` of the free memory
-static int ensure_work(pp_context* c, WorkPools& w, int want_slots, int max_exp, int max_open, int max_open2d, double mem_frac)
+// bytes the search scratch of this context may take (slots + arena)
+static int work_budget(pp_context* c, size_t already, size_t* out)
+{
+    if (c->mem_budget) { *out = c->mem_budget; return PP_SUCCESS; }
+    size_t free_b = 0, total_b = 0;
+    PP_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    *out = (size_t)((free_b + already) * 0.75);
+    return PP_SUCCESS;
+}
+
+// (Re)allocate `w` for up to `want_slots` resident queries.  with_arena: the per-slot pools get the small first-pass
+// capacities (never more than the caller's caps) and whatever the budget leaves goes to the arena the containers grow
+// into; otherwise the pools are fixed at the given capacities (stand-alone lazy A* handle).
+static int ensure_work(pp_context* c, WorkPools& w, int want_slots, int max_exp, int max_open, int max_open2d, bool with_arena)
 {
     size_t nn = nn_of(c);
-    int hc = 1; while (hc < 2 * max_exp) hc <<= 1;
-    size_t per_slot = sizeof(PPNode3) * (size_t)max_open + sizeof(PPClosed3) * (size_t)max_exp + sizeof(PPHashSlot) * (size_t)hc +
-                      nn * 20 + sizeof(PPNode2) * (size_t)max_open2d;
+    const int cap_c = with_arena ? std::min(max_exp, PP_INIT_CLOSED) : max_exp;
+    const int cap_o = with_arena ? std::min(max_open, PP_INIT_OPEN3) : max_open;
+    const int cap_2 = with_arena ? std::min(max_open2d, PP_INIT_OPEN2D) : max_open2d;
+    int hc = 1; while (hc < 2 * cap_c) hc <<= 1;
+    const size_t per_slot = sizeof(PPNode3) * (size_t)cap_o + sizeof(PPClosed3) * (size_t)cap_c + sizeof(PPHashSlot) * (size_t)hc +
+                            nn * 20 + sizeof(PPNode2) * (size_t)cap_2;
+    if (w.alloc_slots >= 1 && w.open3_cap == cap_o && w.closed_cap == cap_c && w.open2_cap == cap_2 &&
+        (w.arena_bytes != 0) == with_arena && (w.alloc_slots >= want_slots || w.clamped))
+        return PP_SUCCESS;      // big enough, or already as large as this context's budget allows
+    size_t had = w.alloc_slots ? (size_t)w.alloc_slots * per_slot + w.arena_bytes : 0;
+    PP_CUDA(cudaStreamSynchronize(c->stream));
+    w.release();
+    size_t budget = 0;
+    int rc = work_budget(c, had, &budget); if (rc) return rc;
     int slots = want_slots;
-    if (!(w.alloc_slots >= slots && w.open3_cap == max_open && w.closed_cap == max_exp && w.open2_cap == max_open2d))
+    size_t arena_bytes = 0;
+    if (with_arena)
     {
-        w.release();
-        size_t free_b = 0, total_b = 0;
-        PP_CUDA(cudaMemGetInfo(&free_b, &total_b));
-        size_t budget = (size_t)(free_b * mem_frac);
+        // the fixed parts may take at most half of the budget; the arena gets the rest (capped: what the caps could ever need)
+        if ((size_t)slots * per_slot > budget / 2) slots = (int)((budget / 2) / per_slot);
+        if (slots < 1) return pp_fail(PP_ERR_CAPACITY, "not enough device memory for one query slot");
+        arena_bytes = budget - (size_t)slots * per_slot;
+        const size_t per_query_max = 2 * (sizeof(PPNode3) * (size_t)max_open + sizeof(PPClosed3) * (size_t)max_exp +
+                                          sizeof(PPHashSlot) * 4 * (size_t)max_exp + sizeof(PPNode2) * (size_t)max_open2d);
+        const double need = (double)per_query_max * slots;
+        if (need < (double)arena_bytes) arena_bytes = (size_t)need;
+        arena_bytes = std::max<size_t>(arena_bytes & ~(size_t)4095, 1 << 16);
+    }
+    else
+    {
         if ((size_t)slots * per_slot > budget) slots = (int)(budget / per_slot);
         if (slots < 1) return pp_fail(PP_ERR_CAPACITY, "not enough device memory for one query slot");
-        PP_CUDA(w.open3.ensure((size_t)slots * max_open));
-        PP_CUDA(w.closed.ensure((size_t)slots * max_exp));
-        PP_CUDA(w.chash.ensure((size_t)slots * hc));
-        PP_CUDA(w.cell_state.ensure((size_t)slots * nn));
-        PP_CUDA(w.nm_g.ensure((size_t)slots * nn));
-        PP_CUDA(w.nm_f.ensure((size_t)slots * nn));
-        PP_CUDA(w.cl_g.ensure((size_t)slots * nn));
-        PP_CUDA(w.cl_prev.ensure((size_t)slots * nn));
-        PP_CUDA(w.open2.ensure((size_t)slots * max_open2d));
-        w.open3_cap = max_open; w.closed_cap = max_exp; w.open2_cap = max_open2d; w.chash_cap = hc;
-        w.alloc_slots = slots;
     }
+    PP_CUDA(w.open3.ensure((size_t)slots * cap_o));
+    PP_CUDA(w.closed.ensure((size_t)slots * cap_c));
+    PP_CUDA(w.chash.ensure((size_t)slots * hc));
+    PP_CUDA(w.cell_state.ensure((size_t)slots * nn));
+    PP_CUDA(w.nm_g.ensure((size_t)slots * nn));
+    PP_CUDA(w.nm_f.ensure((size_t)slots * nn));
+    PP_CUDA(w.cl_g.ensure((size_t)slots * nn));
+    PP_CUDA(w.cl_prev.ensure((size_t)slots * nn));
+    PP_CUDA(w.open2.ensure((size_t)slots * cap_2));
+    if (with_arena)
+    {
+        PP_CUDA(w.arena_mem.ensure(arena_bytes));
+        PP_CUDA(w.arena_ctl.ensure(1));
+        w.arena_bytes = arena_bytes;
+    }
+    w.open3_cap = cap_o; w.closed_cap = cap_c; w.open2_cap = cap_2; w.chash_cap = hc;
+    w.alloc_slots = slots; w.clamped = slots < want_slots;
+    return PP_SUCCESS;
+}
+
+// every launch starts on an empty arena (all blocks of the previous launch went back to their class lists; starting over
+// also undoes the fragmentation across size classes)
+static int arena_reset(pp_context* c, WorkPools& w)
+{
+    if (!w.arena_bytes) return PP_SUCCESS;
+    PPArena a;
+    std::memset(&a, 0, sizeof(a));
+    a.base = (unsigned long long)w.arena_mem.p; a.size = w.arena_bytes;
+    PP_CUDA(cudaMemcpyAsync(w.arena_ctl.p, &a, sizeof(a), cudaMemcpyHostToDevice, c->stream));
     return PP_SUCCESS;
 }
 
@@ -807,9 +996,15 @@ static pp_search_opts default_opts(const pp_search_opts* in)
 {
     pp_search_opts o;
     if (in) o = *in; else std::memset(&o, 0, sizeof(o));
-    if (o.max_expansions <= 0) o.max_expansions = 1 << 17;
-    if (o.max_open <= 0) o.max_open = 1 << 16;
-    if (o.max_open2d <= 0) o.max_open2d = 1 << 14;
+    // the reference's containers are unbounded: the defaults are caps a query only meets when the whole state space of a
+    // 512^2 x 72 grid is in play; containers grow towards them on demand (pp_arena.h)
+    if (o.mode != PP_MODE_KPOP)
+    {
+        if (o.max_expansions <= 0) o.max_expansions = 1 << 24;
+        if (o.max_open <= 0) o.max_open = 1 << 23;
+        if (o.max_open2d <= 0) o.max_open2d = 1 << 20;
+    }
+    else if (o.max_expansions <= 0) o.max_expansions = 1 << 17;      // K-POP pools are fixed per slot (2 nodes per expansion)
     if (o.path_cap <= 0) o.path_cap = 2048;
     if (o.trace_cap < 0) o.trace_cap = 0;
     if (o.mode != PP_MODE_KPOP) o.mode = PP_MODE_EXACT;
@@ -843,8 +1038,9 @@ static int ensure_kpop(pp_context* c, pp_context::KPools& k, int want_slots, int
     size_t arena_cap = (size_t)PP_K_RUN0 * (((size_t)1 << levels) - 1), tmp_cap = (size_t)nodes_cap + 2 * PP_K_RUN0;
     size_t per_slot = sizeof(PPKNode) * (size_t)nodes_cap + sizeof(PPKSlot) * (size_t)tc + sizeof(PPKEntry) * (arena_cap + 2 * tmp_cap);
     int slots = want_slots;
-    if (!(k.alloc_slots >= slots && k.nodes_cap == nodes_cap))
+    if (!((k.alloc_slots >= slots || (k.clamped && k.alloc_slots >= 1)) && k.nodes_cap == nodes_cap))
     {
+        PP_CUDA(cudaStreamSynchronize(c->stream));
         k.release();
         size_t free_b = 0, total_b = 0;
         PP_CUDA(cudaMemGetInfo(&free_b, &total_b));
@@ -858,6 +1054,7 @@ static int ensure_kpop(pp_context* c, pp_context::KPools& k, int want_slots, int
         PP_CUDA(k.tmp_a.ensure((size_t)slots * tmp_cap));
         PP_CUDA(k.tmp_b.ensure((size_t)slots * tmp_cap));
         k.nodes_cap = nodes_cap; k.table_cap = tc; k.levels = levels; k.arena_cap = arena_cap; k.tmp_cap = tmp_cap; k.alloc_slots = slots;
+        k.clamped = slots < want_slots;
     }
     return PP_SUCCESS;
 }
@@ -935,6 +1132,8 @@ int pp_batch_upload(pp_context* c, const pp_query* q, int n, const pp_search_opt
 {
     if (!c || !q || n <= 0) return pp_fail(PP_ERR_INVALID, "pp_batch_upload: bad arguments");
     PP_CUDA(cudaSetDevice(c->device));
+    if (c->run_pending) return pp_fail(PP_ERR_INVALID, "pp_batch_upload: the previous batch is still running (pp_batch_wait first)");
+    int rc = lane_refresh(c); if (rc) return rc;
     pp_search_opts o = default_opts(opts);
     c->opts = o;
     c->h_queries.resize(n); c->h_vel.resize(n);
@@ -950,7 +1149,7 @@ int pp_batch_upload(pp_context* c, const pp_query* q, int n, const pp_search_opt
     // one EXACT-mode query on a group with history enabled continues on that planner's carried 2D cache
     c->batch_hist_group = (n == 1 && o.mode == PP_MODE_EXACT && (int)c->hist.size() > q[0].group && c->hist[q[0].group].on) ? q[0].group : -1;
     int hw_slots = 0;
-    int rc = hw_slots_of(c, &hw_slots); if (rc) return rc;
+    rc = hw_slots_of(c, &hw_slots); if (rc) return rc;
     int want = std::min(n, hw_slots);
     if (o.max_slots > 0) want = std::min(want, o.max_slots);
     PP_CUDA(c->d_queries.ensure(n));
@@ -960,6 +1159,8 @@ int pp_batch_upload(pp_context* c, const pp_query* q, int n, const pp_search_opt
     if (o.mode == PP_MODE_KPOP)
     {
         if (2 * c->model.C.A + 1 > PP_K_MAXSUCC) return pp_fail(PP_ERR_INVALID, "K-POP mode supports at most 8 successors per node (num_actions <= 3)");
+        if (c->parent) return pp_fail(PP_ERR_INVALID, "K-POP batches run on the parent context (lanes serve the EXACT mode)");
+        if (c->wp.alloc_slots) { PP_CUDA(cudaStreamSynchronize(c->stream)); c->wp.release(); }     // the two modes do not share scratch
         // the exact 2D distance field of every group the batch touches (recomputed only after a map / goal change)
         size_t nn_ = nn_of(c);
         PP_CUDA(c->d_field2d.ensure(nn_ * c->num_groups));
@@ -976,7 +1177,8 @@ int pp_batch_upload(pp_context* c, const pp_query* q, int n, const pp_search_opt
     }
     else
     {
-        rc = ensure_work(c, c->wp, want, o.max_expansions, o.max_open, o.max_open2d, 0.6); if (rc) return rc;
+        if (c->kp.alloc_slots || c->kp_retry.alloc_slots) { PP_CUDA(cudaStreamSynchronize(c->stream)); c->kp.release(); c->kp_retry.release(); }
+        rc = ensure_work(c, c->wp, want, o.max_expansions, o.max_open, o.max_open2d, true); if (rc) return rc;
         c->n_slots = std::max(std::min(c->wp.alloc_slots, want), 1);
     }
     PP_CUDA(cudaMemcpyAsync(c->d_queries.p, c->h_queries.data(), sizeof(PPQuery) * n, cudaMemcpyHostToDevice, c->stream));
@@ -985,11 +1187,12 @@ int pp_batch_upload(pp_context* c, const pp_query* q, int n, const pp_search_opt
     return PP_SUCCESS;
 }
 
-static int launch_search(pp_context* c, const WorkPools& w, int n_slots, const int* qmap, int n_work)
+static int launch_search(pp_context* c, const WorkPools& w, const pp_search_opts& o, int n_slots, const int* qmap, int n_work)
 {
     PPBatchArgs a;
-    fill_args(c, w, n_slots, qmap, n_work, a);
+    fill_args(c, w, o, n_slots, qmap, n_work, a);
     PP_CUDA(cudaMemsetAsync(c->d_counter, 0, sizeof(int), c->stream));
+    int rc = arena_reset(c, c->wp); if (rc) return rc;
     int blocks = (n_slots + PP_SEARCH_WARPS - 1) / PP_SEARCH_WARPS;
     pp_search_kernel<<<blocks, PP_SEARCH_WARPS * 32, 0, c->stream>>>(a);
     c->launches += 1;
@@ -997,25 +1200,47 @@ static int launch_search(pp_context* c, const WorkPools& w, int n_slots, const i
     return PP_SUCCESS;
 }
 
-int pp_batch_run(pp_context* c, float* kernel_ms)
+// First pass of the uploaded batch, enqueued on the context's stream; returns at once.  pp_batch_wait completes it.
+int pp_batch_run_async(pp_context* c)
 {
     if (!c || c->n_queries <= 0) return pp_fail(PP_ERR_INVALID, "pp_batch_run: nothing uploaded");
+    if (c->run_pending) return pp_fail(PP_ERR_INVALID, "pp_batch_run_async: a batch is already running");
     PP_CUDA(cudaSetDevice(c->device));
     const int n = c->n_queries;
-    PP_CUDA(cudaEventRecord(c->ev0, c->stream));
     const bool kmode = (c->opts.mode == PP_MODE_KPOP);
     const int hist_g = kmode ? -1 : c->batch_hist_group;
     int rc = 0;
+    PP_CUDA(cudaEventRecord(c->ev_run0, c->stream));
     if (hist_g >= 0) { rc = hist_copy(c, hist_g, false); if (rc) return rc; }
-    rc = kmode ? launch_kpop(c, c->kp, c->n_slots, nullptr, n) : launch_search(c, c->wp, c->n_slots, nullptr, n);
+    rc = kmode ? launch_kpop(c, c->kp, c->n_slots, nullptr, n) : launch_search(c, c->wp, c->opts, c->n_slots, nullptr, n);
     if (rc) return rc;
-    // The reference's containers are unbounded.  Queries that exhausted a pool are re-run from scratch with
-    // 8x larger pools (fewer resident slots), up to 3 escalations; what still overflows stays flagged.
+    PP_CUDA(cudaEventRecord(c->ev_run1, c->stream));
+    c->run_pending = true; c->batch_done = false;
+    return PP_SUCCESS;
+}
+
+// Waits for the first pass and, because the reference's containers are unbounded, re-runs what still hit a cap: queries
+// that met the caller's max_expansions / max_open / max_open2d get caps 8x larger (up to 3 escalations); queries that found
+// the arena empty are re-run with fewer resident neighbours.  What still overflows stays flagged in pp_result.status.
+// kernel_ms = device time of all passes (CUDA events on the context's stream).
+int pp_batch_wait(pp_context* c, float* kernel_ms)
+{
+    if (!c || !c->run_pending) return pp_fail(PP_ERR_INVALID, "pp_batch_wait: nothing is running");
+    PP_CUDA(cudaSetDevice(c->device));
+    c->run_pending = false;
+    const int n = c->n_queries;
+    const bool kmode = (c->opts.mode == PP_MODE_KPOP);
+    const int hist_g = kmode ? -1 : c->batch_hist_group;
+    int rc = 0;
+    PP_CUDA(cudaStreamSynchronize(c->stream));
+    float total_ms = 0.0f;
+    PP_CUDA(cudaEventElapsedTime(&total_ms, c->ev_run0, c->ev_run1));
     c->retried = 0;
-    int max_exp = c->opts.max_expansions, max_open = c->opts.max_open, max_open2d = c->opts.max_open2d;
+    pp_search_opts o = c->opts;
     long long kp_nodes = c->kp.nodes_cap;
     std::vector<PPResult> r(n);
-    const int overflow = PP_STATUS_OPEN_OVERFLOW | PP_STATUS_CLOSED_OVERFLOW | PP_STATUS_OPEN2D_OVERFLOW;
+    const int overflow = PP_STATUS_OPEN_OVERFLOW | PP_STATUS_CLOSED_OVERFLOW | PP_STATUS_OPEN2D_OVERFLOW | PP_STATUS_ARENA_EXHAUSTED;
+    int slots_now = c->n_slots;
     for (int level = 0; level < 3; level++)
     {
         PP_CUDA(cudaMemcpyAsync(r.data(), c->d_results.p, sizeof(PPResult) * n, cudaMemcpyDeviceToHost, c->stream));
@@ -1035,19 +1260,19 @@ int pp_batch_run(pp_context* c, float* kernel_ms)
                 }
         }
         std::vector<int> redo;
-        for (int k = 0; k < n; k++) if (r[k].status & overflow) redo.push_back(k);
+        bool arena_short = false;
+        for (int k = 0; k < n; k++)
+            if (r[k].status & overflow) { redo.push_back(k); if (r[k].status & PP_STATUS_ARENA_EXHAUSTED) arena_short = true; }
         if (redo.empty()) break;
         if (level == 0) c->retried = (int)redo.size();
-        long long e = (long long)max_exp * 8, o3 = (long long)max_open * 8, o2 = (long long)max_open2d * 4;
-        max_exp = (int)std::min<long long>(e, 1 << 26); max_open = (int)std::min<long long>(o3, 1 << 25);
-        max_open2d = (int)std::min<long long>(o2, 1 << 22);
-        int hw_slots = 0;
-        rc = kmode ? kpop_hw_slots(c, &hw_slots) : hw_slots_of(c, &hw_slots); if (rc) return rc;
-        int want = std::min((int)redo.size(), hw_slots);
         PP_CUDA(c->d_qmap.ensure(redo.size()));
         PP_CUDA(cudaMemcpyAsync(c->d_qmap.p, redo.data(), sizeof(int) * redo.size(), cudaMemcpyHostToDevice, c->stream));
+        PP_CUDA(cudaEventRecord(c->ev0, c->stream));
         if (kmode)
         {
+            int hw_slots = 0;
+            rc = kpop_hw_slots(c, &hw_slots); if (rc) return rc;
+            int want = std::min((int)redo.size(), hw_slots);
             kp_nodes = std::min<long long>(kp_nodes * 8, 1ll << 24);
             rc = ensure_kpop(c, c->kp_retry, want, (int)kp_nodes, 0.85); if (rc) return rc;
             int slots = std::max(std::min(c->kp_retry.alloc_slots, want), 1);
@@ -1055,18 +1280,38 @@ int pp_batch_run(pp_context* c, float* kernel_ms)
         }
         else
         {
-            rc = ensure_work(c, c->wp_retry, want, max_exp, max_open, max_open2d, 0.85); if (rc) return rc;
+            o.max_expansions = (int)std::min<long long>((long long)o.max_expansions * 8, 1 << 26);
+            o.max_open = (int)std::min<long long>((long long)o.max_open * 8, 1 << 25);
+            o.max_open2d = (int)std::min<long long>((long long)o.max_open2d * 4, 1 << 22);
+            if (arena_short) slots_now = std::max(1, slots_now / 8);
+            int slots = std::max(1, std::min((int)redo.size(), slots_now));
             if (hist_g >= 0) { rc = hist_copy(c, hist_g, true); if (rc) return rc; }     // the aborted attempt never happened
-            int slots = std::max(std::min(c->wp_retry.alloc_slots, want), 1);
-            rc = launch_search(c, c->wp_retry, slots, c->d_qmap.p, (int)redo.size()); if (rc) return rc;
+            rc = launch_search(c, c->wp, o, slots, c->d_qmap.p, (int)redo.size()); if (rc) return rc;
         }
+        PP_CUDA(cudaEventRecord(c->ev1, c->stream));
         PP_CUDA(cudaStreamSynchronize(c->stream));
+        float ms = 0.0f;
+        PP_CUDA(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+        total_ms += ms;
+        if (level == 2)
+        {
+            // out of escalations: if the last attempt still overflowed on a carried cache, that attempt never happened either
+            PP_CUDA(cudaMemcpyAsync(r.data(), c->d_results.p, sizeof(PPResult) * n, cudaMemcpyDeviceToHost, c->stream));
+            PP_CUDA(cudaStreamSynchronize(c->stream));
+            bool still = false;
+            for (int k : redo) if (r[k].status & overflow) still = true;
+            if (still && hist_g >= 0) { rc = hist_copy(c, hist_g, true); if (rc) return rc; PP_CUDA(cudaStreamSynchronize(c->stream)); }
+        }
     }
-    PP_CUDA(cudaEventRecord(c->ev1, c->stream));
-    PP_CUDA(cudaStreamSynchronize(c->stream));
-    if (kernel_ms) PP_CUDA(cudaEventElapsedTime(kernel_ms, c->ev0, c->ev1));
+    if (kernel_ms) *kernel_ms = total_ms;
     c->batch_done = true;
     return PP_SUCCESS;
+}
+
+int pp_batch_run(pp_context* c, float* kernel_ms)
+{
+    int rc = pp_batch_run_async(c); if (rc) return rc;
+    return pp_batch_wait(c, kernel_ms);
 }
 
 int pp_batch_fetch(pp_context* c, pp_result* results, float* paths_xyh, float* curvature, pp_pop* trace)
@@ -1212,14 +1457,17 @@ static int lazy_run(pp_context* c, int g, const int* ij, int n, float* out, int 
     int rc = check_group(c, g); if (rc) return rc;
     if (n <= 0) return PP_SUCCESS;
     PP_CUDA(cudaSetDevice(c->device));
-    pp_search_opts o = default_opts(nullptr);
+    pp_search_opts o = default_opts(nullptr);      // local: the uploaded batch keeps its own options (and buffers sized for them)
+    o.max_expansions = 16; o.max_open = 16; o.max_open2d = 1 << 18;
     if (c->wp_lazy.alloc_slots < 1 || c->lazy_group != g) restart = 1;      // no cache yet (or another planner's)
-    rc = ensure_work(c, c->wp_lazy, 1, 16, 16, 1 << 18, 0.5); if (rc) return rc;
+    rc = ensure_work(c, c->wp_lazy, 1, o.max_expansions, o.max_open, o.max_open2d, false); if (rc) return rc;
     c->lazy_group = g;
     rc = sync_groups(c); if (rc) return rc;
     PPBatchArgs a;
-    c->opts = o;
-    fill_args(c, c->wp_lazy, 1, nullptr, 0, a);
+    const int keep_hist = c->batch_hist_group;
+    c->batch_hist_group = -1;
+    fill_args(c, c->wp_lazy, o, 1, nullptr, 0, a);
+    c->batch_hist_group = keep_hist;
     PP_CUDA(c->s0.ensure(sizeof(int) * 2 * n));
     PP_CUDA(c->s1.ensure(sizeof(float) * n));
     PP_CUDA(c->s2.ensure(sizeof(int)));
@@ -1251,6 +1499,7 @@ int pp_override_dubins(pp_context* c, float r_min, float step_size)
 int pp_clear_obstacles(pp_context* c, int g)
 {
     int rc = check_group(c, g); if (rc) return rc;
+    rc = lane_guard(c, "pp_clear_obstacles"); if (rc) return rc;
     map_changed(c, g);
     PP_CUDA(cudaSetDevice(c->device));
     PP_CUDA(cudaMemsetAsync(c->d_maps + nn_of(c) * g, 0, sizeof(float) * nn_of(c), c->stream));
@@ -1317,6 +1566,64 @@ int pp_heuristic_field_3d(pp_context* c, int g, int use_h2d, float* out_nnb, flo
         PP_CUDA(cudaMemcpyAsync(out_nnb, c->d_dubins_field.p, sizeof(float) * total, cudaMemcpyDeviceToHost, c->stream));
         PP_CUDA(cudaStreamSynchronize(c->stream));
     }
+    return PP_SUCCESS;
+}
+
+// ---- map replication (north_star: "the map replicated by an NCCL broadcast over NVLink after each update") ----
+int pp_comm_unique_id(void* id128)
+{
+    if (!id128) return pp_fail(PP_ERR_INVALID, "pp_comm_unique_id: null");
+    std::string err;
+    PPNccl* api = nccl_api(err);
+    if (!api) return pp_fail(PP_ERR_INVALID, "pp_comm_unique_id: " + err);
+    int e = api->GetUniqueId(id128);
+    if (e) return pp_fail(PP_ERR_CUDA, std::string("ncclGetUniqueId: ") + (api->GetErrorString ? api->GetErrorString(e) : "error"));
+    return PP_SUCCESS;
+}
+
+int pp_comm_init(pp_context* c, int nranks, int rank, const void* id128)
+{
+    if (!c || !id128 || nranks < 1 || rank < 0 || rank >= nranks) return pp_fail(PP_ERR_INVALID, "pp_comm_init: bad arguments");
+    if (c->nccl_comm) return pp_fail(PP_ERR_INVALID, "pp_comm_init: communicator already initialised");
+    std::string err;
+    PPNccl* api = nccl_api(err);
+    if (!api) return pp_fail(PP_ERR_INVALID, "pp_comm_init: " + err);
+    PP_CUDA(cudaSetDevice(c->device));
+    PPNcclIdByValue id;
+    std::memcpy(&id, id128, sizeof(id));
+    void* comm = nullptr;
+    int e = api->CommInitRank(&comm, nranks, id, rank);
+    if (e) return pp_fail(PP_ERR_CUDA, std::string("ncclCommInitRank: ") + (api->GetErrorString ? api->GetErrorString(e) : "error"));
+    c->nccl_comm = comm; c->comm_rank = rank; c->comm_size = nranks;
+    return PP_SUCCESS;
+}
+
+// Replaces, on every rank but `root`, the maps of groups [first_group, first_group + n_groups) by root's, straight into the
+// context's map storage on the context's stream; the exact 2D field and the scheduling hints of those groups are dropped.
+int pp_broadcast_maps(pp_context* c, int first_group, int n_groups, int root)
+{
+    if (!c || !c->nccl_comm) return pp_fail(PP_ERR_INVALID, "pp_broadcast_maps: pp_comm_init first");
+    int rc = lane_guard(c, "pp_broadcast_maps"); if (rc) return rc;
+    if (n_groups < 1 || first_group < 0 || first_group + n_groups > c->num_groups || root < 0 || root >= c->comm_size)
+        return pp_fail(PP_ERR_INVALID, "pp_broadcast_maps: bad group range or root");
+    std::string err;
+    PPNccl* api = nccl_api(err);
+    if (!api) return pp_fail(PP_ERR_INVALID, "pp_broadcast_maps: " + err);
+    PP_CUDA(cudaSetDevice(c->device));
+    float* p = c->d_maps + nn_of(c) * first_group;
+    int e = api->Broadcast(p, p, nn_of(c) * (size_t)n_groups, 7 /* ncclFloat32 */, root, c->nccl_comm, c->stream);
+    if (e) return pp_fail(PP_ERR_CUDA, std::string("ncclBroadcast: ") + (api->GetErrorString ? api->GetErrorString(e) : "error"));
+    for (int g = first_group; g < first_group + n_groups; g++) map_changed(c, g);
+    return PP_SUCCESS;
+}
+
+int pp_comm_destroy(pp_context* c)
+{
+    if (!c || !c->nccl_comm) return PP_SUCCESS;
+    std::string err;
+    PPNccl* api = nccl_api(err);
+    if (api) { cudaSetDevice(c->device); cudaStreamSynchronize(c->stream); api->CommDestroy(c->nccl_comm); }
+    c->nccl_comm = nullptr; c->comm_rank = -1; c->comm_size = 0;
     return PP_SUCCESS;
 }
 

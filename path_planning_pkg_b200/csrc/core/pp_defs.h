@@ -22,6 +22,14 @@
 #define PP_HD_NOINLINE_FN inline
 #endif
 
+// float -> int as the reference's x86-64 build does it (cvttss2si): NaN and values outside the int range give INT_MIN
+// ("integer indefinite"), which every `> -1` bounds test of the reference then rejects.  CUDA's own conversion gives 0 for
+// NaN and saturates, which would turn a NaN coordinate into a valid cell.
+PP_HD int pp_f2i_x86(float v)
+{
+    return (v >= -2147483648.0f && v < 2147483648.0f) ? (int)v : (int)0x80000000;
+}
+
 #define PP_MAX_STEER 16
 #define PP_MAX_BINS 128   /* heading bins + 1 padding column must fit */
 
@@ -33,6 +41,7 @@
 #define PP_STATUS_OPEN2D_OVERFLOW 4   /* 2D open-list node pool exhausted */
 #define PP_STATUS_PATH_OVERFLOW 8     /* path / dubins sample buffer too small */
 #define PP_STATUS_NULL_TERMINAL 16    /* reference would dereference a null _prev */
+#define PP_STATUS_ARENA_EXHAUSTED 32  /* a container had to grow and the context's arena had no block left */
 #endif
 
 // Constants derived on the host exactly as the reference constructors derive them

@@ -94,10 +94,12 @@ PP_HD void pp_line_cells(const PPLineDesc& d, float res, int n45, int n2, float 
     float ix = d.sx + d.ux * pl, iy = d.sy + d.uy * pl;         // intercept
     float p1x = ix + d.nx * pw, p1y = iy + d.ny * pw;
     float p2x = ix - d.nx * pw, p2y = iy - d.ny * pw;
-    i1 = (int)roundf(p1x / res) + n45;
-    i2 = (int)roundf(p2x / res) + n45;
-    j1 = (int)roundf(p1y / res) + n2;
-    j2 = (int)roundf(p2y / res) + n2;
+    // x86 float -> int (pp_f2i_x86): a degenerate line (start == end: 0/0 direction) or a NaN point gives INT_MIN + n, which
+    // fails the caller's `> -1` test exactly like the reference; the unsigned add keeps that wrap-around defined
+    i1 = (int)((unsigned)pp_f2i_x86(roundf(p1x / res)) + (unsigned)n45);
+    i2 = (int)((unsigned)pp_f2i_x86(roundf(p2x / res)) + (unsigned)n45);
+    j1 = (int)((unsigned)pp_f2i_x86(roundf(p1y / res)) + (unsigned)n2);
+    j2 = (int)((unsigned)pp_f2i_x86(roundf(p2y / res)) + (unsigned)n2);
 }
 
 // ---- map relocation on goal change, Grid3D::relocate_obstacles Grid3D.cpp:169-203 ----

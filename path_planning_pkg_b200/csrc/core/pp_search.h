@@ -20,6 +20,7 @@
 #include "pp_math.h"
 #include "pp_dubins.h"
 #include "pp_rbtree.h"
+#include "pp_arena.h"
 
 #define PP_MAX_SUCC 16
 #define PP_NEAR_CAP 64
@@ -113,6 +114,11 @@ struct PPWork
     // reference planner object and *lazy_sid its running lazy-search id: nothing is cleared, the query continues on
     // whatever the object's earlier find_path calls left behind (AStar::reset() only drops the visited flags).
     unsigned*  lazy_sid = nullptr;
+    // Growable containers (pp_arena.h): the pools above are the slot's small fixed ones; with an arena a container that
+    // fills up moves into a block twice the size, up to the hard caps below (the caller's max_expansions / max_open /
+    // max_open2d).  arena == nullptr: fixed pools, the caps are the pool sizes.
+    PPArena*   arena = nullptr;
+    int        closed_max = 0, open3_max = 0, open2_max = 0;
 };
 
 struct PPSmem   // per-warp staging area (shared memory on the device)
@@ -165,7 +171,29 @@ struct PPLazy
     unsigned search_id;
     int status;
     int n_searches, n_pops;
+    PPArena* arena = nullptr;   // nullptr = fixed pool
+    int max_cap = 0;            // hard cap of the 2D open-list pool
+    int blk = -1;               // arena class of the current pool, -1 = the slot's fixed pool
 };
+
+// The 2D open list outgrew its pool: move it into a block twice the size (single lane: this happens in the middle of the
+// control lane's sequential work; the pool is small and the event rare).  Indices stay valid, so the tree is untouched.
+PP_HD_NOINLINE_FN bool pp_lazy_grow(PPLazy& L)
+{
+    if (!L.arena || L.open.cap >= L.max_cap) return false;
+    long long want = 2ll * L.open.cap;
+    if (want > L.max_cap) want = L.max_cap;
+    const int k = pp_arena_class((unsigned long long)want * sizeof(PPNode2));
+    PPNode2* nb = (PPNode2*)pp_arena_alloc(L.arena, k);
+    if (!nb) return false;
+    const unsigned long long* src = (const unsigned long long*)L.open.n;
+    unsigned long long* dst = (unsigned long long*)nb;
+    const size_t words = (size_t)L.open.next * (sizeof(PPNode2) / 8);
+    for (size_t q = 0; q < words; q++) dst[q] = src[q];
+    if (L.blk >= 0) pp_arena_free(L.arena, L.open.n, L.blk);
+    L.open.n = nb; L.open.cap = (int)want; L.blk = k;
+    return true;
+}
 
 PP_HD void pp_lazy_touch(const PPConsts& C, PPWork& wk, int cell)
 {
@@ -197,6 +225,7 @@ PP_HD_NOINLINE_FN bool pp_lazy_insert(PPLazy& L, int cell, float g, float f, int
     int p; bool left;
     if (!L.open.insert_pos(k, p, left)) return true;   // silently dropped (F5)
     int s = L.open.alloc();
+    if (s == PP_RB_NIL && pp_lazy_grow(L)) s = L.open.alloc();
     if (s == PP_RB_NIL) { L.status |= PP_STATUS_OPEN2D_OVERFLOW; return false; }
     PPNode2& n = L.open.n[s];
     n.w.f = f; n.w.key = (unsigned)cell; n.g = g; n.prev = prev;
@@ -351,16 +380,16 @@ PP_HD bool pp_rollout_one(const PPConsts& C, const float* off_xy, float x, float
 // bounds + collision lookup of Grid3D::get_neighbors (Grid3D.cpp:56-59)
 PP_HD bool pp_collision_free(const PPConsts& C, const float* map, float x, float y, int& ci, int& cj)
 {
-    ci = (int)(x / C.res);
-    cj = (int)(y / C.res);
+    ci = pp_f2i_x86(x / C.res);
+    cj = pp_f2i_x86(y / C.res);
     return (ci > -1) && (ci < C.N) && (cj > -1) && (cj < C.N) && (map[ci * C.N + cj] < C.log_thr);
 }
 
 // rounded-index lookup of Grid3D::check_path (Grid3D.cpp:83-90); true = blocked
 PP_HD bool pp_path_point_blocked(const PPConsts& C, const float* map, float x, float y)
 {
-    int i1 = (int)roundf(x / C.res);
-    int j1 = (int)roundf(y / C.res);
+    int i1 = pp_f2i_x86(roundf(x / C.res));
+    int j1 = pp_f2i_x86(roundf(y / C.res));
     return (i1 < 0) || (i1 >= C.N) || (j1 < 0) || (j1 >= C.N) || (map[i1 * C.N + j1] >= C.log_thr);
 }
 
@@ -574,6 +603,8 @@ PP_HD_NOINLINE_FN void pp_dubins_h2_warp(const W& w, const PPConsts& C, const PP
 }
 
 // ---------------------------------------------------------------------------------------------------
+PP_HD unsigned pp_hash_key(unsigned key) { key *= 2654435761u; return key ^ (key >> 15); }
+
 struct PPSearchState
 {
     PPRbTree<PPNode3> open;
@@ -581,9 +612,115 @@ struct PPSearchState
     int n_closed;
     int status;
     int max_open;
+    int open_blk;        // arena class of the 3D open-list pool, -1 = the slot's fixed pool
 };
 
-PP_HD unsigned pp_hash_key(unsigned key) { key *= 2654435761u; return key ^ (key >> 15); }
+// ---- cooperative growth of the per-query containers (all lanes, at a converged point of the search loop) ----------
+template <class W>
+PP_HD void pp_coop_copy8(const W& w, void* dst, const void* src, size_t bytes)
+{
+    const unsigned long long* s = (const unsigned long long*)src;
+    unsigned long long* d = (unsigned long long*)dst;
+    const size_t words = bytes / 8;
+    for (size_t q = w.lane(); q < words; q += W::LANES) d[q] = s[q];
+}
+
+template <class W, class T>
+PP_HD T* pp_bcast_ptr(const W& w, T* p)
+{
+    unsigned long long v = (unsigned long long)p;
+    unsigned lo = w.shfl((unsigned)(v & 0xffffffffull), 0), hi = w.shfl((unsigned)(v >> 32), 0);
+    return (T*)(((unsigned long long)hi << 32) | (unsigned long long)lo);
+}
+
+PP_HD bool pp_hash_slot_claim(PPHashSlot* slot, unsigned key, int idx)
+{
+    // the table is filled by all lanes at once when the closed set moves to a larger table: claim with one 64-bit CAS
+    union { PPHashSlot s; unsigned long long u; } empty, want;
+    empty.s.key = 0xffffffffu; empty.s.idx = -1;
+    want.s.key = key; want.s.idx = idx;
+#ifdef __CUDA_ARCH__
+    return atomicCAS((unsigned long long*)slot, empty.u, want.u) == empty.u;
+#else
+    return __sync_bool_compare_and_swap((unsigned long long*)slot, empty.u, want.u);
+#endif
+}
+
+// The 3D open-list pool is (nearly) full: move it into a block twice the size.  Node indices stay valid.
+template <class W>
+PP_HD_NOINLINE_FN void pp_grow_open3(const W& w, PPWork& wk, PPSearchState& S)
+{
+    const int lane = w.lane();
+    PPNode3* nb = nullptr; PPNode3* old = nullptr;
+    int used = 0, k = -1, old_blk = -1;
+    long long want = 0;
+    if (lane == 0)
+    {
+        want = 2ll * S.open.cap;
+        if (want > wk.open3_max) want = wk.open3_max;
+        k = pp_arena_class((unsigned long long)want * sizeof(PPNode3));
+        nb = (PPNode3*)pp_arena_alloc(wk.arena, k);
+        old = S.open.n; used = S.open.next; old_blk = S.open_blk;
+        if (!nb) S.status |= PP_STATUS_ARENA_EXHAUSTED;
+    }
+    nb = pp_bcast_ptr(w, nb);
+    if (!nb) return;
+    old = pp_bcast_ptr(w, old);
+    used = w.shfl(used, 0);
+    pp_coop_copy8(w, nb, old, (size_t)used * sizeof(PPNode3));
+    w.sync();
+    if (lane == 0)
+    {
+        if (old_blk >= 0) pp_arena_free(wk.arena, old, old_blk);
+        S.open.n = nb; S.open.cap = (int)want; S.open_blk = k;
+    }
+    w.sync();
+}
+
+// The closed log is full: move it into a block twice the size and rebuild the (cell, bin) hash set in a table twice the
+// size (placement inside an open-addressing table carries no meaning, so the lanes re-insert concurrently).
+// wk.closed / wk.chash of EVERY lane are updated; closed_blk / chash_blk track the arena classes (-1 = fixed pool).
+template <class W>
+PP_HD_NOINLINE_FN bool pp_grow_closed(const W& w, PPWork& wk, int n_closed, int& closed_blk, int& chash_blk, int& status)
+{
+    const int lane = w.lane();
+    long long want = 2ll * wk.closed_cap;
+    if (want > wk.closed_max) want = wk.closed_max;
+    int hc = 1; while (hc < 2 * want) hc <<= 1;
+    const int k1 = pp_arena_class((unsigned long long)want * sizeof(PPClosed3));
+    const int k2 = pp_arena_class((unsigned long long)hc * sizeof(PPHashSlot));
+    PPClosed3* nc = nullptr; PPHashSlot* nh = nullptr;
+    if (lane == 0)
+    {
+        nc = (PPClosed3*)pp_arena_alloc(wk.arena, k1);
+        nh = nc ? (PPHashSlot*)pp_arena_alloc(wk.arena, k2) : nullptr;
+        if (nc && !nh) { pp_arena_free(wk.arena, nc, k1); nc = nullptr; }
+        if (!nc) status |= PP_STATUS_ARENA_EXHAUSTED;
+    }
+    nc = pp_bcast_ptr(w, nc);
+    nh = pp_bcast_ptr(w, nh);
+    if (!nc) return false;
+    pp_coop_copy8(w, nc, wk.closed, (size_t)n_closed * sizeof(PPClosed3));
+    for (int c = lane; c < hc; c += W::LANES) { PPHashSlot e; e.key = 0xffffffffu; e.idx = -1; nh[c] = e; }
+    w.sync();
+    const unsigned mask = (unsigned)hc - 1u;
+    for (int c = lane; c < n_closed; c += W::LANES)
+    {
+        const unsigned key = nc[c].key;
+        unsigned h = pp_hash_key(key) & mask;
+        while (!pp_hash_slot_claim(&nh[h], key, c)) h = (h + 1) & mask;
+    }
+    w.sync();
+    if (lane == 0)
+    {
+        if (closed_blk >= 0) pp_arena_free(wk.arena, wk.closed, closed_blk);
+        if (chash_blk >= 0) pp_arena_free(wk.arena, wk.chash, chash_blk);
+    }
+    closed_blk = k1; chash_blk = k2;
+    wk.closed = nc; wk.closed_cap = (int)want; wk.chash = nh; wk.chash_cap = hc;
+    w.sync();
+    return true;
+}
 
 // closed-set lookup: index into the closed log or -1
 PP_HD int pp_closed_find(const PPWork& wk, unsigned key)
@@ -635,6 +772,8 @@ PP_HD_NOINLINE_FN void pp_search_exact(const W& w, const PPConsts& C, const floa
     const unsigned kb = (unsigned)(C.bins + 1);
 
     PP_PROF_DECL
+    const PPWork wk0 = wk;              // the slot's fixed pools: wk follows the containers as they grow, restored at the end
+    int closed_blk = -1, chash_blk = -1;
     // ---- scratch init (all lanes) ----
     const bool carry = (wk.lazy_sid != nullptr);
     unsigned sid0 = 0u;
@@ -673,7 +812,8 @@ PP_HD_NOINLINE_FN void pp_search_exact(const W& w, const PPConsts& C, const floa
         S.open.init(wk.open3, wk.open3_cap);
         S.lazy.open.init(wk.open2, wk.open2_cap);
         S.lazy.search_id = sid0; S.lazy.status = 0; S.lazy.n_searches = 0; S.lazy.n_pops = 0;
-        S.n_closed = 0; S.status = 0; S.max_open = 0;
+        S.lazy.arena = wk.arena; S.lazy.max_cap = wk.arena ? wk.open2_max : wk.open2_cap; S.lazy.blk = -1;
+        S.n_closed = 0; S.status = 0; S.max_open = 0; S.open_blk = -1;
         // _open_set.insert(start_node), HybridAStar.cpp:103
         PPSucc s0;
         s0.x = start.x; s0.y = start.y; s0.heading = start.heading; s0.g = start.g;
@@ -695,6 +835,26 @@ PP_HD_NOINLINE_FN void pp_search_exact(const W& w, const PPConsts& C, const floa
 
     for (;;)
     {
+        // ---------------- phase 0: make room (all lanes; only with an arena) ----------------
+        if (wk.arena)
+        {
+            int grow = 0, ncl = 0;
+            if (lane == 0)
+            {
+                if (S.open.next + n_succ_max + 2 > S.open.cap && S.open.cap < wk.open3_max) grow |= 1;
+                if (S.n_closed + 1 > wk.closed_cap && wk.closed_cap < wk.closed_max) grow |= 2;
+                ncl = S.n_closed;
+            }
+            grow = w.shfl(grow, 0);
+            if (grow & 1) pp_grow_open3(w, wk, S);
+            if (grow & 2)
+            {
+                ncl = w.shfl(ncl, 0);
+                int st = 0;
+                pp_grow_closed(w, wk, ncl, closed_blk, chash_blk, st);
+                if (lane == 0) S.status |= st;
+            }
+        }
         // ---------------- phase 1: pop (control lane) ----------------
         int action = ACT_EXPAND, cur = -1;
         if (lane == 0)
@@ -887,6 +1047,13 @@ PP_HD_NOINLINE_FN void pp_search_exact(const W& w, const PPConsts& C, const floa
 
     if (lane == 0)
     {
+        if (wk.arena)
+        {
+            if (S.open_blk >= 0) pp_arena_free(wk.arena, S.open.n, S.open_blk);
+            if (S.lazy.blk >= 0) pp_arena_free(wk.arena, S.lazy.open.n, S.lazy.blk);
+            if (closed_blk >= 0) pp_arena_free(wk.arena, wk.closed, closed_blk);
+            if (chash_blk >= 0) pp_arena_free(wk.arena, wk.chash, chash_blk);
+        }
         if (carry) *wk.lazy_sid = S.lazy.search_id;
         res.success = success;
         res.status = S.status;
@@ -901,6 +1068,7 @@ PP_HD_NOINLINE_FN void pp_search_exact(const W& w, const PPConsts& C, const floa
         res.n_closed = S.n_closed;
         res.pad = 0;
     }
+    wk = wk0;
 }
 
 #endif

@@ -204,15 +204,49 @@ std::pair<T, bool> HybridAStar<T>::find_path(const T vel_init, const Vector3D<T>
     }();
     o.mode = env_mode; o.kpop = 32;
     pp_result r;
-    std::vector<float> xyh((size_t)o.path_cap * 3), curv(o.path_cap);
-    check(pp_find_path_batch(_impl->b->ctx, &q, 1, &o, &r, xyh.data(), curv.data(), nullptr), "find_path");
-    _impl->last_expansions = r.n_pops;
-    if (!r.success) return std::pair<T, bool>(std::numeric_limits<T>::max(), false);
-    for (int k = 0; k < r.n_path; k++)
+    std::vector<float> xyh, curv;
+    for (;;)
     {
-        path.push_back(Vector3D<T>((T)xyh[3 * k], (T)xyh[3 * k + 1], (T)xyh[3 * k + 2]));
-        curvature.push_back((T)curv[k]);
+        xyh.resize((size_t)o.path_cap * 3); curv.resize(o.path_cap);
+        check(pp_find_path_batch(_impl->b->ctx, &q, 1, &o, &r, xyh.data(), curv.data(), nullptr), "find_path");
+        // the reference's path vector is unbounded: a truncated path is not an answer, ask again with room for it
+        if ((r.status & PP_STATUS_PATH_OVERFLOW) && o.path_cap < (1 << 20)) { o.path_cap *= 8; continue; }
+        break;
     }
+    _impl->last_expansions = r.n_pops;
+    const int capacity_bits = PP_STATUS_OPEN_OVERFLOW | PP_STATUS_CLOSED_OVERFLOW | PP_STATUS_OPEN2D_OVERFLOW | PP_STATUS_ARENA_EXHAUSTED |
+                              PP_STATUS_PATH_OVERFLOW;
+    if (r.status & capacity_bits)
+    {
+        // The reference has no such bound (its containers are unbounded), so this is NOT its "no path" answer: say so loudly.
+        std::fprintf(stderr, "path_planning_b200: HybridAStar::find_path gave up after the automatic capacity escalations "
+                             "(pp_result.status = %d, %d expansions): reported as failure, the reference would have kept searching\n",
+                     r.status, r.n_pops);
+        return std::pair<T, bool>(std::numeric_limits<T>::max(), false);
+    }
+    if (r.status & PP_STATUS_NULL_TERMINAL)
+        std::fprintf(stderr, "path_planning_b200: Dubins shot accepted from the start node: the reference dereferences a null _prev here "
+                             "(lib/HybridAStar.cpp:137); returning the shot alone\n");
+    if (!r.success) return std::pair<T, bool>(std::numeric_limits<T>::max(), false);
+    // reconstruct_path (lib/HybridAStar.cpp:208-262) on caller vectors that may not be empty: after a Dubins shot it RESIZES path to the
+    // shot's length and overwrites it (and curvature[1..]); without a shot it appends
+    if (r.n_dubins > 0)
+    {
+        const T c0 = curvature.empty() ? T(0) : curvature[0];
+        path.clear(); curvature.clear();
+        for (int k = 0; k < r.n_path; k++)
+        {
+            path.push_back(Vector3D<T>((T)xyh[3 * k], (T)xyh[3 * k + 1], (T)xyh[3 * k + 2]));
+            curvature.push_back((T)curv[k]);
+        }
+        if (!curvature.empty()) curvature[0] = c0;
+    }
+    else
+        for (int k = 0; k < r.n_path; k++)
+        {
+            path.push_back(Vector3D<T>((T)xyh[3 * k], (T)xyh[3 * k + 1], (T)xyh[3 * k + 2]));
+            curvature.push_back((T)curv[k]);
+        }
     return std::pair<T, bool>((T)r.cost, true);
 }
 

@@ -141,6 +141,9 @@ struct PPBatchArgs
     float*          hist_nm_g;
     float*          hist_nm_f;
     unsigned*       hist_sid;   // nullptr = fresh cache per query
+    // growable containers (csrc/core/pp_arena.h): nullptr = the fixed pools above are all a query gets
+    PPArena*        arena;
+    int             closed_max, open3_max, open2_max;   // hard caps (the caller's max_expansions / max_open / max_open2d)
 };
 
 __device__ __forceinline__ void pp_slot_work(const PPBatchArgs& a, int slot, PPWork& wk)
@@ -157,6 +160,7 @@ __device__ __forceinline__ void pp_slot_work(const PPBatchArgs& a, int slot, PPW
     wk.open2 = a.open2 + (size_t)slot * a.open2_cap;   wk.open2_cap = a.open2_cap;
     wk.path = nullptr; wk.path_cap = 0; wk.trace = nullptr; wk.trace_cap = 0;
     wk.lazy_sid = nullptr;
+    wk.arena = a.arena; wk.closed_max = a.closed_max; wk.open3_max = a.open3_max; wk.open2_max = a.open2_max;
     if (a.hist_sid)
     {
         wk.cell_state = a.hist_cell_state; wk.nm_g = a.hist_nm_g; wk.nm_f = a.hist_nm_f; wk.lazy_sid = a.hist_sid;

@@ -43,7 +43,19 @@ namespace
         PPResult last; float last_vel = 0.0f; bool have_last = false;   // the last emu_find_path, for emu_trajectory
         bool hist_on = false;      // planner-object history (pp_set_history): cell_state / nm_g / nm_f carried between queries
         unsigned hist_sid = 0;
+        // growable containers (pp_arena.h): host memory stands in for the context's device arena
+        std::vector<unsigned long long> arena_mem; PPArena arena;
     };
+
+    // emu_find_path runs on tiny fixed pools + the arena (so every CPU search test exercises container growth) unless
+    // PP_EMU_FIXED=1 asks for the round-1 fixed pools
+    void attach_arena(Emu* e, PPWork& wk, int closed_max, int open_max, int open2_max)
+    {
+        if (e->arena_mem.empty()) e->arena_mem.resize((size_t)(768u << 20) / 8);
+        std::memset(&e->arena, 0, sizeof(PPArena));
+        e->arena.base = (unsigned long long)e->arena_mem.data(); e->arena.size = e->arena_mem.size() * 8ull;
+        wk.arena = &e->arena; wk.closed_max = closed_max; wk.open3_max = open_max; wk.open2_max = open2_max;
+    }
 
     PPGroup group_of(Emu* e)
     {
@@ -439,7 +451,9 @@ void emu_find_path(void* h, float vel, const float* s, orc_result* res, float* p
     Emu* e = static_cast<Emu*>(h);
     const PPConsts& C = e->m.C;
     PPWork wk;
-    setup_work(e, wk, 1 << 20, 1 << 19, 1 << 16, 4096);
+    const char* fixed = std::getenv("PP_EMU_FIXED");
+    if (fixed && fixed[0] == '1') setup_work(e, wk, 1 << 20, 1 << 19, 1 << 16, 4096);
+    else { setup_work(e, wk, 64, 48, 32, 4096); attach_arena(e, wk, 1 << 20, 1 << 19, 1 << 16); }
     static_assert(sizeof(PPPop) == sizeof(orc_pop), "pop structs must match");
     wk.trace = reinterpret_cast<PPPop*>(pops); wk.trace_cap = pops ? pop_cap : 0;
     PPState st = pp_host_set_start(C, e->fr, s[0], s[1], s[2], vel);

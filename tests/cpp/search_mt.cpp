@@ -117,10 +117,12 @@ struct ExactPools
     std::vector<float> nm_g, nm_f, cl_g; std::vector<int> cl_prev; std::vector<PPNode2> open2; std::vector<PPPathPt> path;
     std::vector<PPPop> trace;
     unsigned hist_sid = 0;      // planner-object history (PPWork::lazy_sid), used by the carried-cache pass only
+    std::vector<unsigned long long> arena_mem; PPArena arena;   // growable containers (pp_arena.h) on host memory
     PPWork wk;
     explicit ExactPools(int N)
     {
-        const int closed_cap = 1 << 16, open_cap = 1 << 15, open2_cap = 1 << 14;
+        // tiny fixed pools + arena: the cooperative growth paths (copy by all lanes, concurrent re-hash) run under TSan too
+        const int closed_cap = 96, open_cap = 64, open2_cap = 32;
         open3.resize(open_cap); closed.resize(closed_cap);
         int hc = 1; while (hc < 2 * closed_cap) hc <<= 1;
         chash.resize(hc);
@@ -130,6 +132,10 @@ struct ExactPools
         wk.chash = chash.data(); wk.chash_cap = hc; wk.cell_state = cell_state.data(); wk.nm_g = nm_g.data(); wk.nm_f = nm_f.data();
         wk.cl_g = cl_g.data(); wk.cl_prev = cl_prev.data(); wk.open2 = open2.data(); wk.open2_cap = open2_cap;
         wk.path = path.data(); wk.path_cap = (int)path.size(); wk.trace = trace.data(); wk.trace_cap = (int)trace.size();
+        arena_mem.resize((size_t)(256u << 20) / 8);
+        std::memset(&arena, 0, sizeof(PPArena));
+        arena.base = (unsigned long long)arena_mem.data(); arena.size = arena_mem.size() * 8ull;
+        wk.arena = &arena; wk.closed_max = 1 << 16; wk.open3_max = 1 << 15; wk.open2_max = 1 << 14;
     }
 };
 

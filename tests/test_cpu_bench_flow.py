@@ -23,9 +23,20 @@ def _fake_pp(real):
         def __init__(self, ctx):
             self.ctx = ctx
 
-        def pp_find_path_batch(self, h, q, n, opts, res, paths, curv, trace):
-            r = self.ctx._results(n.value)
+        def pp_batch_upload(self, h, q, n, opts):
+            self.ctx._n = n.value
+            return 0
+
+        def pp_batch_fetch(self, h, res, paths, curv, trace):
+            r = self.ctx._results(self.ctx._n)
             C.memmove(res.value, r.ctypes.data, r.nbytes)
+            return 0
+
+        def pp_timer_begin(self, h):
+            return 0
+
+        def pp_timer_end(self, h, ms):
+            ms._obj.value = 2.5
             return 0
 
         def pp_last_error(self):
@@ -36,7 +47,11 @@ def _fake_pp(real):
         make_opts = staticmethod(real.Context.make_opts)
 
         def __init__(self, params, num_groups=1, device=0):
+            self.params, self.num_groups = params, num_groups
             self.N, self.h, self.lib, self._n, self.launches = params.grid_size, C.c_void_p(1), FakeLib(self), 0, 0
+
+        def _chk(self, rc):
+            assert rc == 0
 
         def _results(self, n):
             r = np.zeros(n, RESULT_DT)
@@ -46,35 +61,35 @@ def _fake_pp(real):
         def consts(self):
             return types.SimpleNamespace(log_threshold=0.85)
 
+        def create_lane(self): return FakeContext(self.params, self.num_groups)
+        def set_memory_budget(self, n): pass
+        def close(self): pass
         def update_goal(self, *a, **k): pass
         def update_boxes(self, *a, **k): pass
+        def update_boxes_2d(self, *a, **k): pass
+        def update_apf(self, *a, **k): pass
         def decay(self, *a, **k): pass
         def sync(self): pass
-        def set_footprint(self, *a): pass
-        def map_device_ptr(self, g=0): return 0
         def kernel_launches(self): self.launches += 1; return self.launches
         def batch_retried(self): return 0
         def get_map(self, g=0): return np.zeros((self.N, self.N), np.float32)
+        def field2d(self, group=0, download=True): return None, 12, 0.7
+        def field3d(self, group=0, use_h2d=True, download=True): return None, 3.9
 
         def set_start(self, q):
             return {"ci": np.full(len(q), 10, np.int32), "cj": np.full(len(q), 10, np.int32)}
 
         def batch_upload(self, q, opts=None): self._n = len(q)
         def batch_run(self): return 1.5
+        def batch_run_async(self): pass
+        def batch_wait(self): return 1.5
 
         def batch_fetch(self, want_paths=False):
             return self._results(self._n), None, None
 
         def find_path_batch(self, q, opts=None, want_paths=True):
-            return self._results(len(q)), None, None, None
-
-        def footprint(self, xyh, group=0, want_ms=False):
-            n = len(xyh)
-            out = (np.ones(n, np.int32), np.zeros((n, 2), np.int32), np.zeros(n, np.int32))
-            return out + (0.3,) if want_ms else out
-
-        def footprint_table(self, b):
-            return np.zeros((200, 2), np.int16)
+            n = len(q)
+            return self._results(n), np.zeros((n, 2048, 3), np.float32), np.zeros((n, 2048), np.float32), None
 
     fake = types.ModuleType("path_planning_pkg_b200")
     fake.Context, fake.PPError, fake.make_params, fake._cabi = FakeContext, real.PPError, real.make_params, real._cabi
@@ -86,20 +101,15 @@ def test_default_bench_flow_prints_a_complete_line(monkeypatch, capsys):
     import path_planning_pkg_b200 as real
     import bench
 
-    class Ev:
-        def __init__(self, enable_timing=True): pass
-        def record(self): pass
-        def elapsed_time(self, other): return 1.0
-
     real_tensor = torch.tensor
     monkeypatch.setattr(torch.cuda, "set_device", lambda d: None)
     monkeypatch.setattr(torch.cuda, "synchronize", lambda *a: None)
-    monkeypatch.setattr(torch.cuda, "Event", Ev)
+    monkeypatch.setattr(torch.cuda, "mem_get_info", lambda *a: (100 << 30, 180 << 30))
     monkeypatch.setattr(torch, "tensor", lambda data, dtype=None, device=None: real_tensor(data, dtype=dtype))
     monkeypatch.setattr(torch.Tensor, "pin_memory", lambda self: self)
     monkeypatch.setitem(sys.modules, "path_planning_pkg_b200", _fake_pp(real))
-    monkeypatch.setattr(sys, "argv", ["bench.py", "--groups", "2", "--starts", "4", "--steps", "1", "--warmup", "0", "--cpu-sample", "4",
-                                      "--large-starts", "8"])
+    monkeypatch.setattr(sys, "argv", ["bench.py", "--groups", "2", "--starts", "4", "--steps", "3", "--warmup", "1", "--cpu-sample", "4",
+                                      "--lanes", "2", "--c5-groups", "2", "--c5-steps", "1"])
     for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE"):
         monkeypatch.delenv(k, raising=False)
     bench.main()
@@ -107,12 +117,24 @@ def test_default_bench_flow_prints_a_complete_line(monkeypatch, capsys):
     assert len(out) == 1
     line = json.loads(out[0])
     for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
-                "dtype", "data", "config", "e2e", "gpu_launches", "roofline", "cpu_baseline", "clocks", "kpop", "footprint_kernel",
-                "p50_single_query_ms"):
+                "dtype", "data", "config", "e2e", "gpu_launches", "roofline", "cpu_baseline", "clocks", "kpop", "c5", "c1",
+                "c2_map_update", "c3_fields", "batch_latency_ms", "retried_queries", "queries_with_bin_oob"):
         assert key in line, key
-    assert line["config"]["pools"]["max_expansions"] == 1 << 17 and line["config"]["pools"]["retried_queries"] == 0
+    assert line["steps"] == 3 and line["config"]["workload"].startswith("C4")
     assert set(line["roofline"]) >= {"bound", "achieved", "peak", "unit", "frac", "traffic"}
-    assert set(line["e2e"]) >= {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"}
-    assert "error" not in line["footprint_kernel"] and "error" not in line["cpu_baseline"], line["cpu_baseline"]
-    assert line["cpu_baseline"]["kind"] == "reference" and "one_core" in line["cpu_baseline"] and "error" not in line["cpu_baseline"]["one_core"]
-    assert "c5_batch" in line["kpop"]
+    assert set(line["e2e"]) >= {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} and line["e2e"]["h2d_bytes_per_step"] > 0
+    for blk in ("cpu_baseline", "kpop", "c5", "c2_map_update", "c3_fields"):
+        assert "error" not in line[blk], (blk, line[blk])
+    assert line["cpu_baseline"]["kind"] == "reference" and "identical_to_gpu" in line["cpu_baseline"]
+    assert "cost_vs_reference" in line["kpop"] and line["c5"]["scaling"] == "strong"
+
+
+def test_reference_arm_prints_its_line(monkeypatch, capsys):
+    import bench
+    monkeypatch.setattr(sys, "argv", ["bench.py", "--impl", "reference", "--groups", "1", "--starts", "3", "--steps", "1", "--warmup", "1"])
+    for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE"):
+        monkeypatch.delenv(k, raising=False)
+    bench.main()
+    line = json.loads([l for l in capsys.readouterr().out.split("\n") if l.startswith("{")][0])
+    assert line["impl"] == "reference" and line["value"] > 0 and line["cpu_baseline"]["kind"] == "reference"
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and "busy_time" in line

@@ -81,6 +81,23 @@ def test_empty_and_degenerate_inputs(emu_lib):
     assert np.array_equal(_bits(e.get_map()), _bits(o.get_map()))
 
 
+def test_degenerate_lane_lines_leave_the_map_alone(emu_lib):
+    """A zero-length lane line (start == end -> 0/0 direction) or a NaN point makes every sample NaN.  The reference's x86
+    float -> int conversion turns that into INT_MIN + n, which fails its bounds test: nothing is drawn (Grid2D.cpp:163-172).
+    A conversion that maps NaN to 0 would instead hammer the GOAL cell and block every later find_path."""
+    P = orc.make_params(grid_size=64, resolution=0.5)
+    planners = [_emu(emu_lib, P), orc.port(P)] + ([orc.ref(P)] if orc.have_ref() else [])
+    lines = np.array([[3, 1, 3, 1], [np.nan, 0, 4, 4], [2, -3, 9, 5], [1e30, 0, -1e30, 0]], np.float32)
+    for x in planners:
+        x.update_goal([10, 0, 0], [0, 0, 0])
+        x.update_lines(lines, np.full(len(lines), 0.8, np.float32), 1.0)
+    maps = [x.get_map() for x in planners]
+    for m in maps[1:]:
+        assert np.array_equal(_bits(maps[0]), _bits(m))
+    c = planners[0].consts()
+    assert maps[0][c.goal_ci, c.goal_cj] == 0.0 and (maps[0] != 0).sum() > 10      # only the proper line was drawn
+
+
 @pytest.mark.skipif(not orc.have_ref(), reason="needs the pinned-libm compiled reference")
 def test_search_golden_bitexact(emu_lib):
     P = orc.ref_test_params()

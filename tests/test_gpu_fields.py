@@ -40,6 +40,21 @@ def test_map_c2_shape_bitexact():
     assert int((m >= ctx.consts().log_threshold).sum()) == int(g["occupied"])
 
 
+def test_degenerate_lane_lines_bitexact():
+    """Zero-length / NaN / overflowing lane lines: the reference draws nothing for them (x86 float -> int gives INT_MIN, which
+    fails its bounds test, Grid2D.cpp:163-172); the goal cell in particular must stay free."""
+    P = orc.make_params(grid_size=64, resolution=0.5)
+    ctx, ref = _ctx(P), orc.ref(P)
+    lines = np.array([[3, 1, 3, 1], [np.nan, 0, 4, 4], [2, -3, 9, 5], [1e30, 0, -1e30, 0]], np.float32)
+    for x in (ctx, ref):
+        x.update_goal([10, 0, 0], [0, 0, 0])
+        x.update_lines(lines, np.full(len(lines), 0.8, np.float32), 1.0)
+    a, b = ctx.get_map(), ref.get_map()
+    assert np.array_equal(_bits(a), _bits(b))
+    fr = ctx.frame()
+    assert a[fr.goal_ci, fr.goal_cj] == 0.0 and (a != 0).sum() > 10
+
+
 def test_relocation_bitexact():
     """Grid3D::relocate_obstacles (goal change on a non-empty map) on the device == port == reference."""
     P = orc.make_params(grid_size=120, resolution=0.3)

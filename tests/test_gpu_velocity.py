@@ -40,7 +40,7 @@ def test_trajectory_batch_equals_reference_pipeline(mode):
     trajectory equals the reference's VelocityGenerator applied to the path the C ABI returns for the same query."""
     sc = S.c1_scenario(2)
     P = orc.make_params(grid_size=sc["grid_size"], resolution=sc["resolution"])
-    ctx, o = _ctx(P), orc.crm(P)
+    ctx, o = _ctx(P), orc.ref(P)
     for x in (ctx, o):
         S.build_map(x, sc)
     starts = np.array([[0.0, 0.0, 0.0, 3.0], [1.0, 0.5, 0.1, 1.0], [0.5, -1.0, -0.2, 0.0], [2.0, 1.0, 0.3, 2.0],
