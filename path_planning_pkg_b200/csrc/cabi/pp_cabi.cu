@@ -936,11 +936,10 @@ static int ensure_work(pp_context* c, WorkPools& w, int want_slots, int max_exp,
     if (w.alloc_slots >= 1 && w.open3_cap == cap_o && w.closed_cap == cap_c && w.open2_cap == cap_2 &&
         (w.arena_bytes != 0) == with_arena && (w.alloc_slots >= want_slots || w.clamped))
         return PP_SUCCESS;      // big enough, or already as large as this context's budget allows
-    size_t had = w.alloc_slots ? (size_t)w.alloc_slots * per_slot + w.arena_bytes : 0;
     PP_CUDA(cudaStreamSynchronize(c->stream));
     w.release();
     size_t budget = 0;
-    int rc = work_budget(c, had, &budget); if (rc) return rc;
+    int rc = work_budget(c, 0, &budget); if (rc) return rc;
     int slots = want_slots;
     size_t arena_bytes = 0;
     if (with_arena)
@@ -949,10 +948,17 @@ static int ensure_work(pp_context* c, WorkPools& w, int want_slots, int max_exp,
         if ((size_t)slots * per_slot > budget / 2) slots = (int)((budget / 2) / per_slot);
         if (slots < 1) return pp_fail(PP_ERR_CAPACITY, "not enough device memory for one query slot");
         arena_bytes = budget - (size_t)slots * per_slot;
-        const size_t per_query_max = 2 * (sizeof(PPNode3) * (size_t)max_open + sizeof(PPClosed3) * (size_t)max_exp +
-                                          sizeof(PPHashSlot) * 4 * (size_t)max_exp + sizeof(PPNode2) * (size_t)max_open2d);
-        const double need = (double)per_query_max * slots;
-        if (need < (double)arena_bytes) arena_bytes = (size_t)need;
+        // An explicit budget (pp_set_memory_budget) is taken in full.  Otherwise: what the caps could ever need, but no more than
+        // 1 GB + 64 MB per resident query (the C4 batch's longest query, 1.3 M expansions, needs about 190 MB); a query that finds
+        // the arena empty is re-run by pp_batch_wait on a larger one (arena_grow).
+        if (!c->mem_budget)
+        {
+            const double per_query_max = 2.0 * ((double)sizeof(PPNode3) * max_open + (double)sizeof(PPClosed3) * max_exp +
+                                                (double)sizeof(PPHashSlot) * 4 * max_exp + (double)sizeof(PPNode2) * max_open2d);
+            double need = std::min(per_query_max * slots, (double)((size_t)1 << 30) + (double)((size_t)64 << 20) * slots);
+            need = std::max(need, (double)((size_t)16 << 20));
+            if (need < (double)arena_bytes) arena_bytes = (size_t)need;
+        }
         arena_bytes = std::max<size_t>(arena_bytes & ~(size_t)4095, 1 << 16);
     }
     else
@@ -989,6 +995,28 @@ static int arena_reset(pp_context* c, WorkPools& w)
     std::memset(&a, 0, sizeof(a));
     a.base = (unsigned long long)w.arena_mem.p; a.size = w.arena_bytes;
     PP_CUDA(cudaMemcpyAsync(w.arena_ctl.p, &a, sizeof(a), cudaMemcpyHostToDevice, c->stream));
+    return PP_SUCCESS;
+}
+
+// a query found the arena empty: give the context a larger one (x4, within the budget) before the re-run
+static int arena_grow(pp_context* c, WorkPools& w)
+{
+    if (!w.arena_bytes) return PP_SUCCESS;
+    const size_t nn = nn_of(c);
+    int hc = w.chash_cap;
+    const size_t per_slot = sizeof(PPNode3) * (size_t)w.open3_cap + sizeof(PPClosed3) * (size_t)w.closed_cap + sizeof(PPHashSlot) * (size_t)hc +
+                            nn * 20 + sizeof(PPNode2) * (size_t)w.open2_cap;
+    const size_t fixed = per_slot * (size_t)w.alloc_slots;
+    PP_CUDA(cudaStreamSynchronize(c->stream));
+    const size_t old = w.arena_bytes;
+    w.arena_mem.release();
+    size_t budget = 0;
+    int rc = work_budget(c, fixed, &budget); if (rc) return rc;
+    size_t want = std::min(old * 4, budget > fixed ? budget - fixed : old);
+    want = std::max(want, old) & ~(size_t)4095;
+    cudaError_t e = w.arena_mem.ensure(want);
+    if (e != cudaSuccess) { (void)cudaGetLastError(); want = old; PP_CUDA(w.arena_mem.ensure(want)); }
+    w.arena_bytes = want;
     return PP_SUCCESS;
 }
 
@@ -1283,7 +1311,7 @@ int pp_batch_wait(pp_context* c, float* kernel_ms)
             o.max_expansions = (int)std::min<long long>((long long)o.max_expansions * 8, 1 << 26);
             o.max_open = (int)std::min<long long>((long long)o.max_open * 8, 1 << 25);
             o.max_open2d = (int)std::min<long long>((long long)o.max_open2d * 4, 1 << 22);
-            if (arena_short) slots_now = std::max(1, slots_now / 8);
+            if (arena_short) { slots_now = std::max(1, slots_now / 8); rc = arena_grow(c, c->wp); if (rc) return rc; }
             int slots = std::max(1, std::min((int)redo.size(), slots_now));
             if (hist_g >= 0) { rc = hist_copy(c, hist_g, true); if (rc) return rc; }     // the aborted attempt never happened
             rc = launch_search(c, c->wp, o, slots, c->d_qmap.p, (int)redo.size()); if (rc) return rc;

@@ -64,6 +64,9 @@ PP_HD PPWalk pp_walk_load(const PPWalk* p)
 // the reference's non-strict-weak ordering
 PP_HD bool pp_lt(unsigned ka, float fa, unsigned kb, float fb) { return (ka != kb) && (fa < fb); }
 
+template <class Node> PP_HD int pp_rb_find_walk(const Node* n, const PPKey& k, int* path, int cap, int& n_path);
+template <class Node> PP_HD bool pp_rb_insert_pos_walk(const Node* n, const PPKey& k, int& p, bool& left, int* path, int cap, int& n_path);
+
 template <class Node>
 struct PPRbTree
 {
@@ -72,6 +75,14 @@ struct PPRbTree
     int   next;     // first never-used slot
     int   free_head;  // singly linked (through .parent) list of recycled slots
     int   count;
+    // Optional mutation log (speculative walks, pp_search.h): indices of the nodes whose child pointers changed since the
+    // caller last reset *mcnt (the header stands for the root pointer).  *mcnt > mcap = too many / an erase: everything changed.
+    int*  mlog = nullptr;
+    int*  mcnt = nullptr;
+    int   mcap = 0;
+
+    PP_HD void mut(int x) { if (mlog) { int c = *mcnt; if (c < mcap) mlog[c] = x; *mcnt = c + 1; } }
+    PP_HD void mut_all() { if (mlog) *mcnt = mcap + 1; }
 
     PP_HD void init(Node* pool, int capacity)
     {
@@ -105,6 +116,7 @@ struct PPRbTree
     PP_HD void rotate_left(int x)
     {
         int y = n[x].w.right;
+        mut(x); mut(y); mut(x == n[PP_RB_HEADER].parent ? PP_RB_HEADER : n[x].parent);
         n[x].w.right = n[y].w.left;
         if (n[y].w.left != PP_RB_NIL) n[n[y].w.left].parent = x;
         n[y].parent = n[x].parent;
@@ -118,6 +130,7 @@ struct PPRbTree
     PP_HD void rotate_right(int x)
     {
         int y = n[x].w.left;
+        mut(x); mut(y); mut(x == n[PP_RB_HEADER].parent ? PP_RB_HEADER : n[x].parent);
         n[x].w.left = n[y].w.right;
         if (n[y].w.right != PP_RB_NIL) n[n[y].w.right].parent = x;
         n[y].parent = n[x].parent;
@@ -149,6 +162,7 @@ struct PPRbTree
     {
         PP_ASSUME_GLOBAL(n);
         n[x].parent = p; n[x].w.left = PP_RB_NIL; n[x].w.right = PP_RB_NIL; n[x].color = PP_RB_RED;
+        mut(p);
         if (insert_left)
         {
             n[p].w.left = x;   // also sets leftmost = x when p is the header
@@ -205,6 +219,7 @@ struct PPRbTree
     PP_HD_NOINLINE void erase(int z)
     {
         PP_ASSUME_GLOBAL(n);
+        mut_all();
         int y = z, x = PP_RB_NIL, x_parent = PP_RB_NIL;
         if (n[y].w.left == PP_RB_NIL) x = n[y].w.right;
         else if (n[y].w.right == PP_RB_NIL) x = n[y].w.left;
@@ -335,55 +350,87 @@ struct PPRbTree
         release(z);
     }
 
-    // std::set::find(k): lower-bound walk, then reject when k < *j.
+    // std::set::find(k)
     PP_HD_NOINLINE int find(const PPKey& k) const
     {
-        PP_ASSUME_GLOBAL(n);
-        int x = n[PP_RB_HEADER].parent, y = PP_RB_HEADER;
-        PPWalk yw; yw.left = 0; yw.right = 0; yw.f = 0.0f; yw.key = 0u;
-        while (x != PP_RB_NIL)
-        {
-            const PPWalk r = pp_walk_load(&n[x].w);        // one 128-bit load per level
-            if (!pp_lt(r.key, r.f, k.key, k.f)) { y = x; yw = r; x = r.left; }
-            else x = r.right;
-        }
-        if (y == PP_RB_HEADER || pp_lt(k.key, k.f, yw.key, yw.f)) return PP_RB_NIL;
-        return y;
+        int np;
+        return pp_rb_find_walk(n, k, (int*)0, 0, np);
     }
 
     // std::set::insert(v) position search (_M_get_insert_unique_pos).  Returns true when the key must be
     // inserted under parent `p` (left child iff `left`); false when an equivalent element exists.
     PP_HD_NOINLINE bool insert_pos(const PPKey& k, int& p, bool& left) const
     {
-        PP_ASSUME_GLOBAL(n);
-        int x = n[PP_RB_HEADER].parent, y = PP_RB_HEADER;
-        bool comp = true;
-        while (x != PP_RB_NIL)
-        {
-            const PPWalk r = pp_walk_load(&n[x].w);
-            y = x;
-            comp = pp_lt(k.key, k.f, r.key, r.f);
-            x = comp ? r.left : r.right;
-        }
-        int j = y;
-        if (comp)
-        {
-            if (j == n[PP_RB_HEADER].w.left)   // j == begin(): insert to the left of the leftmost (or into an empty tree)
-            {
-                p = y; left = true;            // _M_insert_: p == header, or k < p (== comp, which is true here)
-                return true;
-            }
-            j = decrement(j);
-        }
-        const PPWalk jw = n[j].w;
-        if (pp_lt(jw.key, jw.f, k.key, k.f))
-        {
-            p = y;
-            left = (y == PP_RB_HEADER) || comp;   // _M_insert_ re-evaluates k < p, which is `comp` of the last step
-            return true;
-        }
-        return false;
+        int np;
+        return pp_rb_insert_pos_walk(n, k, p, left, (int*)0, 0, np);
     }
 };
+
+// ---- the two walks as free functions over a node pool, optionally recording the nodes they visit ---------------------------
+// A recorded path lets the caller decide later whether the walk would still go the same way: node keys and costs never change
+// while a node is in the tree, so a walk is unchanged as long as no node on its path had a child pointer changed (PPRbTree::mut).
+// path[0] is always the header (= the root pointer).  n_path > cap means the path did not fit (treat as "cannot tell").
+
+// std::set::find(k): lower-bound walk, then reject when k < *j.
+template <class Node>
+PP_HD int pp_rb_find_walk(const Node* n, const PPKey& k, int* path, int cap, int& n_path)
+{
+    PP_ASSUME_GLOBAL(n);
+    int x = n[PP_RB_HEADER].parent, y = PP_RB_HEADER;
+    PPWalk yw; yw.left = 0; yw.right = 0; yw.f = 0.0f; yw.key = 0u;
+    int c = 0;
+    if (c < cap) path[c] = PP_RB_HEADER;
+    c++;
+    while (x != PP_RB_NIL)
+    {
+        if (c < cap) path[c] = x;
+        c++;
+        const PPWalk r = pp_walk_load(&n[x].w);        // one 128-bit load per level
+        if (!pp_lt(r.key, r.f, k.key, k.f)) { y = x; yw = r; x = r.left; }
+        else x = r.right;
+    }
+    n_path = c;
+    if (y == PP_RB_HEADER || pp_lt(k.key, k.f, yw.key, yw.f)) return PP_RB_NIL;
+    return y;
+}
+
+// _M_get_insert_unique_pos.  libstdc++ steps to the in-order predecessor of the leaf position with _Rb_tree_decrement when the
+// last turn was to the left; that predecessor is the last node at which the walk turned RIGHT (none: the position is left of
+// begin()), so it is tracked during the walk instead of being looked up by a second pointer chase.
+template <class Node>
+PP_HD bool pp_rb_insert_pos_walk(const Node* n, const PPKey& k, int& p, bool& left, int* path, int cap, int& n_path)
+{
+    PP_ASSUME_GLOBAL(n);
+    int x = n[PP_RB_HEADER].parent, y = PP_RB_HEADER;
+    bool comp = true;
+    int j = PP_RB_NIL;
+    PPWalk jw; jw.left = 0; jw.right = 0; jw.f = 0.0f; jw.key = 0u;
+    int c = 0;
+    if (c < cap) path[c] = PP_RB_HEADER;
+    c++;
+    while (x != PP_RB_NIL)
+    {
+        if (c < cap) path[c] = x;
+        c++;
+        const PPWalk r = pp_walk_load(&n[x].w);
+        y = x;
+        comp = pp_lt(k.key, k.f, r.key, r.f);
+        if (comp) x = r.left;
+        else { j = x; jw = r; x = r.right; }
+    }
+    n_path = c;
+    if (j == PP_RB_NIL)                    // never turned right: left of the leftmost node, or an empty tree
+    {
+        p = y; left = true;                // _M_insert_: p == header, or k < p (== comp, which is true here)
+        return true;
+    }
+    if (pp_lt(jw.key, jw.f, k.key, k.f))
+    {
+        p = y;
+        left = (y == PP_RB_HEADER) || comp;   // _M_insert_ re-evaluates k < p, which is `comp` of the last step
+        return true;
+    }
+    return false;
+}
 
 #endif

@@ -24,6 +24,9 @@
 
 #define PP_MAX_SUCC 16
 #define PP_NEAR_CAP 64
+#define PP_SPEC_WALKS 16      /* speculative tree walks per batch: (successor, find | insert) pairs, or the 8 neighbours of a 2D pop x 2 */
+#define PP_SPEC_PATH 40       /* nodes recorded per walk: header + the height bound of a red-black tree of 2^19 nodes */
+#define PP_MLOG_CAP 48        /* mutated nodes remembered between two speculation batches */
 
 // Optional per-phase cycle accounting (library variant built with -DPP_PROFILE; never in the shipped .so).
 // Phases: 0 scratch init, 1 pop + closed insert + erase, 2 roll-out/collision/APF, 3 Dubins candidates,
@@ -132,7 +135,34 @@ struct PPSmem   // per-warp staging area (shared memory on the device)
     float  d_acos[PP_MAX_SUCC * 2];      // acosf(2r/dist) per (successor, RSL | LSR)
     float  d_sin[PP_MAX_SUCC * 4];       // sin / cos of theta_t1 and p2 per (successor, RSL | LSR)
     float  d_cos[PP_MAX_SUCC * 4];
+    // speculative walks (pp_spec_*): every walk of one expansion is done up front by its own lane on the tree as it stands;
+    // the control lane then commits the successors in the reference's order and re-walks only what an earlier commit touched
+    int    spec_path[PP_SPEC_WALKS][PP_SPEC_PATH];
+    int    spec_np[PP_SPEC_WALKS];       // nodes on the path, -1 = no speculation for this walk
+    int    spec_a[PP_SPEC_WALKS];        // find: the node found (or NIL); insert: the parent
+    int    spec_b[PP_SPEC_WALKS];        // insert: 1 = left child, 0 = right child, -1 = equivalent element exists (dropped)
+    float  spec_f[PP_SPEC_WALKS];        // insert: the f the position was searched for
+    int    mlog[PP_MLOG_CAP];            // PPRbTree::mut log of the 3D open list
+    int    mcount;
 };
+
+// Would the recorded walk still visit the same nodes?  True iff none of them had a child pointer changed since the walk
+// (all lanes; the same answer on every lane).
+template <class W>
+PP_HD bool pp_spec_valid(const W& w, const int* path, int np, const int* mlog, int mcount)
+{
+    // every lane leaves through the ballot: it is also the barrier between these reads of the log and the control lane's next
+    // writes to it
+    bool hit = (np < 0 || np > PP_SPEC_PATH || mcount > PP_MLOG_CAP);
+    if (!hit)
+        for (int base = 0; base < np; base += W::LANES)
+        {
+            const int q = base + w.lane();
+            const int mine = (q < np) ? path[q] : -2;
+            for (int j = 0; j < mcount; j++) hit = hit || (mine == mlog[j]);
+        }
+    return w.ballot(hit) == 0u;
+}
 
 // goal-side constants of the Dubins heuristic, evaluated once per query
 struct PPDubinsGoal { float grx, gry, glx, gly; };
@@ -745,12 +775,9 @@ PP_HD void pp_closed_link(PPWork& wk, unsigned key, int idx)
     wk.chash[h] = s;
 }
 
-// returns false when the pool is exhausted
-PP_HD_NOINLINE_FN bool pp_open3_insert(PPSearchState& S, const PPSucc& s, unsigned key, float f, int prev)
+// links a new node under parent p; returns false when the pool is exhausted
+PP_HD_NOINLINE_FN bool pp_open3_attach(PPSearchState& S, const PPSucc& s, unsigned key, float f, int prev, int p, bool left)
 {
-    PPKey k; k.key = key; k.f = f;
-    int p; bool left;
-    if (!S.open.insert_pos(k, p, left)) return true;   // equal-f drop (F5)
     int slot = S.open.alloc();
     if (slot == PP_RB_NIL) { S.status |= PP_STATUS_OPEN_OVERFLOW; return false; }
     PPNode3& n = S.open.n[slot];
@@ -759,6 +786,14 @@ PP_HD_NOINLINE_FN bool pp_open3_insert(PPSearchState& S, const PPSucc& s, unsign
     S.open.insert_and_rebalance(left, slot, p);
     if (S.open.count > S.max_open) S.max_open = S.open.count;
     return true;
+}
+
+PP_HD_NOINLINE_FN bool pp_open3_insert(PPSearchState& S, const PPSucc& s, unsigned key, float f, int prev)
+{
+    PPKey k; k.key = key; k.f = f;
+    int p; bool left;
+    if (!S.open.insert_pos(k, p, left)) return true;   // equal-f drop (F5)
+    return pp_open3_attach(S, s, key, f, prev, p, left);
 }
 
 // The search.  All lanes of the warp call it with identical arguments.
@@ -810,6 +845,8 @@ PP_HD_NOINLINE_FN void pp_search_exact(const W& w, const PPConsts& C, const floa
     if (lane == 0)
     {
         S.open.init(wk.open3, wk.open3_cap);
+        S.open.mlog = sm.mlog; S.open.mcnt = &sm.mcount; S.open.mcap = PP_MLOG_CAP;
+        sm.mcount = 0;
         S.lazy.open.init(wk.open2, wk.open2_cap);
         S.lazy.search_id = sid0; S.lazy.status = 0; S.lazy.n_searches = 0; S.lazy.n_pops = 0;
         S.lazy.arena = wk.arena; S.lazy.max_cap = wk.arena ? wk.open2_max : wk.open2_cap; S.lazy.blk = -1;
@@ -1011,36 +1048,94 @@ PP_HD_NOINLINE_FN void pp_search_exact(const W& w, const PPConsts& C, const floa
         pp_dubins_h2_warp(w, C, F, gc, sm);
         PP_PROF_MARK(3)
 
-        // ---------------- phase 4: successors into the containers (control lane) ----------------
-        int abort = 0;
-        if (lane == 0)
+        // ---------------- phase 4a: every tree walk of this expansion, speculatively and in parallel (all lanes) ----------------
+        // walk 2s = open.find of successor s (probe f = g + field), walk 2s + 1 = its insert position (f = g + max(h1, h2)), the
+        // latter only when h1 is already cached (the cell is _visted: its cost can no longer change, AStar.cpp:100-105)
+        PPNode3* pool = pp_bcast_ptr(w, (lane == 0) ? S.open.n : (PPNode3*)0);
+        if (lane == 0) sm.mcount = 0;
+        for (int q = lane; q < 2 * n_succ_max; q += W::LANES)
         {
-            for (int s = 0; s < n_succ_max && !abort; s++)
+            const int s = q >> 1;
+            sm.spec_np[q] = -1;
+            if (!sm.succ[s].ok) continue;
+            const PPSucc& sc = sm.succ[s];
+            PPKey k; k.key = (unsigned)(sc.ci * N + sc.cj) * kb + (unsigned)sc.bin;
+            int np = 0;
+            if ((q & 1) == 0)
             {
-                const PPSucc& sc = sm.succ[s];
-                if (!sc.ok) continue;
-                unsigned key = (unsigned)(sc.ci * N + sc.cj) * kb + (unsigned)sc.bin;
-                PPKey k; k.key = key; k.f = sc.g;                           // f == g + field at find time
-                int it_node = S.open.find(k);
-                bool do_insert = false;
-                if (it_node == PP_RB_NIL) do_insert = true;
-                else if (sc.g < S.open.n[it_node].g) { S.open.erase(it_node); do_insert = true; }
-                PP_PROF_MARK(5)
-                if (do_insert)
+                k.f = sc.g;
+                sm.spec_a[q] = pp_rb_find_walk(pool, k, sm.spec_path[q], PP_SPEC_PATH, np);
+                sm.spec_np[q] = np;
+            }
+            else
+            {
+                const int cell = sc.ci * N + sc.cj;
+                if (wk.cell_state[cell] & PP_CS_VISITED)
                 {
-                    float h1 = pp_lazy_astar(C, G.map, F, wk, S.lazy, sc.ci, sc.cj);
-                    PP_PROF_MARK(6)
+                    const float h1 = wk.nm_f[cell];
                     float h2 = sm.cand[4 * s];
                     for (int t = 1; t < 4; t++) if (sm.cand[4 * s + t] < h2) h2 = sm.cand[4 * s + t];
-                    float f = sc.g + ((h1 < h2) ? h2 : h1);
-                    if (!pp_open3_insert(S, sc, key, f, cur)) abort = 1;
-                    if (S.lazy.status) { S.status |= S.lazy.status; abort = 1; }
-                    PP_PROF_MARK(7)
+                    k.f = sc.g + ((h1 < h2) ? h2 : h1);
+                    int p; bool left;
+                    const bool ins = pp_rb_insert_pos_walk(pool, k, p, left, sm.spec_path[q], PP_SPEC_PATH, np);
+                    sm.spec_a[q] = p; sm.spec_b[q] = ins ? (left ? 1 : 0) : -1; sm.spec_f[q] = k.f;
+                    sm.spec_np[q] = np;
                 }
             }
         }
-        abort = w.shfl(abort, 0);
         w.sync();
+        PP_PROF_MARK(5)
+
+        // ---------------- phase 4b: successors into the containers, in the reference's order (HybridAStar.cpp:159-193) ----------------
+        // The control lane commits; before each use of a speculative walk all lanes check it against the nodes the earlier
+        // commits of this expansion touched (pp_spec_valid) and the control lane walks again only when they meet.
+        int abort = 0;
+        for (int s = 0; s < n_succ_max; s++)
+        {
+            if (!sm.succ[s].ok) continue;            // uniform: shared memory
+            const PPSucc& sc = sm.succ[s];
+            const unsigned key = (unsigned)(sc.ci * N + sc.cj) * kb + (unsigned)sc.bin;
+            const bool v_find = pp_spec_valid(w, sm.spec_path[2 * s], sm.spec_np[2 * s], sm.mlog, sm.mcount);
+            int todo = 0;                            // bit 0: insert, bit 1: h1 still has to come from the lazy A*
+            if (lane == 0)
+            {
+                PPKey k; k.key = key; k.f = sc.g;                           // f == g + field at find time
+                int it_node = v_find ? sm.spec_a[2 * s] : S.open.find(k);
+                if (it_node == PP_RB_NIL) todo = 1;
+                else if (sc.g < S.open.n[it_node].g) { S.open.erase(it_node); todo = 1; }
+                if (todo && sm.spec_np[2 * s + 1] < 0) todo |= 2;
+            }
+            todo = w.shfl(todo, 0);
+            PP_PROF_MARK(5)
+            if (!todo) continue;
+            float f = 0.0f;
+            if (todo & 2)
+            {
+                if (lane == 0)
+                {
+                    float h1 = pp_lazy_astar(C, G.map, F, wk, S.lazy, sc.ci, sc.cj);
+                    float h2 = sm.cand[4 * s];
+                    for (int t = 1; t < 4; t++) if (sm.cand[4 * s + t] < h2) h2 = sm.cand[4 * s + t];
+                    f = sc.g + ((h1 < h2) ? h2 : h1);
+                }
+                PP_PROF_MARK(6)
+            }
+            w.sync();                                // sm.mcount after a possible erase above
+            const bool v_ins = pp_spec_valid(w, sm.spec_path[2 * s + 1], (todo & 2) ? -1 : sm.spec_np[2 * s + 1], sm.mlog, sm.mcount);
+            if (lane == 0)
+            {
+                int p = 0; bool left = false, ins;
+                if (!(todo & 2)) f = sm.spec_f[2 * s + 1];
+                if (v_ins) { p = sm.spec_a[2 * s + 1]; ins = sm.spec_b[2 * s + 1] >= 0; left = sm.spec_b[2 * s + 1] == 1; }
+                else { PPKey k; k.key = key; k.f = f; ins = S.open.insert_pos(k, p, left); }
+                if (ins && !pp_open3_attach(S, sc, key, f, cur, p, left)) abort = 1;     // !ins: equal-f drop (F5)
+                if (S.lazy.status) { S.status |= S.lazy.status; abort = 1; }
+            }
+            abort = w.shfl(abort, 0);
+            w.sync();                                // sm.mlog / sm.mcount of this commit
+            PP_PROF_MARK(7)
+            if (abort) break;
+        }
         if (abort) break;
     }
     PP_PROF_FLUSH
