@@ -1680,13 +1680,13 @@ int pp_timer_end(pp_context* c, float* ms)
 
 #ifdef PP_PROFILE
 // development variant only (lib/libpp_b200_prof.so): per-phase SM cycles summed over all queries; reset on read
-int pp_profile_read(pp_context* c, unsigned long long* out8)
+int pp_profile_read(pp_context* c, unsigned long long* out16)
 {
     if (!c) return pp_fail(PP_ERR_INVALID, "null context");
     PP_CUDA(cudaSetDevice(c->device));
     PP_CUDA(cudaStreamSynchronize(c->stream));
-    PP_CUDA(cudaMemcpyFromSymbol(out8, pp_prof_acc, sizeof(unsigned long long) * 8));
-    unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    PP_CUDA(cudaMemcpyFromSymbol(out16, pp_prof_acc, sizeof(unsigned long long) * 16));
+    unsigned long long z[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     PP_CUDA(cudaMemcpyToSymbol(pp_prof_acc, z, sizeof(z)));
     return PP_SUCCESS;
 }

@@ -64,15 +64,21 @@ PP_HD PPWalk pp_walk_load(const PPWalk* p)
 // the reference's non-strict-weak ordering
 PP_HD bool pp_lt(unsigned ka, float fa, unsigned kb, float fb) { return (ka != kb) && (fa < fb); }
 
-template <class Node> PP_HD int pp_rb_find_walk(const Node* n, const PPKey& k, int* path, int cap, int& n_path);
-template <class Node> PP_HD bool pp_rb_insert_pos_walk(const Node* n, const PPKey& k, int& p, bool& left, int* path, int cap, int& n_path);
-
-template <class Node>
-struct PPRbTree
+// Everything the tree algorithms touch of a node: both node types (PPNode3, PPNode2 in pp_search.h) start with it, so ONE copy
+// of the walks and of the rebalancing code serves both trees (pool addressed as bytes + stride).  The search kernel is bound
+// by instruction fetch when many warps are resident (ncu: `no_instruction` is the top stall at bench occupancy), so code that
+// two containers can share is code that is fetched once.
+struct PPRbHead
 {
-    Node* n;        // pool; n[0] is the header
-    int   cap;      // pool capacity (including header)
-    int   next;     // first never-used slot
+    PPWalk w;
+    int    parent, color;
+};
+
+// container state without the pool pointer (the typed wrapper below owns that)
+struct PPRbState
+{
+    int   cap;        // pool capacity (including header)
+    int   next;       // first never-used slot
     int   free_head;  // singly linked (through .parent) list of recycled slots
     int   count;
     // Optional mutation log (speculative walks, pp_search.h): indices of the nodes whose child pointers changed since the
@@ -83,299 +89,244 @@ struct PPRbTree
 
     PP_HD void mut(int x) { if (mlog) { int c = *mcnt; if (c < mcap) mlog[c] = x; *mcnt = c + 1; } }
     PP_HD void mut_all() { if (mlog) *mcnt = mcap + 1; }
+};
 
-    PP_HD void init(Node* pool, int capacity)
+struct PPRbPool
+{
+    char* base; int stride;
+    PP_HD PPRbHead& operator[](int i) const { return *reinterpret_cast<PPRbHead*>(base + (size_t)i * (size_t)stride); }
+};
+
+PP_HD_NOINLINE_FN void pp_rb_rotate_left(PPRbState& t, const PPRbPool n, int x)
+{
+    int y = n[x].w.right;
+    t.mut(x); t.mut(y); t.mut(x == n[PP_RB_HEADER].parent ? PP_RB_HEADER : n[x].parent);
+    n[x].w.right = n[y].w.left;
+    if (n[y].w.left != PP_RB_NIL) n[n[y].w.left].parent = x;
+    n[y].parent = n[x].parent;
+    if (x == n[PP_RB_HEADER].parent) n[PP_RB_HEADER].parent = y;
+    else if (x == n[n[x].parent].w.left) n[n[x].parent].w.left = y;
+    else n[n[x].parent].w.right = y;
+    n[y].w.left = x;
+    n[x].parent = y;
+}
+
+PP_HD_NOINLINE_FN void pp_rb_rotate_right(PPRbState& t, const PPRbPool n, int x)
+{
+    int y = n[x].w.left;
+    t.mut(x); t.mut(y); t.mut(x == n[PP_RB_HEADER].parent ? PP_RB_HEADER : n[x].parent);
+    n[x].w.left = n[y].w.right;
+    if (n[y].w.right != PP_RB_NIL) n[n[y].w.right].parent = x;
+    n[y].parent = n[x].parent;
+    if (x == n[PP_RB_HEADER].parent) n[PP_RB_HEADER].parent = y;
+    else if (x == n[n[x].parent].w.right) n[n[x].parent].w.right = y;
+    else n[n[x].parent].w.left = y;
+    n[y].w.right = x;
+    n[x].parent = y;
+}
+
+// _Rb_tree_insert_and_rebalance
+PP_HD_NOINLINE_FN void pp_rb_insert_and_rebalance(PPRbState& t, const PPRbPool n, bool insert_left, int x, int p)
+{
+    PP_ASSUME_GLOBAL(n.base);
+    n[x].parent = p; n[x].w.left = PP_RB_NIL; n[x].w.right = PP_RB_NIL; n[x].color = PP_RB_RED;
+    t.mut(p);
+    if (insert_left)
     {
-        n = pool; cap = capacity;
-        clear();
+        n[p].w.left = x;   // also sets leftmost = x when p is the header
+        if (p == PP_RB_HEADER) { n[PP_RB_HEADER].parent = x; n[PP_RB_HEADER].w.right = x; }
+        else if (p == n[PP_RB_HEADER].w.left) n[PP_RB_HEADER].w.left = x;
     }
-
-    PP_HD void clear()
+    else
     {
-        n[PP_RB_HEADER].parent = PP_RB_NIL;
-        n[PP_RB_HEADER].w.left = PP_RB_HEADER;
-        n[PP_RB_HEADER].w.right = PP_RB_HEADER;
-        n[PP_RB_HEADER].color = PP_RB_RED;
-        next = 1; free_head = PP_RB_NIL; count = 0;
+        n[p].w.right = x;
+        if (p == n[PP_RB_HEADER].w.right) n[PP_RB_HEADER].w.right = x;
     }
-
-    PP_HD bool empty() const { return count == 0; }
-    PP_HD int  begin() const { return n[PP_RB_HEADER].w.left; }
-    PP_HD int  root() const { return n[PP_RB_HEADER].parent; }
-
-    // returns a free slot or PP_RB_NIL when the pool is exhausted
-    PP_HD int alloc()
+    while (x != n[PP_RB_HEADER].parent && n[n[x].parent].color == PP_RB_RED)
     {
-        if (free_head != PP_RB_NIL) { int s = free_head; free_head = n[s].parent; return s; }
-        if (next < cap) return next++;
-        return PP_RB_NIL;
-    }
-
-    PP_HD void release(int s) { n[s].parent = free_head; free_head = s; }
-
-    PP_HD void rotate_left(int x)
-    {
-        int y = n[x].w.right;
-        mut(x); mut(y); mut(x == n[PP_RB_HEADER].parent ? PP_RB_HEADER : n[x].parent);
-        n[x].w.right = n[y].w.left;
-        if (n[y].w.left != PP_RB_NIL) n[n[y].w.left].parent = x;
-        n[y].parent = n[x].parent;
-        if (x == n[PP_RB_HEADER].parent) n[PP_RB_HEADER].parent = y;
-        else if (x == n[n[x].parent].w.left) n[n[x].parent].w.left = y;
-        else n[n[x].parent].w.right = y;
-        n[y].w.left = x;
-        n[x].parent = y;
-    }
-
-    PP_HD void rotate_right(int x)
-    {
-        int y = n[x].w.left;
-        mut(x); mut(y); mut(x == n[PP_RB_HEADER].parent ? PP_RB_HEADER : n[x].parent);
-        n[x].w.left = n[y].w.right;
-        if (n[y].w.right != PP_RB_NIL) n[n[y].w.right].parent = x;
-        n[y].parent = n[x].parent;
-        if (x == n[PP_RB_HEADER].parent) n[PP_RB_HEADER].parent = y;
-        else if (x == n[n[x].parent].w.right) n[n[x].parent].w.right = y;
-        else n[n[x].parent].w.left = y;
-        n[y].w.right = x;
-        n[x].parent = y;
-    }
-
-    // _Rb_tree_decrement
-    PP_HD_NOINLINE int decrement(int x) const
-    {
-        PP_ASSUME_GLOBAL(n);
-        if (x == PP_RB_HEADER) return n[x].w.right;   // end() -> rightmost
-        if (n[x].w.left != PP_RB_NIL)
+        int xp = n[x].parent;
+        int xpp = n[xp].parent;
+        if (xp == n[xpp].w.left)
         {
-            int y = n[x].w.left;
-            while (n[y].w.right != PP_RB_NIL) y = n[y].w.right;
-            return y;
-        }
-        int y = n[x].parent;
-        while (x == n[y].w.left) { x = y; y = n[y].parent; }
-        return y;
-    }
-
-    // _Rb_tree_insert_and_rebalance
-    PP_HD_NOINLINE void insert_and_rebalance(bool insert_left, int x, int p)
-    {
-        PP_ASSUME_GLOBAL(n);
-        n[x].parent = p; n[x].w.left = PP_RB_NIL; n[x].w.right = PP_RB_NIL; n[x].color = PP_RB_RED;
-        mut(p);
-        if (insert_left)
-        {
-            n[p].w.left = x;   // also sets leftmost = x when p is the header
-            if (p == PP_RB_HEADER) { n[PP_RB_HEADER].parent = x; n[PP_RB_HEADER].w.right = x; }
-            else if (p == n[PP_RB_HEADER].w.left) n[PP_RB_HEADER].w.left = x;
+            int y = n[xpp].w.right;
+            if (y != PP_RB_NIL && n[y].color == PP_RB_RED)
+            {
+                n[xp].color = PP_RB_BLACK; n[y].color = PP_RB_BLACK; n[xpp].color = PP_RB_RED;
+                x = xpp;
+            }
+            else
+            {
+                if (x == n[xp].w.right) { x = xp; pp_rb_rotate_left(t, n, x); }
+                n[n[x].parent].color = PP_RB_BLACK;
+                n[xpp].color = PP_RB_RED;
+                pp_rb_rotate_right(t, n, xpp);
+            }
         }
         else
         {
-            n[p].w.right = x;
-            if (p == n[PP_RB_HEADER].w.right) n[PP_RB_HEADER].w.right = x;
-        }
-        while (x != n[PP_RB_HEADER].parent && n[n[x].parent].color == PP_RB_RED)
-        {
-            int xp = n[x].parent;
-            int xpp = n[xp].parent;
-            if (xp == n[xpp].w.left)
+            int y = n[xpp].w.left;
+            if (y != PP_RB_NIL && n[y].color == PP_RB_RED)
             {
-                int y = n[xpp].w.right;
-                if (y != PP_RB_NIL && n[y].color == PP_RB_RED)
+                n[xp].color = PP_RB_BLACK; n[y].color = PP_RB_BLACK; n[xpp].color = PP_RB_RED;
+                x = xpp;
+            }
+            else
+            {
+                if (x == n[xp].w.left) { x = xp; pp_rb_rotate_right(t, n, x); }
+                n[n[x].parent].color = PP_RB_BLACK;
+                n[xpp].color = PP_RB_RED;
+                pp_rb_rotate_left(t, n, xpp);
+            }
+        }
+    }
+    n[n[PP_RB_HEADER].parent].color = PP_RB_BLACK;
+    t.count++;
+}
+
+// _Rb_tree_rebalance_for_erase; recycles slot z
+PP_HD_NOINLINE_FN void pp_rb_erase(PPRbState& t, const PPRbPool n, int z)
+{
+    PP_ASSUME_GLOBAL(n.base);
+    t.mut_all();
+    int y = z, x = PP_RB_NIL, x_parent = PP_RB_NIL;
+    if (n[y].w.left == PP_RB_NIL) x = n[y].w.right;
+    else if (n[y].w.right == PP_RB_NIL) x = n[y].w.left;
+    else
+    {
+        y = n[y].w.right;
+        while (n[y].w.left != PP_RB_NIL) y = n[y].w.left;
+        x = n[y].w.right;
+    }
+    if (y != z)
+    {
+        // relink y in place of z
+        n[n[z].w.left].parent = y;
+        n[y].w.left = n[z].w.left;
+        if (y != n[z].w.right)
+        {
+            x_parent = n[y].parent;
+            if (x != PP_RB_NIL) n[x].parent = n[y].parent;
+            n[n[y].parent].w.left = x;
+            n[y].w.right = n[z].w.right;
+            n[n[z].w.right].parent = y;
+        }
+        else x_parent = y;
+        if (n[PP_RB_HEADER].parent == z) n[PP_RB_HEADER].parent = y;
+        else if (n[n[z].parent].w.left == z) n[n[z].parent].w.left = y;
+        else n[n[z].parent].w.right = y;
+        n[y].parent = n[z].parent;
+        int c = n[y].color; n[y].color = n[z].color; n[z].color = c;
+        y = z;
+    }
+    else
+    {
+        x_parent = n[y].parent;
+        if (x != PP_RB_NIL) n[x].parent = n[y].parent;
+        if (n[PP_RB_HEADER].parent == z) n[PP_RB_HEADER].parent = x;
+        else if (n[n[z].parent].w.left == z) n[n[z].parent].w.left = x;
+        else n[n[z].parent].w.right = x;
+        if (n[PP_RB_HEADER].w.left == z)
+        {
+            if (n[z].w.right == PP_RB_NIL) n[PP_RB_HEADER].w.left = n[z].parent;
+            else { int m = x; while (n[m].w.left != PP_RB_NIL) m = n[m].w.left; n[PP_RB_HEADER].w.left = m; }
+        }
+        if (n[PP_RB_HEADER].w.right == z)
+        {
+            if (n[z].w.left == PP_RB_NIL) n[PP_RB_HEADER].w.right = n[z].parent;
+            else { int m = x; while (n[m].w.right != PP_RB_NIL) m = n[m].w.right; n[PP_RB_HEADER].w.right = m; }
+        }
+    }
+    if (n[y].color != PP_RB_RED)
+    {
+        while (x != n[PP_RB_HEADER].parent && (x == PP_RB_NIL || n[x].color == PP_RB_BLACK))
+        {
+            if (x == n[x_parent].w.left)
+            {
+                int w = n[x_parent].w.right;
+                if (n[w].color == PP_RB_RED)
                 {
-                    n[xp].color = PP_RB_BLACK; n[y].color = PP_RB_BLACK; n[xpp].color = PP_RB_RED;
-                    x = xpp;
+                    n[w].color = PP_RB_BLACK; n[x_parent].color = PP_RB_RED;
+                    pp_rb_rotate_left(t, n, x_parent);
+                    w = n[x_parent].w.right;
+                }
+                if ((n[w].w.left == PP_RB_NIL || n[n[w].w.left].color == PP_RB_BLACK) &&
+                    (n[w].w.right == PP_RB_NIL || n[n[w].w.right].color == PP_RB_BLACK))
+                {
+                    n[w].color = PP_RB_RED;
+                    x = x_parent;
+                    x_parent = n[x_parent].parent;
                 }
                 else
                 {
-                    if (x == n[xp].w.right) { x = xp; rotate_left(x); }
-                    n[n[x].parent].color = PP_RB_BLACK;
-                    n[xpp].color = PP_RB_RED;
-                    rotate_right(xpp);
+                    if (n[w].w.right == PP_RB_NIL || n[n[w].w.right].color == PP_RB_BLACK)
+                    {
+                        n[n[w].w.left].color = PP_RB_BLACK;
+                        n[w].color = PP_RB_RED;
+                        pp_rb_rotate_right(t, n, w);
+                        w = n[x_parent].w.right;
+                    }
+                    n[w].color = n[x_parent].color;
+                    n[x_parent].color = PP_RB_BLACK;
+                    if (n[w].w.right != PP_RB_NIL) n[n[w].w.right].color = PP_RB_BLACK;
+                    pp_rb_rotate_left(t, n, x_parent);
+                    break;
                 }
             }
             else
             {
-                int y = n[xpp].w.left;
-                if (y != PP_RB_NIL && n[y].color == PP_RB_RED)
+                int w = n[x_parent].w.left;
+                if (n[w].color == PP_RB_RED)
                 {
-                    n[xp].color = PP_RB_BLACK; n[y].color = PP_RB_BLACK; n[xpp].color = PP_RB_RED;
-                    x = xpp;
+                    n[w].color = PP_RB_BLACK; n[x_parent].color = PP_RB_RED;
+                    pp_rb_rotate_right(t, n, x_parent);
+                    w = n[x_parent].w.left;
+                }
+                if ((n[w].w.right == PP_RB_NIL || n[n[w].w.right].color == PP_RB_BLACK) &&
+                    (n[w].w.left == PP_RB_NIL || n[n[w].w.left].color == PP_RB_BLACK))
+                {
+                    n[w].color = PP_RB_RED;
+                    x = x_parent;
+                    x_parent = n[x_parent].parent;
                 }
                 else
                 {
-                    if (x == n[xp].w.left) { x = xp; rotate_right(x); }
-                    n[n[x].parent].color = PP_RB_BLACK;
-                    n[xpp].color = PP_RB_RED;
-                    rotate_left(xpp);
-                }
-            }
-        }
-        n[n[PP_RB_HEADER].parent].color = PP_RB_BLACK;
-        count++;
-    }
-
-    // _Rb_tree_rebalance_for_erase; recycles slot z
-    PP_HD_NOINLINE void erase(int z)
-    {
-        PP_ASSUME_GLOBAL(n);
-        mut_all();
-        int y = z, x = PP_RB_NIL, x_parent = PP_RB_NIL;
-        if (n[y].w.left == PP_RB_NIL) x = n[y].w.right;
-        else if (n[y].w.right == PP_RB_NIL) x = n[y].w.left;
-        else
-        {
-            y = n[y].w.right;
-            while (n[y].w.left != PP_RB_NIL) y = n[y].w.left;
-            x = n[y].w.right;
-        }
-        if (y != z)
-        {
-            // relink y in place of z
-            n[n[z].w.left].parent = y;
-            n[y].w.left = n[z].w.left;
-            if (y != n[z].w.right)
-            {
-                x_parent = n[y].parent;
-                if (x != PP_RB_NIL) n[x].parent = n[y].parent;
-                n[n[y].parent].w.left = x;
-                n[y].w.right = n[z].w.right;
-                n[n[z].w.right].parent = y;
-            }
-            else x_parent = y;
-            if (n[PP_RB_HEADER].parent == z) n[PP_RB_HEADER].parent = y;
-            else if (n[n[z].parent].w.left == z) n[n[z].parent].w.left = y;
-            else n[n[z].parent].w.right = y;
-            n[y].parent = n[z].parent;
-            int c = n[y].color; n[y].color = n[z].color; n[z].color = c;
-            y = z;
-        }
-        else
-        {
-            x_parent = n[y].parent;
-            if (x != PP_RB_NIL) n[x].parent = n[y].parent;
-            if (n[PP_RB_HEADER].parent == z) n[PP_RB_HEADER].parent = x;
-            else if (n[n[z].parent].w.left == z) n[n[z].parent].w.left = x;
-            else n[n[z].parent].w.right = x;
-            if (n[PP_RB_HEADER].w.left == z)
-            {
-                if (n[z].w.right == PP_RB_NIL) n[PP_RB_HEADER].w.left = n[z].parent;
-                else { int m = x; while (n[m].w.left != PP_RB_NIL) m = n[m].w.left; n[PP_RB_HEADER].w.left = m; }
-            }
-            if (n[PP_RB_HEADER].w.right == z)
-            {
-                if (n[z].w.left == PP_RB_NIL) n[PP_RB_HEADER].w.right = n[z].parent;
-                else { int m = x; while (n[m].w.right != PP_RB_NIL) m = n[m].w.right; n[PP_RB_HEADER].w.right = m; }
-            }
-        }
-        if (n[y].color != PP_RB_RED)
-        {
-            while (x != n[PP_RB_HEADER].parent && (x == PP_RB_NIL || n[x].color == PP_RB_BLACK))
-            {
-                if (x == n[x_parent].w.left)
-                {
-                    int w = n[x_parent].w.right;
-                    if (n[w].color == PP_RB_RED)
+                    if (n[w].w.left == PP_RB_NIL || n[n[w].w.left].color == PP_RB_BLACK)
                     {
-                        n[w].color = PP_RB_BLACK; n[x_parent].color = PP_RB_RED;
-                        rotate_left(x_parent);
-                        w = n[x_parent].w.right;
-                    }
-                    if ((n[w].w.left == PP_RB_NIL || n[n[w].w.left].color == PP_RB_BLACK) &&
-                        (n[w].w.right == PP_RB_NIL || n[n[w].w.right].color == PP_RB_BLACK))
-                    {
+                        n[n[w].w.right].color = PP_RB_BLACK;
                         n[w].color = PP_RB_RED;
-                        x = x_parent;
-                        x_parent = n[x_parent].parent;
-                    }
-                    else
-                    {
-                        if (n[w].w.right == PP_RB_NIL || n[n[w].w.right].color == PP_RB_BLACK)
-                        {
-                            n[n[w].w.left].color = PP_RB_BLACK;
-                            n[w].color = PP_RB_RED;
-                            rotate_right(w);
-                            w = n[x_parent].w.right;
-                        }
-                        n[w].color = n[x_parent].color;
-                        n[x_parent].color = PP_RB_BLACK;
-                        if (n[w].w.right != PP_RB_NIL) n[n[w].w.right].color = PP_RB_BLACK;
-                        rotate_left(x_parent);
-                        break;
-                    }
-                }
-                else
-                {
-                    int w = n[x_parent].w.left;
-                    if (n[w].color == PP_RB_RED)
-                    {
-                        n[w].color = PP_RB_BLACK; n[x_parent].color = PP_RB_RED;
-                        rotate_right(x_parent);
+                        pp_rb_rotate_left(t, n, w);
                         w = n[x_parent].w.left;
                     }
-                    if ((n[w].w.right == PP_RB_NIL || n[n[w].w.right].color == PP_RB_BLACK) &&
-                        (n[w].w.left == PP_RB_NIL || n[n[w].w.left].color == PP_RB_BLACK))
-                    {
-                        n[w].color = PP_RB_RED;
-                        x = x_parent;
-                        x_parent = n[x_parent].parent;
-                    }
-                    else
-                    {
-                        if (n[w].w.left == PP_RB_NIL || n[n[w].w.left].color == PP_RB_BLACK)
-                        {
-                            n[n[w].w.right].color = PP_RB_BLACK;
-                            n[w].color = PP_RB_RED;
-                            rotate_left(w);
-                            w = n[x_parent].w.left;
-                        }
-                        n[w].color = n[x_parent].color;
-                        n[x_parent].color = PP_RB_BLACK;
-                        if (n[w].w.left != PP_RB_NIL) n[n[w].w.left].color = PP_RB_BLACK;
-                        rotate_right(x_parent);
-                        break;
-                    }
+                    n[w].color = n[x_parent].color;
+                    n[x_parent].color = PP_RB_BLACK;
+                    if (n[w].w.left != PP_RB_NIL) n[n[w].w.left].color = PP_RB_BLACK;
+                    pp_rb_rotate_right(t, n, x_parent);
+                    break;
                 }
             }
-            if (x != PP_RB_NIL) n[x].color = PP_RB_BLACK;
         }
-        count--;
-        if (count == 0)
-        {
-            // libstdc++ leaves header.left/right == header when the tree becomes empty
-            n[PP_RB_HEADER].parent = PP_RB_NIL;
-            n[PP_RB_HEADER].w.left = PP_RB_HEADER;
-            n[PP_RB_HEADER].w.right = PP_RB_HEADER;
-        }
-        release(z);
+        if (x != PP_RB_NIL) n[x].color = PP_RB_BLACK;
     }
-
-    // std::set::find(k)
-    PP_HD_NOINLINE int find(const PPKey& k) const
+    t.count--;
+    if (t.count == 0)
     {
-        int np;
-        return pp_rb_find_walk(n, k, (int*)0, 0, np);
+        // libstdc++ leaves header.left/right == header when the tree becomes empty
+        n[PP_RB_HEADER].parent = PP_RB_NIL;
+        n[PP_RB_HEADER].w.left = PP_RB_HEADER;
+        n[PP_RB_HEADER].w.right = PP_RB_HEADER;
     }
+    n[z].parent = t.free_head; t.free_head = z;        // release(z)
+}
 
-    // std::set::insert(v) position search (_M_get_insert_unique_pos).  Returns true when the key must be
-    // inserted under parent `p` (left child iff `left`); false when an equivalent element exists.
-    PP_HD_NOINLINE bool insert_pos(const PPKey& k, int& p, bool& left) const
-    {
-        int np;
-        return pp_rb_insert_pos_walk(n, k, p, left, (int*)0, 0, np);
-    }
-};
-
-// ---- the two walks as free functions over a node pool, optionally recording the nodes they visit ---------------------------
+// ---- the two walks, optionally recording the nodes they visit ----------------------------------------------------------------
 // A recorded path lets the caller decide later whether the walk would still go the same way: node keys and costs never change
-// while a node is in the tree, so a walk is unchanged as long as no node on its path had a child pointer changed (PPRbTree::mut).
+// while a node is in the tree, so a walk is unchanged as long as no node on its path had a child pointer changed (PPRbState::mut).
 // path[0] is always the header (= the root pointer).  n_path > cap means the path did not fit (treat as "cannot tell").
 
 // std::set::find(k): lower-bound walk, then reject when k < *j.
-template <class Node>
-PP_HD int pp_rb_find_walk(const Node* n, const PPKey& k, int* path, int cap, int& n_path)
+PP_HD int pp_rb_find_walk(const PPRbPool n, const PPKey& k, int* path, int cap, int& n_path)
 {
-    PP_ASSUME_GLOBAL(n);
+    PP_ASSUME_GLOBAL(n.base);
     int x = n[PP_RB_HEADER].parent, y = PP_RB_HEADER;
     PPWalk yw; yw.left = 0; yw.right = 0; yw.f = 0.0f; yw.key = 0u;
     int c = 0;
@@ -397,10 +348,9 @@ PP_HD int pp_rb_find_walk(const Node* n, const PPKey& k, int* path, int cap, int
 // _M_get_insert_unique_pos.  libstdc++ steps to the in-order predecessor of the leaf position with _Rb_tree_decrement when the
 // last turn was to the left; that predecessor is the last node at which the walk turned RIGHT (none: the position is left of
 // begin()), so it is tracked during the walk instead of being looked up by a second pointer chase.
-template <class Node>
-PP_HD bool pp_rb_insert_pos_walk(const Node* n, const PPKey& k, int& p, bool& left, int* path, int cap, int& n_path)
+PP_HD bool pp_rb_insert_pos_walk(const PPRbPool n, const PPKey& k, int& p, bool& left, int* path, int cap, int& n_path)
 {
-    PP_ASSUME_GLOBAL(n);
+    PP_ASSUME_GLOBAL(n.base);
     int x = n[PP_RB_HEADER].parent, y = PP_RB_HEADER;
     bool comp = true;
     int j = PP_RB_NIL;
@@ -432,5 +382,58 @@ PP_HD bool pp_rb_insert_pos_walk(const Node* n, const PPKey& k, int& p, bool& le
     }
     return false;
 }
+
+PP_HD_NOINLINE_FN int pp_rb_find(const PPRbPool n, const PPKey& k)
+{
+    int np;
+    return pp_rb_find_walk(n, k, (int*)0, 0, np);
+}
+
+PP_HD_NOINLINE_FN bool pp_rb_insert_pos(const PPRbPool n, const PPKey& k, int& p, bool& left)
+{
+    int np;
+    return pp_rb_insert_pos_walk(n, k, p, left, (int*)0, 0, np);
+}
+
+// Typed view: `Node` starts with a PPRbHead-compatible prefix (PPWalk w; int parent, color;) followed by its payload.
+template <class Node>
+struct PPRbTree : PPRbState
+{
+    Node* n;        // pool; n[0] is the header
+
+    PP_HD PPRbPool pool() const { PPRbPool p; p.base = (char*)n; p.stride = (int)sizeof(Node); return p; }
+
+    PP_HD void init(Node* pool_, int capacity)
+    {
+        n = pool_; cap = capacity;
+        clear();
+    }
+
+    PP_HD void clear()
+    {
+        n[PP_RB_HEADER].parent = PP_RB_NIL;
+        n[PP_RB_HEADER].w.left = PP_RB_HEADER;
+        n[PP_RB_HEADER].w.right = PP_RB_HEADER;
+        n[PP_RB_HEADER].color = PP_RB_RED;
+        next = 1; free_head = PP_RB_NIL; count = 0;
+    }
+
+    PP_HD bool empty() const { return count == 0; }
+    PP_HD int  begin() const { return n[PP_RB_HEADER].w.left; }
+    PP_HD int  root() const { return n[PP_RB_HEADER].parent; }
+
+    // returns a free slot or PP_RB_NIL when the pool is exhausted
+    PP_HD int alloc()
+    {
+        if (free_head != PP_RB_NIL) { int s = free_head; free_head = n[s].parent; return s; }
+        if (next < cap) return next++;
+        return PP_RB_NIL;
+    }
+
+    PP_HD void insert_and_rebalance(bool insert_left, int x, int p) { pp_rb_insert_and_rebalance(*this, pool(), insert_left, x, p); }
+    PP_HD void erase(int z) { pp_rb_erase(*this, pool(), z); }
+    PP_HD int  find(const PPKey& k) const { return pp_rb_find(pool(), k); }
+    PP_HD bool insert_pos(const PPKey& k, int& p, bool& left) const { return pp_rb_insert_pos(pool(), k, p, left); }
+};
 
 #endif

@@ -16,6 +16,7 @@
 #ifndef PP_SEARCH_H
 #define PP_SEARCH_H
 
+#include <stddef.h>
 #include "pp_defs.h"
 #include "pp_math.h"
 #include "pp_dubins.h"
@@ -24,6 +25,13 @@
 
 #define PP_MAX_SUCC 16
 #define PP_NEAR_CAP 64
+// Speculative parallel walks (phase 4a / 4b below): measured on B200 they shorten nothing -- a lone warp is bound by the
+// dependent-issue latency of the commit code, a crowded SM by instruction fetch, and the extra code and shared memory cost more
+// than the walks save -- so the default build commits sequentially.  -DPP_EXACT_SPEC=1 builds the variant;
+// the CPU race harness (tests/cpp/search_mt.cpp) compiles it in both forms.
+#ifndef PP_EXACT_SPEC
+#define PP_EXACT_SPEC 0
+#endif
 #define PP_SPEC_WALKS 16      /* speculative tree walks per batch: (successor, find | insert) pairs, or the 8 neighbours of a 2D pop x 2 */
 #define PP_SPEC_PATH 40       /* nodes recorded per walk: header + the height bound of a red-black tree of 2^19 nodes */
 #define PP_MLOG_CAP 48        /* mutated nodes remembered between two speculation batches */
@@ -34,8 +42,15 @@
 #if defined(PP_PROFILE) && defined(__CUDA_ARCH__)
 #define PP_PROF_DECL long long pp_prof_t = clock64(); long long pp_prof_a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #define PP_PROF_MARK(k) { long long t__ = clock64(); pp_prof_a[k] += t__ - pp_prof_t; pp_prof_t = t__; }
-#define PP_PROF_FLUSH if (lane == 0) { for (int q__ = 0; q__ < 8; q__++) atomicAdd(&pp_prof_acc[q__], (unsigned long long)pp_prof_a[q__]); }
+#define PP_PROF_FLUSH if (lane == 0) { for (int q__ = 0; q__ < 8; q__++) atomicAdd(&pp_prof_acc[q__], (unsigned long long)pp_prof_a[q__]); \
+                                        for (int q__ = 0; q__ < 8; q__++) atomicAdd(&pp_prof_acc[8 + q__], (unsigned long long)pp_prof_c[q__]); }
+// event counters: 0 find walks used as speculated, 1 find walks redone, 2 insert walks speculated and used, 3 speculated but redone,
+// 4 insert walks without speculation (h1 not cached), 5 successors committed, 6 inserts attached, 7 mutation-log entries
+#define PP_PROF_COUNT(k, v) { pp_prof_c[k] += (v); }
+#define PP_PROF_CDECL long long pp_prof_c[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #else
+#define PP_PROF_COUNT(k, v)
+#define PP_PROF_CDECL
 #define PP_PROF_DECL
 #define PP_PROF_MARK(k)
 #define PP_PROF_FLUSH
@@ -65,6 +80,11 @@ struct PPNode2   // 2D open-list entry (copy of a Node2D at insertion time), 32 
     float    g;
     int      prev;       // cell of the closed parent, -1 = none
 };
+
+static_assert(sizeof(PPNode3) == 64 && sizeof(PPNode2) == 32, "node sizes");
+static_assert(offsetof(PPNode3, parent) == offsetof(PPRbHead, parent) && offsetof(PPNode3, color) == offsetof(PPRbHead, color) &&
+              offsetof(PPNode2, parent) == offsetof(PPRbHead, parent) && offsetof(PPNode2, color) == offsetof(PPRbHead, color),
+              "both node types must start with the PPRbHead prefix (pp_rbtree.h)");
 
 struct PPClosed3
 {
@@ -135,6 +155,7 @@ struct PPSmem   // per-warp staging area (shared memory on the device)
     float  d_acos[PP_MAX_SUCC * 2];      // acosf(2r/dist) per (successor, RSL | LSR)
     float  d_sin[PP_MAX_SUCC * 4];       // sin / cos of theta_t1 and p2 per (successor, RSL | LSR)
     float  d_cos[PP_MAX_SUCC * 4];
+#if PP_EXACT_SPEC
     // speculative walks (pp_spec_*): every walk of one expansion is done up front by its own lane on the tree as it stands;
     // the control lane then commits the successors in the reference's order and re-walks only what an earlier commit touched
     int    spec_path[PP_SPEC_WALKS][PP_SPEC_PATH];
@@ -144,8 +165,10 @@ struct PPSmem   // per-warp staging area (shared memory on the device)
     float  spec_f[PP_SPEC_WALKS];        // insert: the f the position was searched for
     int    mlog[PP_MLOG_CAP];            // PPRbTree::mut log of the 3D open list
     int    mcount;
+#endif
 };
 
+#if PP_EXACT_SPEC
 // Would the recorded walk still visit the same nodes?  True iff none of them had a child pointer changed since the walk
 // (all lanes; the same answer on every lane).
 template <class W>
@@ -163,6 +186,7 @@ PP_HD bool pp_spec_valid(const W& w, const int* path, int np, const int* mlog, i
         }
     return w.ballot(hit) == 0u;
 }
+#endif
 
 // goal-side constants of the Dubins heuristic, evaluated once per query
 struct PPDubinsGoal { float grx, gry, glx, gly; };
@@ -796,6 +820,66 @@ PP_HD_NOINLINE_FN bool pp_open3_insert(PPSearchState& S, const PPSucc& s, unsign
     return pp_open3_attach(S, s, key, f, prev, p, left);
 }
 
+// Rarely executed pieces of the search loop, out of line so that the loop body stays small (the kernel is bound by
+// instruction fetch at bench occupancy).
+
+// parent chain of closed state `c` (-1 = none) into path[at ...]: reconstruct_path's second half (HybridAStar.cpp:238-256);
+// returns the number of chain points (counted even when they no longer fit)
+PP_HD_NOINLINE_FN int pp_chain_to_path(const PPConsts& C, PPWork& wk, int c, int at, int& status)
+{
+    int n_chain = 0;
+    while (c >= 0)
+    {
+        const int pos = at + n_chain;
+        if (pos < wk.path_cap)
+        {
+            PPPathPt& p = wk.path[pos];
+            p.x = wk.closed[c].x; p.y = wk.closed[c].y; p.heading = wk.closed[c].heading;
+            p.curvature = C.abs_curv[wk.closed[c].curv];
+        }
+        else status |= PP_STATUS_PATH_OVERFLOW;
+        n_chain++;
+        c = wk.closed[c].prev;
+    }
+    return n_chain;
+}
+
+// The analytic expansion from closed state cn (HybridAStar.cpp:129-149): Dubins::get_shortest_path (Dubins.cpp:125-153) sampled by
+// the lanes into path[0 .. total) + Grid3D::check_path (Grid3D.cpp:78-93).  True = shot accepted (all lanes agree).
+template <class W>
+PP_HD_NOINLINE_FN bool pp_dubins_shot(const W& w, const PPConsts& C, const PPGroup& G, PPWork& wk, const PPClosed3& cn,
+                                      int& total, float& len, int& status)
+{
+    const int lane = w.lane();
+    const PPFrame& F = G.frame;
+    int type; float p[4]; PPDubinsCenters cen; PPDubinsPlan pl;
+    len = pp_dubins_shortest(C.r_min, cn.x, cn.y, cn.heading, F.goal_x, F.goal_y, F.goal_h, type, p, cen);
+    if (fabsf(p[1]) > (float)PP_PI_2) return false;      // first arc longer than 90 degrees: Dubins.cpp:152, HybridAStar.cpp:135
+    pp_dubins_plan(C.r_min, C.step, C.ang_step, type, p, cen, pl);
+    total = pl.size_3 + 1;
+    bool blocked = false, overflow = false;
+    float acc = p[0];
+    for (int k = 0; k < total; k++)
+    {
+        if (k == pl.size_1) acc = 0.0f;       // straight segment: dist accumulator
+        if (k == pl.size_2) acc = p[2];       // goal arc: theta accumulator
+        if ((k % W::LANES) == lane)
+        {
+            float x, y, h, kappa;
+            pp_dubins_sample(pl, C.r_min, k, acc, x, y, h, kappa);
+            if (pp_path_point_blocked(C, G.map, x, y)) blocked = true;
+            if (k < wk.path_cap) { PPPathPt& q = wk.path[k]; q.x = x; q.y = y; q.heading = h; q.curvature = kappa; }
+            else overflow = true;
+        }
+        if (k < pl.size_1) acc = (pl.s1 < 0) ? acc - C.ang_step : acc + C.ang_step;
+        else if (k < pl.size_2) acc = acc + C.step;
+        else if (k < pl.size_3) acc = (pl.s2 < 0) ? acc - C.ang_step : acc + C.ang_step;
+    }
+    const bool ok = (w.ballot(blocked) == 0u);
+    if (ok && w.ballot(overflow) != 0u) status |= PP_STATUS_PATH_OVERFLOW;
+    return ok;
+}
+
 // The search.  All lanes of the warp call it with identical arguments.
 template <class W>
 PP_HD_NOINLINE_FN void pp_search_exact(const W& w, const PPConsts& C, const float* off_xy, const PPGroup& G,
@@ -807,6 +891,7 @@ PP_HD_NOINLINE_FN void pp_search_exact(const W& w, const PPConsts& C, const floa
     const unsigned kb = (unsigned)(C.bins + 1);
 
     PP_PROF_DECL
+    PP_PROF_CDECL
     const PPWork wk0 = wk;              // the slot's fixed pools: wk follows the containers as they grow, restored at the end
     int closed_blk = -1, chash_blk = -1;
     // ---- scratch init (all lanes) ----
@@ -845,8 +930,10 @@ PP_HD_NOINLINE_FN void pp_search_exact(const W& w, const PPConsts& C, const floa
     if (lane == 0)
     {
         S.open.init(wk.open3, wk.open3_cap);
+#if PP_EXACT_SPEC
         S.open.mlog = sm.mlog; S.open.mcnt = &sm.mcount; S.open.mcap = PP_MLOG_CAP;
         sm.mcount = 0;
+#endif
         S.lazy.open.init(wk.open2, wk.open2_cap);
         S.lazy.search_id = sid0; S.lazy.status = 0; S.lazy.n_searches = 0; S.lazy.n_pops = 0;
         S.lazy.arena = wk.arena; S.lazy.max_cap = wk.arena ? wk.open2_max : wk.open2_cap; S.lazy.blk = -1;
@@ -939,80 +1026,25 @@ PP_HD_NOINLINE_FN void pp_search_exact(const W& w, const PPConsts& C, const floa
         if (action == ACT_GOAL)
         {
             success = 1; cost = cn.g;
-            if (lane == 0)
-            {
-                // reconstruct_path from _terminal_node = *it_first (HybridAStar.cpp:118, :238-256)
-                int c = cur;
-                while (c >= 0)
-                {
-                    if (n_chain < wk.path_cap)
-                    {
-                        PPPathPt& p = wk.path[n_chain];
-                        p.x = wk.closed[c].x; p.y = wk.closed[c].y; p.heading = wk.closed[c].heading;
-                        p.curvature = C.abs_curv[wk.closed[c].curv];
-                    }
-                    else S.status |= PP_STATUS_PATH_OVERFLOW;
-                    n_chain++;
-                    c = wk.closed[c].prev;
-                }
-            }
+            // reconstruct_path from _terminal_node = *it_first (HybridAStar.cpp:118, :238-256)
+            if (lane == 0) { int st = 0; n_chain = pp_chain_to_path(C, wk, cur, 0, st); S.status |= st; }
             break;
         }
 
         if (action == ACT_SHOT)
         {
             // ---------------- Dubins shot (all lanes), HybridAStar.cpp:129-149 ----------------
-            int type; float p[4]; PPDubinsCenters cen; PPDubinsPlan pl;
-            float len = pp_dubins_shortest(C.r_min, cn.x, cn.y, cn.heading, F.goal_x, F.goal_y, F.goal_h, type, p, cen);
-            bool long_turn = fabsf(p[1]) > (float)PP_PI_2;     // Dubins.cpp:152
-            bool ok = !long_turn;
-            int total = 0;
-            if (ok)
-            {
-                pp_dubins_plan(C.r_min, C.step, C.ang_step, type, p, cen, pl);
-                total = pl.size_3 + 1;
-                bool blocked = false, overflow = false;
-                float acc = p[0];
-                for (int k = 0; k < total; k++)
-                {
-                    if (k == pl.size_1) acc = 0.0f;       // straight segment: dist accumulator
-                    if (k == pl.size_2) acc = p[2];       // goal arc: theta accumulator
-                    if ((k % W::LANES) == lane)
-                    {
-                        float x, y, h, kappa;
-                        pp_dubins_sample(pl, C.r_min, k, acc, x, y, h, kappa);
-                        if (pp_path_point_blocked(C, G.map, x, y)) blocked = true;
-                        if (k < wk.path_cap) { PPPathPt& q = wk.path[k]; q.x = x; q.y = y; q.heading = h; q.curvature = kappa; }
-                        else overflow = true;
-                    }
-                    if (k < pl.size_1) acc = (pl.s1 < 0) ? acc - C.ang_step : acc + C.ang_step;
-                    else if (k < pl.size_2) acc = acc + C.step;
-                    else if (k < pl.size_3) acc = (pl.s2 < 0) ? acc - C.ang_step : acc + C.ang_step;
-                }
-                ok = (w.ballot(blocked) == 0u);
-                if (ok && w.ballot(overflow) != 0u && lane == 0) S.status |= PP_STATUS_PATH_OVERFLOW;
-            }
-            if (ok)
+            int st = 0, total = 0;
+            float len = 0.0f;
+            if (pp_dubins_shot(w, C, G, wk, cn, total, len, st))
             {
                 success = 1; cost = cn.g + len; n_dubins = total;
                 if (lane == 0)
                 {
                     // _terminal_node = *(it_first->_prev), HybridAStar.cpp:137
-                    int c = cn.prev;
-                    if (c < 0) S.status |= PP_STATUS_NULL_TERMINAL;
-                    while (c >= 0)
-                    {
-                        int at = n_dubins + n_chain;
-                        if (at < wk.path_cap)
-                        {
-                            PPPathPt& q = wk.path[at];
-                            q.x = wk.closed[c].x; q.y = wk.closed[c].y; q.heading = wk.closed[c].heading;
-                            q.curvature = C.abs_curv[wk.closed[c].curv];
-                        }
-                        else S.status |= PP_STATUS_PATH_OVERFLOW;
-                        n_chain++;
-                        c = wk.closed[c].prev;
-                    }
+                    if (cn.prev < 0) st |= PP_STATUS_NULL_TERMINAL;
+                    n_chain = pp_chain_to_path(C, wk, cn.prev, n_dubins, st);
+                    S.status |= st;
                 }
                 break;
             }
@@ -1048,10 +1080,11 @@ PP_HD_NOINLINE_FN void pp_search_exact(const W& w, const PPConsts& C, const floa
         pp_dubins_h2_warp(w, C, F, gc, sm);
         PP_PROF_MARK(3)
 
+#if PP_EXACT_SPEC
         // ---------------- phase 4a: every tree walk of this expansion, speculatively and in parallel (all lanes) ----------------
         // walk 2s = open.find of successor s (probe f = g + field), walk 2s + 1 = its insert position (f = g + max(h1, h2)), the
         // latter only when h1 is already cached (the cell is _visted: its cost can no longer change, AStar.cpp:100-105)
-        PPNode3* pool = pp_bcast_ptr(w, (lane == 0) ? S.open.n : (PPNode3*)0);
+        PPRbPool pool; pool.base = (char*)pp_bcast_ptr(w, (lane == 0) ? S.open.n : (PPNode3*)0); pool.stride = (int)sizeof(PPNode3);
         if (lane == 0) sm.mcount = 0;
         for (int q = lane; q < 2 * n_succ_max; q += W::LANES)
         {
@@ -1101,6 +1134,7 @@ PP_HD_NOINLINE_FN void pp_search_exact(const W& w, const PPConsts& C, const floa
             {
                 PPKey k; k.key = key; k.f = sc.g;                           // f == g + field at find time
                 int it_node = v_find ? sm.spec_a[2 * s] : S.open.find(k);
+                PP_PROF_COUNT(v_find ? 0 : 1, 1) PP_PROF_COUNT(5, 1)
                 if (it_node == PP_RB_NIL) todo = 1;
                 else if (sc.g < S.open.n[it_node].g) { S.open.erase(it_node); todo = 1; }
                 if (todo && sm.spec_np[2 * s + 1] < 0) todo |= 2;
@@ -1128,6 +1162,7 @@ PP_HD_NOINLINE_FN void pp_search_exact(const W& w, const PPConsts& C, const floa
                 if (!(todo & 2)) f = sm.spec_f[2 * s + 1];
                 if (v_ins) { p = sm.spec_a[2 * s + 1]; ins = sm.spec_b[2 * s + 1] >= 0; left = sm.spec_b[2 * s + 1] == 1; }
                 else { PPKey k; k.key = key; k.f = f; ins = S.open.insert_pos(k, p, left); }
+                PP_PROF_COUNT(v_ins ? 2 : ((todo & 2) ? 4 : 3), 1) PP_PROF_COUNT(6, ins ? 1 : 0) PP_PROF_COUNT(7, sm.mcount)
                 if (ins && !pp_open3_attach(S, sc, key, f, cur, p, left)) abort = 1;     // !ins: equal-f drop (F5)
                 if (S.lazy.status) { S.status |= S.lazy.status; abort = 1; }
             }
@@ -1136,6 +1171,38 @@ PP_HD_NOINLINE_FN void pp_search_exact(const W& w, const PPConsts& C, const floa
             PP_PROF_MARK(7)
             if (abort) break;
         }
+#else
+        // ---------------- phase 4: successors into the containers (control lane), HybridAStar.cpp:159-193 ----------------
+        int abort = 0;
+        if (lane == 0)
+        {
+            for (int s = 0; s < n_succ_max && !abort; s++)
+            {
+                const PPSucc& sc = sm.succ[s];
+                if (!sc.ok) continue;
+                unsigned key = (unsigned)(sc.ci * N + sc.cj) * kb + (unsigned)sc.bin;
+                PPKey k; k.key = key; k.f = sc.g;                           // f == g + field at find time
+                int it_node = S.open.find(k);
+                bool do_insert = false;
+                if (it_node == PP_RB_NIL) do_insert = true;
+                else if (sc.g < S.open.n[it_node].g) { S.open.erase(it_node); do_insert = true; }
+                PP_PROF_MARK(5)
+                if (do_insert)
+                {
+                    float h1 = pp_lazy_astar(C, G.map, F, wk, S.lazy, sc.ci, sc.cj);
+                    PP_PROF_MARK(6)
+                    float h2 = sm.cand[4 * s];
+                    for (int t = 1; t < 4; t++) if (sm.cand[4 * s + t] < h2) h2 = sm.cand[4 * s + t];
+                    float f = sc.g + ((h1 < h2) ? h2 : h1);
+                    if (!pp_open3_insert(S, sc, key, f, cur)) abort = 1;
+                    if (S.lazy.status) { S.status |= S.lazy.status; abort = 1; }
+                    PP_PROF_MARK(7)
+                }
+            }
+        }
+        abort = w.shfl(abort, 0);
+        w.sync();
+#endif
         if (abort) break;
     }
     PP_PROF_FLUSH

@@ -21,7 +21,7 @@
 
 #include <cuda_runtime.h>
 #ifdef PP_PROFILE
-__device__ unsigned long long pp_prof_acc[8];
+__device__ unsigned long long pp_prof_acc[16];
 #endif
 #include "../core/pp_search.h"
 #include "../core/pp_kpop.h"

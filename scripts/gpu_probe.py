@@ -16,8 +16,8 @@ import scenarios as S  # noqa: E402
 import path_planning_pkg_b200 as pp  # noqa: E402
 import bench  # noqa: E402
 
-PHASES = ["init", "pop+closed.insert+erase", "rollout+collision+apf", "dubins cand", "closed.find", "open.find(+erase)",
-          "lazy 2D A*", "open.insert"]
+PHASES = ["init", "pop+closed.insert+erase", "rollout+collision+apf", "dubins cand", "closed.find", "spec walks + find commit",
+          "lazy 2D A*", "insert commit"]
 KPHASES = ["init", "queue pop (select k)", "validate+close", "expand: rollout+collision+apf+hash", "winners: dubins+node write",
            "sort + LSM insert", "goal / dubins shot", "-"]
 
@@ -28,8 +28,8 @@ def main():
     ap.add_argument("--starts", type=int, default=64)
     ap.add_argument("--slots", type=int, default=0)
     ap.add_argument("--reps", type=int, default=1)
-    ap.add_argument("--max-expansions", type=int, default=1 << 17)
-    ap.add_argument("--max-open", type=int, default=1 << 16)
+    ap.add_argument("--max-expansions", type=int, default=0)
+    ap.add_argument("--max-open", type=int, default=0)
     ap.add_argument("--mode", type=int, default=0)
     ap.add_argument("--k", type=int, default=32)
     ap.add_argument("--dump", default="", help="write per-query statistics to this .npz")
@@ -37,12 +37,13 @@ def main():
     P = pp.make_params(grid_size=512, resolution=0.2)
     ctx = pp.Context(P, num_groups=a.groups)
     groups = bench.build_workload(a.groups, a.starts, 0)
-    queries, qgroups, maps = bench.apply_groups(ctx, groups)
+    bench.apply_groups(ctx, groups)
+    queries, qgroups, maps = bench.select_queries(ctx, groups)
     q = ctx.make_queries(queries, qgroups)
     opts = ctx.make_opts(max_expansions=a.max_expansions, max_open=a.max_open, max_slots=a.slots, mode=a.mode, kpop=a.k)
     ctx.batch_upload(q, opts)
     prof = hasattr(ctx.lib, "pp_profile_read")
-    buf = (C.c_ulonglong * 8)()
+    buf = (C.c_ulonglong * 16)()
     if prof:
         ctx.lib.pp_profile_read(ctx.h, buf)
     for rep in range(a.reps):
@@ -88,9 +89,14 @@ def main():
         print("  last finishers: start", t0[order], "end", t1[order], "iterations", res["n_lazy_searches"][order])
     if prof:
         ctx.lib.pp_profile_read(ctx.h, buf)
-        tot = sum(buf)
-        for name, v in zip(KPHASES if a.mode == 1 else PHASES, buf):
+        tot = sum(buf[:8])
+        for name, v in zip(KPHASES if a.mode == 1 else PHASES, buf[:8]):
             print(f"  {name:28s} {100.0 * v / max(tot, 1):6.2f} %   {v / max(pops, 1):10.0f} cycles/expansion")
+        if a.mode == 0:
+            names = ["find walks used as speculated", "find walks redone", "insert walks speculated + used", "insert walks speculated, redone",
+                     "insert walks without speculation", "successors committed", "inserts attached", "mutation-log entries seen"]
+            for name, v in zip(names, buf[8:]):
+                print(f"  {name:36s} {v / max(pops, 1):8.3f} per expansion")
 
 
 if __name__ == "__main__":

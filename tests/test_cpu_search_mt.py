@@ -16,11 +16,13 @@ BIN = os.path.join(orc.ROOT, "tests", "cpp", "bin")
 SRC = os.path.join(orc.ROOT, "tests", "cpp", "search_mt.cpp")
 
 
-@pytest.fixture(scope="module")
-def exe():
+@pytest.fixture(scope="module", params=[0, 1], ids=["sequential-commit", "speculative-walks"])
+def exe(request):
+    """search_mt built twice: the default EXACT core and the -DPP_EXACT_SPEC=1 variant (speculative parallel walks)."""
     os.makedirs(BIN, exist_ok=True)
-    out = os.path.join(BIN, "search_mt")
-    cmd = ["g++", "-std=c++14", "-O1", "-g", "-fsanitize=thread", "-ffp-contract=off", "-Wno-unknown-pragmas", "-o", out, SRC, "-lpthread"]
+    out = os.path.join(BIN, "search_mt" + ("_spec" if request.param else ""))
+    cmd = ["g++", "-std=c++14", "-O1", "-g", "-fsanitize=thread", "-ffp-contract=off", "-Wno-unknown-pragmas",
+           f"-DPP_EXACT_SPEC={request.param}", "-o", out, SRC, "-lpthread"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0 and "sanitize" in r.stderr:
         pytest.skip("ThreadSanitizer runtime not available: " + r.stderr[-200:])
