@@ -112,6 +112,8 @@ struct pp_context
     pp_context* parent = nullptr;   // lane context (pp_create_lane): shares the parent's maps / groups / tables, read-only
     cudaEvent_t ev_run0 = nullptr, ev_run1 = nullptr;   // bracket of the asynchronous first pass of a batch
     bool run_pending = false;
+    unsigned long long map_epoch = 1;     // bumped by every change of a map, goal frame or APF list (what lanes mirror)
+    unsigned long long seen_epoch = 0;    // lane: the parent's epoch at the last refresh
     void* nccl_comm = nullptr;      // ncclComm_t of pp_comm_init (map replication, pp_broadcast_maps)
     int comm_rank = -1, comm_size = 0;
     unsigned* d_lazy_sid = nullptr;
@@ -162,6 +164,7 @@ static int sync_groups(pp_context* c)
 
 static void map_changed(pp_context* c, int g)
 {
+    c->map_epoch++;
     if (g >= 0 && g < (int)c->field2d_valid.size()) c->field2d_valid[g] = 0;
     if (g >= 0 && g < (int)c->kpop_group_cost.size() && c->kpop_group_cost[g] != 0.0f) { c->kpop_group_cost[g] = 0.0f; c->group_cost_dirty = true; }
 }
@@ -178,6 +181,9 @@ static int lane_refresh(pp_context* c)
 {
     pp_context* p = c->parent;
     if (!p) return PP_SUCCESS;
+    // nothing changed since the last look: do not wait for whatever the parent's stream is busy with (its own batch)
+    if (c->seen_epoch == p->map_epoch && !p->groups_dirty) return PP_SUCCESS;
+    c->seen_epoch = p->map_epoch;
     int rc = sync_groups(p); if (rc) return rc;
     PP_CUDA(cudaStreamSynchronize(p->stream));
     c->frames = p->frames; c->groups = p->groups;

@@ -29,9 +29,14 @@ __device__ unsigned long long pp_prof_acc[16];
 #include "../core/pp_footprint.h"
 #include "../core/pp_velocity.h"
 
-#define PP_SEARCH_WARPS 4
+// ONE warp per CTA: a query that runs on long after its neighbours have finished (expansion counts span three orders of
+// magnitude) then holds one warp's worth of registers, not a whole CTA's.  With 4-warp CTAs the tail CTAs of the batches in flight
+// kept a third of the SMs' warp slots idle (streamed C4 batches: 14.2 M expansions/s with 4 warps per CTA, 23.9 M with 1).
+#ifndef PP_SEARCH_WARPS
+#define PP_SEARCH_WARPS 1
+#endif
 #ifndef PP_SEARCH_MIN_BLOCKS
-#define PP_SEARCH_MIN_BLOCKS 4     // resident CTAs per SM the register allocation is tuned for (x4 warps)
+#define PP_SEARCH_MIN_BLOCKS 16    // resident CTAs per SM the register allocation is tuned for (128 registers per thread)
 #endif
 #define PP_TILE 32
 
