@@ -188,6 +188,10 @@ int  pp_update_obstacles_boxes(pp_context* ctx, int group, const float* boxes_xy
                                int n, float apf_added_radius);
 /* Grid2D::update_obstacles(boxes, confidence) only (no APF list rebuild), lib/Grid2D.cpp:99-139 */
 int  pp_update_obstacles_boxes_2d(pp_context* ctx, int group, const float* boxes_xydxdy, const float* confidence, int n);
+/* One round of the Grid2D map update in a single pass over the map: Grid2D::update_obstacles(boxes, confidence) immediately followed
+ * by Grid2D::update_obstacles() (lib/Grid2D.cpp:99-139 then :197-208) -- what src/local_planner.cpp:241 and :288 do one after the
+ * other; every cell is read and written once.  Asynchronous on the context's stream (pp_sync waits). */
+int  pp_update_obstacles_boxes_2d_decay(pp_context* ctx, int group, const float* boxes_xydxdy, const float* confidence, int n);
 /* HybridAStar::update_obstacles(lines, confidence, line_width) (lib/HybridAStar.cpp:36-40 -> Grid2D.cpp:142-194) */
 int  pp_update_obstacles_lines(pp_context* ctx, int group, const float* lines_x1y1x2y2, const float* confidence,
                                int n, float line_width);

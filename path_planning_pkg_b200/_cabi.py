@@ -181,6 +181,11 @@ class Context:
         b = np.ascontiguousarray(boxes, np.float32); c = np.ascontiguousarray(conf, np.float32)
         self._chk(self.lib.pp_update_obstacles_boxes_2d(self.h, C.c_int(group), _p(b), _p(c), C.c_int(len(c))))
 
+    def update_boxes_2d_decay(self, boxes, conf, group=0):
+        """pp_update_obstacles_boxes_2d_decay: boxes + whole-map decay in one pass (asynchronous)."""
+        b = np.ascontiguousarray(boxes, np.float32); c = np.ascontiguousarray(conf, np.float32)
+        self._chk(self.lib.pp_update_obstacles_boxes_2d_decay(self.h, C.c_int(group), _p(b), _p(c), C.c_int(len(c))))
+
     def update_lines(self, lines, conf, width, group=0):
         b = np.ascontiguousarray(lines, np.float32); c = np.ascontiguousarray(conf, np.float32)
         self._chk(self.lib.pp_update_obstacles_lines(self.h, C.c_int(group), _p(b), _p(c), C.c_int(len(c)), C.c_float(width)))

@@ -95,6 +95,10 @@ struct pp_context
     bool groups_dirty = true;
     // generic scratch for stateless calls and map descriptors
     DevBuf<unsigned char> s0, s1, s2, s3, s4;
+    // box descriptors of the map update: pinned host ring + device ring, so that an update is H2D + one launch with no
+    // synchronisation (a slot is reused only after the launch that read it has finished)
+    struct BoxStage { PPBoxDescDev* h = nullptr; PPBoxDescDev* d = nullptr; int cap = 0; unsigned next = 0;
+                      cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr}; bool used[4] = {false, false, false, false}; } box_stage;
     // batch state
     int n_queries = 0;
     pp_search_opts opts;
@@ -111,6 +115,7 @@ struct pp_context
     size_t mem_budget = 0; // bytes the search scratch (slots + arena) may take; 0 = 75 % of the free device memory
     pp_context* parent = nullptr;   // lane context (pp_create_lane): shares the parent's maps / groups / tables, read-only
     cudaEvent_t ev_run0 = nullptr, ev_run1 = nullptr;   // bracket of the asynchronous first pass of a batch
+    cudaEvent_t ev_re0 = nullptr, ev_re1 = nullptr;     // bracket of a re-run pass (ev0 / ev1 belong to pp_timer_begin / _end)
     bool run_pending = false;
     unsigned long long map_epoch = 1;     // bumped by every change of a map, goal frame or APF list (what lanes mirror)
     unsigned long long seen_epoch = 0;    // lane: the parent's epoch at the last refresh
@@ -146,7 +151,7 @@ struct pp_context
     std::vector<float> kpop_group_cost;
     DevBuf<float> d_group_cost;
     bool group_cost_dirty = true;
-    DevBuf<unsigned> d_f2d_work; DevBuf<unsigned char> d_f2d_flags; DevBuf<float> d_dubins_field;
+    DevBuf<unsigned> d_f2d_work; DevBuf<unsigned char> d_f2d_flags; DevBuf<float> d_dubins_field; DevBuf<int> d_f2d_ctl;
     DevBuf<int> d_qmap, d_order;
     int retried = 0;       // queries re-run in the last pp_batch_run
     unsigned long long launches = 0;      // kernels launched by this context
@@ -251,6 +256,8 @@ static int create_impl(pp_context* c, int num_groups)
     PP_CUDA(cudaEventCreate(&c->ev1));
     PP_CUDA(cudaEventCreate(&c->ev_run0));
     PP_CUDA(cudaEventCreate(&c->ev_run1));
+    PP_CUDA(cudaEventCreate(&c->ev_re0));
+    PP_CUDA(cudaEventCreate(&c->ev_re1));
     c->num_groups = num_groups;
     PP_CUDA(cudaMalloc(&c->d_counter, sizeof(int)));
     PP_CUDA(cudaMalloc(&c->d_lazy_sid, sizeof(unsigned)));
@@ -346,6 +353,9 @@ void pp_destroy(pp_context* c)
         cudaFree(c->d_groups);
     }
     cudaFree(c->d_counter);
+    if (c->box_stage.h) cudaFreeHost(c->box_stage.h);
+    if (c->box_stage.d) cudaFree(c->box_stage.d);
+    for (int q = 0; q < 4; q++) if (c->box_stage.ev[q]) cudaEventDestroy(c->box_stage.ev[q]);
     c->s0.release(); c->s1.release(); c->s2.release(); c->s3.release(); c->s4.release();
     c->d_queries.release(); c->d_results.release(); c->d_paths.release(); c->d_trace.release();
     c->wp.release(); c->wp_lazy.release(); c->d_qmap.release(); c->d_order.release(); c->d_group_cost.release();
@@ -354,11 +364,13 @@ void pp_destroy(pp_context* c)
     c->d_foot_bins.release(); c->d_foot_offs.release(); c->d_foot_lin.release(); c->d_foot_xyh.release(); c->d_foot_out.release();
     c->d_traj.release(); c->d_traj_tmp.release(); c->d_vel_in.release(); c->d_traj_int.release(); c->d_wframes.release();
     c->kp.release(); c->kp_retry.release();
-    c->d_field2d.release(); c->d_f2d_work.release(); c->d_f2d_flags.release(); c->d_dubins_field.release();
+    c->d_field2d.release(); c->d_f2d_work.release(); c->d_f2d_flags.release(); c->d_dubins_field.release(); c->d_f2d_ctl.release();
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->ev_run0) cudaEventDestroy(c->ev_run0);
     if (c->ev_run1) cudaEventDestroy(c->ev_run1);
+    if (c->ev_re0) cudaEventDestroy(c->ev_re0);
+    if (c->ev_re1) cudaEventDestroy(c->ev_re1);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -483,54 +495,85 @@ int pp_update_obstacles_decay(pp_context* c, int g)
     return PP_SUCCESS;
 }
 
+static int box_stage_slot(pp_context* c, int n, int* slot_out)
+{
+    pp_context::BoxStage& st = c->box_stage;
+    if (n > st.cap)
+    {
+        PP_CUDA(cudaStreamSynchronize(c->stream));
+        if (st.h) cudaFreeHost(st.h);
+        if (st.d) cudaFree(st.d);
+        st.h = nullptr; st.d = nullptr;
+        int cap = 256; while (cap < n) cap <<= 1;
+        PP_CUDA(cudaMallocHost(&st.h, sizeof(PPBoxDescDev) * (size_t)cap * 4));
+        PP_CUDA(cudaMalloc(&st.d, sizeof(PPBoxDescDev) * (size_t)cap * 4));
+        for (int q = 0; q < 4; q++) { if (!st.ev[q]) PP_CUDA(cudaEventCreateWithFlags(&st.ev[q], cudaEventDisableTiming)); st.used[q] = false; }
+        st.cap = cap;
+    }
+    const int slot = (int)(st.next++ & 3u);
+    if (st.used[slot]) PP_CUDA(cudaEventSynchronize(st.ev[slot]));
+    *slot_out = slot;
+    return PP_SUCCESS;
+}
+
+// Grid2D::update_obstacles(boxes, conf) [+ Grid2D::update_obstacles()] as one asynchronous launch
+static int map_update_launch(pp_context* c, int g, const float* boxes, const float* conf, int n, int do_decay)
+{
+    const PPConsts& C = c->model.C;
+    float ch = 1.0f, sh = 0.0f;
+    int slot = 0;
+    const PPBoxDescDev* d_desc = nullptr;
+    if (n > 0)
+    {
+        std::vector<PPBoxDesc> d;
+        pp_host_box_descs(C, c->frames[g], boxes, conf, n, ch, sh, d);
+        int rc = box_stage_slot(c, n, &slot); if (rc) return rc;
+        pp_context::BoxStage& st = c->box_stage;
+        PPBoxDescDev* h = st.h + (size_t)slot * st.cap;
+        for (int k = 0; k < n; k++)
+        {
+            PPBoxDescDev& o = h[k];
+            o.start_i = d[k].start_i; o.start_j = d[k].start_j; o.ni = d[k].ni; o.nj = d[k].nj; o.delta = d[k].delta; o.pad = 0;
+            const bool empty = d[k].lo_i > d[k].hi_i || d[k].lo_j > d[k].hi_j || d[k].ni <= 0 || d[k].nj <= 0;
+            o.lo_i = (short)(empty ? 1 : d[k].lo_i); o.hi_i = (short)(empty ? 0 : d[k].hi_i);
+            o.lo_j = (short)(empty ? 1 : d[k].lo_j); o.hi_j = (short)(empty ? 0 : d[k].hi_j);
+        }
+        PP_CUDA(cudaMemcpyAsync(st.d + (size_t)slot * st.cap, h, sizeof(PPBoxDescDev) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+        d_desc = st.d + (size_t)slot * st.cap;
+    }
+    else if (!do_decay) return PP_SUCCESS;
+    const int T = (C.N + PP_TILE - 1) / PP_TILE;
+    pp_map_update_kernel<<<dim3(T, T), 256, 0, c->stream>>>(c->d_maps + nn_of(c) * g, C.N, d_desc, n, ch, sh, C.log_min, C.log_max,
+                                                            do_decay, C.log_free);
+    c->launches += 1;
+    PP_CUDA(cudaGetLastError());
+    if (n > 0) { PP_CUDA(cudaEventRecord(c->box_stage.ev[slot], c->stream)); c->box_stage.used[slot] = true; }
+    return PP_SUCCESS;
+}
+
 int pp_update_obstacles_boxes_2d(pp_context* c, int g, const float* boxes, const float* conf, int n)
 {
     int rc = check_group(c, g); if (rc) return rc;
     rc = lane_guard(c, "pp_update_obstacles_boxes_2d"); if (rc) return rc;
     map_changed(c, g);
     if (n < 0 || (n > 0 && (!boxes || !conf))) return pp_fail(PP_ERR_INVALID, "boxes: bad arguments");
+    if (c->model.C.N > 32767) return pp_fail(PP_ERR_INVALID, "boxes: at most 32767 cells per side");
     if (n == 0) return PP_SUCCESS;
     PP_CUDA(cudaSetDevice(c->device));
-    const PPConsts& C = c->model.C;
-    float ch, sh;
-    std::vector<PPBoxDesc> d;
-    pp_host_box_descs(C, c->frames[g], boxes, conf, n, ch, sh, d);
-    // bin boxes (ascending index) into the 32x32 tiles their sample bounding box overlaps
-    int T = (C.N + PP_TILE - 1) / PP_TILE;
-    std::vector<std::vector<int>> bins((size_t)T * T);
-    std::vector<PPBoxDescDev> dd(n);
-    for (int k = 0; k < n; k++)
-    {
-        dd[k].start_i = d[k].start_i; dd[k].start_j = d[k].start_j; dd[k].ni = d[k].ni; dd[k].nj = d[k].nj; dd[k].delta = d[k].delta;
-        if (d[k].lo_i > d[k].hi_i || d[k].lo_j > d[k].hi_j || d[k].ni <= 0 || d[k].nj <= 0) continue;
-        for (int ti = d[k].lo_i / PP_TILE; ti <= d[k].hi_i / PP_TILE; ti++)
-            for (int tj = d[k].lo_j / PP_TILE; tj <= d[k].hi_j / PP_TILE; tj++)
-                bins[(size_t)ti * T + tj].push_back(k);
-    }
-    std::vector<int> tile_ids, tile_off(1, 0), tile_boxes;
-    for (int t = 0; t < T * T; t++)
-        if (!bins[t].empty())
-        {
-            tile_ids.push_back(t);
-            tile_boxes.insert(tile_boxes.end(), bins[t].begin(), bins[t].end());
-            tile_off.push_back((int)tile_boxes.size());
-        }
-    if (tile_ids.empty()) return PP_SUCCESS;
-    PP_CUDA(c->s0.ensure(sizeof(int) * tile_ids.size()));
-    PP_CUDA(c->s1.ensure(sizeof(int) * tile_off.size()));
-    PP_CUDA(c->s2.ensure(sizeof(int) * tile_boxes.size()));
-    PP_CUDA(c->s3.ensure(sizeof(PPBoxDescDev) * dd.size()));
-    PP_CUDA(cudaMemcpyAsync(c->s0.p, tile_ids.data(), sizeof(int) * tile_ids.size(), cudaMemcpyHostToDevice, c->stream));
-    PP_CUDA(cudaMemcpyAsync(c->s1.p, tile_off.data(), sizeof(int) * tile_off.size(), cudaMemcpyHostToDevice, c->stream));
-    PP_CUDA(cudaMemcpyAsync(c->s2.p, tile_boxes.data(), sizeof(int) * tile_boxes.size(), cudaMemcpyHostToDevice, c->stream));
-    PP_CUDA(cudaMemcpyAsync(c->s3.p, dd.data(), sizeof(PPBoxDescDev) * dd.size(), cudaMemcpyHostToDevice, c->stream));
-    pp_map_boxes_kernel<<<(int)tile_ids.size(), 256, 0, c->stream>>>(c->d_maps + nn_of(c) * g, C.N, (const int*)c->s0.p,
-        (const int*)c->s1.p, (const int*)c->s2.p, (const PPBoxDescDev*)c->s3.p, ch, sh, C.log_min, C.log_max, T);
-    c->launches += 1;
-    PP_CUDA(cudaGetLastError());
-    // the pageable host vectors above die at return: make sure the copies have been consumed
-    PP_CUDA(cudaStreamSynchronize(c->stream));
-    return PP_SUCCESS;
+    return map_update_launch(c, g, boxes, conf, n, 0);
+}
+
+// One round of the map update -- Grid2D::update_obstacles(boxes, conf) followed by Grid2D::update_obstacles() -- as a single pass
+// over the map (BASELINE configs[1]: every cell is read and written once).
+int pp_update_obstacles_boxes_2d_decay(pp_context* c, int g, const float* boxes, const float* conf, int n)
+{
+    int rc = check_group(c, g); if (rc) return rc;
+    rc = lane_guard(c, "pp_update_obstacles_boxes_2d_decay"); if (rc) return rc;
+    map_changed(c, g);
+    if (n < 0 || (n > 0 && (!boxes || !conf))) return pp_fail(PP_ERR_INVALID, "boxes: bad arguments");
+    if (c->model.C.N > 32767) return pp_fail(PP_ERR_INVALID, "boxes: at most 32767 cells per side");
+    PP_CUDA(cudaSetDevice(c->device));
+    return map_update_launch(c, g, boxes, conf, n, 1);
 }
 
 // Grid3D::update_obstacles' own part (Grid3D.cpp:22-44): the APF obstacle list of the group, rebuilt from the boxes; the map is
@@ -593,8 +636,9 @@ int pp_update_obstacles_lines(pp_context* c, int g, const float* lines, const fl
     pp_host_line_descs(C, c->frames[g], lines, conf, n, d);
     PP_CUDA(c->s4.ensure(sizeof(PPLineDesc) * n));
     PP_CUDA(cudaMemcpyAsync(c->s4.p, d.data(), sizeof(PPLineDesc) * n, cudaMemcpyHostToDevice, c->stream));
-    pp_map_lines_kernel<<<1, 1024, 0, c->stream>>>(c->d_maps + nn_of(c) * g, c->d_cell_scratch, C.N, C.n45, C.n2, C.res,
-                                                  (const PPLineDesc*)c->s4.p, n, width, C.log_min, C.log_max);
+    const int T = (C.N + PP_TILE - 1) / PP_TILE;
+    pp_map_lines_kernel<<<dim3(T, T), 256, 0, c->stream>>>(c->d_maps + nn_of(c) * g, C.N, C.n45, C.n2, C.res,
+                                                          (const PPLineDesc*)c->s4.p, n, width, C.log_min, C.log_max);
     c->launches += 1;
     PP_CUDA(cudaGetLastError());
     PP_CUDA(cudaStreamSynchronize(c->stream));
@@ -1301,7 +1345,7 @@ int pp_batch_wait(pp_context* c, float* kernel_ms)
         if (level == 0) c->retried = (int)redo.size();
         PP_CUDA(c->d_qmap.ensure(redo.size()));
         PP_CUDA(cudaMemcpyAsync(c->d_qmap.p, redo.data(), sizeof(int) * redo.size(), cudaMemcpyHostToDevice, c->stream));
-        PP_CUDA(cudaEventRecord(c->ev0, c->stream));
+        PP_CUDA(cudaEventRecord(c->ev_re0, c->stream));
         if (kmode)
         {
             int hw_slots = 0;
@@ -1322,10 +1366,10 @@ int pp_batch_wait(pp_context* c, float* kernel_ms)
             if (hist_g >= 0) { rc = hist_copy(c, hist_g, true); if (rc) return rc; }     // the aborted attempt never happened
             rc = launch_search(c, c->wp, o, slots, c->d_qmap.p, (int)redo.size()); if (rc) return rc;
         }
-        PP_CUDA(cudaEventRecord(c->ev1, c->stream));
+        PP_CUDA(cudaEventRecord(c->ev_re1, c->stream));
         PP_CUDA(cudaStreamSynchronize(c->stream));
         float ms = 0.0f;
-        PP_CUDA(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+        PP_CUDA(cudaEventElapsedTime(&ms, c->ev_re0, c->ev_re1));
         total_ms += ms;
         if (level == 2)
         {
@@ -1550,11 +1594,12 @@ static int field2d_run(pp_context* c, int g, int* sweeps, float* ms)
     if ((int)c->field2d_valid.size() != c->num_groups) c->field2d_valid.assign(c->num_groups, 0);
     PP_CUDA(c->d_f2d_work.ensure(nn));
     PP_CUDA(c->d_f2d_flags.ensure((size_t)2 * T * T));
+    PP_CUDA(c->d_f2d_ctl.ensure(4));
     float diag = C.n_act2d == 8 ? C.act_cost[1] : 0.0f;
     PP_CUDA(cudaEventRecord(c->ev0, c->stream));
     int sw = 0;
     int e = pp_launch_field2d(c->stream, c->groups[g].map, C.N, C.log_thr, C.act_cost[0], diag, C.n_act2d == 8 ? 1 : 0,
-                              c->frames[g].F.goal_ci, c->frames[g].F.goal_cj, c->d_f2d_work.p, c->d_f2d_flags.p, c->d_counter,
+                              c->frames[g].F.goal_ci, c->frames[g].F.goal_cj, c->d_f2d_work.p, c->d_f2d_flags.p, c->d_f2d_ctl.p,
                               c->d_field2d.p + nn * g, c->sm_count, &sw, &c->launches);
     if (e != 0) return pp_fail(PP_ERR_CUDA, std::string("field2d: ") + cudaGetErrorString((cudaError_t)e));
     PP_CUDA(cudaEventRecord(c->ev1, c->stream));

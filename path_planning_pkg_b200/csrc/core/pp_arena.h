@@ -57,9 +57,12 @@ PP_HD void pp_arena_unlock(PPArena* A)
 #endif
 }
 
-// one block of class k, or nullptr when the arena is exhausted.  Call from ONE lane.
-PP_HD_NOINLINE_FN void* pp_arena_alloc(PPArena* A, int k)
+// One block of class k or, when neither its free list nor the never-used part of the arena has one, a free block of a larger
+// class (blocks are never split or merged); nullptr when the arena is exhausted.  k_got = the class of the block handed out:
+// the caller frees it with that class.  Call from ONE lane.
+PP_HD_NOINLINE_FN void* pp_arena_alloc(PPArena* A, int k, int& k_got)
 {
+    k_got = k;
     if (!A || k >= PP_ARENA_CLASSES) return nullptr;
     const unsigned long long bytes = pp_arena_block_bytes(k);
     void* out = nullptr;
@@ -81,10 +84,34 @@ PP_HD_NOINLINE_FN void* pp_arena_alloc(PPArena* A, int k)
             out = (void*)(A->base + off);
             if (off + bytes > A->peak) A->peak = off + bytes;
         }
+        else
+            for (int q = k + 1; q < PP_ARENA_CLASSES && !out; q++)
+                if (fh[q] != 0ull)
+                {
+                    out = (void*)(A->base + (fh[q] - 1ull));
+                    fh[q] = *(volatile unsigned long long*)out;
+                    k_got = q;
+                }
     }
     if (out) A->n_alloc++; else A->n_fail++;
     pp_arena_unlock(A);
     return out;
+}
+
+// pp_arena_alloc that waits for other queries to give blocks back when the arena is momentarily empty: resident queries finish
+// (and free) all the time, so a short bounded wait often succeeds; only then does the caller give up (and the query is re-run
+// later with fewer neighbours, pp_batch_wait).  A host lane never waits.
+PP_HD_NOINLINE_FN void* pp_arena_alloc_patient(PPArena* A, int k, int& k_got)
+{
+    void* p = pp_arena_alloc(A, k, k_got);
+#ifdef __CUDA_ARCH__
+    for (int tries = 0; !p && tries < 2000; tries++)      // up to ~0.2 s
+    {
+        __nanosleep(100000);
+        p = pp_arena_alloc(A, k, k_got);
+    }
+#endif
+    return p;
 }
 
 PP_HD_NOINLINE_FN void pp_arena_free(PPArena* A, void* p, int k)

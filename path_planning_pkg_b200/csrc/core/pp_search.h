@@ -237,8 +237,8 @@ PP_HD_NOINLINE_FN bool pp_lazy_grow(PPLazy& L)
     if (!L.arena || L.open.cap >= L.max_cap) return false;
     long long want = 2ll * L.open.cap;
     if (want > L.max_cap) want = L.max_cap;
-    const int k = pp_arena_class((unsigned long long)want * sizeof(PPNode2));
-    PPNode2* nb = (PPNode2*)pp_arena_alloc(L.arena, k);
+    int k = pp_arena_class((unsigned long long)want * sizeof(PPNode2));
+    PPNode2* nb = (PPNode2*)pp_arena_alloc_patient(L.arena, k, k);
     if (!nb) return false;
     const unsigned long long* src = (const unsigned long long*)L.open.n;
     unsigned long long* dst = (unsigned long long*)nb;
@@ -713,7 +713,7 @@ PP_HD_NOINLINE_FN void pp_grow_open3(const W& w, PPWork& wk, PPSearchState& S)
         want = 2ll * S.open.cap;
         if (want > wk.open3_max) want = wk.open3_max;
         k = pp_arena_class((unsigned long long)want * sizeof(PPNode3));
-        nb = (PPNode3*)pp_arena_alloc(wk.arena, k);
+        nb = (PPNode3*)pp_arena_alloc_patient(wk.arena, k, k);
         old = S.open.n; used = S.open.next; old_blk = S.open_blk;
         if (!nb) S.status |= PP_STATUS_ARENA_EXHAUSTED;
     }
@@ -741,13 +741,13 @@ PP_HD_NOINLINE_FN bool pp_grow_closed(const W& w, PPWork& wk, int n_closed, int&
     long long want = 2ll * wk.closed_cap;
     if (want > wk.closed_max) want = wk.closed_max;
     int hc = 1; while (hc < 2 * want) hc <<= 1;
-    const int k1 = pp_arena_class((unsigned long long)want * sizeof(PPClosed3));
-    const int k2 = pp_arena_class((unsigned long long)hc * sizeof(PPHashSlot));
+    int k1 = pp_arena_class((unsigned long long)want * sizeof(PPClosed3));
+    int k2 = pp_arena_class((unsigned long long)hc * sizeof(PPHashSlot));
     PPClosed3* nc = nullptr; PPHashSlot* nh = nullptr;
     if (lane == 0)
     {
-        nc = (PPClosed3*)pp_arena_alloc(wk.arena, k1);
-        nh = nc ? (PPHashSlot*)pp_arena_alloc(wk.arena, k2) : nullptr;
+        nc = (PPClosed3*)pp_arena_alloc_patient(wk.arena, k1, k1);
+        nh = nc ? (PPHashSlot*)pp_arena_alloc_patient(wk.arena, k2, k2) : nullptr;
         if (nc && !nh) { pp_arena_free(wk.arena, nc, k1); nc = nullptr; }
         if (!nc) status |= PP_STATUS_ARENA_EXHAUSTED;
     }
@@ -770,7 +770,7 @@ PP_HD_NOINLINE_FN bool pp_grow_closed(const W& w, PPWork& wk, int n_closed, int&
         if (closed_blk >= 0) pp_arena_free(wk.arena, wk.closed, closed_blk);
         if (chash_blk >= 0) pp_arena_free(wk.arena, wk.chash, chash_blk);
     }
-    closed_blk = k1; chash_blk = k2;
+    closed_blk = w.shfl(k1, 0); chash_blk = w.shfl(k2, 0);        // the classes actually handed out (lane 0 knows)
     wk.closed = nc; wk.closed_cap = (int)want; wk.chash = nh; wk.chash_cap = hc;
     w.sync();
     return true;

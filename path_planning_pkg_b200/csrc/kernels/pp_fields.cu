@@ -2,9 +2,10 @@
 // throughput modes instead of the reference's lazily evaluated per-query heuristics.
 //
 //   pp_field2d_*          2D holonomic-with-obstacles distance field: block-tiled Bellman relaxation (fast iterative
-//                         method).  Each CTA pulls a 32x32 tile + halo of the field into shared memory, relaxes it to
-//                         a local fixed point, writes it back; tiles whose neighbourhood did not change are skipped;
-//                         global sweeps repeat until nothing changes.  A distance is stored as the exact pair
+//                         method) in ONE cooperative launch of persistent CTAs.  A CTA pulls a 32x32 tile + halo of the
+//                         field into shared memory, relaxes it to a local fixed point, writes it back; tiles whose
+//                         neighbourhood did not change are skipped; global sweeps (separated by a grid barrier) repeat
+//                         until nothing changes.  A distance is stored as the exact pair
 //                         (#straight steps, #diagonal steps) of its path, so there is no accumulation error: the
 //                         result equals a double-precision Dijkstra to one rounding (it is NOT the reference's
 //                         AStar::find_path value, which is order dependent and inadmissible -- SURVEY F4).
@@ -14,12 +15,15 @@
 // This translation unit is compiled WITH fused multiply-add (default -fmad=true): its outputs carry a tolerance
 // (1e-5 relative, north_star), not bit-exactness, and FFMA doubles the FP32 pipe rate.
 #include <cuda_runtime.h>
+#include <cooperative_groups.h>
 #include <math.h>
 #include <float.h>
 
 #include "../core/pp_defs.h"
 #include "../core/pp_dubins.h"
 #include "pp_fields.h"
+
+namespace cg = cooperative_groups;
 
 #define F2D_TILE 32
 #define F2D_UNREACHED 0xffffffffu
@@ -30,44 +34,17 @@ __device__ __forceinline__ double f2d_value(unsigned ab, double c1, double c2)
     return (double)(ab >> 16) * c1 + (double)(ab & 0xffffu) * c2;
 }
 
-__global__ void pp_field2d_init_kernel(unsigned* __restrict__ field, unsigned char* __restrict__ tile_active, int N, int T,
-                                       int goal_i, int goal_j)
+// One tile of one global sweep (all F2D_TILE x F2D_TILE threads of the CTA).  Returns (to every thread) whether the tile changed.
+__device__ __forceinline__ int f2d_relax_tile(const float* __restrict__ map, unsigned* __restrict__ field, int ti, int tj, int N,
+                                              float log_thr, double c1, double c2, int allow_diag,
+                                              unsigned (*s)[F2D_TILE + 2])
 {
-    // the goal cell is the source even when it is marked occupied (the reference never tests the start cell of a search)
-    size_t n = (size_t)N * N, stride = (size_t)gridDim.x * blockDim.x;
-    const size_t goal = (size_t)goal_i * N + goal_j, goal_tile = (size_t)(goal_i / F2D_TILE) * T + goal_j / F2D_TILE;
-    for (size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x; c < n; c += stride) field[c] = (c == goal) ? 0u : F2D_UNREACHED;
-    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < (size_t)2 * T * T; t += stride)
-        tile_active[t] = (t == goal_tile) ? 1 : 0;
-}
-
-// One global sweep.  active_in / active_out: per-tile flags of the previous / next sweep.
-__global__ void __launch_bounds__(F2D_TILE * F2D_TILE)
-pp_field2d_sweep_kernel(const float* __restrict__ map, unsigned* __restrict__ field, const unsigned char* __restrict__ active_in,
-                        unsigned char* __restrict__ active_out, int* __restrict__ any_change, int N, int T, float log_thr,
-                        double c1, double c2, int allow_diag)
-{
-    const int ti = blockIdx.y, tj = blockIdx.x;
-    // run only when this tile or one of its 8 neighbours changed in the previous sweep
-    __shared__ int run;
-    if (threadIdx.x == 0 && threadIdx.y == 0)
-    {
-        int r = 0;
-        for (int di = -1; di <= 1; di++)
-            for (int dj = -1; dj <= 1; dj++)
-            {
-                int a = ti + di, b = tj + dj;
-                if (a >= 0 && a < T && b >= 0 && b < T) r |= active_in[a * T + b];
-            }
-        run = r;
-    }
-    __syncthreads();
-    if (!run) return;
-
-    __shared__ unsigned s[F2D_TILE + 2][F2D_TILE + 2];
     const int li = threadIdx.y, lj = threadIdx.x;           // lj fastest = grid j (contiguous in memory)
     const int gi = ti * F2D_TILE + li, gj = tj * F2D_TILE + lj;
-    auto load = [&](int i, int j) -> unsigned { return (i >= 0 && i < N && j >= 0 && j < N) ? field[(size_t)i * N + j] : F2D_UNREACHED; };
+    // halo reads may race with the neighbouring tiles' write-back of the same sweep: values only ever decrease towards the same
+    // fixed point, so a stale read costs at most another sweep (volatile: always from L2, never a stale L1 line)
+    auto load = [&](int i, int j) -> unsigned
+    { return (i >= 0 && i < N && j >= 0 && j < N) ? *(volatile const unsigned*)&field[(size_t)i * N + j] : F2D_UNREACHED; };
     s[li + 1][lj + 1] = load(gi, gj);
     if (li == 0) s[0][lj + 1] = load(gi - 1, gj);
     if (li == F2D_TILE - 1) s[F2D_TILE + 1][lj + 1] = load(gi + 1, gj);
@@ -111,19 +88,72 @@ pp_field2d_sweep_kernel(const float* __restrict__ map, unsigned* __restrict__ fi
         if (changed) s[li + 1][lj + 1] = cur;
         if (!__syncthreads_or(changed)) break;
     }
-    int tile_changed = __syncthreads_or(cur != start_val);
+    const int tile_changed = __syncthreads_or(cur != start_val);
     if (cur != start_val) field[(size_t)gi * N + gj] = cur;
-    if (tile_changed && threadIdx.x == 0 && threadIdx.y == 0)
-    {
-        active_out[ti * T + tj] = 1;
-        *any_change = 1;
-    }
+    return tile_changed;
 }
 
-__global__ void pp_field2d_finish_kernel(const unsigned* __restrict__ field, float* __restrict__ out, size_t n, double c1, double c2)
+// The whole field in ONE cooperative launch: persistent CTAs (one per SM slot, all co-resident) sweep the active tiles, meet at a
+// grid barrier, and go on until a sweep changes nothing -- no kernel launch and no host round trip per sweep (the first version
+// needed 68 launches and 17 host read-backs for a 2048^2 map).
+//   flags: 2 x T*T bytes (tiles that changed in the previous / this sweep); ctl: [0..2] change flags of three consecutive sweeps,
+//   [3] = number of sweeps done (read back by the host afterwards).
+__global__ void __launch_bounds__(F2D_TILE * F2D_TILE)
+pp_field2d_persistent_kernel(const float* __restrict__ map, unsigned* __restrict__ field, unsigned char* __restrict__ flags,
+                             int* __restrict__ ctl, float* __restrict__ out, int N, int T, float log_thr, double c1, double c2,
+                             int allow_diag, int goal_i, int goal_j, int max_sweeps)
 {
-    size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x; c < n; c += stride)
+    cg::grid_group grid = cg::this_grid();
+    __shared__ unsigned s[F2D_TILE + 2][F2D_TILE + 2];
+    __shared__ int run;
+    const int tid = threadIdx.y * F2D_TILE + threadIdx.x;
+    const size_t n = (size_t)N * N, gstride = (size_t)gridDim.x * (F2D_TILE * F2D_TILE);
+    // the goal cell is the source even when it is marked occupied (the reference never tests the start cell of a search)
+    const size_t goal = (size_t)goal_i * N + goal_j;
+    const int goal_tile = (goal_i / F2D_TILE) * T + goal_j / F2D_TILE;
+    for (size_t c = (size_t)blockIdx.x * (F2D_TILE * F2D_TILE) + tid; c < n; c += gstride) field[c] = (c == goal) ? 0u : F2D_UNREACHED;
+    for (size_t t = (size_t)blockIdx.x * (F2D_TILE * F2D_TILE) + tid; t < (size_t)2 * T * T; t += gstride) flags[t] = (t == (size_t)goal_tile) ? 1 : 0;
+    if (blockIdx.x == 0 && tid < 4) ctl[tid] = 0;
+    grid.sync();
+
+    int sweep = 0;
+    for (; sweep < max_sweeps; sweep++)
+    {
+        const unsigned char* fa = flags + (size_t)(sweep & 1) * T * T;
+        unsigned char* fb = flags + (size_t)((sweep + 1) & 1) * T * T;
+        if (blockIdx.x == 0 && tid == 0) ctl[(sweep + 1) % 3] = 0;           // written from the next sweep on, last read two barriers ago
+        for (int t = blockIdx.x; t < T * T; t += gridDim.x)
+        {
+            const int ti = t / T, tj = t - ti * T;
+            if (tid == 0)
+            {
+                // run only when this tile or one of its 8 neighbours changed in the previous sweep
+                int r = 0;
+                for (int di = -1; di <= 1; di++)
+                    for (int dj = -1; dj <= 1; dj++)
+                    {
+                        int a = ti + di, b = tj + dj;
+                        if (a >= 0 && a < T && b >= 0 && b < T) r |= fa[a * T + b];
+                    }
+                run = r;
+            }
+            __syncthreads();
+            const int do_run = run;
+            __syncthreads();
+            int changed = 0;
+            if (do_run) changed = f2d_relax_tile(map, field, ti, tj, N, log_thr, c1, c2, allow_diag, s);
+            if (tid == 0)
+            {
+                fb[t] = changed ? 1 : 0;       // the tile's own CTA is the only writer of its flag
+                if (changed) ctl[sweep % 3] = 1;
+            }
+        }
+        __threadfence();
+        grid.sync();
+        if (*(volatile int*)&ctl[sweep % 3] == 0) { sweep++; break; }
+    }
+    if (blockIdx.x == 0 && tid == 0) ctl[3] = sweep;
+    for (size_t c = (size_t)blockIdx.x * (F2D_TILE * F2D_TILE) + tid; c < n; c += gstride)
     {
         unsigned ab = field[c];
         out[c] = (ab == F2D_UNREACHED) ? FLT_MAX : (float)f2d_value(ab, c1, c2);
@@ -131,36 +161,29 @@ __global__ void pp_field2d_finish_kernel(const unsigned* __restrict__ field, flo
 }
 
 int pp_launch_field2d(cudaStream_t stream, const float* map, int N, float log_thr, float cost_straight, float cost_diag, int allow_diag,
-                      int goal_i, int goal_j, unsigned* work, unsigned char* tile_flags, int* d_flag, float* out, int sm_count,
+                      int goal_i, int goal_j, unsigned* work, unsigned char* tile_flags, int* d_ctl, float* out, int sm_count,
                       int* sweeps_out, unsigned long long* launches)
 {
-    const int T = (N + F2D_TILE - 1) / F2D_TILE;
-    const double c1 = (double)cost_straight, c2 = (double)cost_diag;
-    pp_field2d_init_kernel<<<sm_count * 4, 256, 0, stream>>>(work, tile_flags, N, T, goal_i, goal_j);
+    int T = (N + F2D_TILE - 1) / F2D_TILE;
+    double c1 = (double)cost_straight, c2 = (double)cost_diag;
+    int occ = 0;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pp_field2d_persistent_kernel, F2D_TILE * F2D_TILE, 0);
+    if (e != cudaSuccess) return (int)e;
+    if (occ < 1) return (int)cudaErrorLaunchOutOfResources;
+    int blocks = occ * sm_count;                    // all CTAs co-resident: the grid barrier needs that
+    if (blocks > T * T) blocks = T * T;
+    int max_sweeps = 16 * T + 64;
+    void* args[] = {(void*)&map, (void*)&work, (void*)&tile_flags, (void*)&d_ctl, (void*)&out, (void*)&N, (void*)&T, (void*)&log_thr,
+                    (void*)&c1, (void*)&c2, (void*)&allow_diag, (void*)&goal_i, (void*)&goal_j, (void*)&max_sweeps};
+    e = cudaLaunchCooperativeKernel((const void*)pp_field2d_persistent_kernel, dim3(blocks), dim3(F2D_TILE, F2D_TILE), args, 0, stream);
+    if (e != cudaSuccess) return (int)e;
     *launches += 1;
-    dim3 grid(T, T), block(F2D_TILE, F2D_TILE);
-    int sweeps = 0, h_flag = 1;
-    unsigned char* fa = tile_flags;
-    unsigned char* fb = tile_flags + (size_t)T * T;
-    while (h_flag && sweeps < 16 * T + 64)
-    {
-        cudaMemsetAsync(d_flag, 0, sizeof(int), stream);
-        // a few sweeps per host round trip
-        for (int k = 0; k < 4; k++)
-        {
-            cudaMemsetAsync(fb, 0, (size_t)T * T, stream);
-            pp_field2d_sweep_kernel<<<grid, block, 0, stream>>>(map, work, fa, fb, d_flag, N, T, log_thr, c1, c2, allow_diag);
-            *launches += 1;
-            unsigned char* t = fa; fa = fb; fb = t;
-            sweeps++;
-        }
-        cudaMemcpyAsync(&h_flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, stream);
-        cudaError_t e = cudaStreamSynchronize(stream);
-        if (e != cudaSuccess) return (int)e;
-    }
-    pp_field2d_finish_kernel<<<sm_count * 4, 256, 0, stream>>>(work, out, (size_t)N * N, c1, c2);
-    *launches += 1;
-    *sweeps_out = sweeps;
+    int h_sweeps = 0;
+    e = cudaMemcpyAsync(&h_sweeps, d_ctl + 3, sizeof(int), cudaMemcpyDeviceToHost, stream);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaStreamSynchronize(stream);
+    if (e != cudaSuccess) return (int)e;
+    *sweeps_out = h_sweeps;
     return (int)cudaGetLastError();
 }
 

@@ -13,8 +13,8 @@
 //   pp_dubins_path_kernel   one warp: plan + parallel sampling
 //   pp_lazy_astar_kernel    one control lane: the lazy cached 2D A* on a fresh cache (parity tests)
 //   pp_map_decay_kernel     float4 grid-stride streaming, HBM/L2 bound
-//   pp_map_boxes_kernel     gather-form log-odds rasterisation, one CTA per touched 32x32 tile
-//   pp_map_lines_kernel     ordered (line by line) counted scatter, single CTA
+//   pp_map_update_kernel    gather-form log-odds rasterisation (+ optional fused decay), one CTA per 32x32 tile, device-side binning
+//   pp_map_lines_kernel     lane-line rasteriser, one CTA per 32x32 tile, lines in order, shared-memory sample counters
 //   pp_map_reloc_*          forward-scatter resample with atomicMax(source index) = "last writer wins"
 #ifndef PP_KERNELS_CUH
 #define PP_KERNELS_CUH
@@ -705,92 +705,170 @@ __global__ void __launch_bounds__(256) pp_map_decay_kernel(float* __restrict__ m
         map[i] = pp_map_decay_cell(map[i], log_free, lo, hi);
 }
 
-struct PPBoxDescDev { int start_i, start_j, ni, nj; float delta; };
+// one box as the device sees it: Grid2D.cpp:104-123's per-box prologue (done on the host with the host libm, like the reference)
+// plus the bounding rectangle of its samples' cells, clipped to the grid (lo > hi: nothing to draw)
+struct PPBoxDescDev { int start_i, start_j, ni, nj; float delta; int pad; short lo_i, hi_i, lo_j, hi_j; };
+static_assert(sizeof(PPBoxDescDev) == 32, "box descriptor layout");
 
-// Grid2D::update_obstacles(boxes, conf), Grid2D.cpp:99-139, gather form.  One CTA per touched 32x32 tile;
-// tile_off/tile_boxes = CSR list (ascending box index) of the boxes whose sample bounding box overlaps the tile.
-__global__ void __launch_bounds__(256) pp_map_boxes_kernel(float* __restrict__ map, int N, const int* __restrict__ tile_ids,
-                                                            const int* __restrict__ tile_off, const int* __restrict__ tile_boxes,
-                                                            const PPBoxDescDev* __restrict__ descs, float cos_h, float sin_h,
-                                                            float lo, float hi, int tiles_per_row)
+// Grid2D::update_obstacles(boxes, conf) (Grid2D.cpp:99-139), optionally followed by Grid2D::update_obstacles() (the whole-map
+// decay, Grid2D.cpp:197-208), in ONE pass over the map: gather form, one CTA per 32x32 tile, 4 cells per thread.
+// Every CTA bins the boxes itself -- it scans the n descriptors' bounding rectangles (index order, 256 per step, ballot
+// compaction keeps the order the reference applies them in) -- so the host sends the descriptors and nothing else.
+// A tile that no box touches streams through the decay (or exits untouched when there is none).
+__global__ void __launch_bounds__(256) pp_map_update_kernel(float* __restrict__ map, int N, const PPBoxDescDev* __restrict__ descs,
+                                                             int n_boxes, float cos_h, float sin_h, float lo, float hi,
+                                                             int do_decay, float log_free)
 {
+    __shared__ int s_list[256];
+    __shared__ int s_warp[8];
     __shared__ PPBoxDescDev sd[64];
-    const int tile = tile_ids[blockIdx.x];
-    const int ti = tile / tiles_per_row, tj = tile - ti * tiles_per_row;
-    const int beg = tile_off[blockIdx.x], end = tile_off[blockIdx.x + 1];
+    const int ti = blockIdx.y, tj = blockIdx.x;
+    const int t_lo_i = ti * PP_TILE, t_hi_i = t_lo_i + PP_TILE - 1, t_lo_j = tj * PP_TILE, t_hi_j = t_lo_j + PP_TILE - 1;
     const int lj = threadIdx.x & 31, li0 = threadIdx.x >> 5;   // 8 rows per pass, 4 passes
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int cj = t_lo_j + lj;
     float v[4];
     int   ci[4];
-    const int cj = tj * PP_TILE + lj;
+    bool  loaded = false;
 #pragma unroll
-    for (int r = 0; r < 4; r++)
+    for (int r = 0; r < 4; r++) { ci[r] = t_lo_i + li0 + 8 * r; v[r] = 0.0f; }
+    for (int base = 0; base < n_boxes; base += 256)
     {
-        ci[r] = ti * PP_TILE + li0 + 8 * r;
-        v[r] = (ci[r] < N && cj < N) ? map[(size_t)ci[r] * N + cj] : 0.0f;
-    }
-    for (int b0 = beg; b0 < end; b0 += 64)
-    {
-        int nb = min(64, end - b0);
-        __syncthreads();
-        if (threadIdx.x < nb) sd[threadIdx.x] = descs[tile_boxes[b0 + threadIdx.x]];
-        __syncthreads();
-        for (int b = 0; b < nb; b++)
+        const int k = base + threadIdx.x;
+        bool hit = false;
+        if (k < n_boxes)
         {
-            const PPBoxDescDev d = sd[b];
+            // bounding rectangles only (8 bytes of the 32-byte record)
+            const short4 bb = *reinterpret_cast<const short4*>(&descs[k].lo_i);
+            hit = bb.x <= bb.y && bb.z <= bb.w && bb.x <= t_hi_i && bb.y >= t_lo_i && bb.z <= t_hi_j && bb.w >= t_lo_j;
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, hit);
+        if (lane == 0) s_warp[warp] = __popc(m);
+        __syncthreads();
+        int off = 0, total = 0;
 #pragma unroll
-            for (int r = 0; r < 4; r++)
+        for (int q = 0; q < 8; q++) { const int c = s_warp[q]; if (q < warp) off += c; total += c; }
+        if (hit) s_list[off + __popc(m & ((1u << lane) - 1u))] = k;
+        __syncthreads();
+        if (total > 0 && !loaded)
+        {
+            loaded = true;
+#pragma unroll
+            for (int r = 0; r < 4; r++) v[r] = (ci[r] < N && cj < N) ? map[(size_t)ci[r] * N + cj] : 0.0f;
+        }
+        for (int b0 = 0; b0 < total; b0 += 64)
+        {
+            const int nb = min(64, total - b0);
+            if (threadIdx.x < nb) sd[threadIdx.x] = descs[s_list[b0 + threadIdx.x]];
+            __syncthreads();
+            for (int b = 0; b < nb; b++)
             {
-                int cnt = pp_box_count(d.ni, d.nj, cos_h, sin_h, ci[r] - d.start_i, cj - d.start_j);
-                if (cnt) v[r] = pp_box_apply(v[r], cnt, d.delta, lo, hi);
+                const PPBoxDescDev d = sd[b];
+                if (cj < d.lo_j || cj > d.hi_j) continue;
+#pragma unroll
+                for (int r = 0; r < 4; r++)
+                {
+                    if (ci[r] < d.lo_i || ci[r] > d.hi_i) continue;
+                    const int cnt = pp_box_count(d.ni, d.nj, cos_h, sin_h, ci[r] - d.start_i, cj - d.start_j);
+                    if (cnt) v[r] = pp_box_apply(v[r], cnt, d.delta, lo, hi);
+                }
             }
+            __syncthreads();
         }
     }
+    if (!loaded && !do_decay) return;
+    if (!loaded)
+    {
+#pragma unroll
+        for (int r = 0; r < 4; r++) v[r] = (ci[r] < N && cj < N) ? map[(size_t)ci[r] * N + cj] : 0.0f;
+    }
 #pragma unroll
     for (int r = 0; r < 4; r++)
-        if (ci[r] < N && cj < N) map[(size_t)ci[r] * N + cj] = v[r];
+        if (ci[r] < N && cj < N)
+            map[(size_t)ci[r] * N + cj] = do_decay ? pp_map_decay_cell(v[r], log_free, lo, hi) : v[r];
 }
 
-// Grid2D::update_obstacles(lines, conf, width), Grid2D.cpp:142-194.  Lines are applied one after the other
-// (clamping is order dependent across lines); inside a line every sample adds the same delta, so samples are
-// counted per cell with atomics and the owner applies clamp(v + delta) `count` times.  cnt = N*N zeroed ints.
-__global__ void __launch_bounds__(1024) pp_map_lines_kernel(float* map, int* cnt, int N, int n45, int n2, float res,
-                                                             const PPLineDesc* lines, int n_lines, float width, float lo, float hi)
+// Grid2D::update_obstacles(lines, conf, width), Grid2D.cpp:142-194, one CTA per 32x32 tile.  Lines are applied one after the
+// other (clamping is order dependent across lines); inside a line every sample adds the same delta, so a tile counts the
+// samples of the line that fall on each of its cells (shared-memory counters) and applies clamp(v + delta) `count` times.
+// Every CTA walks the line list itself and skips the lines whose sample rectangle misses its tile.
+__global__ void __launch_bounds__(256) pp_map_lines_kernel(float* __restrict__ map, int N, int n45, int n2, float res,
+                                                            const PPLineDesc* __restrict__ lines, int n_lines, float width,
+                                                            float lo, float hi)
 {
+    __shared__ int   s_cnt[PP_TILE * PP_TILE];
+    __shared__ int   s_any;
+    const int ti = blockIdx.y, tj = blockIdx.x;
+    const int t_lo_i = ti * PP_TILE, t_lo_j = tj * PP_TILE;
+    const int lj = threadIdx.x & 31, li0 = threadIdx.x >> 5;
+    const int cj = t_lo_j + lj;
+    float v[4];
+    bool loaded = false, dirty = false;
+#pragma unroll
+    for (int r = 0; r < 4; r++) v[r] = 0.0f;
     for (int k = 0; k < n_lines; k++)
     {
         const PPLineDesc d = lines[k];
+        // conservative rectangle of the line's samples in cells (NaN anywhere: every comparison fails, the line is skipped -- it
+        // draws nothing in the reference either, see pp_line_cells)
+        const float reach = fminf(d.length, 100.0f * res) + res;
+        const float ex = d.sx + d.ux * reach, ey = d.sy + d.uy * reach;
+        const float wx = fabsf(d.nx) * (width + res), wy = fabsf(d.ny) * (width + res);
+        const float x_lo = fminf(d.sx, ex) - wx, x_hi = fmaxf(d.sx, ex) + wx, y_lo = fminf(d.sy, ey) - wy, y_hi = fmaxf(d.sy, ey) + wy;
+        const float ci_lo = x_lo / res + (float)n45 - 2.0f, ci_hi = x_hi / res + (float)n45 + 2.0f;
+        const float cj_lo = y_lo / res + (float)n2 - 2.0f, cj_hi = y_hi / res + (float)n2 + 2.0f;
+        const bool overlap = ci_lo <= (float)(t_lo_i + PP_TILE - 1) && ci_hi >= (float)t_lo_i &&
+                             cj_lo <= (float)(t_lo_j + PP_TILE - 1) && cj_hi >= (float)t_lo_j;
+        if (!overlap) continue;                       // uniform over the CTA
+        for (int q = threadIdx.x; q < PP_TILE * PP_TILE; q += 256) s_cnt[q] = 0;
+        if (threadIdx.x == 0) s_any = 0;
+        __syncthreads();
         const int t = threadIdx.x;
-        bool active = false;
-        float pl = 0.0f;
-        if (t < 100) { pl = pp_accumulate_steps(res, t); active = (pl <= d.length); }
-        if (active)
-            for (float pw = 0.0f; pw <= width; pw += res)
-            {
-                int i1, j1, i2, j2;
-                pp_line_cells(d, res, n45, n2, pl, pw, i1, j1, i2, j2);
-                if (i1 > -1 && i1 < N && j1 > -1 && j1 < N) atomicAdd(&cnt[(size_t)i1 * N + j1], 1);
-                if (i2 > -1 && i2 < N && j2 > -1 && j2 < N) atomicAdd(&cnt[(size_t)i2 * N + j2], 1);
-            }
-        __syncthreads();
-        if (active)
-            for (float pw = 0.0f; pw <= width; pw += res)
-            {
-                int i1, j1, i2, j2;
-                pp_line_cells(d, res, n45, n2, pl, pw, i1, j1, i2, j2);
-                if (i1 > -1 && i1 < N && j1 > -1 && j1 < N)
+        if (t < 100)
+        {
+            const float pl = pp_accumulate_steps(res, t);
+            if (pl <= d.length)
+                for (float pw = 0.0f; pw <= width; pw += res)
                 {
-                    size_t c = (size_t)i1 * N + j1;
-                    int q = atomicExch(&cnt[c], 0);
-                    if (q) map[c] = pp_box_apply(map[c], q, d.delta, lo, hi);
+                    int i1, j1, i2, j2;
+                    pp_line_cells(d, res, n45, n2, pl, pw, i1, j1, i2, j2);
+                    i1 -= t_lo_i; j1 -= t_lo_j; i2 -= t_lo_i; j2 -= t_lo_j;
+                    if (i1 > -1 && i1 < PP_TILE && j1 > -1 && j1 < PP_TILE && i1 + t_lo_i < N && j1 + t_lo_j < N)
+                    { atomicAdd(&s_cnt[i1 * PP_TILE + j1], 1); s_any = 1; }
+                    if (i2 > -1 && i2 < PP_TILE && j2 > -1 && j2 < PP_TILE && i2 + t_lo_i < N && j2 + t_lo_j < N)
+                    { atomicAdd(&s_cnt[i2 * PP_TILE + j2], 1); s_any = 1; }
                 }
-                if (i2 > -1 && i2 < N && j2 > -1 && j2 < N)
+        }
+        __syncthreads();
+        if (s_any)
+        {
+            if (!loaded)
+            {
+                loaded = true;
+#pragma unroll
+                for (int r = 0; r < 4; r++)
                 {
-                    size_t c = (size_t)i2 * N + j2;
-                    int q = atomicExch(&cnt[c], 0);
-                    if (q) map[c] = pp_box_apply(map[c], q, d.delta, lo, hi);
+                    const int ci = t_lo_i + li0 + 8 * r;
+                    v[r] = (ci < N && cj < N) ? map[(size_t)ci * N + cj] : 0.0f;
                 }
             }
+#pragma unroll
+            for (int r = 0; r < 4; r++)
+            {
+                const int q = s_cnt[(li0 + 8 * r) * PP_TILE + lj];
+                if (q) { v[r] = pp_box_apply(v[r], q, d.delta, lo, hi); dirty = true; }
+            }
+        }
         __syncthreads();
+    }
+    if (dirty)
+    {
+#pragma unroll
+        for (int r = 0; r < 4; r++)
+        {
+            const int ci = t_lo_i + li0 + 8 * r;
+            if (ci < N && cj < N) map[(size_t)ci * N + cj] = v[r];
+        }
     }
 }
 

@@ -67,6 +67,7 @@ def _fake_pp(real):
         def update_goal(self, *a, **k): pass
         def update_boxes(self, *a, **k): pass
         def update_boxes_2d(self, *a, **k): pass
+        def update_boxes_2d_decay(self, *a, **k): pass
         def update_apf(self, *a, **k): pass
         def decay(self, *a, **k): pass
         def sync(self): pass
@@ -105,6 +106,7 @@ def test_default_bench_flow_prints_a_complete_line(monkeypatch, capsys):
     monkeypatch.setattr(torch.cuda, "set_device", lambda d: None)
     monkeypatch.setattr(torch.cuda, "synchronize", lambda *a: None)
     monkeypatch.setattr(torch.cuda, "mem_get_info", lambda *a: (100 << 30, 180 << 30))
+    monkeypatch.setattr(torch.cuda, "get_device_properties", lambda *a: types.SimpleNamespace(multi_processor_count=148))
     monkeypatch.setattr(torch, "tensor", lambda data, dtype=None, device=None: real_tensor(data, dtype=dtype))
     monkeypatch.setattr(torch.Tensor, "pin_memory", lambda self: self)
     monkeypatch.setitem(sys.modules, "path_planning_pkg_b200", _fake_pp(real))
