@@ -170,6 +170,9 @@ int  pp_get_tables(pp_context* ctx, float* offset_xy, float* offset_heading, flo
 /* HybridAStar::update_goal (lib/HybridAStar.cpp:55-59 -> Grid3D::update_goal_heading, Grid3D.cpp:102-124,
  * including relocate_obstacles, Grid3D.cpp:169-203). */
 int  pp_update_goal(pp_context* ctx, int group, const float* goal3, const float* start3);
+/* Grid2D::update_goal_heading (lib/Grid2D.cpp:260-266): goal location + grid heading only, the map stays where it is (the
+ * relocating form above is Grid3D's override). */
+int  pp_update_goal_frame(pp_context* ctx, int group, const float* goal3, const float* start3);
 /* HybridAStar::reset (lib/HybridAStar.cpp:49-52 -> AStar::reset, lib/AStar.cpp:56-60).  Without history (below) every query
  * starts on a fresh 2D heuristic cache and this is a no-op; with history it drops the carried cache's visited flags and, like
  * the reference, keeps the node costs. */
@@ -258,6 +261,8 @@ int  pp_dubins_path(pp_context* ctx, const float* start3, const float* goal3, fl
 int  pp_astar_lazy_batch(pp_context* ctx, int group, const int* ij, int n, float* out);
 /* same, continuing on the cache left by the previous call (AStar::find_path between two AStar::reset(), lib/AStar.cpp:56-60) */
 int  pp_astar_lazy_continue(pp_context* ctx, int group, const int* ij, int n, float* out);
+/* AStar::reset() (lib/AStar.cpp:56-60) on that cache: drops the visited flags, keeps the node costs */
+int  pp_astar_lazy_reset(pp_context* ctx, int group);
 /* Dubins::Dubins(r_min, step_size) (lib/Dubins.cpp:7-16) for a stand-alone Dubins<T> handle */
 int  pp_override_dubins(pp_context* ctx, float r_min, float step_size);
 /* Grid2D::clear_obstacles (lib/Grid2D.cpp:211-216) */

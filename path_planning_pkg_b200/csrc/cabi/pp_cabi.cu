@@ -153,6 +153,7 @@ struct pp_context
     bool group_cost_dirty = true;
     DevBuf<unsigned> d_f2d_work; DevBuf<unsigned char> d_f2d_flags; DevBuf<float> d_dubins_field; DevBuf<int> d_f2d_ctl;
     DevBuf<int> d_qmap, d_order;
+    DevBuf<int> d_exact_order; bool exact_order_valid = false;    // fetch order of the uploaded EXACT batch (longest expected first)
     int retried = 0;       // queries re-run in the last pp_batch_run
     unsigned long long launches = 0;      // kernels launched by this context
 };
@@ -189,6 +190,7 @@ static int lane_refresh(pp_context* c)
     // nothing changed since the last look: do not wait for whatever the parent's stream is busy with (its own batch)
     if (c->seen_epoch == p->map_epoch && !p->groups_dirty) return PP_SUCCESS;
     c->seen_epoch = p->map_epoch;
+    c->field2d_valid.assign(c->field2d_valid.size(), 0);      // fields derived from the parent's old maps
     int rc = sync_groups(p); if (rc) return rc;
     PP_CUDA(cudaStreamSynchronize(p->stream));
     c->frames = p->frames; c->groups = p->groups;
@@ -358,7 +360,7 @@ void pp_destroy(pp_context* c)
     for (int q = 0; q < 4; q++) if (c->box_stage.ev[q]) cudaEventDestroy(c->box_stage.ev[q]);
     c->s0.release(); c->s1.release(); c->s2.release(); c->s3.release(); c->s4.release();
     c->d_queries.release(); c->d_results.release(); c->d_paths.release(); c->d_trace.release();
-    c->wp.release(); c->wp_lazy.release(); c->d_qmap.release(); c->d_order.release(); c->d_group_cost.release();
+    c->wp.release(); c->wp_lazy.release(); c->d_qmap.release(); c->d_order.release(); c->d_exact_order.release(); c->d_group_cost.release();
     cudaFree(c->d_lazy_sid);
     for (auto& h : c->hist) h.release();
     c->d_foot_bins.release(); c->d_foot_offs.release(); c->d_foot_lin.release(); c->d_foot_xyh.release(); c->d_foot_out.release();
@@ -444,6 +446,20 @@ int pp_update_goal(pp_context* c, int g, const float* goal3, const float* start3
     c->launches += 3;
     PP_CUDA(cudaMemcpyAsync(map, c->d_map_tmp, sizeof(float) * nn, cudaMemcpyDeviceToDevice, c->stream));
     PP_CUDA(cudaGetLastError());
+    return PP_SUCCESS;
+}
+
+// Grid2D::update_goal_heading (lib/Grid2D.cpp:260-266): goal location and grid heading only -- the map is NOT relocated (that is
+// Grid3D's override, pp_update_goal)
+int pp_update_goal_frame(pp_context* c, int g, const float* goal3, const float* start3)
+{
+    int rc = check_group(c, g); if (rc) return rc;
+    rc = lane_guard(c, "pp_update_goal_frame"); if (rc) return rc;
+    if (!goal3 || !start3) return pp_fail(PP_ERR_INVALID, "pp_update_goal_frame: null");
+    map_changed(c, g);
+    pp_host_update_goal(c->model.C, goal3, start3, c->frames[g]);
+    c->groups[g].frame = c->frames[g].F;
+    c->groups_dirty = true;
     return PP_SUCCESS;
 }
 
@@ -929,7 +945,7 @@ int pp_dubins_path(pp_context* c, const float* s, const float* g, float* xyh, fl
 static void fill_args(pp_context* c, const WorkPools& w, const pp_search_opts& o, int n_slots, const int* qmap, int n_work, PPBatchArgs& a)
 {
     a.C = c->model.C; a.off_xy = c->d_off_xy; a.groups = c->d_groups; a.queries = c->d_queries.p; a.n_queries = n_work;
-    a.qmap = qmap;
+    a.qmap = qmap; a.order = nullptr;
     a.n_slots = n_slots; a.counter = c->d_counter; a.results = c->d_results.p;
     a.paths = c->d_paths.p; a.path_cap = o.path_cap;
     a.trace = o.trace_cap > 0 ? c->d_trace.p : nullptr; a.trace_cap = o.trace_cap;
@@ -1261,6 +1277,23 @@ int pp_batch_upload(pp_context* c, const pp_query* q, int n, const pp_search_opt
     }
     PP_CUDA(cudaMemcpyAsync(c->d_queries.p, c->h_queries.data(), sizeof(PPQuery) * n, cudaMemcpyHostToDevice, c->stream));
     rc = sync_groups(c); if (rc) return rc;
+    c->exact_order_valid = false;
+    if (o.mode == PP_MODE_EXACT && n > c->n_slots && n <= (1 << 16))
+    {
+        // More queries than resident slots: fetch the ones expected to run longest first (unreachable goal in the exact 2D field,
+        // then by distance), so that they run beside the bulk instead of after it.  Scheduling only -- no result depends on it.
+        size_t nn_ = nn_of(c);
+        PP_CUDA(c->d_field2d.ensure(nn_ * c->num_groups));
+        if ((int)c->field2d_valid.size() != c->num_groups) c->field2d_valid.assign(c->num_groups, 0);
+        for (int k = 0; k < n; k++)
+            if (!c->field2d_valid[q[k].group]) { rc = field2d_run(c, q[k].group, nullptr, nullptr); if (rc) return rc; }
+        PP_CUDA(c->d_exact_order.ensure((size_t)n));
+        pp_kpop_order_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(c->d_queries.p, nullptr, n, c->d_field2d.p, c->model.C.N, nullptr, 1.0f,
+                                                                      c->d_exact_order.p);
+        c->launches += 1;
+        PP_CUDA(cudaGetLastError());
+        c->exact_order_valid = true;
+    }
     PP_CUDA(cudaStreamSynchronize(c->stream));
     return PP_SUCCESS;
 }
@@ -1269,6 +1302,7 @@ static int launch_search(pp_context* c, const WorkPools& w, const pp_search_opts
 {
     PPBatchArgs a;
     fill_args(c, w, o, n_slots, qmap, n_work, a);
+    if (!qmap && c->exact_order_valid && n_work == c->n_queries) a.order = c->d_exact_order.p;
     PP_CUDA(cudaMemsetAsync(c->d_counter, 0, sizeof(int), c->stream));
     int rc = arena_reset(c, c->wp); if (rc) return rc;
     int blocks = (n_slots + PP_SEARCH_WARPS - 1) / PP_SEARCH_WARPS;
@@ -1559,6 +1593,20 @@ static int lazy_run(pp_context* c, int g, const int* ij, int n, float* out, int 
     PP_CUDA(cudaMemcpyAsync(&status, c->s2.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     PP_CUDA(cudaStreamSynchronize(c->stream));
     if (status) return pp_fail(PP_ERR_CAPACITY, "lazy A*: 2D open-list pool exhausted");
+    return PP_SUCCESS;
+}
+
+// AStar::reset() (lib/AStar.cpp:56-60) on the stand-alone cache of pp_astar_lazy_*: only the visited flags go, the node costs of
+// earlier searches stay
+int pp_astar_lazy_reset(pp_context* c, int g)
+{
+    int rc = check_group(c, g); if (rc) return rc;
+    if (c->wp_lazy.alloc_slots < 1 || c->lazy_group != g) return PP_SUCCESS;      // no cache yet: nothing visited
+    PP_CUDA(cudaSetDevice(c->device));
+    int nn = (int)nn_of(c);
+    pp_hist_reset_kernel<<<std::min((nn + 255) / 256, 4 * c->sm_count), 256, 0, c->stream>>>(c->wp_lazy.cell_state.p, nn);
+    c->launches += 1;
+    PP_CUDA(cudaGetLastError());
     return PP_SUCCESS;
 }
 

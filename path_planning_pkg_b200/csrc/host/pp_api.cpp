@@ -473,18 +473,27 @@ template <typename T> const std::vector<std::vector<T>>& Grid2D<T>::get_obstacle
 
 template <typename T> Node2D<T> Grid2D<T>::update_goal_heading(const Vector2D<T>& goal, const Vector2D<T>& start)
 {
+    // Grid2D.cpp:260-266: goal + heading only; relocating the map is Grid3D's job
     float g[3] = {(float)goal._x, (float)goal._y, 0.0f}, s[3] = {(float)start._x, (float)start._y, 0.0f};
-    check(pp_update_goal(_backend->ctx, 0, g, s), "update_goal_heading");
-    _backend->map_dirty = true;
+    check(pp_update_goal_frame(_backend->ctx, 0, g, s), "update_goal_heading");
     pp_frame_info f; check(pp_get_frame(_backend->ctx, 0, &f), "frame");
     return _node_map[f.goal_ci][f.goal_cj];
 }
 
 template <typename T> Node2D<T> Grid2D<T>::set_start_node(const Vector2D<T>& start)
 {
-    pp_query q; q.x = (float)start._x; q.y = (float)start._y; q.heading = 0.0f; q.vel = 0.0f; q.group = 0;
-    pp_state s; check(pp_set_start_batch(_backend->ctx, &q, 1, &s), "set_start_node");
-    return set_start_node_grid(s.ci, s.cj);
+    // Grid2D.cpp:270-291: int(rel / res) + offset (Grid3D's variant adds the offset BEFORE dividing, which truncates differently
+    // for negative coordinates); an invalid start becomes node (0, 0)
+    pp_frame_info f; check(pp_get_frame(_backend->ctx, 0, &f), "frame");
+    pp_consts_info k; check(pp_get_consts(_backend->ctx, &k), "consts");
+    const T dx = start._x - (T)f.goal_world[0], dy = start._y - (T)f.goal_world[1];
+    const T h = (T)f.grid_heading, ch = std::cos(h), sh = std::sin(h);
+    const T rx = dx * ch + dy * sh, ry = -dx * sh + dy * ch;
+    const T res = (T)_backend->params.resolution;
+    const int N = _backend->params.grid_size;
+    int i = static_cast<int>(rx / res) + k.n45, j = static_cast<int>(ry / res) + k.n2;
+    if (!((i > -1) && (i < N) && (j > -1) && (j < N))) { i = 0; j = 0; }
+    return set_start_node_grid(i, j);
 }
 template <typename T> Node2D<T> Grid2D<T>::set_start_node_grid(const int i, const int j)
 {
@@ -589,7 +598,8 @@ template <typename T> void AStar<T>::update_obstacles(const std::vector<Obstacle
 template <typename T>
 void AStar<T>::update_obstacles(const std::vector<std::pair<Vector2D<T>, Vector2D<T>>>& l, const std::vector<T>& c, const T w) { _grid->update_obstacles(l, c, w); }
 template <typename T> void AStar<T>::update_obstacles() { _grid->update_obstacles(); }
-template <typename T> void AStar<T>::reset() { _fresh = true; }
+// AStar.cpp:56-60: only the visited flags are cleared; the node costs earlier searches left stay
+template <typename T> void AStar<T>::reset() { if (!_fresh) check(pp_astar_lazy_reset(_grid->backend()->ctx, 0), "AStar::reset"); }
 template <typename T> const std::vector<std::vector<T>>& AStar<T>::get_obstacles() const { return _grid->get_obstacle_map(); }
 
 template <typename T> T AStar<T>::find_path(const int start_i, const int start_j)

@@ -27,6 +27,7 @@ namespace cg = cooperative_groups;
 
 #define F2D_TILE 32
 #define F2D_UNREACHED 0xffffffffu
+#define F2D_MAX_OWN 1024          /* tiles one persistent CTA may own (the launcher keeps T*T / grid below it) */
 
 // value of a packed (a << 16 | b) path descriptor: a straight steps, b diagonal steps
 __device__ __forceinline__ double f2d_value(unsigned ab, double c1, double c2)
@@ -105,7 +106,7 @@ pp_field2d_persistent_kernel(const float* __restrict__ map, unsigned* __restrict
 {
     cg::grid_group grid = cg::this_grid();
     __shared__ unsigned s[F2D_TILE + 2][F2D_TILE + 2];
-    __shared__ int run;
+    __shared__ unsigned char s_run[F2D_MAX_OWN];
     const int tid = threadIdx.y * F2D_TILE + threadIdx.x;
     const size_t n = (size_t)N * N, gstride = (size_t)gridDim.x * (F2D_TILE * F2D_TILE);
     // the goal cell is the source even when it is marked occupied (the reference never tests the start cell of a search)
@@ -122,31 +123,37 @@ pp_field2d_persistent_kernel(const float* __restrict__ map, unsigned* __restrict
         const unsigned char* fa = flags + (size_t)(sweep & 1) * T * T;
         unsigned char* fb = flags + (size_t)((sweep + 1) & 1) * T * T;
         if (blockIdx.x == 0 && tid == 0) ctl[(sweep + 1) % 3] = 0;           // written from the next sweep on, last read two barriers ago
-        for (int t = blockIdx.x; t < T * T; t += gridDim.x)
+        // which of this CTA's tiles (blockIdx, blockIdx + grid, ...) run in this sweep: a tile runs only when it or one of its 8
+        // neighbours changed in the previous sweep.  One thread per tile decides (and clears the flag of the tiles that sit out).
+        for (int q = tid; q < F2D_MAX_OWN; q += F2D_TILE * F2D_TILE)
         {
-            const int ti = t / T, tj = t - ti * T;
-            if (tid == 0)
+            const int t = blockIdx.x + q * gridDim.x;
+            int r = 0;
+            if (t < T * T)
             {
-                // run only when this tile or one of its 8 neighbours changed in the previous sweep
-                int r = 0;
+                const int ti = t / T, tj = t - ti * T;
                 for (int di = -1; di <= 1; di++)
                     for (int dj = -1; dj <= 1; dj++)
                     {
                         int a = ti + di, b = tj + dj;
                         if (a >= 0 && a < T && b >= 0 && b < T) r |= fa[a * T + b];
                     }
-                run = r;
+                if (!r) fb[t] = 0;
             }
-            __syncthreads();
-            const int do_run = run;
-            __syncthreads();
-            int changed = 0;
-            if (do_run) changed = f2d_relax_tile(map, field, ti, tj, N, log_thr, c1, c2, allow_diag, s);
+            s_run[q] = (unsigned char)r;
+        }
+        __syncthreads();
+        for (int q = 0, t = blockIdx.x; t < T * T; q++, t += gridDim.x)
+        {
+            if (!s_run[q]) continue;                  // uniform: shared memory
+            const int ti = t / T, tj = t - ti * T;
+            const int changed = f2d_relax_tile(map, field, ti, tj, N, log_thr, c1, c2, allow_diag, s);
             if (tid == 0)
             {
                 fb[t] = changed ? 1 : 0;       // the tile's own CTA is the only writer of its flag
                 if (changed) ctl[sweep % 3] = 1;
             }
+            __syncthreads();
         }
         __threadfence();
         grid.sync();
@@ -172,6 +179,7 @@ int pp_launch_field2d(cudaStream_t stream, const float* map, int N, float log_th
     if (occ < 1) return (int)cudaErrorLaunchOutOfResources;
     int blocks = occ * sm_count;                    // all CTAs co-resident: the grid barrier needs that
     if (blocks > T * T) blocks = T * T;
+    if ((T * T + blocks - 1) / blocks > F2D_MAX_OWN) return (int)cudaErrorInvalidValue;      // grids beyond ~12 000 cells per side
     int max_sweeps = 16 * T + 64;
     void* args[] = {(void*)&map, (void*)&work, (void*)&tile_flags, (void*)&d_ctl, (void*)&out, (void*)&N, (void*)&T, (void*)&log_thr,
                     (void*)&c1, (void*)&c2, (void*)&allow_diag, (void*)&goal_i, (void*)&goal_j, (void*)&max_sweeps};

@@ -125,6 +125,7 @@ struct PPBatchArgs
     const PPGroup*  groups;
     const PPQuery*  queries;
     const int*      qmap;       // optional indirection (retry pass): work item -> query index
+    const int*      order;      // optional fetch order of the work items (longest expected first), nullptr = as given
     int             n_queries;  // number of work items
     int             n_slots;
     int*            counter;
@@ -194,6 +195,7 @@ pp_search_kernel(const __grid_constant__ PPBatchArgs a)
         if (w.lane() == 0) q = atomicAdd(a.counter, 1);
         q = w.shfl(q, 0);
         if (q >= a.n_queries) break;
+        if (a.order) q = a.order[q];
         if (a.qmap) q = a.qmap[q];
         wk.path = a.paths + (size_t)q * a.path_cap; wk.path_cap = a.path_cap;
         wk.trace = a.trace ? a.trace + (size_t)q * a.trace_cap : nullptr;
@@ -284,11 +286,14 @@ __global__ void __launch_bounds__(32 * NW, PP_KPOP_MIN_BLOCKS) pp_kpop_kernel(co
 // (how many iterations per query the item's group needed in the previous batch, when known), descending, ties by index.
 // Only the order in which the resident slots fetch queries changes -- every query is independent, results are
 // unaffected -- but the batch no longer ends on a long query that was fetched last.
+// group_cost == nullptr selects the EXACT-mode key: a start the exact 2D field cannot connect to the goal makes the reference's
+// search exhaust the whole reachable state space (its longest queries by far), so those go first; the rest by distance.
 __device__ __forceinline__ float pp_kpop_order_key(const PPQuery& Q, const float* field2d, int N, const float* group_cost, float unknown_cost)
 {
     const bool in = Q.start.ci >= 0 && Q.start.ci < N && Q.start.cj >= 0 && Q.start.cj < N;
     float k = in ? field2d[(size_t)N * N * Q.group + (size_t)Q.start.ci * N + Q.start.cj] : 0.0f;
-    if (!(k < 3.0e38f)) return 0.0f;                                  // unreachable: ends at once
+    if (!group_cost) return (k < 3.0e38f) ? k : 3.4e38f;
+    if (!(k < 3.0e38f)) return 0.0f;                                  // K-POP: unreachable ends at once
     const float gc = group_cost[Q.group];
     return k * (gc > 0.0f ? gc : unknown_cost);
 }
