@@ -448,7 +448,7 @@ def main():
     ap.add_argument("--lanes", type=int, default=8, help="lane contexts the steps are submitted over (1 = one batch at a time)")
     ap.add_argument("--cpu-sample", type=int, default=0, help="queries in the cpu_baseline sample (0 = 8 per host thread, 64..256)")
     ap.add_argument("--max-slots", type=int, default=0)
-    ap.add_argument("--e2e-steps", type=int, default=0, help="timed end-to-end steps (0 = min(steps, lanes))")
+    ap.add_argument("--e2e-steps", type=int, default=0, help="timed end-to-end steps (0 = min(steps, lanes + 2))")
     ap.add_argument("--budget-s", type=float, default=540.0, help="wall-clock budget: optional blocks are shortened / skipped beyond it")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-kpop", action="store_true")
@@ -510,7 +510,7 @@ def main():
     # ---- warm-up + end to end through the C ABI, one continuous stream of W + E batches: pinned host queries in, results + paths +
     # curvature out, EVERY step.  The first W steps are the warm-up (cold kernels, cold arenas); the e2e clock starts when step W is
     # submitted -- the pipeline is full by then -- and stops when the last batch has been collected (full drain included). ----
-    e2e_steps = args.e2e_steps if args.e2e_steps > 0 else min(args.steps, lanes)
+    e2e_steps = args.e2e_steps if args.e2e_steps > 0 else min(args.steps, lanes + 2)
     barrier()
     t_mark = pipe.run(args.warmup + e2e_steps, True, mark_at=args.warmup)
     torch.cuda.synchronize()
