@@ -39,17 +39,20 @@ PP_HD void pp_box_sample_offset(int i, int j, float cos_h, float sin_h, int& a, 
 // number of samples (i, j) in [0, ni) x [0, nj) whose rounded rotated offset equals (a, b)
 PP_HD int pp_box_count(int ni, int nj, float cos_h, float sin_h, int a, int b)
 {
-    // inverse rotation of the cell offset gives the lattice neighbourhood to test; the pre-image of
-    // the unit rounding square is a square of side 2 in (i, j), so +-2 around the centre is exhaustive
+    // Inverse rotation of the cell offset gives the lattice neighbourhood to test.  The pre-image of the unit rounding square
+    // around (a, b) is a rotated unit square; in (i, j) lattice units (half cells) its bounding box reaches at most
+    // |cos| + |sin| <= 1.4143 from the centre (ic, jc), so i in [ic - 1.4143, ic + 1.4143] is a subset of {i0 - 1, i0, i0 + 1}
+    // with i0 = round(ic) (|ic - i0| <= 0.5, margin 0.085 -- the float error of ic, jc is below 1e-3 for offsets up to 2^13).
+    // Every candidate is then checked with the reference's exact forward arithmetic, so a superset is all that is needed.
     float ic = 2.0f * ((float)a * cos_h - (float)b * sin_h);
     float jc = 2.0f * ((float)a * sin_h + (float)b * cos_h);
     int i0 = (int)roundf(ic), j0 = (int)roundf(jc);
     int count = 0;
-    for (int di = -2; di <= 2; di++)
+    for (int di = -1; di <= 1; di++)
     {
         int i = i0 + di;
         if (i < 0 || i >= ni) continue;
-        for (int dj = -2; dj <= 2; dj++)
+        for (int dj = -1; dj <= 1; dj++)
         {
             int j = j0 + dj;
             if (j < 0 || j >= nj) continue;
