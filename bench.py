@@ -448,14 +448,14 @@ def main():
     ap.add_argument("--lanes", type=int, default=8, help="lane contexts the steps are submitted over (1 = one batch at a time)")
     ap.add_argument("--cpu-sample", type=int, default=0, help="queries in the cpu_baseline sample (0 = 8 per host thread, 64..256)")
     ap.add_argument("--max-slots", type=int, default=0)
-    ap.add_argument("--e2e-steps", type=int, default=0, help="timed end-to-end steps (0 = min(steps, lanes + 2))")
-    ap.add_argument("--budget-s", type=float, default=540.0, help="wall-clock budget: optional blocks are shortened / skipped beyond it")
+    ap.add_argument("--e2e-steps", type=int, default=0, help="timed end-to-end steps (0 = min(steps, lanes))")
+    ap.add_argument("--budget-s", type=float, default=555.0, help="wall-clock budget: optional blocks are shortened / skipped beyond it")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-kpop", action="store_true")
     ap.add_argument("--no-c5", action="store_true")
     ap.add_argument("--no-blocks", action="store_true", help="skip the c1 / c2 / c3 blocks")
     ap.add_argument("--c5-groups", type=int, default=1024)
-    ap.add_argument("--c5-steps", type=int, default=3)
+    ap.add_argument("--c5-steps", type=int, default=2)
     args = ap.parse_args()
     rank, local_rank, world = dist_env()
     workload = (f"C4: {args.groups} groups x {args.starts} starts = {args.groups * args.starts} Hybrid A* queries per GPU per step, "
@@ -510,7 +510,7 @@ def main():
     # ---- warm-up + end to end through the C ABI, one continuous stream of W + E batches: pinned host queries in, results + paths +
     # curvature out, EVERY step.  The first W steps are the warm-up (cold kernels, cold arenas); the e2e clock starts when step W is
     # submitted -- the pipeline is full by then -- and stops when the last batch has been collected (full drain included). ----
-    e2e_steps = args.e2e_steps if args.e2e_steps > 0 else min(args.steps, lanes + 2)
+    e2e_steps = args.e2e_steps if args.e2e_steps > 0 else min(args.steps, lanes)
     barrier()
     t_mark = pipe.run(args.warmup + e2e_steps, True, mark_at=args.warmup)
     torch.cuda.synchronize()
@@ -618,12 +618,12 @@ def main():
         except Exception as e:
             return {"error": repr(e)}
 
-    if not args.no_kpop and in_time():
+    if not args.no_kpop and in_time(margin=15.0):
         k = guarded("kpop", lambda: block_kpop(args, pp, ctx, q, res, barrier, cpu, in_time()))
         if rank == 0:
             line["kpop"] = k
     ctx.close()
-    if not args.no_c5 and in_time():
+    if not args.no_c5 and in_time(margin=30.0):
         c5 = guarded("c5", lambda: block_c5(args, pp, torch, dist, rank, local_rank, world, barrier, in_time))
         if rank == 0:
             line["c5"] = c5

@@ -19,7 +19,7 @@ CSRC = os.path.join(HERE, "csrc")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-fmad=false", "-prec-div=true", "-prec-sqrt=true", "-ftz=false",
               "-Xcompiler", "-fPIC,-ffp-contract=off,-O2", "-cudart", "static"]
-CXX_FLAGS = ["-std=c++14", "-O2", "-Wall", "-fPIC", "-ffp-contract=off"]
+CXX_FLAGS = ["-std=c++14", "-O2", "-Wall", "-Wno-unknown-pragmas", "-fPIC", "-ffp-contract=off"]
 
 
 def _newer(target, sources):

@@ -892,7 +892,9 @@ PP_HD_NOINLINE_FN void pp_search_exact(const W& w, const PPConsts& C, const floa
 
     PP_PROF_DECL
     PP_PROF_CDECL
-    const PPWork wk0 = wk;              // the slot's fixed pools: wk follows the containers as they grow, restored at the end
+    // the slot's fixed closed log / hash: wk follows these two containers as they grow and gets them back at the end
+    PPClosed3* const closed0 = wk.closed; PPHashSlot* const chash0 = wk.chash;
+    const int closed_cap0 = wk.closed_cap, chash_cap0 = wk.chash_cap;
     int closed_blk = -1, chash_blk = -1;
     // ---- scratch init (all lanes) ----
     const bool carry = (wk.lazy_sid != nullptr);
@@ -1230,7 +1232,7 @@ PP_HD_NOINLINE_FN void pp_search_exact(const W& w, const PPConsts& C, const floa
         res.n_closed = S.n_closed;
         res.pad = 0;
     }
-    wk = wk0;
+    wk.closed = closed0; wk.closed_cap = closed_cap0; wk.chash = chash0; wk.chash_cap = chash_cap0;
 }
 
 #endif
