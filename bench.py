@@ -445,11 +445,13 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--groups", type=int, default=64)
     ap.add_argument("--starts", type=int, default=64)
-    ap.add_argument("--lanes", type=int, default=20, help="lane contexts the steps are submitted over (1 = one batch at a time); never more "
-                                                          "than the steps of the longest timed region")
+    ap.add_argument("--lanes", type=int, default=10, help="lane contexts the steps are submitted over (1 = one batch at a time).  10: the "
+                                                          "driver's 20 timed steps are two rounds, warm-up + e2e one round; 20 (every timed "
+                                                          "batch in flight at once) measured 9 %% slower, 8 leaves a third round to four lanes")
     ap.add_argument("--cpu-sample", type=int, default=0, help="queries in the cpu_baseline sample (0 = 8 per host thread, 64..256)")
     ap.add_argument("--max-slots", type=int, default=0)
-    ap.add_argument("--e2e-steps", type=int, default=0, help="timed end-to-end steps (0 = min(steps, 8))")
+    ap.add_argument("--e2e-steps", type=int, default=0, help="timed end-to-end steps (0 = lanes - warmup, at least 3: warm-up + e2e fill "
+                                                             "every lane once)")
     ap.add_argument("--budget-s", type=float, default=555.0, help="wall-clock budget: optional blocks are shortened / skipped beyond it")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-kpop", action="store_true")
@@ -498,7 +500,7 @@ def main():
     queries, qgroups, maps = select_queries(ctx, groups)
     q = ctx.make_queries(queries, qgroups)
     nq = len(q)
-    lanes = max(1, min(args.lanes, max(args.steps, args.warmup + (args.e2e_steps if args.e2e_steps > 0 else 8))))
+    lanes = max(1, min(args.lanes, args.steps))
     # resident queries per lane: the GPU holds 16 warps per SM in all; twice its share lets a lane fill the SMs the others leave idle
     # and keeps most of the lane's memory budget for the arena its queries grow into
     hw_slots = 16 * torch.cuda.get_device_properties(local_rank).multi_processor_count
@@ -511,7 +513,7 @@ def main():
     # ---- warm-up + end to end through the C ABI, one continuous stream of W + E batches: pinned host queries in, results + paths +
     # curvature out, EVERY step.  The first W steps are the warm-up (cold kernels, cold arenas); the e2e clock starts when step W is
     # submitted -- the pipeline is full by then -- and stops when the last batch has been collected (full drain included). ----
-    e2e_steps = args.e2e_steps if args.e2e_steps > 0 else min(args.steps, 8)
+    e2e_steps = args.e2e_steps if args.e2e_steps > 0 else max(3, min(args.steps, lanes - args.warmup))
     barrier()
     t_mark = pipe.run(args.warmup + e2e_steps, True, mark_at=args.warmup)
     torch.cuda.synchronize()

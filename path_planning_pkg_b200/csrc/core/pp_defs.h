@@ -30,6 +30,24 @@ PP_HD int pp_f2i_x86(float v)
     return (v >= -2147483648.0f && v < 2147483648.0f) ? (int)v : (int)0x80000000;
 }
 
+// set bits / index of the lowest set bit (m != 0) of a ballot mask
+PP_HD int pp_popc(unsigned m)
+{
+#ifdef __CUDA_ARCH__
+    return __popc(m);
+#else
+    return __builtin_popcount(m);
+#endif
+}
+PP_HD int pp_ctz(unsigned m)
+{
+#ifdef __CUDA_ARCH__
+    return __ffs((int)m) - 1;
+#else
+    return __builtin_ctz(m);
+#endif
+}
+
 #define PP_MAX_STEER 16
 #define PP_MAX_BINS 128   /* heading bins + 1 padding column must fit */
 

@@ -51,64 +51,40 @@ PP_HD float pp_dubins_p2(int type, float theta_t1)
     return (type == PP_RSL) ? (float)((double)theta_t1 - PP_PI) : (float)((double)theta_t1 + PP_PI);
 }
 
+// One body for the four types (the kernel is bound by instruction fetch: four specialised copies were 5.8 KB of SASS).  With
+// sr / gr = "the start / goal circle is the right-hand one", Dubins.cpp:180-323 reads, for every type:
+//   p0 = +-pi/2 + sh (+ iff sr), theta_g = +-pi/2 + gh (+ iff gr)                      [double sum, stored as float]
+//   theta_t1 = +-pi/2 + theta (RSR +, LSL -) or +-ac + theta (RSL +, LSR -); p2 = theta_t1 (RSR, LSL) or theta_t1 -+ pi
+//   p1 = theta_t1 - p0, brought to <= 0 (sr) or >= 0 (!sr) by ONE -+2pi step; p3 = theta_g - p2 likewise with gr
+//   straight segment between the centres (RSR, LSL) or between the tangent points (RSL, LSR)
+//   length = dist + r * (-+p1 -+ p3) (- iff right-hand circle); -(a + b) == (-a) + (-b) in IEEE arithmetic
 PP_HD float pp_dubins_finish(int type, float r, float sh, float gh, float csx, float csy, float cgx, float cgy,
                              float theta, float ac, float cos_t1, float sin_t1, float cos_p2, float sin_p2, float p[4])
 {
-    float dcx = cgx - csx, dcy = cgy - csy;
-    if (type == PP_RSR)
+    const bool sr = (type == PP_RSR) || (type == PP_RSL), gr = (type == PP_RSR) || (type == PP_LSR);
+    const bool same = (sr == gr);                    // RSR, LSL
+    const double hs = sr ? PP_PI_2 : -PP_PI_2, hg = gr ? PP_PI_2 : -PP_PI_2;
+    const float p0 = (float)(hs + (double)sh);
+    const float theta_g = (float)(hg + (double)gh);
+    float theta_t1, p2;
+    if (same) { theta_t1 = (float)(hs + (double)theta); p2 = theta_t1; }
+    else { theta_t1 = pp_dubins_theta_t1(type, ac, theta); p2 = pp_dubins_p2(type, theta_t1); }
+    float p1 = theta_t1 - p0;
+    if (sr ? (p1 > 0) : (p1 < 0)) p1 = (float)((double)p1 + (sr ? -2 * PP_PI : 2 * PP_PI));
+    float p3 = theta_g - p2;
+    if (gr ? (p3 > 0) : (p3 < 0)) p3 = (float)((double)p3 + (gr ? -2 * PP_PI : 2 * PP_PI));
+    p[0] = p0; p[1] = p1; p[2] = p2; p[3] = p3;
+    float dx = cgx - csx, dy = cgy - csy;
+    if (!same)
     {
-        p[0] = (float)(PP_PI_2 + (double)sh);
-        float theta_t1 = (float)(PP_PI_2 + (double)theta);
-        p[2] = theta_t1;
-        float theta_g = (float)(PP_PI_2 + (double)gh);
-        p[1] = theta_t1 - p[0];
-        if (p[1] > 0) p[1] = (float)((double)p[1] - 2 * PP_PI);
-        p[3] = theta_g - p[2];
-        if (p[3] > 0) p[3] = (float)((double)p[3] - 2 * PP_PI);
-        float dist_st = sqrtf(dcx * dcx + dcy * dcy);
-        return dist_st + r * -(p[1] + p[3]);
+        float ssx = csx + r * cos_t1;
+        float ssy = csy + r * sin_t1;
+        float esx = cgx + r * cos_p2;
+        float esy = cgy + r * sin_p2;
+        dx = esx - ssx; dy = esy - ssy;
     }
-    if (type == PP_LSL)
-    {
-        p[0] = (float)(-PP_PI_2 + (double)sh);
-        float theta_t1 = (float)(-PP_PI_2 + (double)theta);
-        p[2] = theta_t1;
-        float theta_g = (float)(-PP_PI_2 + (double)gh);
-        p[1] = theta_t1 - p[0];
-        if (p[1] < 0) p[1] = (float)((double)p[1] + 2 * PP_PI);
-        p[3] = theta_g - p[2];
-        if (p[3] < 0) p[3] = (float)((double)p[3] + 2 * PP_PI);
-        float dist_st = sqrtf(dcx * dcx + dcy * dcy);
-        return dist_st + r * (p[1] + p[3]);
-    }
-    float theta_t1 = pp_dubins_theta_t1(type, ac, theta);
-    p[2] = pp_dubins_p2(type, theta_t1);
-    if (type == PP_RSL)
-    {
-        p[0] = (float)(PP_PI_2 + (double)sh);
-        float theta_g = (float)(-PP_PI_2 + (double)gh);
-        p[1] = theta_t1 - p[0];
-        if (p[1] > 0) p[1] = (float)((double)p[1] - 2 * PP_PI);
-        p[3] = theta_g - p[2];
-        if (p[3] < 0) p[3] = (float)((double)p[3] + 2 * PP_PI);
-    }
-    else // PP_LSR
-    {
-        p[0] = (float)(-PP_PI_2 + (double)sh);
-        float theta_g = (float)(PP_PI_2 + (double)gh);
-        p[1] = theta_t1 - p[0];
-        if (p[1] < 0) p[1] = (float)((double)p[1] + 2 * PP_PI);
-        p[3] = theta_g - p[2];
-        if (p[3] > 0) p[3] = (float)((double)p[3] - 2 * PP_PI);
-    }
-    float ssx = csx + r * cos_t1;
-    float ssy = csy + r * sin_t1;
-    float esx = cgx + r * cos_p2;
-    float esy = cgy + r * sin_p2;
-    float dx = esx - ssx, dy = esy - ssy;
-    float dist_st = sqrtf(dx * dx + dy * dy);
-    if (type == PP_RSL) return dist_st + r * (-p[1] + p[3]);
-    return dist_st + r * (p[1] - p[3]);
+    const float dist_st = sqrtf(dx * dx + dy * dy);
+    return dist_st + r * ((sr ? -p1 : p1) + (gr ? -p3 : p3));
 }
 
 // acosf(2 r / dist) of the RSL / LSR candidates (NaN when the circle centres are closer than 2r)

@@ -131,6 +131,46 @@ PP_HD float pp_g_sincos(float y, bool want_cos)
 PP_HD_NOINLINE_FN float pp_g_sinf(float x) { return pp_g_sincos(x, false); }
 PP_HD_NOINLINE_FN float pp_g_cosf(float x) { return pp_g_sincos(x, true); }
 
+// (sinf(y), cosf(y)) with ONE argument reduction: both results are the two polynomials of the same reduced argument, swapped by
+// the quadrant (what glibc's own sincosf does; the reference's `sin(h); cos(h)` pairs compile to it, Dubins.cpp:23-33).  Same bits
+// as pp_g_sinf / pp_g_cosf by construction -- checked over all arguments by tests/cpp/gmath_check.cpp -- at half the instructions
+// and, since the search kernel is bound by instruction fetch, one hot routine instead of two.
+PP_HD_NOINLINE_FN void pp_g_sincosf(float y, float* sn, float* cs)
+{
+    double x = (double)y;
+    const uint32_t iy = PP_G_F2U(y);
+    const uint32_t top = (iy >> 20) & 0x7ffu;
+    if (top < 0x3f4u)
+    {
+        if (top < 0x398u) { *sn = y; *cs = 1.0f; return; }
+        const double x2 = x * x;
+        *sn = pp_g_sin_poly(x, x2); *cs = pp_g_cos_poly(x2, false);
+        return;
+    }
+    int n;
+    int sign_off = 0;
+    if (top < 0x42fu)
+    {
+        double r = x * PP_G_HPI_INV;
+        n = ((int32_t)r + 0x800000) >> 24;
+        x = PP_G_FMA(-(double)n, PP_G_HPI, x);
+    }
+    else if (top < 0x7f8u)
+    {
+        x = pp_g_reduce_large(iy, &n);
+        sign_off = (int)(iy >> 31);
+    }
+    else { *sn = y - y; *cs = y - y; return; }
+    const int q = n + sign_off;
+    const double s = pp_g_quadrant_sign(q);
+    const bool neg = (q & 2) != 0;
+    const double x2 = x * x;
+    const float a = pp_g_cos_poly(x2, neg), b = pp_g_sin_poly(x * s, x2);
+    const bool odd = (n & 1) != 0;
+    *sn = odd ? a : b;
+    *cs = odd ? b : a;
+}
+
 // ---- atanf (s_atanf.c) ------------------------------------------------------------------------------
 PP_HD float pp_g_atanf_core(float x)
 {
@@ -155,17 +195,21 @@ PP_HD float pp_g_atanf_core(float x)
     }
     else
     {
+        // the four argument reductions of s_atanf.c, written as numerator / denominator so that the IEEE division (a long
+        // instruction sequence on the device) is emitted once; the operands are the ones of the original expressions
         x = fabsf(x);
+        float num, den;
         if (ix < 0x3f980000u)                          // |x| < 1.1875
         {
-            if (ix < 0x3f300000u) { id = 0; x = (2.0f * x - 1.0f) / (2.0f + x); }
-            else { id = 1; x = (x - 1.0f) / (x + 1.0f); }
+            if (ix < 0x3f300000u) { id = 0; num = 2.0f * x - 1.0f; den = 2.0f + x; }
+            else { id = 1; num = x - 1.0f; den = x + 1.0f; }
         }
         else
         {
-            if (ix < 0x401c0000u) { id = 2; x = (x - 1.5f) / (1.0f + 1.5f * x); }
-            else { id = 3; x = -1.0f / x; }
+            if (ix < 0x401c0000u) { id = 2; num = x - 1.5f; den = 1.0f + 1.5f * x; }
+            else { id = 3; num = -1.0f; den = x; }
         }
+        x = num / den;
     }
     float z = x * x;
     float w = z * z;
@@ -283,6 +327,7 @@ struct PPMathGlibc
 {
     PP_HD static float sin(float x) { return pp_g_sinf(x); }
     PP_HD static float cos(float x) { return pp_g_cosf(x); }
+    PP_HD static void  sincos(float x, float& s, float& c) { pp_g_sincosf(x, &s, &c); }
     PP_HD static float atan2(float y, float x) { return pp_g_atan2f(y, x); }
     PP_HD static float acos(float x) { return pp_g_acosf(x); }
 };

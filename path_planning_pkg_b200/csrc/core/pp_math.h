@@ -28,6 +28,7 @@ struct PPMathPinned
 {
     PP_HD static float sin(float x) { return pp_pin_sinf(x); }
     PP_HD static float cos(float x) { return pp_pin_cosf(x); }
+    PP_HD static void  sincos(float x, float& s, float& c) { s = pp_pin_sinf(x); c = pp_pin_cosf(x); }
     PP_HD static float atan2(float y, float x) { return pp_pin_atan2f(y, x); }
     PP_HD static float acos(float x) { return pp_pin_acosf(x); }
 };
@@ -40,6 +41,7 @@ typedef PPMathGlibc PPMathExact;
 #endif
 PP_HD float pp_sinf(float x) { return PPMathExact::sin(x); }
 PP_HD float pp_cosf(float x) { return PPMathExact::cos(x); }
+PP_HD void  pp_sincosf(float x, float& s, float& c) { PPMathExact::sincos(x, s, c); }
 PP_HD float pp_atan2f(float y, float x) { return PPMathExact::atan2(y, x); }
 PP_HD float pp_acosf(float x) { return PPMathExact::acos(x); }
 

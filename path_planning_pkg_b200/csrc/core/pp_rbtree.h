@@ -22,6 +22,10 @@
 
 #include "pp_defs.h"
 
+#ifndef PP_EXACT_SPEC      /* speculative parallel walks (pp_search.h): a build variant, off by default */
+#define PP_EXACT_SPEC 0
+#endif
+
 #define PP_RB_NIL (-1)
 #define PP_RB_RED 0
 #define PP_RB_BLACK 1
@@ -87,8 +91,13 @@ struct PPRbState
     int*  mcnt = nullptr;
     int   mcap = 0;
 
+#if PP_EXACT_SPEC
     PP_HD void mut(int x) { if (mlog) { int c = *mcnt; if (c < mcap) mlog[c] = x; *mcnt = c + 1; } }
     PP_HD void mut_all() { if (mlog) *mcnt = mcap + 1; }
+#else       // no speculative walks in this build: no log, and no test for one in every rotation
+    PP_HD void mut(int) {}
+    PP_HD void mut_all() {}
+#endif
 };
 
 struct PPRbPool
@@ -97,31 +106,27 @@ struct PPRbPool
     PP_HD PPRbHead& operator[](int i) const { return *reinterpret_cast<PPRbHead*>(base + (size_t)i * (size_t)stride); }
 };
 
-PP_HD_NOINLINE_FN void pp_rb_rotate_left(PPRbState& t, const PPRbPool n, int x)
-{
-    int y = n[x].w.right;
-    t.mut(x); t.mut(y); t.mut(x == n[PP_RB_HEADER].parent ? PP_RB_HEADER : n[x].parent);
-    n[x].w.right = n[y].w.left;
-    if (n[y].w.left != PP_RB_NIL) n[n[y].w.left].parent = x;
-    n[y].parent = n[x].parent;
-    if (x == n[PP_RB_HEADER].parent) n[PP_RB_HEADER].parent = y;
-    else if (x == n[n[x].parent].w.left) n[n[x].parent].w.left = y;
-    else n[n[x].parent].w.right = y;
-    n[y].w.left = x;
-    n[x].parent = y;
-}
+// child `side` of node x: 0 = left, 1 = right (PPWalk starts with {left, right})
+PP_HD int& pp_rb_child(const PPRbPool n, int x, int side) { return (&n[x].w.left)[side]; }
 
-PP_HD_NOINLINE_FN void pp_rb_rotate_right(PPRbState& t, const PPRbPool n, int x)
+// local_Rb_tree_rotate_left (up = 1: x's RIGHT child moves up) and local_Rb_tree_rotate_right (up = 0) of tree.cc as one body:
+// the two are mirror images, and the kernel that runs them is bound by instruction fetch, so every mirrored pair below
+// (rotations, the two halves of the insert and of the erase rebalancing loops) is written once over a side index.
+PP_HD_NOINLINE_FN void pp_rb_rotate(PPRbState& t, const PPRbPool n, int x, int up)
 {
-    int y = n[x].w.left;
-    t.mut(x); t.mut(y); t.mut(x == n[PP_RB_HEADER].parent ? PP_RB_HEADER : n[x].parent);
-    n[x].w.left = n[y].w.right;
-    if (n[y].w.right != PP_RB_NIL) n[n[y].w.right].parent = x;
-    n[y].parent = n[x].parent;
-    if (x == n[PP_RB_HEADER].parent) n[PP_RB_HEADER].parent = y;
-    else if (x == n[n[x].parent].w.right) n[n[x].parent].w.right = y;
-    else n[n[x].parent].w.left = y;
-    n[y].w.right = x;
+    const int dn = up ^ 1;
+    const int y = pp_rb_child(n, x, up);
+    const int xp = n[x].parent;
+    const bool x_is_root = (x == n[PP_RB_HEADER].parent);
+    t.mut(x); t.mut(y); t.mut(x_is_root ? PP_RB_HEADER : xp);
+    const int yd = pp_rb_child(n, y, dn);
+    pp_rb_child(n, x, up) = yd;
+    if (yd != PP_RB_NIL) n[yd].parent = x;
+    n[y].parent = xp;
+    if (x_is_root) n[PP_RB_HEADER].parent = y;
+    else if (x == pp_rb_child(n, xp, dn)) pp_rb_child(n, xp, dn) = y;
+    else pp_rb_child(n, xp, up) = y;
+    pp_rb_child(n, y, dn) = x;
     n[x].parent = y;
 }
 
@@ -144,39 +149,21 @@ PP_HD_NOINLINE_FN void pp_rb_insert_and_rebalance(PPRbState& t, const PPRbPool n
     }
     while (x != n[PP_RB_HEADER].parent && n[n[x].parent].color == PP_RB_RED)
     {
-        int xp = n[x].parent;
-        int xpp = n[xp].parent;
-        if (xp == n[xpp].w.left)
+        const int xp = n[x].parent;
+        const int xpp = n[xp].parent;
+        const int side = (xp == n[xpp].w.left) ? 0 : 1;       // which child of the grandparent the parent is
+        const int y = pp_rb_child(n, xpp, side ^ 1);          // the uncle
+        if (y != PP_RB_NIL && n[y].color == PP_RB_RED)
         {
-            int y = n[xpp].w.right;
-            if (y != PP_RB_NIL && n[y].color == PP_RB_RED)
-            {
-                n[xp].color = PP_RB_BLACK; n[y].color = PP_RB_BLACK; n[xpp].color = PP_RB_RED;
-                x = xpp;
-            }
-            else
-            {
-                if (x == n[xp].w.right) { x = xp; pp_rb_rotate_left(t, n, x); }
-                n[n[x].parent].color = PP_RB_BLACK;
-                n[xpp].color = PP_RB_RED;
-                pp_rb_rotate_right(t, n, xpp);
-            }
+            n[xp].color = PP_RB_BLACK; n[y].color = PP_RB_BLACK; n[xpp].color = PP_RB_RED;
+            x = xpp;
         }
         else
         {
-            int y = n[xpp].w.left;
-            if (y != PP_RB_NIL && n[y].color == PP_RB_RED)
-            {
-                n[xp].color = PP_RB_BLACK; n[y].color = PP_RB_BLACK; n[xpp].color = PP_RB_RED;
-                x = xpp;
-            }
-            else
-            {
-                if (x == n[xp].w.left) { x = xp; pp_rb_rotate_right(t, n, x); }
-                n[n[x].parent].color = PP_RB_BLACK;
-                n[xpp].color = PP_RB_RED;
-                pp_rb_rotate_left(t, n, xpp);
-            }
+            if (x == pp_rb_child(n, xp, side ^ 1)) { x = xp; pp_rb_rotate(t, n, x, side ^ 1); }
+            n[n[x].parent].color = PP_RB_BLACK;
+            n[xpp].color = PP_RB_RED;
+            pp_rb_rotate(t, n, xpp, side);
         }
     }
     n[n[PP_RB_HEADER].parent].color = PP_RB_BLACK;
@@ -240,69 +227,38 @@ PP_HD_NOINLINE_FN void pp_rb_erase(PPRbState& t, const PPRbPool n, int z)
     {
         while (x != n[PP_RB_HEADER].parent && (x == PP_RB_NIL || n[x].color == PP_RB_BLACK))
         {
-            if (x == n[x_parent].w.left)
+            const int side = (x == n[x_parent].w.left) ? 0 : 1;      // which child of x_parent x is; far = the other side
+            const int far = side ^ 1;
+            int w = pp_rb_child(n, x_parent, far);                   // the sibling
+            if (n[w].color == PP_RB_RED)
             {
-                int w = n[x_parent].w.right;
-                if (n[w].color == PP_RB_RED)
-                {
-                    n[w].color = PP_RB_BLACK; n[x_parent].color = PP_RB_RED;
-                    pp_rb_rotate_left(t, n, x_parent);
-                    w = n[x_parent].w.right;
-                }
-                if ((n[w].w.left == PP_RB_NIL || n[n[w].w.left].color == PP_RB_BLACK) &&
-                    (n[w].w.right == PP_RB_NIL || n[n[w].w.right].color == PP_RB_BLACK))
-                {
-                    n[w].color = PP_RB_RED;
-                    x = x_parent;
-                    x_parent = n[x_parent].parent;
-                }
-                else
-                {
-                    if (n[w].w.right == PP_RB_NIL || n[n[w].w.right].color == PP_RB_BLACK)
-                    {
-                        n[n[w].w.left].color = PP_RB_BLACK;
-                        n[w].color = PP_RB_RED;
-                        pp_rb_rotate_right(t, n, w);
-                        w = n[x_parent].w.right;
-                    }
-                    n[w].color = n[x_parent].color;
-                    n[x_parent].color = PP_RB_BLACK;
-                    if (n[w].w.right != PP_RB_NIL) n[n[w].w.right].color = PP_RB_BLACK;
-                    pp_rb_rotate_left(t, n, x_parent);
-                    break;
-                }
+                n[w].color = PP_RB_BLACK; n[x_parent].color = PP_RB_RED;
+                pp_rb_rotate(t, n, x_parent, far);
+                w = pp_rb_child(n, x_parent, far);
+            }
+            const int wn = pp_rb_child(n, w, side), wf = pp_rb_child(n, w, far);      // the sibling's near and far child
+            const bool wf_black = (wf == PP_RB_NIL || n[wf].color == PP_RB_BLACK);
+            if (wf_black && (wn == PP_RB_NIL || n[wn].color == PP_RB_BLACK))
+            {
+                n[w].color = PP_RB_RED;
+                x = x_parent;
+                x_parent = n[x_parent].parent;
             }
             else
             {
-                int w = n[x_parent].w.left;
-                if (n[w].color == PP_RB_RED)
+                if (wf_black)
                 {
-                    n[w].color = PP_RB_BLACK; n[x_parent].color = PP_RB_RED;
-                    pp_rb_rotate_right(t, n, x_parent);
-                    w = n[x_parent].w.left;
-                }
-                if ((n[w].w.right == PP_RB_NIL || n[n[w].w.right].color == PP_RB_BLACK) &&
-                    (n[w].w.left == PP_RB_NIL || n[n[w].w.left].color == PP_RB_BLACK))
-                {
+                    n[wn].color = PP_RB_BLACK;
                     n[w].color = PP_RB_RED;
-                    x = x_parent;
-                    x_parent = n[x_parent].parent;
+                    pp_rb_rotate(t, n, w, side);
+                    w = pp_rb_child(n, x_parent, far);
                 }
-                else
-                {
-                    if (n[w].w.left == PP_RB_NIL || n[n[w].w.left].color == PP_RB_BLACK)
-                    {
-                        n[n[w].w.right].color = PP_RB_BLACK;
-                        n[w].color = PP_RB_RED;
-                        pp_rb_rotate_left(t, n, w);
-                        w = n[x_parent].w.left;
-                    }
-                    n[w].color = n[x_parent].color;
-                    n[x_parent].color = PP_RB_BLACK;
-                    if (n[w].w.left != PP_RB_NIL) n[n[w].w.left].color = PP_RB_BLACK;
-                    pp_rb_rotate_right(t, n, x_parent);
-                    break;
-                }
+                n[w].color = n[x_parent].color;
+                n[x_parent].color = PP_RB_BLACK;
+                const int wf2 = pp_rb_child(n, w, far);
+                if (wf2 != PP_RB_NIL) n[wf2].color = PP_RB_BLACK;
+                pp_rb_rotate(t, n, x_parent, far);
+                break;
             }
         }
         if (x != PP_RB_NIL) n[x].color = PP_RB_BLACK;

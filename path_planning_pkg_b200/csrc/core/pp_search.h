@@ -144,11 +144,19 @@ struct PPWork
     int        closed_max = 0, open3_max = 0, open2_max = 0;
 };
 
+// one neighbour of the 2D node being expanded, as fetched up front (pp_lazy_astar); 16 B = one shared-memory word quad
+struct
+#if defined(__CUDACC__) || defined(__GNUC__)
+__attribute__((aligned(16)))
+#endif
+PPLazyNb { int cell; float map; unsigned state; float nmf; };
+
 struct PPSmem   // per-warp staging area (shared memory on the device)
 {
     PPSucc succ[PP_MAX_SUCC];
     float  cand[PP_MAX_SUCC * 4];        // Dubins candidate lengths [successor][type] (also APF accumulators)
     int    near_idx[PP_NEAR_CAP];
+    PPLazyNb lazy_nb[8];                 // neighbour staging of the control lane's lazy 2D A* (pp_lazy_astar)
     // staged Dubins evaluation (pp_dubins_h2_warp)
     float  d_centre[PP_MAX_SUCC * 4];    // start circle centres per successor: right x, y, left x, y
     float  d_theta[PP_MAX_SUCC * 4];     // atan2f of the centre offset per (successor, type)
@@ -219,6 +227,9 @@ PP_HD float pp_h2d(const PPConsts& C, int i, int j)
     return sqrtf(dx * dx + dy * dy);
 }
 
+// out-of-line copy for the sites that run once per lazy search (the per-neighbour one stays inline)
+PP_HD_NOINLINE_FN float pp_h2d_call(const PPConsts& C, int i, int j) { return pp_h2d(C, i, j); }
+
 struct PPLazy
 {
     PPRbTree<PPNode2> open;
@@ -255,7 +266,7 @@ PP_HD void pp_lazy_touch(const PPConsts& C, PPWork& wk, int cell)
     if (!(st & PP_CS_TOUCHED))
     {
         wk.nm_g[cell] = 0.0f;
-        wk.nm_f[cell] = pp_h2d(C, cell / C.N, cell % C.N);
+        wk.nm_f[cell] = pp_h2d_call(C, cell / C.N, cell % C.N);
         wk.cell_state[cell] = st | PP_CS_TOUCHED;
     }
 }
@@ -290,7 +301,7 @@ PP_HD_NOINLINE_FN bool pp_lazy_insert(PPLazy& L, int cell, float g, float f, int
 // AStar::find_path(i, j) + a_star_search (AStar.cpp:100-113, :118-186) on per-query scratch that
 // starts in the freshly-constructed state (g = 0, f = Euclidean h, nothing visited).
 PP_HD_NOINLINE_FN float pp_lazy_astar(const PPConsts& C, const float* map, const PPFrame& F, PPWork& wk,
-                                   PPLazy& L, int ci, int cj)
+                                   PPLazy& L, int ci, int cj, PPLazyNb* nbs)
 {
     const int N = C.N;
     int cell = ci * N + cj;
@@ -298,7 +309,7 @@ PP_HD_NOINLINE_FN float pp_lazy_astar(const PPConsts& C, const float* map, const
     if (st & PP_CS_VISITED) return wk.nm_f[cell];
 
     // Grid2D::set_start_node_grid -> soft_reset (Node2D.cpp:34-39)
-    float h0 = pp_h2d(C, ci, cj);
+    float h0 = pp_h2d_call(C, ci, cj);
     wk.nm_g[cell] = 0.0f;
     wk.nm_f[cell] = h0;
     wk.cell_state[cell] = st | PP_CS_TOUCHED;
@@ -329,72 +340,59 @@ PP_HD_NOINLINE_FN float pp_lazy_astar(const PPConsts& C, const float* map, const
         int pi = c / N, pj = c - pi * N;
         if (c == goal_cell)
         {
-            float total = cg + pp_h2d(C, pi, pj);   // copy's _cost_f = g + h
+            float total = cg + pp_h2d_call(C, pi, pj);   // copy's _cost_f = g + h
             pp_lazy_update_visited(C, wk, total, c);
             return total;
         }
 
-        // Grid2D::get_neighbors (Grid2D.cpp:72-96): all valid neighbours first, in action order
-        // The 8 neighbours are distinct cells whose per-cell words nobody else touches while this node is expanded,
-        // so the map value, cell_state and node_map f of all of them are fetched up front as 24 independent loads
-        // (one memory round trip instead of 24 dependent ones); they are consumed in action order below.
-        int      nb_all[8];
-        float    nb_map[8], nb_f[8];
-        unsigned nb_cs[8];
+        // Grid2D::get_neighbors (Grid2D.cpp:72-96): all valid neighbours first, in action order.
+        // The 8 neighbours are distinct cells whose per-cell words nobody else touches while this node is expanded, so the
+        // map value, cell_state and node_map f of all of them are fetched up front as 24 independent loads (one memory round
+        // trip instead of 24 dependent ones) into the staging records `nbs`; they are consumed in action order by ONE rolled
+        // loop.  (Until round 2 the consuming loop ran over register arrays, which made the compiler unroll it 8 times: 46 KB
+        // of SASS for this function, more than the SM's 32 KB instruction cache, in a kernel that is bound by instruction
+        // fetch at bench occupancy -- DESIGN.md section 7.)
 #pragma unroll
         for (int k = 0; k < 8; k++)
         {
-            int i = pi + C.act_di[k], j = pj + C.act_dj[k];
-            nb_all[k] = (k < C.n_act2d && i > -1 && i < N && j > -1 && j < N) ? i * N + j : -1;
+            const int i = pi + C.act_di[k], j = pj + C.act_dj[k];
+            const bool in = (k < C.n_act2d && i > -1 && i < N && j > -1 && j < N);
+            const int a = in ? i * N + j : c;                // harmless in-bounds address for the masked-out slots
+            PPLazyNb e;
+            e.cell = in ? a : -1; e.map = map[a]; e.state = wk.cell_state[a]; e.nmf = wk.nm_f[a];
+            nbs[k] = e;
         }
-#pragma unroll
+#pragma unroll 1
         for (int k = 0; k < 8; k++)
         {
-            int a = nb_all[k] < 0 ? c : nb_all[k];          // harmless in-bounds address for the masked-out slots
-            nb_map[k] = map[a]; nb_cs[k] = wk.cell_state[a]; nb_f[k] = wk.nm_f[a];
-        }
-        int      nb_cell[8];
-        float    nb_cost[8], nb_nmf[8];
-        unsigned nb_state[8];
-        int      nn = 0;
-#pragma unroll
-        for (int k = 0; k < 8; k++)
-            if (nb_all[k] >= 0 && nb_map[k] < C.log_thr)
-            {
-                nb_cell[nn] = nb_all[k]; nb_cost[nn] = C.act_cost[k]; nb_state[nn] = nb_cs[k]; nb_nmf[nn] = nb_f[k]; nn++;
-            }
-        for (int q = 0; q < nn; q++)
-        {
-            int nb = nb_cell[q];
-            float w = nb_cost[q];
-            unsigned ns = nb_state[q];
+            const PPLazyNb e = nbs[k];
+            if (e.cell < 0 || !(e.map < C.log_thr)) continue;
+            const int nb = e.cell;
+            const float w = C.act_cost[k];
+            const unsigned ns = e.state;
             if (ns & PP_CS_VISITED)
             {
-                float total = nb_nmf[q] + cg + w;
+                float total = e.nmf + cg + w;
                 pp_lazy_update_visited(C, wk, total, c);
                 return total;
             }
             if ((ns & PP_CS_STAMP) == sid) continue;    // in the closed set of this search
-            float cur_f = nb_nmf[q];
+            const float hn = pp_h2d(C, pi + C.act_di[k], pj + C.act_dj[k]);
+            float cur_f = e.nmf;
             if (!(ns & PP_CS_TOUCHED))                  // pp_lazy_touch: first use this query -> g = 0, f = h
             {
-                cur_f = pp_h2d(C, nb / N, nb % N);
+                cur_f = hn;
                 wk.nm_g[nb] = 0.0f; wk.nm_f[nb] = cur_f;
                 wk.cell_state[nb] = ns | PP_CS_TOUCHED;
             }
-            PPKey k; k.key = (unsigned)nb; k.f = cur_f;          // node_map's current (possibly stale) f
-            int it_node = L.open.find(k);
-            float newg = cg + w;
-            if (it_node == PP_RB_NIL)
+            PPKey key; key.key = (unsigned)nb; key.f = cur_f;    // node_map's current (possibly stale) f
+            const int it_node = L.open.find(key);
+            const float newg = cg + w;
+            bool ins = (it_node == PP_RB_NIL);
+            if (!ins && newg < L.open.n[it_node].g) { L.open.erase(it_node); ins = true; }
+            if (ins)
             {
-                float nf = newg + pp_h2d(C, nb / N, nb % N);
-                wk.nm_g[nb] = newg; wk.nm_f[nb] = nf;
-                if (!pp_lazy_insert(L, nb, newg, nf, c)) return FLT_MAX;
-            }
-            else if (newg < L.open.n[it_node].g)
-            {
-                L.open.erase(it_node);
-                float nf = newg + pp_h2d(C, nb / N, nb % N);
+                const float nf = newg + hn;
                 wk.nm_g[nb] = newg; wk.nm_f[nb] = nf;
                 if (!pp_lazy_insert(L, nb, newg, nf, c)) return FLT_MAX;
             }
@@ -470,6 +468,7 @@ PP_HD_NOINLINE_FN float pp_apf_sum(const W& w, const PPConsts& C, const float* a
                        float x, float y, float heading)
 {
     float acc = 0.0f;
+#pragma unroll 1
     for (int base = 0; base < n; base += W::LANES)
     {
         int q = base + w.lane();
@@ -485,10 +484,7 @@ PP_HD_NOINLINE_FN float pp_apf_sum(const W& w, const PPConsts& C, const float* a
         unsigned m = w.ballot(term != 0.0f);
         while (m)
         {
-            int src = 0;
-            unsigned t = m;
-            while (!(t & 1u)) { t >>= 1; src++; }
-            acc = acc + w.shfl(term, src);
+            acc = acc + w.shfl(term, pp_ctz(m));
             m &= m - 1;
         }
     }
@@ -506,6 +502,7 @@ PP_HD_NOINLINE_FN void pp_expand_warp(const W& w, const PPConsts& C, const float
     const int n_succ_max = 2 * C.A + 1;
     int start_index = pcurv - C.A;
     if (start_index < 0) start_index = 0;
+#pragma unroll 1
     for (int s = lane; s < n_succ_max; s += W::LANES)
     {
         PPSucc o; o.ok = 0;
@@ -517,6 +514,7 @@ PP_HD_NOINLINE_FN void pp_expand_warp(const W& w, const PPConsts& C, const float
     }
     // obstacles that can reach any successor (successors lie within ts of the parent), order kept
     int n_near = 0;
+#pragma unroll 1
     for (int base = 0; base < G.K; base += W::LANES)
     {
         int k = base + lane;
@@ -530,12 +528,10 @@ PP_HD_NOINLINE_FN void pp_expand_warp(const W& w, const PPConsts& C, const float
         unsigned m = w.ballot(nearp);
         if (nearp)
         {
-            int pos = n_near;
-            unsigned below = m & w.lanemask_lt();
-            while (below) { pos++; below &= below - 1; }
+            const int pos = n_near + pp_popc(m & w.lanemask_lt());
             if (pos < PP_NEAR_CAP) sm.near_idx[pos] = k;
         }
-        while (m) { n_near++; m &= m - 1; }
+        n_near += pp_popc(m);
     }
     const bool near_overflow = (n_near > PP_NEAR_CAP);
     w.sync();
@@ -543,6 +539,7 @@ PP_HD_NOINLINE_FN void pp_expand_warp(const W& w, const PPConsts& C, const float
     if (near_overflow)
     {
         // rare: more obstacles in reach than the staging list holds -> one successor at a time over the full list
+#pragma unroll 1
         for (int s = 0; s < n_succ_max; s++)
         {
             if (!sm.succ[s].ok) continue;
@@ -555,9 +552,11 @@ PP_HD_NOINLINE_FN void pp_expand_warp(const W& w, const PPConsts& C, const float
     {
         // one lane per (successor, near obstacle) pair, successor-major so that a successor's terms are met in
         // obstacle order; sm.cand[s] accumulates successor s's field (std::accumulate order, Grid3D.cpp:226)
+#pragma unroll 1
         for (int s = lane; s < n_succ_max; s += W::LANES) sm.cand[s] = 0.0f;
         w.sync();
         const int n_pairs = n_succ_max * n_near;
+#pragma unroll 1
         for (int base = 0; base < n_pairs; base += W::LANES)
         {
             int q = base + lane;
@@ -578,9 +577,7 @@ PP_HD_NOINLINE_FN void pp_expand_warp(const W& w, const PPConsts& C, const float
             unsigned m = w.ballot(term != 0.0f);
             while (m)       // non-zero terms one by one, in pair order; zero terms are skipped (x + 0 == x)
             {
-                int src = 0;
-                unsigned t = m;
-                while (!(t & 1u)) { t >>= 1; src++; }
+                const int src = pp_ctz(m);
                 float tv = w.shfl(term, src);
                 int ts = w.shfl(s, src);
                 if (lane == 0) sm.cand[ts] = sm.cand[ts] + tv;
@@ -588,6 +585,7 @@ PP_HD_NOINLINE_FN void pp_expand_warp(const W& w, const PPConsts& C, const float
             }
         }
         w.sync();
+#pragma unroll 1
         for (int s = lane; s < n_succ_max; s += W::LANES)
             if (sm.succ[s].ok) sm.succ[s].g = sm.succ[s].g + sm.cand[s];
     }
@@ -607,14 +605,17 @@ PP_HD_NOINLINE_FN void pp_dubins_h2_warp(const W& w, const PPConsts& C, const PP
     const int lane = w.lane();
     const int n = 2 * C.A + 1;
     const float r = C.r_min;
+#pragma unroll 1
     for (int s = lane; s < n; s += W::LANES)                                   // stage A
         if (sm.succ[s].ok)
         {
-            float sn = pp_sinf(sm.succ[s].heading), cs = pp_cosf(sm.succ[s].heading);
+            float sn, cs;
+            pp_sincosf(sm.succ[s].heading, sn, cs);
             sm.d_centre[4 * s] = sm.succ[s].x + r * sn;     sm.d_centre[4 * s + 1] = sm.succ[s].y - r * cs;
             sm.d_centre[4 * s + 2] = sm.succ[s].x - r * sn; sm.d_centre[4 * s + 3] = sm.succ[s].y + r * cs;
         }
     w.sync();
+#pragma unroll 1
     for (int q = lane; q < 6 * n; q += W::LANES)                               // stage B
     {
         int s, type;
@@ -627,16 +628,20 @@ PP_HD_NOINLINE_FN void pp_dubins_h2_warp(const W& w, const PPConsts& C, const PP
         else sm.d_acos[q - 4 * n] = pp_acosf(pp_dubins_acos_arg(r, csx, csy, cgx, cgy));
     }
     w.sync();
+#pragma unroll 1
     for (int q = lane; q < 4 * n; q += W::LANES)                               // stage C
     {
         int s = q >> 2, type = 1 + ((q >> 1) & 1), which = q & 1;
         if (!sm.succ[s].ok) continue;
         float t1 = pp_dubins_theta_t1(type, sm.d_acos[2 * s + (type - 1)], sm.d_theta[4 * s + type]);
         float ang = which ? pp_dubins_p2(type, t1) : t1;
-        sm.d_sin[q] = pp_sinf(ang);
-        sm.d_cos[q] = pp_cosf(ang);
+        float sa, ca;
+        pp_sincosf(ang, sa, ca);
+        sm.d_sin[q] = sa;
+        sm.d_cos[q] = ca;
     }
     w.sync();
+#pragma unroll 1
     for (int q = lane; q < 4 * n; q += W::LANES)                               // stage D
     {
         int s = q >> 2, type = q & 3;
@@ -676,6 +681,7 @@ PP_HD void pp_coop_copy8(const W& w, void* dst, const void* src, size_t bytes)
     const unsigned long long* s = (const unsigned long long*)src;
     unsigned long long* d = (unsigned long long*)dst;
     const size_t words = bytes / 8;
+#pragma unroll 1
     for (size_t q = w.lane(); q < words; q += W::LANES) d[q] = s[q];
 }
 
@@ -954,7 +960,8 @@ PP_HD_NOINLINE_FN void pp_search_exact(const W& w, const PPConsts& C, const floa
     // goal circle centres (Dubins.cpp:29-33): the same for every heuristic evaluation of this query
     PPDubinsGoal gc;
     {
-        float sg = pp_sinf(F.goal_h), cg = pp_cosf(F.goal_h);
+        float sg, cg;
+        pp_sincosf(F.goal_h, sg, cg);
         gc.grx = F.goal_x + C.r_min * sg; gc.gry = F.goal_y - C.r_min * cg;
         gc.glx = F.goal_x - C.r_min * sg; gc.gly = F.goal_y + C.r_min * cg;
     }
@@ -1070,6 +1077,7 @@ PP_HD_NOINLINE_FN void pp_search_exact(const W& w, const PPConsts& C, const floa
         PP_PROF_MARK(2)
         // closed-set membership of all successors at once (one probe per lane; the closed set only changes at a
         // pop, so this equals the per-successor `_closed_set.find(node)` of HybridAStar.cpp:162); members drop out
+#pragma unroll 1
         for (int s = lane; s < n_succ_max; s += W::LANES)
             if (sm.succ[s].ok)
             {
@@ -1149,7 +1157,7 @@ PP_HD_NOINLINE_FN void pp_search_exact(const W& w, const PPConsts& C, const floa
             {
                 if (lane == 0)
                 {
-                    float h1 = pp_lazy_astar(C, G.map, F, wk, S.lazy, sc.ci, sc.cj);
+                    float h1 = pp_lazy_astar(C, G.map, F, wk, S.lazy, sc.ci, sc.cj, sm.lazy_nb);
                     float h2 = sm.cand[4 * s];
                     for (int t = 1; t < 4; t++) if (sm.cand[4 * s + t] < h2) h2 = sm.cand[4 * s + t];
                     f = sc.g + ((h1 < h2) ? h2 : h1);
@@ -1178,6 +1186,7 @@ PP_HD_NOINLINE_FN void pp_search_exact(const W& w, const PPConsts& C, const floa
         int abort = 0;
         if (lane == 0)
         {
+#pragma unroll 1
             for (int s = 0; s < n_succ_max && !abort; s++)
             {
                 const PPSucc& sc = sm.succ[s];
@@ -1191,7 +1200,7 @@ PP_HD_NOINLINE_FN void pp_search_exact(const W& w, const PPConsts& C, const floa
                 PP_PROF_MARK(5)
                 if (do_insert)
                 {
-                    float h1 = pp_lazy_astar(C, G.map, F, wk, S.lazy, sc.ci, sc.cj);
+                    float h1 = pp_lazy_astar(C, G.map, F, wk, S.lazy, sc.ci, sc.cj, sm.lazy_nb);
                     PP_PROF_MARK(6)
                     float h2 = sm.cand[4 * s];
                     for (int t = 1; t < 4; t++) if (sm.cand[4 * s + t] < h2) h2 = sm.cand[4 * s + t];

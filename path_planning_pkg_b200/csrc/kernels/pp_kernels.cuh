@@ -680,9 +680,10 @@ __global__ void __launch_bounds__(32) pp_lazy_astar_kernel(const __grid_constant
     if (lane == 0)
     {
         PPLazy L;
+        PPLazyNb nbs[8];
         L.open.init(wk.open2, wk.open2_cap);
         L.search_id = restart ? 0u : *sid_io; L.status = 0; L.n_searches = 0; L.n_pops = 0;
-        for (int k = 0; k < n; k++) out[k] = pp_lazy_astar(a.C, G.map, G.frame, wk, L, ij[2 * k], ij[2 * k + 1]);
+        for (int k = 0; k < n; k++) out[k] = pp_lazy_astar(a.C, G.map, G.frame, wk, L, ij[2 * k], ij[2 * k + 1], nbs);
         *status = L.status;
         *sid_io = L.search_id;
     }

@@ -23,7 +23,7 @@ static inline bool same(float a, float b)
     return pp_g_f2u(a) == pp_g_f2u(b);
 }
 
-struct Job { uint64_t lo, hi, stride; uint64_t bad[5]; uint64_t n; uint32_t first_bad[5]; };
+struct Job { uint64_t lo, hi, stride; uint64_t bad[6]; uint64_t n; uint32_t first_bad[6]; };
 
 static void* run_exhaustive(void* p)
 {
@@ -39,6 +39,9 @@ static void* run_exhaustive(void* p)
         if (!same(ra, pp_g_atanf(x))) { if (!j->bad[2]++) j->first_bad[2] = (uint32_t)u; }
         if (!same(rk, pp_g_acosf(x))) { if (!j->bad[3]++) j->first_bad[3] = (uint32_t)u; }
         if (!same(ss, rs) || !same(cc, rc)) { if (!j->bad[4]++) j->first_bad[4] = (uint32_t)u; }
+        float ps, pc;
+        pp_g_sincosf(x, &ps, &pc);             // the shared-reduction form the search kernel calls
+        if (!same(ps, rs) || !same(pc, rc)) { if (!j->bad[5]++) j->first_bad[5] = (uint32_t)u; }
         j->n++;
     }
     return 0;
@@ -63,15 +66,15 @@ int main(int argc, char** argv)
             jobs[t].lo = span * t; jobs[t].hi = span * (t + 1); jobs[t].stride = stride;
             pthread_create(&th[t], 0, run_exhaustive, &jobs[t]);
         }
-        uint64_t bad[5] = {0, 0, 0, 0, 0}, n = 0; uint32_t fb[5] = {0, 0, 0, 0, 0};
+        uint64_t bad[6] = {0, 0, 0, 0, 0, 0}, n = 0; uint32_t fb[6] = {0, 0, 0, 0, 0, 0};
         for (int t = 0; t < T; t++)
         {
             pthread_join(th[t], 0);
-            for (int k = 0; k < 5; k++) { if (jobs[t].bad[k] && !bad[k]) fb[k] = jobs[t].first_bad[k]; bad[k] += jobs[t].bad[k]; }
+            for (int k = 0; k < 6; k++) { if (jobs[t].bad[k] && !bad[k]) fb[k] = jobs[t].first_bad[k]; bad[k] += jobs[t].bad[k]; }
             n += jobs[t].n;
         }
-        const char* names[5] = {"sinf", "cosf", "atanf", "acosf", "sincosf_vs_sinf_cosf"};
-        for (int k = 0; k < 5; k++)
+        const char* names[6] = {"sinf", "cosf", "atanf", "acosf", "sincosf_vs_sinf_cosf", "pp_g_sincosf"};
+        for (int k = 0; k < 6; k++)
         {
             printf("%s checked %llu mismatches %llu", names[k], (unsigned long long)n, (unsigned long long)bad[k]);
             if (bad[k]) { printf(" first 0x%08x", fb[k]); rc = 1; }

@@ -428,7 +428,8 @@ void emu_astar_lazy_batch(void* h, const int* ij, int n, float* out)
         e->lazy_init = true;
     }
     else setup_work(e, wk, 16, 16, 1 << 16, 16);
-    for (int k = 0; k < n; k++) out[k] = pp_lazy_astar(C, e->map.data(), e->fr.F, wk, e->lazy, ij[2 * k], ij[2 * k + 1]);
+    PPLazyNb nbs[8];
+    for (int k = 0; k < n; k++) out[k] = pp_lazy_astar(C, e->map.data(), e->fr.F, wk, e->lazy, ij[2 * k], ij[2 * k + 1], nbs);
 }
 
 void emu_astar_dump(void* h, unsigned char* visited, float* g, float* f)
