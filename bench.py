@@ -445,13 +445,14 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--groups", type=int, default=64)
     ap.add_argument("--starts", type=int, default=64)
-    ap.add_argument("--lanes", type=int, default=10, help="lane contexts the steps are submitted over (1 = one batch at a time).  10: the "
-                                                          "driver's 20 timed steps are two rounds, warm-up + e2e one round; 20 (every timed "
-                                                          "batch in flight at once) measured 9 %% slower, 8 leaves a third round to four lanes")
+    ap.add_argument("--lanes", type=int, default=20, help="lane contexts the steps are submitted over (1 = one batch at a time), never more "
+                                                          "than the timed steps.  With every timed batch in flight each batch's longest "
+                                                          "queries start at once and run beside the bulk of all the others; with fewer lanes "
+                                                          "a lane's next batch waits for the drain of its previous one")
     ap.add_argument("--cpu-sample", type=int, default=0, help="queries in the cpu_baseline sample (0 = 8 per host thread, 64..256)")
     ap.add_argument("--max-slots", type=int, default=0)
-    ap.add_argument("--e2e-steps", type=int, default=0, help="timed end-to-end steps (0 = lanes - warmup, at least 3: warm-up + e2e fill "
-                                                             "every lane once)")
+    ap.add_argument("--e2e-steps", type=int, default=0, help="timed end-to-end steps (0 = lanes / 2 at N = 1, lanes / 4 at N > 1 where the "
+                                                             "slowest rank's drain sets the wall clock; at least 3)")
     ap.add_argument("--budget-s", type=float, default=555.0, help="wall-clock budget: optional blocks are shortened / skipped beyond it")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-kpop", action="store_true")
@@ -510,12 +511,20 @@ def main():
     pipe = Pipeline(ctx, lanes, q, opts, pp)
     pipe.set_budget(int(free_b * 0.80 / lanes))
 
-    # ---- warm-up + end to end through the C ABI, one continuous stream of W + E batches: pinned host queries in, results + paths +
-    # curvature out, EVERY step.  The first W steps are the warm-up (cold kernels, cold arenas); the e2e clock starts when step W is
-    # submitted -- the pipeline is full by then -- and stops when the last batch has been collected (full drain included). ----
-    e2e_steps = args.e2e_steps if args.e2e_steps > 0 else max(3, min(args.steps, lanes - args.warmup))
+    # ---- warm-up, then end to end through the C ABI: pinned host queries in, results + paths + curvature out, EVERY step.  The W
+    # warm-up steps run the same way (cold kernels, cold arenas, pinned buffers touched) and are collected completely before the
+    # e2e clock starts, so the e2e region holds exactly its own E batches: ramp-up, bulk and the full drain of the last one.
+    # (Until this revision warm-up and e2e were one stream and the clock started while the warm-up batches were still running:
+    # the region did the work of W + E batches and was credited with E.) ----
+    if args.e2e_steps > 0:
+        e2e_steps = args.e2e_steps
+    else:
+        e2e_steps = max(3, min(args.steps, lanes // 2 if world == 1 else lanes // 4))
     barrier()
-    t_mark = pipe.run(args.warmup + e2e_steps, True, mark_at=args.warmup)
+    pipe.run(args.warmup, True)
+    barrier()
+    t_mark = time.perf_counter()
+    pipe.run(e2e_steps, True)
     torch.cuda.synchronize()
     e2e_ms = (time.perf_counter() - t_mark) * 1e3
     r2 = pipe.results(0).copy()
@@ -534,7 +543,7 @@ def main():
     h2d, d2h = pipe.h2d, pipe.d2h
     # one batch alone on an idle GPU (latency of a step without overlap), when the budget allows
     lat_ms = float("nan")
-    if in_time(margin=150.0):
+    if world == 1 and in_time(margin=150.0):        # N > 1: the slowest rank's longest query (80 s and more) is not worth the wall clock
         lat_ms, _ = timed(ctx, barrier, lambda: pipe.run(1, False))
     pipe.close()
 
@@ -573,8 +582,8 @@ def main():
                        "map_build_s": map_build_s, "timed_region_wall_s": value_wall},
             "e2e": {"value": e2e_value, "unit": "expansions/s", "steps": e2e_steps, "ms_per_step": max_e2e_ms / e2e_steps,
                     "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
-                    "timed": "host clock from the submission of the first timed batch (pipeline already full with the warm-up batches) to "
-                             "the collection of the last one"},
+                    "timed": "host clock from the submission of the first e2e batch (GPU idle, warm-up collected) to the collection of "
+                             "the last one: ramp-up and the full drain of the longest query are inside the region"},
             "gpu_launches": int(timed_launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": committed_traffic("pp_search_kernel"), "kernel": "pp_search_kernel", "peak_source": peak_src,

@@ -339,16 +339,24 @@ PP_HD bool pp_rb_insert_pos_walk(const PPRbPool n, const PPKey& k, int& p, bool&
     return false;
 }
 
-PP_HD_NOINLINE_FN int pp_rb_find(const PPRbPool n, const PPKey& k)
+// Out-of-line entry points of the two walks.  Key in, position out, all in registers: a by-reference key and by-reference results
+// would make each call a round trip through the caller's stack frame (local memory) on the latency-critical path of the control lane.
+PP_HD_NOINLINE_FN int pp_rb_find(const PPRbPool n, unsigned key, float f)
 {
+    PPKey k; k.key = key; k.f = f;
     int np;
     return pp_rb_find_walk(n, k, (int*)0, 0, np);
 }
 
-PP_HD_NOINLINE_FN bool pp_rb_insert_pos(const PPRbPool n, const PPKey& k, int& p, bool& left)
+// returns the parent in the low word and, in the high word, 1 = attach as left child, 0 = as right child, -1 = an equivalent
+// element exists (the insert is dropped)
+PP_HD_NOINLINE_FN long long pp_rb_insert_pos(const PPRbPool n, unsigned key, float f)
 {
-    int np;
-    return pp_rb_insert_pos_walk(n, k, p, left, (int*)0, 0, np);
+    PPKey k; k.key = key; k.f = f;
+    int np, p = PP_RB_NIL; bool left = false;
+    const bool ins = pp_rb_insert_pos_walk(n, k, p, left, (int*)0, 0, np);
+    const int how = ins ? (left ? 1 : 0) : -1;
+    return (long long)(((unsigned long long)(unsigned)how << 32) | (unsigned long long)(unsigned)p);
 }
 
 // Typed view: `Node` starts with a PPRbHead-compatible prefix (PPWalk w; int parent, color;) followed by its payload.
@@ -388,8 +396,14 @@ struct PPRbTree : PPRbState
 
     PP_HD void insert_and_rebalance(bool insert_left, int x, int p) { pp_rb_insert_and_rebalance(*this, pool(), insert_left, x, p); }
     PP_HD void erase(int z) { pp_rb_erase(*this, pool(), z); }
-    PP_HD int  find(const PPKey& k) const { return pp_rb_find(pool(), k); }
-    PP_HD bool insert_pos(const PPKey& k, int& p, bool& left) const { return pp_rb_insert_pos(pool(), k, p, left); }
+    PP_HD int  find(const PPKey& k) const { return pp_rb_find(pool(), k.key, k.f); }
+    PP_HD bool insert_pos(const PPKey& k, int& p, bool& left) const
+    {
+        const long long r = pp_rb_insert_pos(pool(), k.key, k.f);
+        const int how = (int)(r >> 32);
+        p = (int)(unsigned)(r & 0xffffffffll); left = (how == 1);
+        return how >= 0;
+    }
 };
 
 #endif

@@ -305,14 +305,21 @@ PP_HD_NOINLINE_FN float pp_lazy_astar(const PPConsts& C, const float* map, const
 {
     const int N = C.N;
     int cell = ci * N + cj;
-    unsigned st = wk.cell_state[cell];
-    if (st & PP_CS_VISITED) return wk.nm_f[cell];
+    // the per-cell arrays, held in registers across the tree calls below (wk lives in the caller's stack frame: every use
+    // through the reference would be a local-memory load first)
+    unsigned* const cell_state = wk.cell_state;
+    float* const nm_g = wk.nm_g;
+    float* const nm_f = wk.nm_f;
+    float* const cl_g = wk.cl_g;
+    int* const cl_prev = wk.cl_prev;
+    unsigned st = cell_state[cell];
+    if (st & PP_CS_VISITED) return nm_f[cell];
 
     // Grid2D::set_start_node_grid -> soft_reset (Node2D.cpp:34-39)
     float h0 = pp_h2d_call(C, ci, cj);
-    wk.nm_g[cell] = 0.0f;
-    wk.nm_f[cell] = h0;
-    wk.cell_state[cell] = st | PP_CS_TOUCHED;
+    nm_g[cell] = 0.0f;
+    nm_f[cell] = h0;
+    cell_state[cell] = st | PP_CS_TOUCHED;
 
     unsigned sid = ++L.search_id;
     L.n_searches++;
@@ -325,14 +332,14 @@ PP_HD_NOINLINE_FN float pp_lazy_astar(const PPConsts& C, const float* map, const
         int it = L.open.begin();
         int c = (int)L.open.n[it].w.key;
         float cg;
-        unsigned cs = wk.cell_state[c];
-        if ((cs & PP_CS_STAMP) == sid) cg = wk.cl_g[c];   // re-pop: unordered_set::insert returns the old copy
+        unsigned cs = cell_state[c];
+        if ((cs & PP_CS_STAMP) == sid) cg = cl_g[c];   // re-pop: unordered_set::insert returns the old copy
         else
         {
             cg = L.open.n[it].g;
-            wk.cl_g[c] = cg;
-            wk.cl_prev[c] = L.open.n[it].prev;
-            wk.cell_state[c] = (cs & ~PP_CS_STAMP) | sid;
+            cl_g[c] = cg;
+            cl_prev[c] = L.open.n[it].prev;
+            cell_state[c] = (cs & ~PP_CS_STAMP) | sid;
         }
         L.open.erase(it);
         L.n_pops++;
@@ -359,7 +366,7 @@ PP_HD_NOINLINE_FN float pp_lazy_astar(const PPConsts& C, const float* map, const
             const bool in = (k < C.n_act2d && i > -1 && i < N && j > -1 && j < N);
             const int a = in ? i * N + j : c;                // harmless in-bounds address for the masked-out slots
             PPLazyNb e;
-            e.cell = in ? a : -1; e.map = map[a]; e.state = wk.cell_state[a]; e.nmf = wk.nm_f[a];
+            e.cell = in ? a : -1; e.map = map[a]; e.state = cell_state[a]; e.nmf = nm_f[a];
             nbs[k] = e;
         }
 #pragma unroll 1
@@ -382,8 +389,8 @@ PP_HD_NOINLINE_FN float pp_lazy_astar(const PPConsts& C, const float* map, const
             if (!(ns & PP_CS_TOUCHED))                  // pp_lazy_touch: first use this query -> g = 0, f = h
             {
                 cur_f = hn;
-                wk.nm_g[nb] = 0.0f; wk.nm_f[nb] = cur_f;
-                wk.cell_state[nb] = ns | PP_CS_TOUCHED;
+                nm_g[nb] = 0.0f; nm_f[nb] = cur_f;
+                cell_state[nb] = ns | PP_CS_TOUCHED;
             }
             PPKey key; key.key = (unsigned)nb; key.f = cur_f;    // node_map's current (possibly stale) f
             const int it_node = L.open.find(key);
@@ -393,7 +400,7 @@ PP_HD_NOINLINE_FN float pp_lazy_astar(const PPConsts& C, const float* map, const
             if (ins)
             {
                 const float nf = newg + hn;
-                wk.nm_g[nb] = newg; wk.nm_f[nb] = nf;
+                nm_g[nb] = newg; nm_f[nb] = nf;
                 if (!pp_lazy_insert(L, nb, newg, nf, c)) return FLT_MAX;
             }
         }

@@ -127,3 +127,30 @@ def test_dubins_field_vs_reference():
     f2, _ = ctx.field3d(use_h2d=True)
     f1, _ = ctx.field3d(use_h2d=False)
     assert np.array_equal(_bits(f2), _bits(np.maximum(h2d[:, :, None], f1)))
+
+
+def test_dubins_field_c3_full_size_sample():
+    """BASELINE configs[2] at its full size, 2048 x 2048 x 72 = 302 M states: every 64th state (stride 61 over the flat
+    index, so that all heading bins and both grid axes are visited) against Dubins<float>::get_shortest_path_length of the
+    reference arithmetic (port oracle, stock libm).  Bar: 1e-5 relative (north_star), +-2pi branch flips counted."""
+    sc = S.c2_scenario()
+    n = sc["grid_size"]
+    P = orc.make_params(grid_size=n, resolution=sc["resolution"])
+    ctx, port = _ctx(P), orc.port(P)
+    for o in (ctx, port):
+        o.update_goal(sc["goal"], sc["frame_start"])
+    f, ms = ctx.field3d(use_h2d=False)
+    c = port.consts()
+    goal = np.array(list(c.goal_grid), np.float32)
+    prec, res = np.float32(c.precision), np.float32(sc["resolution"])
+    flat = np.arange(0, n * n * 72, 61, dtype=np.int64)
+    ii, jj, bb = flat // (n * 72), (flat // 72) % n, flat % 72
+    head = (-np.pi + (bb.astype(np.float32) * prec).astype(np.float64)).astype(np.float32)
+    starts = np.stack([(ii.astype(np.float32) * res).astype(np.float32), (jj.astype(np.float32) * res).astype(np.float32), head], -1)
+    ref_len, _, _ = port.dubins_length(starts, goal)
+    got = f.reshape(-1)[flat]
+    rel = np.abs(got - ref_len) / np.maximum(ref_len, 1e-6)
+    flips = int((rel > 1e-5).sum())
+    print(f"C3 dubins field: {n}x{n}x72 in {ms:.3f} ms; {len(flat)} sampled states, max rel err (non-flip) "
+          f"{rel[rel <= 1e-5].max():.3g}, +-2pi branch flips {flips}")
+    assert flips <= len(flat) // 1000

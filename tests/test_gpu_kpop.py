@@ -114,3 +114,32 @@ def test_kpop_unreachable_goal_fails_cleanly():
     assert not b["success"] and not res[0]["success"] and res[0]["status"] == 0
     assert int(res[0]["n_pops"]) == b["n_pops"] and b["n_pops"] > 100
     assert np.float32(res[0]["cost"]) == np.finfo(np.float32).max
+
+
+def test_kpop_c5_sample_identical_to_restatement():
+    """BASELINE configs[4] shape (512^2 x 72 clutter maps, k = 32): 4 groups x 16 starts, every query bit-identical to the K-POP
+    restatement (pop sequence, cost, path); the deviation from the unmodified reference is printed (bench.py reports it on its
+    CPU sample as `kpop.cost_vs_reference`)."""
+    groups = [S.c4_group(s, n_starts=16) for s in (1, 2, 3, 4)]
+    P = orc.make_params(grid_size=512, resolution=0.2)
+    ctx = _ctx(P, groups=len(groups))
+    ports, queries, qg = [], [], []
+    for gi, sc in enumerate(groups):
+        port = orc.port(P)
+        S.build_map(port, sc)
+        ctx.update_goal(sc["goal"], sc["frame_start"], group=gi)
+        for _ in range(sc["rounds"]):
+            ctx.update_boxes(sc["boxes"], sc["conf"], S.APF_ADDED_RADIUS, group=gi)
+            ctx.decay(group=gi)
+        qs = S.select_starts(sc, port.get_map(), port.consts().log_threshold, port.set_start)
+        queries += list(qs); qg += [gi] * len(qs); ports.append(port)
+    q = ctx.make_queries(np.array(queries), qg)
+    opts = ctx.make_opts(trace_cap=1 << 18, path_cap=2048, mode=1, kpop=32)
+    res, paths, curv, trace = ctx.find_path_batch(q, opts)
+    fields = [ctx.field2d(g)[0] for g in range(len(groups))]
+    for i in range(len(q)):
+        assert res[i]["status"] == 0
+        b = port_kpop(ports[qg[i]], float(q["vel"][i]), [q["x"][i], q["y"][i], q["heading"][i]], 32, fields[qg[i]])
+        _same(res[i], trace[i], paths[i], curv[i], b)
+    print(f"k=32: {len(q)} C5-shaped queries identical to the K-POP restatement, {int(res['n_pops'].sum())} expansions, "
+          f"success {float(res['success'].mean()):.3f}")
