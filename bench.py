@@ -521,7 +521,20 @@ def main():
     else:
         e2e_steps = max(3, min(args.steps, lanes // 2 if world == 1 else lanes // 4))
     barrier()
+    t_w0 = time.perf_counter()
     pipe.run(args.warmup, True)
+    torch.cuda.synchronize()
+    t_warm = time.perf_counter() - t_w0
+    # wall-clock guard (SCALE runs have a per-N limit): the warm-up just showed what W batches cost on this rank, drain included;
+    # if E more of them plus the K timed steps would not fit the budget, the e2e region shrinks to 3 steps -- on every rank
+    if args.e2e_steps <= 0 and e2e_steps > 3:
+        per_step = t_warm / max(args.warmup, 1)
+        fits = elapsed() + per_step * (e2e_steps + args.steps) + 60.0 < args.budget_s
+        flag = torch.tensor([1.0 if fits else 0.0], device="cuda")
+        if world > 1:
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if flag.item() != 1.0:
+            e2e_steps = 3
     barrier()
     t_mark = time.perf_counter()
     pipe.run(e2e_steps, True)

@@ -103,7 +103,12 @@ struct PPRbState
 struct PPRbPool
 {
     char* base; int stride;
-    PP_HD PPRbHead& operator[](int i) const { return *reinterpret_cast<PPRbHead*>(base + (size_t)i * (size_t)stride); }
+    // unsigned 32 x 32 -> 64-bit product: ONE multiply-add per node address (a signed index costs a sign extension and a second
+    // multiply on the dependent chain of every tree level); PP_RB_NIL is never dereferenced
+    PP_HD PPRbHead& operator[](int i) const
+    {
+        return *reinterpret_cast<PPRbHead*>(base + (unsigned long long)(unsigned)i * (unsigned long long)(unsigned)stride);
+    }
 };
 
 // child `side` of node x: 0 = left, 1 = right (PPWalk starts with {left, right})
