@@ -527,8 +527,10 @@ def main():
     t_warm = time.perf_counter() - t_w0
     # wall-clock guard (SCALE runs have a per-N limit): the warm-up just showed what W batches cost on this rank, drain included;
     # if E more of them plus the K timed steps would not fit the budget, the e2e region shrinks to 3 steps -- on every rank
-    if args.e2e_steps <= 0 and e2e_steps > 3:
-        per_step = t_warm / max(args.warmup, 1)
+    # (N = 1 fits with room to spare: 445 s with 10 e2e steps; the 0.75 is the drain's share of the warm-up, which does not grow
+    # with the number of batches in flight)
+    if args.e2e_steps <= 0 and e2e_steps > 3 and world > 1:
+        per_step = 0.75 * t_warm / max(args.warmup, 1)
         fits = elapsed() + per_step * (e2e_steps + args.steps) + 60.0 < args.budget_s
         flag = torch.tensor([1.0 if fits else 0.0], device="cuda")
         if world > 1:
