@@ -507,9 +507,19 @@ def main():
     hw_slots = 16 * torch.cuda.get_device_properties(local_rank).multi_processor_count
     lane_slots = args.max_slots if args.max_slots > 0 else max(256, min(hw_slots, (2 * hw_slots + lanes - 1) // lanes))
     opts = ctx.make_opts(path_cap=2048, max_slots=lane_slots)
+    # end to end every step uploads its queries, and the upload orders them with a small kernel on the lane's stream: that kernel
+    # needs a warp slot.  With lanes x lane_slots CTAs above what the SMs hold, a freed slot goes to the next waiting search CTA and
+    # the upload waits for a whole lane to drain (the first 10-step e2e region took 145 s instead of 95 s, together with the 2D
+    # fields each fresh lane computed inside it).  So the e2e batches ask for one warp slot per SM less than the GPU holds.
+    sm_count = torch.cuda.get_device_properties(local_rank).multi_processor_count
+
+    def e2e_opts(batches_in_flight):
+        n = args.max_slots if args.max_slots > 0 else max(32, min(lane_slots, (hw_slots - sm_count) // max(1, min(lanes, batches_in_flight))))
+        return n, ctx.make_opts(path_cap=2048, max_slots=n)
     free_b, total_b = torch.cuda.mem_get_info()
     pipe = Pipeline(ctx, lanes, q, opts, pp)
     pipe.set_budget(int(free_b * 0.80 / lanes))
+    pipe.upload_all()       # every lane allocates its pools and computes its groups' 2D fields (launch order) before anything is timed
 
     # ---- warm-up, then end to end through the C ABI: pinned host queries in, results + paths + curvature out, EVERY step.  The W
     # warm-up steps run the same way (cold kernels, cold arenas, pinned buffers touched) and are collected completely before the
@@ -521,6 +531,7 @@ def main():
     else:
         e2e_steps = max(3, min(args.steps, lanes // 2 if world == 1 else lanes // 4))
     barrier()
+    e2e_slots, pipe.opts = e2e_opts(e2e_steps)
     t_w0 = time.perf_counter()
     pipe.run(args.warmup, True)
     torch.cuda.synchronize()
@@ -537,6 +548,7 @@ def main():
             dist.all_reduce(flag, op=dist.ReduceOp.MIN)
         if flag.item() != 1.0:
             e2e_steps = 3
+    e2e_slots, pipe.opts = e2e_opts(e2e_steps)
     barrier()
     t_mark = time.perf_counter()
     pipe.run(e2e_steps, True)
@@ -544,6 +556,7 @@ def main():
     e2e_ms = (time.perf_counter() - t_mark) * 1e3
     r2 = pipe.results(0).copy()
     # ---- device-resident timing (value): exactly K steps, queries already in HBM, CUDA events on the context's stream ----
+    pipe.opts = opts
     pipe.upload_all()
     sampler = ClockSampler(local_rank); sampler.start()
     l0 = sum(l.kernel_launches() for l in pipe.lanes)
@@ -592,7 +605,8 @@ def main():
                                           "shared maps) with one synchronisation at the end: the drain of batch k overlaps batch k+1 "
                                           "(continuous batching); batch_latency_ms = one batch alone on an idle GPU",
                        "pools": "per-query containers start at 8192 closed / 4096 open / 2048 2D-open entries and grow x2 from the lane's arena "
-                                f"(library defaults); {lane_slots} resident queries per lane; retried_queries = re-executions after a capacity miss",
+                                f"(library defaults); {lane_slots} resident queries per lane ({e2e_slots} in the e2e region, which leaves "
+                                "the upload kernels a warp slot per SM); retried_queries = re-executions after a capacity miss",
                        "l2": "per-query scratch (open / closed sets, lazy-A* cache) of the resident queries is tens of GB, far larger than the 126 MB L2",
                        "map_build_s": map_build_s, "timed_region_wall_s": value_wall},
             "e2e": {"value": e2e_value, "unit": "expansions/s", "steps": e2e_steps, "ms_per_step": max_e2e_ms / e2e_steps,

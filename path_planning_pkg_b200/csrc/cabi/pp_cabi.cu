@@ -1288,8 +1288,9 @@ int pp_batch_upload(pp_context* c, const pp_query* q, int n, const pp_search_opt
         for (int k = 0; k < n; k++)
             if (!c->field2d_valid[q[k].group]) { rc = field2d_run(c, q[k].group, nullptr, nullptr); if (rc) return rc; }
         PP_CUDA(c->d_exact_order.ensure((size_t)n));
-        pp_kpop_order_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(c->d_queries.p, nullptr, n, c->d_field2d.p, c->model.C.N, nullptr, 1.0f,
-                                                                      c->d_exact_order.p);
+        // one warp per CTA: fits into a single freed warp slot while other lanes' search kernels occupy the SMs
+        pp_kpop_order_kernel<<<(n + 31) / 32, 32, 0, c->stream>>>(c->d_queries.p, nullptr, n, c->d_field2d.p, c->model.C.N, nullptr, 1.0f,
+                                                                   c->d_exact_order.p);
         c->launches += 1;
         PP_CUDA(cudaGetLastError());
         c->exact_order_valid = true;

@@ -298,20 +298,23 @@ __device__ __forceinline__ float pp_kpop_order_key(const PPQuery& Q, const float
     return k * (gc > 0.0f ? gc : unknown_cost);
 }
 
+// Any block size up to 256 threads.  The EXACT-mode upload launches it with ONE warp per CTA: while other lanes' search kernels
+// fill the GPU a freed warp slot is all there is, and a 256-thread CTA would wait for eight of them on one SM.
 __global__ void __launch_bounds__(256) pp_kpop_order_kernel(const PPQuery* queries, const int* qmap, int n, const float* field2d,
                                                             int N, const float* group_cost, float unknown_cost, int* order)
 {
     __shared__ float s_key[256];
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int B = (int)blockDim.x;
+    const int i = blockIdx.x * B + threadIdx.x;
     const float ki = (i < n) ? pp_kpop_order_key(queries[qmap ? qmap[i] : i], field2d, N, group_cost, unknown_cost) : 0.0f;
     int rank = 0;
-    for (int base = 0; base < n; base += 256)                          // tiles of 256 keys staged in shared memory
+    for (int base = 0; base < n; base += B)                            // tiles of B keys staged in shared memory
     {
         const int j = base + threadIdx.x;
         __syncthreads();
         s_key[threadIdx.x] = (j < n) ? pp_kpop_order_key(queries[qmap ? qmap[j] : j], field2d, N, group_cost, unknown_cost) : -1.0f;
         __syncthreads();
-        const int m = min(256, n - base);
+        const int m = min(B, n - base);
         for (int t = 0; t < m; t++)
         {
             const float kj = s_key[t];
