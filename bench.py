@@ -136,17 +136,20 @@ def committed_traffic(kernel):
 class Pipeline:
     """K independent batches over S lane contexts: submit round-robin, collect a lane's previous batch before reusing it."""
 
-    def __init__(self, ctx, lanes, q, opts, pp):
+    def __init__(self, ctx, lanes, q, opts, pp, fetch_lanes=None):
+        """fetch_lanes: how many lanes (the first ones) ever run end-to-end steps; only those get pinned host buffers for the results
+        (134 MB per lane at C4 size -- 20 lanes x 8 ranks would pin 21 GB for buffers the device-resident steps never touch)."""
         import torch
         self.pp, self.ctx, self.q, self.opts, self.n = pp, ctx, q, opts, len(q)
         self.lanes = [ctx] + [ctx.create_lane() for _ in range(max(lanes, 1) - 1)]
         self.busy = [False] * len(self.lanes)
         self.kernel_ms = []
         pc = opts.path_cap
+        n_f = len(self.lanes) if fetch_lanes is None else max(1, min(len(self.lanes), int(fetch_lanes)))
         self.hq = torch.from_numpy(q.view(np.uint8).copy()).pin_memory()
-        self.hres = [torch.zeros(self.n * pp._cabi.RESULT_DT.itemsize, dtype=torch.uint8).pin_memory() for _ in self.lanes]
-        self.hpath = [torch.zeros(self.n * pc * 3, dtype=torch.float32).pin_memory() for _ in self.lanes]
-        self.hcurv = [torch.zeros(self.n * pc, dtype=torch.float32).pin_memory() for _ in self.lanes]
+        self.hres = [torch.zeros(self.n * pp._cabi.RESULT_DT.itemsize, dtype=torch.uint8).pin_memory() for _ in range(n_f)]
+        self.hpath = [torch.zeros(self.n * pc * 3, dtype=torch.float32).pin_memory() for _ in range(n_f)]
+        self.hcurv = [torch.zeros(self.n * pc, dtype=torch.float32).pin_memory() for _ in range(n_f)]
         self.h2d = int(q.nbytes)
         self.d2h = int(self.hres[0].numel() + self.hpath[0].numel() * 4 + self.hcurv[0].numel() * 4)
 
@@ -162,6 +165,8 @@ class Pipeline:
         l = self.lanes[i]
         self.kernel_ms.append(l.batch_wait())
         if e2e:
+            if i >= len(self.hres):
+                raise RuntimeError(f"lane {i} has no host buffers (fetch_lanes = {len(self.hres)})")
             rc = l.lib.pp_batch_fetch(l.h, C.c_void_p(self.hres[i].data_ptr()), C.c_void_p(self.hpath[i].data_ptr()),
                                       C.c_void_p(self.hcurv[i].data_ptr()), None)
             if rc != 0:
@@ -516,9 +521,13 @@ def main():
     def e2e_opts(batches_in_flight):
         n = args.max_slots if args.max_slots > 0 else max(32, min(lane_slots, (hw_slots - sm_count) // max(1, min(lanes, batches_in_flight))))
         return n, ctx.make_opts(path_cap=2048, max_slots=n)
+    if args.e2e_steps > 0:
+        e2e_steps = args.e2e_steps
+    else:
+        e2e_steps = max(3, min(args.steps, lanes // 2 if world == 1 else lanes // 4))
     free_b, total_b = torch.cuda.mem_get_info()
-    pipe = Pipeline(ctx, lanes, q, opts, pp)
-    pipe.set_budget(int(free_b * 0.80 / lanes))
+    pipe = Pipeline(ctx, lanes, q, opts, pp, fetch_lanes=max(args.warmup, e2e_steps))
+    pipe.set_budget(int(free_b * 0.88 / lanes))      # pools + arena of every lane; the rest stays free for NCCL and the allocator
     pipe.upload_all()       # every lane allocates its pools and computes its groups' 2D fields (launch order) before anything is timed
 
     # ---- warm-up, then end to end through the C ABI: pinned host queries in, results + paths + curvature out, EVERY step.  The W
@@ -526,10 +535,6 @@ def main():
     # e2e clock starts, so the e2e region holds exactly its own E batches: ramp-up, bulk and the full drain of the last one.
     # (Until this revision warm-up and e2e were one stream and the clock started while the warm-up batches were still running:
     # the region did the work of W + E batches and was credited with E.) ----
-    if args.e2e_steps > 0:
-        e2e_steps = args.e2e_steps
-    else:
-        e2e_steps = max(3, min(args.steps, lanes // 2 if world == 1 else lanes // 4))
     barrier()
     e2e_slots, pipe.opts = e2e_opts(e2e_steps)
     t_w0 = time.perf_counter()
