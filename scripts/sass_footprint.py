@@ -10,6 +10,7 @@ line that looks like a function header).  Used for the instruction-footprint wor
 import collections, os, re, subprocess, sys, tempfile
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SRC_ROOT = os.environ.get("PP_SRC_ROOT", ROOT)      # tree the object was compiled from (line -> function mapping)
 OBJ = os.path.join(ROOT, "path_planning_pkg_b200", "lib", "obj", "libpp_b200_cabi.o")
 
 
@@ -47,7 +48,7 @@ def main():
     headers = {}
     for f in set(k[0] for k in per_line):
         path = None
-        for r, _, fs in os.walk(os.path.join(ROOT, "path_planning_pkg_b200", "csrc")):
+        for r, _, fs in os.walk(os.path.join(SRC_ROOT, "path_planning_pkg_b200", "csrc")):
             if f in fs:
                 path = os.path.join(r, f)
         hs = []
